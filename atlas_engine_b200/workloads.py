@@ -1,0 +1,266 @@
+"""Synthetic inputs for the BASELINE.json configurations and the parity edge cases.
+
+Everything here is plain numpy on the host and deterministic for a given seed; the same arrays are fed to the CUDA
+path, to the oracle and to the reference so parity never depends on how an input was made.
+
+Conventions: triangles are (n, 9) float32 (v0, v1, v2); boxes are (n, 6) float32 (min, max) computed like
+MeshData::BuildBVH does (/root/reference/src/engine/mesh/MeshData.cpp:143-146); rays are PackedRay rows of 12 float32
+(/root/reference/data/shader/raytracer/structures.hsh:9-13): origin.xyz, bits(ID), direction.xyz, -, hit.xyzw.
+"""
+import numpy as np
+
+INF = np.float32(1e12)            # common.hsh:8
+MASK_ALL = 1 << 7                 # RTStructures.h:9-12
+MASK_SHADOW = 1 << 6
+
+
+def tri_boxes(tris):
+    t = np.asarray(tris, dtype=np.float32).reshape(-1, 3, 3)
+    return np.concatenate([t.min(axis=1), t.max(axis=1)], axis=1).astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------------------- geometry
+def soup(n, seed=1234, extent=0.01):
+    """C2: centre ~ U[0,1)^3, each vertex = centre + extent * U[-0.5,0.5)^3."""
+    rng = np.random.default_rng(seed)
+    c = rng.random((n, 1, 3), dtype=np.float32)
+    off = (rng.random((n, 3, 3), dtype=np.float32) - np.float32(0.5)) * np.float32(extent)
+    return (c + off).reshape(n, 9).astype(np.float32)
+
+
+def soup_with_giants(n, seed=99, frac=0.02):
+    """Soup where a fraction of triangles is huge, so the root SBVH spatial split fires and duplicates refs."""
+    t = soup(n, seed).reshape(n, 3, 3)
+    rng = np.random.default_rng(seed + 1)
+    k = max(1, int(n * frac))
+    pick = rng.choice(n, k, replace=False)
+    c = rng.random((k, 1, 3), dtype=np.float32)
+    t[pick] = c + (rng.random((k, 3, 3), dtype=np.float32) - np.float32(0.5)) * np.float32(0.6)
+    return t.reshape(n, 9)
+
+
+def heightfield(nx, nz, spacing=1.0):
+    """C3: nx x nz quads = 2*nx*nz triangles, y = 20 sin(.013x) cos(.017z) + 5 sin(.11x + .07z)."""
+    xs = (np.arange(nx + 1, dtype=np.float64) * spacing)
+    zs = (np.arange(nz + 1, dtype=np.float64) * spacing)
+    X, Z = np.meshgrid(xs, zs, indexing="ij")
+    Y = 20.0 * np.sin(0.013 * X) * np.cos(0.017 * Z) + 5.0 * np.sin(0.11 * X + 0.07 * Z)
+    P = np.stack([X, Y, Z], axis=-1).astype(np.float32)
+    p00, p10, p01, p11 = P[:-1, :-1], P[1:, :-1], P[:-1, 1:], P[1:, 1:]
+    a = np.stack([p00, p10, p11], axis=2)
+    b = np.stack([p00, p11, p01], axis=2)
+    return np.stack([a, b], axis=2).reshape(-1, 9).astype(np.float32)
+
+
+def flat_grid(n):
+    """n x n quads in the plane y == 0: one axis is always skipped (extent < 1e-3) and quads share boxes."""
+    t = heightfield(n, n).reshape(-1, 3, 3)
+    t[:, :, 1] = 0.0
+    return t.reshape(-1, 9)
+
+
+def uv_sphere(segments=32, rings=16, radius=1.0, centre=(0.0, 0.0, 0.0)):
+    th = np.linspace(0.0, np.pi, rings + 1)
+    ph = np.linspace(0.0, 2.0 * np.pi, segments + 1)
+    T, Pn = np.meshgrid(th, ph, indexing="ij")
+    P = np.stack([np.sin(T) * np.cos(Pn), np.cos(T), np.sin(T) * np.sin(Pn)], axis=-1) * radius + np.asarray(centre)
+    P = P.astype(np.float32)
+    tris = []
+    for i in range(rings):
+        for j in range(segments):
+            a, b, c, d = P[i, j], P[i + 1, j], P[i + 1, j + 1], P[i, j + 1]
+            if i != 0:
+                tris.append(np.concatenate([a, b, d]))
+            if i != rings - 1:
+                tris.append(np.concatenate([b, c, d]))
+    return np.asarray(tris, dtype=np.float32)
+
+
+def _quad_wall(origin, du, dv, nu, nv):
+    o, du, dv = (np.asarray(x, dtype=np.float64) for x in (origin, du, dv))
+    U, V = np.meshgrid(np.arange(nu + 1) / nu, np.arange(nv + 1) / nv, indexing="ij")
+    P = (o + U[..., None] * du + V[..., None] * dv).astype(np.float32)
+    p00, p10, p01, p11 = P[:-1, :-1], P[1:, :-1], P[:-1, 1:], P[1:, 1:]
+    a = np.stack([p00, p10, p11], axis=2)
+    b = np.stack([p00, p11, p01], axis=2)
+    return np.stack([a, b], axis=2).reshape(-1, 9)
+
+
+def atrium(detail=64, seed=7, scale=0.05, clutter=20000):
+    """C1 stand-in for the missing sponza: a closed hall (tessellated floor, ceiling, four walls), two rows of
+    12-sided columns, a few long thin triangles that span the hall (so the root spatial split fires) and small
+    clutter triangles. detail=64 gives ~75 k triangles, detail=128 ~262 k."""
+    parts = []
+    L, W, H = 600.0, 250.0, 200.0
+    n = detail
+    parts.append(_quad_wall((0, 0, 0), (L, 0, 0), (0, 0, W), 2 * n, n))            # floor
+    parts.append(_quad_wall((0, H, 0), (L, 0, 0), (0, 0, W), 2 * n, n))            # ceiling
+    parts.append(_quad_wall((0, 0, 0), (L, 0, 0), (0, H, 0), 2 * n, n))            # wall z=0
+    parts.append(_quad_wall((0, 0, W), (L, 0, 0), (0, H, 0), 2 * n, n))            # wall z=W
+    parts.append(_quad_wall((0, 0, 0), (0, 0, W), (0, H, 0), n, n))                # wall x=0
+    parts.append(_quad_wall((L, 0, 0), (0, 0, W), (0, H, 0), n, n))                # wall x=L
+    ang = np.linspace(0.0, 2.0 * np.pi, 13)
+    for row_z in (60.0, W - 60.0):
+        for cx in np.linspace(60.0, L - 60.0, 8):
+            ring = np.stack([cx + 12.0 * np.cos(ang), np.zeros(13), row_z + 12.0 * np.sin(ang)], axis=-1)
+            for k in range(12):
+                for seg in range(max(2, n // 8)):
+                    y0 = H * 0.8 * seg / max(2, n // 8)
+                    y1 = H * 0.8 * (seg + 1) / max(2, n // 8)
+                    a, b = ring[k].copy(), ring[k + 1].copy()
+                    a0, b0, a1, b1 = a.copy(), b.copy(), a.copy(), b.copy()
+                    a0[1] = b0[1] = y0
+                    a1[1] = b1[1] = y1
+                    parts.append(np.concatenate([a0, b0, b1])[None].astype(np.float32))
+                    parts.append(np.concatenate([a0, b1, a1])[None].astype(np.float32))
+    rng = np.random.default_rng(seed)
+    beams = []
+    for _ in range(100):   # long thin triangles (banners/beams)
+        p = rng.random(3) * (L, H, W)
+        q = p + (rng.random(3) - 0.5) * (L * 0.9, 10.0, W * 0.9)
+        r = p + (0.0, 2.0, 0.0)
+        beams.append(np.concatenate([p, q, r]))
+    parts.append(np.asarray(beams, dtype=np.float32))
+    c = rng.random((clutter, 1, 3)) * (L, H, W)
+    parts.append((c + (rng.random((clutter, 3, 3)) - 0.5) * 3.0).reshape(clutter, 9).astype(np.float32))
+    t = np.concatenate(parts, axis=0).astype(np.float32)
+    return (t * np.float32(scale)).astype(np.float32)
+
+
+def coincident(n_same=200, n_concentric=200):
+    """Pathological: n_same identical triangles plus n_concentric concentric ones (forces the std::sort fallback
+    of PerformMedianSplit with large n)."""
+    base = np.array([0, 0, 0, 1, 0, 0, 0, 1, 0], dtype=np.float32)
+    same = np.tile(base, (n_same, 1))
+    s = (1.0 + np.arange(n_concentric, dtype=np.float32)[:, None] * np.float32(0.01))
+    conc = (base.reshape(3, 3)[None] - np.float32(1 / 3)) * s[:, :, None] + np.float32(1 / 3)
+    return np.concatenate([same, conc.reshape(n_concentric, 9)]).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------------- rays
+def pack_rays(origins, dirs, ids=None, t=None):
+    n = origins.shape[0]
+    r = np.zeros((n, 12), dtype=np.float32)
+    r[:, 0:3] = origins
+    r[:, 4:7] = dirs
+    ids = np.arange(n, dtype=np.int32) if ids is None else np.asarray(ids, dtype=np.int32)
+    r[:, 3] = ids.view(np.float32)
+    if t is not None:
+        r[:, 8] = t
+    r[:, 9] = np.full(n, -1, dtype=np.int32).view(np.float32)
+    return r
+
+
+def random_rays(n, lo, hi, seed=5678):
+    """C2 rays: origin ~ U over the box, direction = normalize(U[-0.5,0.5)^3), rejecting |d| < 1e-3 or any
+    component below 1e-6 in magnitude."""
+    rng = np.random.default_rng(seed)
+    lo, hi = np.asarray(lo, dtype=np.float32), np.asarray(hi, dtype=np.float32)
+    o = lo + rng.random((n, 3), dtype=np.float32) * (hi - lo)
+    d = rng.random((n, 3), dtype=np.float32) - np.float32(0.5)
+    for _ in range(8):
+        nrm = np.linalg.norm(d, axis=1)
+        bad = (nrm < 1e-3) | (np.abs(d / np.maximum(nrm, 1e-20)[:, None]).min(axis=1) < 1e-6)
+        if not bad.any():
+            break
+        d[bad] = rng.random((int(bad.sum()), 3), dtype=np.float32) - np.float32(0.5)
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    return pack_rays(o.astype(np.float32), d)
+
+
+def camera_frame(eye, target, up=(0, 1, 0), fov_deg=47.0, aspect=16 / 9):
+    """origin/right/bottom of the near-plane rectangle as PathTracingRenderer.cpp:157-162 derives them from frustum
+    corners 4,5,6 (upper-left, upper-right, lower-left of the near plane, CameraComponent.cpp:125-153)."""
+    eye, target, up = (np.asarray(x, dtype=np.float64) for x in (eye, target, up))
+    f = target - eye
+    f /= np.linalg.norm(f)
+    r = np.cross(f, up)
+    r /= np.linalg.norm(r)
+    u = np.cross(r, f)
+    near = 0.1
+    hh = np.tan(np.radians(fov_deg) / 2.0) * near
+    hw = hh * aspect
+    c = eye + f * near
+    ul, ur, ll = c + u * hh - r * hw, c + u * hh + r * hw, c - u * hh - r * hw
+    return (eye.astype(np.float32), ul.astype(np.float32), (ur - ul).astype(np.float32), (ll - ul).astype(np.float32))
+
+
+def primary_rays(width, height, eye, origin, right, bottom, jitter=(0.5, 0.5), tile_order=False):
+    """rayGen.csh:25-91 without the storage permutation unless tile_order: dir = normalize(origin + right*u +
+    bottom*v - eye), ID = y*w + x."""
+    x, y = np.meshgrid(np.arange(width, dtype=np.float32), np.arange(height, dtype=np.float32), indexing="xy")
+    u = (x + np.float32(jitter[0])) / np.float32(width)
+    v = (y + np.float32(jitter[1])) / np.float32(height)
+    d = origin[None, None] + right[None, None] * u[..., None] + bottom[None, None] * v[..., None] - eye[None, None]
+    d = (d / np.linalg.norm(d, axis=-1, keepdims=True)).astype(np.float32).reshape(-1, 3)
+    o = np.broadcast_to(eye, d.shape).astype(np.float32)
+    ids = (y.astype(np.int32) * width + x.astype(np.int32)).reshape(-1)
+    rays = pack_rays(o, d, ids)
+    if tile_order and width % 8 == 0 and height % 8 == 0:
+        yy, xx = np.divmod(np.arange(width * height), width)
+        key = ((yy // 8) * (width // 8) + (xx // 8)) * 64 + (yy % 8) * 8 + (xx % 8)
+        rays = rays[np.argsort(key, kind="stable")]
+    return rays
+
+
+# -------------------------------------------------------------------------------------------------- instances
+def transform_box(box, M):
+    """AABB::Transform (/root/reference/src/engine/volume/AABB.cpp:35-60): transform 8 corners, take min/max.
+    Computed in float64 and rounded once; instance world boxes are harness INPUTS."""
+    lo, hi = box[:3].astype(np.float64), box[3:].astype(np.float64)
+    corners = np.array([[x, y, z, 1.0] for x in (lo[0], hi[0]) for y in (lo[1], hi[1]) for z in (lo[2], hi[2])])
+    w = corners @ M.T
+    return np.concatenate([w[:, :3].min(axis=0), w[:, :3].max(axis=0)]).astype(np.float32)
+
+
+def random_instances(n, mesh_boxes, seed=4242, extent=(2000.0, 200.0, 2000.0), scale=(0.5, 4.0)):
+    """C4: n instances of len(mesh_boxes) meshes. Returns (world boxes (n,6) f32, GPUBVHInstance records (n,16) u32)
+    with inverseMatrix = rows 0-2 of the inverse world matrix (RayTracingWorld.cpp:100), mask = MaskAll|MaskShadow."""
+    rng = np.random.default_rng(seed)
+    m = len(mesh_boxes)
+    boxes = np.zeros((n, 6), dtype=np.float32)
+    inst = np.zeros((n, 16), dtype=np.uint32)
+    for i in range(n):
+        mesh = int(rng.integers(0, m))
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        w, x, y, z = q
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                      [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        s = rng.uniform(*scale)
+        M = np.eye(4)
+        M[:3, :3] = R * s
+        M[:3, 3] = rng.random(3) * np.asarray(extent)
+        boxes[i] = transform_box(mesh_boxes[mesh], M)
+        inv = np.linalg.inv(M)
+        inst[i, :12] = inv[:3, :].astype(np.float32).reshape(-1).view(np.uint32)
+        inst[i, 12] = mesh
+        inst[i, 13] = 0
+        inst[i, 14] = np.uint32(0xFFFFFFFF)
+        inst[i, 15] = MASK_ALL | MASK_SHADOW
+    return boxes, inst
+
+
+def identity_instance(mesh=0, mask=MASK_ALL | MASK_SHADOW):
+    inst = np.zeros((1, 16), dtype=np.uint32)
+    inst[0, :12] = np.eye(4, dtype=np.float32)[:3].reshape(-1).view(np.uint32)
+    inst[0, 12] = mesh
+    inst[0, 14] = np.uint32(0xFFFFFFFF)
+    inst[0, 15] = mask
+    return inst
+
+
+# ------------------------------------------------------------------------------------------------------ packing
+def pack_bvh_triangles(tris, order, end_of_node, material_idx=0, opacity=1.0):
+    """GPUBVHTriangle rows (12 float32) as MeshData.cpp:242-247 emits them: v0.xyz, endOfNode ? 1 : -1; v1.xyz,
+    bits(materialIdx); v2.xyz, opacity. numpy mirror used by tests to cross-check the CUDA pack kernel."""
+    t = np.asarray(tris, dtype=np.float32).reshape(-1, 9)[np.asarray(order, dtype=np.int64)]
+    out = np.zeros((t.shape[0], 12), dtype=np.float32)
+    out[:, 0:3] = t[:, 0:3]
+    out[:, 3] = np.where(np.asarray(end_of_node) != 0, np.float32(1.0), np.float32(-1.0))
+    out[:, 4:7] = t[:, 3:6]
+    out[:, 7] = np.full(t.shape[0], material_idx, dtype=np.int32).view(np.float32)
+    out[:, 8:11] = t[:, 6:9]
+    out[:, 11] = np.float32(opacity)
+    return out
