@@ -1,0 +1,262 @@
+"""ctypes binding of include/atlas_rt.h (libatlas_rt.so, built in-tree by __graft_entry__.build()).
+
+This is plumbing for tests and bench.py; the product is the CUDA library. There is NO fallback: if the shared object
+is missing or a call fails, an exception is raised.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libatlas_rt.so")
+
+DEVICE_INPUT, DEVICE_OUTPUT, ASYNC, PER_RAY_TMAX, COUNTERS = 1, 2, 4, 8, 16
+MASK_ALL, MASK_SHADOW = 1 << 7, 1 << 6
+INF = 1e12
+STATUS = {0: "OK", -1: "ERR_INVALID", -2: "ERR_CUDA", -3: "ERR_OOM", -4: "ERR_UNSUPPORTED", -5: "ERR_STACK"}
+
+_vp, _u64, _u32, _i32, _f32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_float
+
+# name -> (restype, argtypes); every symbol include/atlas_rt.h declares (tests/test_abi.py checks the two agree)
+SIGNATURES = {
+    "atlas_rt_version": (_i32, []),
+    "atlas_rt_context_create": (_i32, [_i32, _vp, C.POINTER(_vp)]),
+    "atlas_rt_context_destroy": (None, [_vp]),
+    "atlas_rt_context_synchronize": (_i32, [_vp]),
+    "atlas_rt_last_error": (C.c_char_p, [_vp]),
+    "atlas_rt_kernel_launches": (_u64, [_vp]),
+    "atlas_rt_build_blas": (_i32, [_vp, _vp, _vp, _u64, _u32, C.POINTER(_vp)]),
+    "atlas_rt_build_tlas": (_i32, [_vp, _vp, _u64, _u32, C.POINTER(_vp)]),
+    "atlas_rt_bvh_upload": (_i32, [_vp, _vp, _u64, _vp, _vp, _u64, C.POINTER(_vp)]),
+    "atlas_rt_bvh_counts": (_i32, [_vp, C.POINTER(_u64), C.POINTER(_u64)]),
+    "atlas_rt_bvh_download": (_i32, [_vp, _vp, _vp, _vp, _u32]),
+    "atlas_rt_bvh_device_ptrs": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "atlas_rt_bvh_stats": (_i32, [_vp, _vp]),
+    "atlas_rt_bvh_free": (None, [_vp]),
+    "atlas_rt_pack_mesh": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _u32, C.POINTER(_vp)]),
+    "atlas_rt_mesh_counts": (_i32, [_vp, C.POINTER(_u64), C.POINTER(_u64)]),
+    "atlas_rt_mesh_download": (_i32, [_vp, _vp, _vp, _u32]),
+    "atlas_rt_mesh_free": (None, [_vp]),
+    "atlas_rt_scene_create": (_i32, [_vp, _vp, _u32, _vp, _u64, _vp, _u32, C.POINTER(_vp)]),
+    "atlas_rt_scene_download": (_i32, [_vp, _vp, _vp, _u32]),
+    "atlas_rt_scene_free": (None, [_vp]),
+    "atlas_rt_trace_closest": (_i32, [_vp, _vp, _vp, _u64, _u32, _f32, _f32, _vp, _u32]),
+    "atlas_rt_trace_any": (_i32, [_vp, _vp, _vp, _u64, _u32, _f32, _f32, _vp, _u32]),
+    "atlas_rt_trace_counters": (_i32, [_vp, _vp]),
+    "atlas_rt_generate_primary_rays": (_i32, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _u32]),
+    "atlas_rt_pathtrace_bounce": (_i32, [_vp, _vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, C.POINTER(_u64), _u32]),
+    "atlas_rt_shard_range": (_i32, [_u64, _u32, _u32, _u32, C.POINTER(_u64), C.POINTER(_u64)]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libatlas_rt.so (once). Raises if it has not been built — there is no CPU path to fall back to."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(nvcc, sm_100a). atlas_engine_b200 has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+class AtlasError(RuntimeError):
+    pass
+
+
+def _addr(x):
+    """Pointer value of a numpy array (host), an int (device pointer) or None."""
+    if x is None:
+        return None
+    if isinstance(x, (int, np.integer)):
+        return int(x)
+    if isinstance(x, np.ndarray):
+        assert x.flags["C_CONTIGUOUS"]
+        return x.ctypes.data
+    if hasattr(x, "data_ptr"):   # torch tensor
+        return int(x.data_ptr())
+    raise TypeError(type(x))
+
+
+def _is_device(x):
+    return isinstance(x, (int, np.integer)) or (hasattr(x, "is_cuda") and x.is_cuda)
+
+
+class Context:
+    """atlas_rt_context: one CUDA device + stream. stream = raw cudaStream_t value (e.g. torch stream .cuda_stream)."""
+
+    def __init__(self, device=0, stream=None):
+        self.L = lib()
+        h = _vp()
+        rc = self.L.atlas_rt_context_create(device, stream, C.byref(h))
+        if rc != 0:
+            raise AtlasError(f"atlas_rt_context_create(device={device}) -> {STATUS.get(rc, rc)} (no usable CUDA device?)")
+        self.h = h
+        self.device = device
+
+    def check(self, rc):
+        if rc != 0:
+            msg = self.L.atlas_rt_last_error(self.h)
+            raise AtlasError(f"{STATUS.get(rc, rc)}: {msg.decode() if msg else ''}")
+
+    def synchronize(self):
+        self.check(self.L.atlas_rt_context_synchronize(self.h))
+
+    def launches(self):
+        return int(self.L.atlas_rt_kernel_launches(self.h))
+
+    def close(self):
+        if self.h:
+            self.L.atlas_rt_context_destroy(self.h)
+            self.h = None
+
+    # ------------------------------------------------------------------------------------------------ build
+    def build_blas(self, aabbs, tris, count=None, flags=0):
+        dev = _is_device(aabbs)
+        if not dev:
+            aabbs = np.ascontiguousarray(aabbs, dtype=np.float32)
+            tris = np.ascontiguousarray(tris, dtype=np.float32)
+            count = aabbs.shape[0]
+        h = _vp()
+        self.check(self.L.atlas_rt_build_blas(self.h, _addr(aabbs), _addr(tris), count, flags | (DEVICE_INPUT if dev else 0), C.byref(h)))
+        return BVH(self, h)
+
+    def build_tlas(self, aabbs, count=None, flags=0):
+        dev = _is_device(aabbs)
+        if not dev:
+            aabbs = np.ascontiguousarray(aabbs, dtype=np.float32)
+            count = aabbs.shape[0]
+        h = _vp()
+        self.check(self.L.atlas_rt_build_tlas(self.h, _addr(aabbs), count, flags | (DEVICE_INPUT if dev else 0), C.byref(h)))
+        return BVH(self, h)
+
+    def upload_bvh(self, nodes56, order, end_of_node):
+        nodes56 = np.ascontiguousarray(nodes56, dtype=np.uint32).reshape(-1, 14)
+        order = np.ascontiguousarray(order, dtype=np.uint32)
+        end_of_node = np.ascontiguousarray(end_of_node, dtype=np.uint8)
+        h = _vp()
+        self.check(self.L.atlas_rt_bvh_upload(self.h, _addr(nodes56), nodes56.shape[0], _addr(order), _addr(end_of_node), order.shape[0], C.byref(h)))
+        return BVH(self, h)
+
+    def pack_mesh(self, blas, tris, count=None, material_idx=None, opacity=None, flags=0):
+        dev = _is_device(tris)
+        if not dev:
+            tris = np.ascontiguousarray(tris, dtype=np.float32)
+            count = tris.shape[0]
+            if material_idx is not None:
+                material_idx = np.ascontiguousarray(material_idx, dtype=np.int32)
+            if opacity is not None:
+                opacity = np.ascontiguousarray(opacity, dtype=np.float32)
+        h = _vp()
+        self.check(self.L.atlas_rt_pack_mesh(self.h, blas.h, _addr(tris), count, _addr(material_idx), _addr(opacity),
+                                             flags | (DEVICE_INPUT if dev else 0), C.byref(h)))
+        return Mesh(self, h, blas)
+
+    def create_scene(self, meshes, instances, tlas, flags=0):
+        instances = np.ascontiguousarray(instances).view(np.uint32).reshape(-1, 16)
+        arr = (_vp * len(meshes))(*[m.h for m in meshes])
+        h = _vp()
+        self.check(self.L.atlas_rt_scene_create(self.h, arr, len(meshes), _addr(instances), instances.shape[0], tlas.h, flags, C.byref(h)))
+        return Scene(self, h, meshes, tlas)
+
+    # ------------------------------------------------------------------------------------------------ trace
+    def trace(self, scene, rays, count=None, out=None, cull_mask=MASK_ALL, t_min=0.0, t_max=INF, any_hit=False, flags=0):
+        """rays: (n, 12) float32 numpy array (host) or a device pointer / CUDA tensor with `count` given.
+        Returns the output array for host input, or None for device input (results land in `out`)."""
+        fn = self.L.atlas_rt_trace_any if any_hit else self.L.atlas_rt_trace_closest
+        if _is_device(rays):
+            out = rays if out is None else out
+            self.check(fn(self.h, scene.h, _addr(rays), count, cull_mask, t_min, t_max, _addr(out), flags | DEVICE_INPUT | DEVICE_OUTPUT))
+            return None
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 12)
+        res = np.empty_like(rays) if out is None else out
+        self.check(fn(self.h, scene.h, _addr(rays), rays.shape[0], cull_mask, t_min, t_max, _addr(res), flags))
+        return res
+
+    def trace_counters(self):
+        out = np.zeros(6, dtype=np.uint64)
+        self.check(self.L.atlas_rt_trace_counters(self.h, _addr(out)))
+        names = ("tlas_nodes", "instances", "blas_nodes", "triangles", "max_stack", "rays_stack_gt32")
+        return dict(zip(names, (int(x) for x in out)))
+
+
+class BVH:
+    def __init__(self, ctx, h):
+        self.ctx, self.h = ctx, h
+
+    def counts(self):
+        n, m = _u64(), _u64()
+        self.ctx.check(self.ctx.L.atlas_rt_bvh_counts(self.h, C.byref(n), C.byref(m)))
+        return int(n.value), int(m.value)
+
+    def download(self):
+        """(nodes (n,14) uint32 in the 56 B BVHNode layout, order (m,) uint32, end_of_node (m,) uint8)."""
+        n, m = self.counts()
+        nodes = np.zeros((n, 14), dtype=np.uint32)
+        order = np.zeros(m, dtype=np.uint32)
+        flags = np.zeros(m, dtype=np.uint8)
+        self.ctx.check(self.ctx.L.atlas_rt_bvh_download(self.h, _addr(nodes), _addr(order), _addr(flags), 0))
+        return nodes, order, flags
+
+    def stats(self):
+        out = np.zeros(8, dtype=np.uint64)
+        self.ctx.check(self.ctx.L.atlas_rt_bvh_stats(self.h, _addr(out)))
+        names = ("spatial_tried", "spatial_chosen", "duplicates", "median_splits", "sort_fallbacks", "sort_fallback_max_n",
+                 "levels", "neg_zero")
+        return dict(zip(names, (int(x) for x in out)))
+
+    def free(self):
+        if self.h:
+            self.ctx.L.atlas_rt_bvh_free(self.h)
+            self.h = None
+
+
+class Mesh:
+    def __init__(self, ctx, h, blas):
+        self.ctx, self.h, self.blas = ctx, h, blas
+
+    def download(self):
+        n, m = _u64(), _u64()
+        self.ctx.check(self.ctx.L.atlas_rt_mesh_counts(self.h, C.byref(n), C.byref(m)))
+        nodes = np.zeros((n.value, 16), dtype=np.float32)
+        tris = np.zeros((m.value, 12), dtype=np.float32)
+        self.ctx.check(self.ctx.L.atlas_rt_mesh_download(self.h, _addr(nodes), _addr(tris), 0))
+        return nodes, tris
+
+    def free(self):
+        if self.h:
+            self.ctx.L.atlas_rt_mesh_free(self.h)
+            self.h = None
+
+
+class Scene:
+    def __init__(self, ctx, h, meshes, tlas):
+        self.ctx, self.h, self.meshes, self.tlas = ctx, h, list(meshes), tlas
+
+    def download(self):
+        n, m = self.tlas.counts()
+        inst = np.zeros((m, 16), dtype=np.uint32)
+        nodes = np.zeros((n, 16), dtype=np.float32)
+        self.ctx.check(self.ctx.L.atlas_rt_scene_download(self.h, _addr(inst), _addr(nodes), 0))
+        return inst, nodes
+
+    def free(self):
+        if self.h:
+            self.ctx.L.atlas_rt_scene_free(self.h)
+            self.h = None
+
+
+def shard_range(count, rank, world, align=64):
+    b, e = _u64(), _u64()
+    rc = lib().atlas_rt_shard_range(count, rank, world, align, C.byref(b), C.byref(e))
+    if rc != 0:
+        raise AtlasError(STATUS.get(rc, rc))
+    return int(b.value), int(e.value)

@@ -1,0 +1,451 @@
+// api.cu — C ABI glue (include/atlas_rt.h): contexts, object lifetime, host<->device staging, pack and scene kernels.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace atlas {
+
+int fail(atlas_rt_context* ctx, int status, const char* what, cudaError_t e) {
+    if (ctx) {
+        ctx->error = what ? what : "error";
+        if (e != cudaSuccess) {
+            ctx->error += ": ";
+            ctx->error += cudaGetErrorString(e);
+        }
+    }
+    return status;
+}
+
+cudaError_t copy_in(atlas_rt_context* ctx, void* dst, const void* src, size_t bytes, bool srcDevice) {
+    if (bytes == 0) return cudaSuccess;
+    return cudaMemcpyAsync(dst, src, bytes, srcDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream);
+}
+
+cudaError_t copy_out(atlas_rt_context* ctx, void* dst, const void* src, size_t bytes, bool dstDevice) {
+    if (bytes == 0) return cudaSuccess;
+    return cudaMemcpyAsync(dst, src, bytes, dstDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream);
+}
+
+namespace {
+
+constexpr int kBlock = 256;
+inline uint32_t grid_for(uint64_t n, int block = kBlock) { return uint32_t((n + block - 1) / block); }
+
+// BVHNode (56 B, 14 words) <-> GPUBVHNode (64 B, 16 words) — the field-by-field copy of mesh/MeshData.cpp:256-268 and
+// raytracing/RayTracingWorld.cpp:272-284.
+__global__ void nodes56_to_64(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint64_t nodes) {
+    const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if (i >= nodes * 16) return;
+    const uint64_t n = i >> 4;
+    const uint32_t w = uint32_t(i & 15);
+    out[i] = w < 14 ? in[n * 14 + w] : 0u;
+}
+__global__ void nodes64_to_56(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint64_t nodes) {
+    const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if (i >= nodes * 14) return;
+    const uint64_t n = i / 14;
+    const uint32_t w = uint32_t(i - n * 14);
+    out[i] = in[n * 16 + w];
+}
+
+// GPUBVHTriangle records in flattened order — mesh/MeshData.cpp:242-247.
+__global__ void pack_bvh_triangles(const float* __restrict__ tris, const uint32_t* __restrict__ order,
+                                   const uint8_t* __restrict__ endOfNode, const int32_t* __restrict__ material,
+                                   const float* __restrict__ opacity, float4* __restrict__ out, uint64_t refs) {
+    const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if (i >= refs) return;
+    const uint32_t src = order[i];
+    const float* t = tris + 9 * size_t(src);
+    const int32_t mat = material ? material[src] : 0;
+    const float op = opacity ? opacity[src] : 1.0f;
+    out[3 * i + 0] = make_float4(t[0], t[1], t[2], endOfNode[i] ? 1.0f : -1.0f);
+    out[3 * i + 1] = make_float4(t[3], t[4], t[5], __int_as_float(mat));
+    out[3 * i + 2] = make_float4(t[6], t[7], t[8], op);
+}
+
+// Instance permutation of RayTracingWorld.cpp:287-295.
+__global__ void reorder_instances(const float4* __restrict__ src, const uint32_t* __restrict__ order,
+                                  const uint8_t* __restrict__ endOfNode, float4* __restrict__ dst, uint64_t refs) {
+    const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if (i >= refs) return;
+    const float4* s = src + 4 * size_t(order[i]);
+    float4 last = s[3];
+    last.z = __int_as_float(endOfNode[i] ? -1 : int(i) + 1);
+    dst[4 * i + 0] = s[0];
+    dst[4 * i + 1] = s[1];
+    dst[4 * i + 2] = s[2];
+    dst[4 * i + 3] = last;
+}
+
+int sync_unless_async(atlas_rt_context* ctx, uint32_t flags) {
+    if (flags & ATLAS_RT_ASYNC) return ATLAS_RT_OK;
+    ATLAS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ATLAS_RT_OK;
+}
+
+}   // namespace
+}   // namespace atlas
+
+using namespace atlas;
+
+extern "C" {
+
+int atlas_rt_version(void) { return ATLAS_RT_VERSION; }
+
+int atlas_rt_context_create(int device, void* stream, atlas_rt_context** out_ctx) {
+    if (!out_ctx) return ATLAS_RT_ERR_INVALID;
+    *out_ctx = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return ATLAS_RT_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return ATLAS_RT_ERR_CUDA;
+    auto* ctx = new (std::nothrow) atlas_rt_context;
+    if (!ctx) return ATLAS_RT_ERR_OOM;
+    ctx->device = device;
+    if (stream) {
+        ctx->stream = static_cast<cudaStream_t>(stream);
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ATLAS_RT_ERR_CUDA; }
+        ctx->ownStream = true;
+    }
+    cudaDeviceGetAttribute(&ctx->smCount, cudaDevAttrMultiProcessorCount, device);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    if (cudaMalloc(&ctx->dCounters, 8 * sizeof(unsigned long long)) != cudaSuccess) { delete ctx; return ATLAS_RT_ERR_OOM; }
+    cudaMemset(ctx->dCounters, 0, 8 * sizeof(unsigned long long));
+    ctx->pinnedBytes = 4096;
+    if (cudaMallocHost(&ctx->pinned, ctx->pinnedBytes) != cudaSuccess) { cudaFree(ctx->dCounters); delete ctx; return ATLAS_RT_ERR_OOM; }
+    *out_ctx = ctx;
+    return ATLAS_RT_OK;
+}
+
+void atlas_rt_context_destroy(atlas_rt_context* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->dCounters);
+    cudaFreeHost(ctx->pinned);
+    if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int atlas_rt_context_synchronize(atlas_rt_context* ctx) {
+    if (!ctx) return ATLAS_RT_ERR_INVALID;
+    ATLAS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ATLAS_RT_OK;
+}
+
+const char* atlas_rt_last_error(const atlas_rt_context* ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+uint64_t atlas_rt_kernel_launches(const atlas_rt_context* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------------- build
+static int build_common(atlas_rt_context* ctx, const float* aabbs, const float* tris, uint64_t count, uint32_t flags,
+                        bool tlas, atlas_rt_bvh** out_bvh) {
+    if (!ctx || !out_bvh || (count && !aabbs) || (!tlas && count && !tris)) return fail(ctx, ATLAS_RT_ERR_INVALID, "null argument");
+    *out_bvh = nullptr;
+    if (count > 0x3fffffffull) return fail(ctx, ATLAS_RT_ERR_UNSUPPORTED, "more than 2^30-1 primitives");
+    ATLAS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const bool dev = flags & ATLAS_RT_DEVICE_INPUT;
+    float *dA = nullptr, *dT = nullptr;
+    if (!dev) {
+        ATLAS_CUDA(ctx, dev_alloc(ctx, &dA, count * 6));
+        ATLAS_CUDA(ctx, copy_in(ctx, dA, aabbs, count * 24, false));
+        if (!tlas) {
+            ATLAS_CUDA(ctx, dev_alloc(ctx, &dT, count * 9));
+            ATLAS_CUDA(ctx, copy_in(ctx, dT, tris, count * 36, false));
+        }
+    }
+    auto* bvh = new (std::nothrow) atlas_rt_bvh;
+    if (!bvh) return fail(ctx, ATLAS_RT_ERR_OOM, "host allocation");
+    bvh->ctx = ctx;
+    int rc = build_bvh(ctx, dev ? aabbs : dA, tlas ? nullptr : (dev ? tris : dT), count, tlas, bvh);
+    if (!dev) { dev_free(ctx, dA); dev_free(ctx, dT); }
+    if (rc != ATLAS_RT_OK) { atlas_rt_bvh_free(bvh); return rc; }
+    rc = sync_unless_async(ctx, flags);
+    if (rc != ATLAS_RT_OK) { atlas_rt_bvh_free(bvh); return rc; }
+    *out_bvh = bvh;
+    return ATLAS_RT_OK;
+}
+
+int atlas_rt_build_blas(atlas_rt_context* ctx, const float* aabbs, const float* tris, uint64_t count, uint32_t flags,
+                        atlas_rt_bvh** out_bvh) {
+    return build_common(ctx, aabbs, tris, count, flags, false, out_bvh);
+}
+
+int atlas_rt_build_tlas(atlas_rt_context* ctx, const float* aabbs, uint64_t count, uint32_t flags, atlas_rt_bvh** out_bvh) {
+    return build_common(ctx, aabbs, nullptr, count, flags, true, out_bvh);
+}
+
+int atlas_rt_bvh_upload(atlas_rt_context* ctx, const void* nodes56, uint64_t node_count, const uint32_t* order,
+                        const uint8_t* end_of_node, uint64_t ref_count, atlas_rt_bvh** out_bvh) {
+    if (!ctx || !out_bvh || (node_count && !nodes56) || (ref_count && (!order || !end_of_node))) return fail(ctx, ATLAS_RT_ERR_INVALID, "null argument");
+    *out_bvh = nullptr;
+    ATLAS_CUDA(ctx, cudaSetDevice(ctx->device));
+    auto* bvh = new (std::nothrow) atlas_rt_bvh;
+    if (!bvh) return fail(ctx, ATLAS_RT_ERR_OOM, "host allocation");
+    bvh->ctx = ctx;
+    bvh->nodeCount = node_count;
+    bvh->refCount = ref_count;
+    uint32_t* staging = nullptr;
+    ATLAS_CUDA(ctx, dev_alloc(ctx, &bvh->nodes, node_count * 4));
+    ATLAS_CUDA(ctx, dev_alloc(ctx, &bvh->order, ref_count));
+    ATLAS_CUDA(ctx, dev_alloc(ctx, &bvh->endOfNode, ref_count));
+    ATLAS_CUDA(ctx, dev_alloc(ctx, &staging, node_count * 14));
+    ATLAS_CUDA(ctx, copy_in(ctx, staging, nodes56, node_count * 56, false));
+    ATLAS_CUDA(ctx, copy_in(ctx, bvh->order, order, ref_count * 4, false));
+    ATLAS_CUDA(ctx, copy_in(ctx, bvh->endOfNode, end_of_node, ref_count, false));
+    if (node_count) {
+        nodes56_to_64<<<grid_for(node_count * 16), kBlock, 0, ctx->stream>>>(staging, reinterpret_cast<uint32_t*>(bvh->nodes), node_count);
+        ATLAS_LAUNCH_CHECK(ctx);
+    }
+    dev_free(ctx, staging);
+    ATLAS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out_bvh = bvh;
+    return ATLAS_RT_OK;
+}
+
+int atlas_rt_bvh_counts(const atlas_rt_bvh* bvh, uint64_t* node_count, uint64_t* ref_count) {
+    if (!bvh) return ATLAS_RT_ERR_INVALID;
+    if (node_count) *node_count = bvh->nodeCount;
+    if (ref_count) *ref_count = bvh->refCount;
+    return ATLAS_RT_OK;
+}
+
+int atlas_rt_bvh_download(const atlas_rt_bvh* bvh, void* nodes56, uint32_t* order, uint8_t* end_of_node, uint32_t flags) {
+    if (!bvh) return ATLAS_RT_ERR_INVALID;
+    atlas_rt_context* ctx = bvh->ctx;
+    ATLAS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const bool dev = flags & ATLAS_RT_DEVICE_OUTPUT;
+    if (nodes56 && bvh->nodeCount) {
+        uint32_t* staging = nullptr;
+        ATLAS_CUDA(ctx, dev_alloc(ctx, &staging, bvh->nodeCount * 14));
+        nodes64_to_56<<<grid_for(bvh->nodeCount * 14), kBlock, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(bvh->nodes), staging, bvh->nodeCount);
+        ATLAS_LAUNCH_CHECK(ctx);
+        ATLAS_CUDA(ctx, copy_out(ctx, nodes56, staging, bvh->nodeCount * 56, dev));
+        dev_free(ctx, staging);
+    }
+    if (order) ATLAS_CUDA(ctx, copy_out(ctx, order, bvh->order, bvh->refCount * 4, dev));
+    if (end_of_node) ATLAS_CUDA(ctx, copy_out(ctx, end_of_node, bvh->endOfNode, bvh->refCount, dev));
+    return sync_unless_async(ctx, flags);
+}
+
+int atlas_rt_bvh_device_ptrs(const atlas_rt_bvh* bvh, const void** gpu_nodes64, const uint32_t** order, const uint8_t** end_of_node) {
+    if (!bvh) return ATLAS_RT_ERR_INVALID;
+    if (gpu_nodes64) *gpu_nodes64 = bvh->nodes;
+    if (order) *order = bvh->order;
+    if (end_of_node) *end_of_node = bvh->endOfNode;
+    return ATLAS_RT_OK;
+}
+
+int atlas_rt_bvh_stats(const atlas_rt_bvh* bvh, uint64_t out[8]) {
+    if (!bvh || !out) return ATLAS_RT_ERR_INVALID;
+    memcpy(out, bvh->stats, sizeof(bvh->stats));
+    return ATLAS_RT_OK;
+}
+
+void atlas_rt_bvh_free(atlas_rt_bvh* bvh) {
+    if (!bvh) return;
+    atlas_rt_context* ctx = bvh->ctx;
+    cudaSetDevice(ctx->device);
+    dev_free(ctx, bvh->nodes);
+    dev_free(ctx, bvh->order);
+    dev_free(ctx, bvh->endOfNode);
+    delete bvh;
+}
+
+// ----------------------------------------------------------------------------------------------------- pack
+int atlas_rt_pack_mesh(atlas_rt_context* ctx, const atlas_rt_bvh* blas, const float* tris, uint64_t count,
+                       const int32_t* material_idx, const float* opacity, uint32_t flags, atlas_rt_mesh** out_mesh) {
+    if (!ctx || !blas || !out_mesh || (count && !tris) || blas->ctx != ctx) return fail(ctx, ATLAS_RT_ERR_INVALID, "bad argument");
+    *out_mesh = nullptr;
+    ATLAS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const bool dev = flags & ATLAS_RT_DEVICE_INPUT;
+    float* dT = nullptr;
+    int32_t* dM = nullptr;
+    float* dO = nullptr;
+    if (!dev) {
+        ATLAS_CUDA(ctx, dev_alloc(ctx, &dT, count * 9));
+        ATLAS_CUDA(ctx, copy_in(ctx, dT, tris, count * 36, false));
+        if (material_idx) { ATLAS_CUDA(ctx, dev_alloc(ctx, &dM, count)); ATLAS_CUDA(ctx, copy_in(ctx, dM, material_idx, count * 4, false)); }
+        if (opacity) { ATLAS_CUDA(ctx, dev_alloc(ctx, &dO, count)); ATLAS_CUDA(ctx, copy_in(ctx, dO, opacity, count * 4, false)); }
+    }
+    auto* mesh = new (std::nothrow) atlas_rt_mesh;
+    if (!mesh) return fail(ctx, ATLAS_RT_ERR_OOM, "host allocation");
+    mesh->ctx = ctx;
+    mesh->blas = blas;
+    mesh->triCount = blas->refCount;
+    ATLAS_CUDA(ctx, dev_alloc(ctx, &mesh->tris, mesh->triCount * 3));
+    if (mesh->triCount) {
+        pack_bvh_triangles<<<grid_for(mesh->triCount), kBlock, 0, ctx->stream>>>(
+            dev ? tris : dT, blas->order, blas->endOfNode, dev ? material_idx : dM, dev ? opacity : dO, mesh->tris, mesh->triCount);
+        ATLAS_LAUNCH_CHECK(ctx);
+    }
+    if (!dev) { dev_free(ctx, dT); dev_free(ctx, dM); dev_free(ctx, dO); }
+    int rc = sync_unless_async(ctx, flags);
+    if (rc != ATLAS_RT_OK) { atlas_rt_mesh_free(mesh); return rc; }
+    *out_mesh = mesh;
+    return ATLAS_RT_OK;
+}
+
+int atlas_rt_mesh_counts(const atlas_rt_mesh* mesh, uint64_t* node_count, uint64_t* triangle_count) {
+    if (!mesh) return ATLAS_RT_ERR_INVALID;
+    if (node_count) *node_count = mesh->blas->nodeCount;
+    if (triangle_count) *triangle_count = mesh->triCount;
+    return ATLAS_RT_OK;
+}
+
+int atlas_rt_mesh_download(const atlas_rt_mesh* mesh, void* gpu_nodes64, void* gpu_bvh_triangles48, uint32_t flags) {
+    if (!mesh) return ATLAS_RT_ERR_INVALID;
+    atlas_rt_context* ctx = mesh->ctx;
+    ATLAS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const bool dev = flags & ATLAS_RT_DEVICE_OUTPUT;
+    if (gpu_nodes64) ATLAS_CUDA(ctx, copy_out(ctx, gpu_nodes64, mesh->blas->nodes, mesh->blas->nodeCount * 64, dev));
+    if (gpu_bvh_triangles48) ATLAS_CUDA(ctx, copy_out(ctx, gpu_bvh_triangles48, mesh->tris, mesh->triCount * 48, dev));
+    return sync_unless_async(ctx, flags);
+}
+
+void atlas_rt_mesh_free(atlas_rt_mesh* mesh) {
+    if (!mesh) return;
+    cudaSetDevice(mesh->ctx->device);
+    dev_free(mesh->ctx, mesh->tris);
+    delete mesh;
+}
+
+// ---------------------------------------------------------------------------------------------------- scene
+int atlas_rt_scene_create(atlas_rt_context* ctx, const atlas_rt_mesh* const* meshes, uint32_t mesh_count,
+                          const void* instances64, uint64_t instance_count, const atlas_rt_bvh* tlas, uint32_t flags,
+                          atlas_rt_scene** out_scene) {
+    if (!ctx || !meshes || !mesh_count || !instances64 || !tlas || !out_scene || tlas->ctx != ctx) return fail(ctx, ATLAS_RT_ERR_INVALID, "bad argument");
+    *out_scene = nullptr;
+    ATLAS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const bool dev = flags & ATLAS_RT_DEVICE_INPUT;
+    auto* scene = new (std::nothrow) atlas_rt_scene;
+    if (!scene) return fail(ctx, ATLAS_RT_ERR_OOM, "host allocation");
+    scene->ctx = ctx;
+    scene->tlas = tlas;
+    scene->meshCount = mesh_count;
+    scene->instanceCount = tlas->refCount;
+    std::vector<const float4*> nodePtrs(mesh_count), triPtrs(mesh_count);
+    for (uint32_t m = 0; m < mesh_count; m++) {
+        if (!meshes[m] || meshes[m]->ctx != ctx) { delete scene; return fail(ctx, ATLAS_RT_ERR_INVALID, "mesh from another context"); }
+        nodePtrs[m] = meshes[m]->blas->nodes;
+        triPtrs[m] = meshes[m]->tris;
+    }
+    float4* dSrc = nullptr;
+    ATLAS_CUDA(ctx, dev_alloc(ctx, &scene->blasNodes, mesh_count));
+    ATLAS_CUDA(ctx, dev_alloc(ctx, &scene->bvhTris, mesh_count));
+    ATLAS_CUDA(ctx, dev_alloc(ctx, &scene->instances, scene->instanceCount * 4));
+    // pointer tables are tiny: plain synchronous copies from pageable memory are fine here
+    ATLAS_CUDA(ctx, cudaMemcpyAsync(scene->blasNodes, nodePtrs.data(), mesh_count * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
+    ATLAS_CUDA(ctx, cudaMemcpyAsync(scene->bvhTris, triPtrs.data(), mesh_count * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
+    ATLAS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the std::vectors die at scope exit
+    const float4* src = static_cast<const float4*>(instances64);
+    if (!dev) {
+        ATLAS_CUDA(ctx, dev_alloc(ctx, &dSrc, instance_count * 4));
+        ATLAS_CUDA(ctx, copy_in(ctx, dSrc, instances64, instance_count * 64, false));
+        src = dSrc;
+    }
+    if (scene->instanceCount) {
+        reorder_instances<<<grid_for(scene->instanceCount), kBlock, 0, ctx->stream>>>(src, tlas->order, tlas->endOfNode, scene->instances, scene->instanceCount);
+        ATLAS_LAUNCH_CHECK(ctx);
+    }
+    dev_free(ctx, dSrc);
+    int rc = sync_unless_async(ctx, flags);
+    if (rc != ATLAS_RT_OK) { atlas_rt_scene_free(scene); return rc; }
+    *out_scene = scene;
+    return ATLAS_RT_OK;
+}
+
+int atlas_rt_scene_download(const atlas_rt_scene* scene, void* instances64, void* tlas_nodes64, uint32_t flags) {
+    if (!scene) return ATLAS_RT_ERR_INVALID;
+    atlas_rt_context* ctx = scene->ctx;
+    ATLAS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const bool dev = flags & ATLAS_RT_DEVICE_OUTPUT;
+    if (instances64) ATLAS_CUDA(ctx, copy_out(ctx, instances64, scene->instances, scene->instanceCount * 64, dev));
+    if (tlas_nodes64) ATLAS_CUDA(ctx, copy_out(ctx, tlas_nodes64, scene->tlas->nodes, scene->tlas->nodeCount * 64, dev));
+    return sync_unless_async(ctx, flags);
+}
+
+void atlas_rt_scene_free(atlas_rt_scene* scene) {
+    if (!scene) return;
+    cudaSetDevice(scene->ctx->device);
+    dev_free(scene->ctx, scene->instances);
+    dev_free(scene->ctx, scene->blasNodes);
+    dev_free(scene->ctx, scene->bvhTris);
+    delete scene;
+}
+
+// ---------------------------------------------------------------------------------------------------- trace
+static int trace_common(atlas_rt_context* ctx, const atlas_rt_scene* scene, const void* rays_in, uint64_t count,
+                        uint32_t cull_mask, float t_min, float t_max, void* rays_out, uint32_t flags, bool any) {
+    if (!ctx || !scene || scene->ctx != ctx || (count && (!rays_in || !rays_out))) return fail(ctx, ATLAS_RT_ERR_INVALID, "bad argument");
+    ATLAS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const bool devIn = flags & ATLAS_RT_DEVICE_INPUT, devOut = flags & ATLAS_RT_DEVICE_OUTPUT;
+    float4 *dIn = nullptr, *dOut = nullptr;
+    const float4* in = static_cast<const float4*>(rays_in);
+    float4* out = static_cast<float4*>(rays_out);
+    if (!devIn) {
+        ATLAS_CUDA(ctx, dev_alloc(ctx, &dIn, count * 3));
+        ATLAS_CUDA(ctx, copy_in(ctx, dIn, rays_in, count * 48, false));
+        in = dIn;
+    }
+    if (!devOut) {
+        if (dIn) out = dIn;   // in-place on the staging buffer
+        else { ATLAS_CUDA(ctx, dev_alloc(ctx, &dOut, count * 3)); out = dOut; }
+    }
+    int rc = launch_trace(ctx, scene, in, out, count, cull_mask, t_min, t_max, any, (flags & ATLAS_RT_PER_RAY_TMAX) != 0,
+                          (flags & ATLAS_RT_COUNTERS) != 0);
+    if (rc == ATLAS_RT_OK && !devOut) {
+        cudaError_t e = copy_out(ctx, rays_out, out, count * 48, false);
+        if (e != cudaSuccess) rc = fail(ctx, ATLAS_RT_ERR_CUDA, "copy_out", e);
+    }
+    dev_free(ctx, dIn);
+    dev_free(ctx, dOut);
+    if (rc != ATLAS_RT_OK) return rc;
+    if (flags & ATLAS_RT_ASYNC) return ATLAS_RT_OK;
+    // synchronous call: also report rays that ran out of the reference's 32-entry stack
+    ATLAS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, ctx->dCounters + 5, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    ATLAS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    uint64_t overflowed = 0;
+    memcpy(&overflowed, ctx->pinned, sizeof(overflowed));
+    if (overflowed) return fail(ctx, ATLAS_RT_ERR_STACK, "rays exceeded the 32-entry traversal stack (undefined behaviour in the reference)");
+    return ATLAS_RT_OK;
+}
+
+int atlas_rt_trace_closest(atlas_rt_context* ctx, const atlas_rt_scene* scene, const void* rays_in, uint64_t count,
+                           uint32_t cull_mask, float t_min, float t_max, void* rays_out, uint32_t flags) {
+    return trace_common(ctx, scene, rays_in, count, cull_mask, t_min, t_max, rays_out, flags, false);
+}
+
+int atlas_rt_trace_any(atlas_rt_context* ctx, const atlas_rt_scene* scene, const void* rays_in, uint64_t count,
+                       uint32_t cull_mask, float t_min, float t_max, void* rays_out, uint32_t flags) {
+    return trace_common(ctx, scene, rays_in, count, cull_mask, t_min, t_max, rays_out, flags, true);
+}
+
+int atlas_rt_trace_counters(atlas_rt_context* ctx, uint64_t out[6]) {
+    if (!ctx || !out) return ATLAS_RT_ERR_INVALID;
+    ATLAS_CUDA(ctx, cudaSetDevice(ctx->device));
+    ATLAS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, ctx->dCounters, 6 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    ATLAS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(out, ctx->pinned, 6 * sizeof(uint64_t));
+    return ATLAS_RT_OK;
+}
+
+int atlas_rt_shard_range(uint64_t count, uint32_t rank, uint32_t world, uint32_t align, uint64_t* begin, uint64_t* end) {
+    if (!begin || !end || world == 0 || rank >= world) return ATLAS_RT_ERR_INVALID;
+    if (align == 0) align = 1;
+    const uint64_t units = (count + align - 1) / align;
+    const uint64_t base = units / world, extra = units % world;
+    const uint64_t b = (base * rank + (rank < extra ? rank : extra)) * align;
+    const uint64_t e = b + (base + (rank < extra ? 1 : 0)) * align;
+    *begin = b < count ? b : count;
+    *end = e < count ? e : count;
+    return ATLAS_RT_OK;
+}
+
+}   // extern "C"

@@ -1,0 +1,1513 @@
+// build.cu — BLAS / TLAS construction on the GPU, reproducing the split decisions, primitive order and flattened
+// numbering of src/engine/volume/BVH.cpp bit for bit.
+//
+// Reference behaviour being reproduced (paths relative to the reference root):
+//   BVH::BVH(aabbs, data, parallel)  BVH.cpp:14-56     root = Build #1 (:249-341): object split with 256 bins, SBVH
+//                                                      spatial split attempt, median fallback; below the root Build #2.
+//   BVH::BVH(aabbs, parallel)        BVH.cpp:58-101    TLAS: Build #2 (:343-406) everywhere, 64 bins.
+//   Build #2                                           leaf iff one ref; FindObjectSplit (:444-528) else
+//                                                      PerformMedianSplit (:800-855, std::sort fallback); no depth cap.
+//   Flatten                          BVH.cpp:408-441   DFS pre-order, larger-area child first.
+//
+// GPU formulation. Every leaf holds exactly one reference, so a subtree over n refs has n-1 inner nodes and the
+// reference's pre-order numbering can be computed top-down while building: a node with flat index i whose refs occupy
+// final slots [b, b+n) gives its first child (the one with the larger surface area) index i+1 and slots
+// [b, b+n1), its second child index i+n1 and slots [b+n1, b+n); a child with one ref becomes the leaf pointer ~slot.
+// The GPUBVHNode array and the final primitive order are therefore written directly by the build — there is no
+// separate flatten pass. Refs are kept as two float4 arrays (min.xyz|idx, max.xyz|-) and every node owns a contiguous
+// segment; partitioning is stable (scan based) because ref order inside a node is observable through the median
+// fallback's sort (SURVEY.md §7 "hard parts").
+//
+// Two regimes:
+//   big nodes   (more than kSubtreeMax refs, or still in the first levels where more than 32 bins are used): processed
+//               level by level, many CTAs per node; per-CTA bin histograms in shared memory (integer min/max/add
+//               atomics, exact under any order) merged with global atomics; one warp per node does the SAH sweep;
+//               three-kernel stable partition (count, scan, scatter) with coalesced float4 traffic.
+//   subtrees    (<= kSubtreeMax refs and <= 32 bins): one CTA builds the whole subtree in shared memory, one warp per
+//               node, level-synchronous inside the CTA; only node records and final slots go back to HBM.
+// The root of a BLAS additionally runs the spatial-split search in parallel and, if that split wins, the
+// order-dependent straddler loop of PerformSpatialSplit (:699-756) sequentially on one thread fed from shared memory.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "build_common.cuh"
+
+namespace atlas {
+namespace {
+
+constexpr uint32_t kSubtreeMax = 1024;   // refs a shared-memory subtree CTA can hold
+constexpr uint32_t kSubtreeBins = 32;    // ... and the bin count it supports (one bin per lane)
+constexpr uint32_t kChunk = 1024;        // refs per CTA pass in the big-node kernels
+constexpr int kBigBlock = 256;
+constexpr int kSubBlock = 256;
+constexpr int kSubWarps = kSubBlock / 32;
+
+enum TaskKind : int32_t { kObject = 0, kMedian = 1, kDone = 2, kSpatial = 3, kPending = 4 };
+
+struct Task {   // one big node of the current level (64 B)
+    float lo[3], hi[3];
+    uint32_t start, count, flatIdx, depth;
+    int32_t kind, axis;
+    uint32_t bin;
+    float cutoff;
+    uint32_t nFirst, leftIsSecond;
+};
+
+struct SmallTask {   // root of a shared-memory subtree (48 B)
+    float lo[3], hi[3];
+    uint32_t start, count, flatIdx, depth, buf, pad;
+};
+
+struct LevelInfo {   // device-resident, read back once per level
+    uint32_t nTasks, nChunks, nNext, nSmall, nMedian, rootNeedSpatial, rootKind, rootLeaf;
+    uint32_t totalRefs, negZero, nStraddle, nL0, nR0, pad0, pad1, pad2;
+    unsigned long long stats[8];   // [2] duplicates [3] median splits [4] sort fallbacks [5] largest sort fallback
+};
+
+struct RootSplit {   // state of the BLAS root decision (Build #1)
+    float objCost, spaCost;
+    int32_t objAxis, spaAxis;
+    uint32_t objBin, spaBin;
+    float spaPos;
+    float minOverlap;
+    int splitBox[12];   // ord: left.lo, left.hi, right.lo, right.hi of the split being performed (grown by atomics)
+    float finalBox[12];
+    uint32_t nL, nR;
+};
+
+struct BuildBuffers {
+    float4* lo[2];
+    float4* hi[2];
+    float4* nodes;
+    uint32_t* order;
+    uint8_t* eon;
+    Task* tasks[2];
+    SmallTask* small;
+    LevelInfo* info;
+    RootSplit* root;
+    int* bins;          // [task][axis][bin][8]
+    int* sfx;           // [task][bin][6]
+    int* spaBins;       // [axis][256][8] root spatial bins
+    int* medAcc;        // [task][16]
+    uint32_t* chunkBase;    // [task]
+    uint32_t* chunkFirst;   // [chunk]
+    int* rootBox;       // 6 ord ints
+    const float* tris;
+    uint32_t budget;
+    uint32_t cap;
+};
+
+__device__ __forceinline__ void load_box(const Task& t, float lo[3], float hi[3]) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { lo[k] = t.lo[k]; hi[k] = t.hi[k]; }
+}
+
+__device__ __forceinline__ float comp(const float4& v, int axis) { return axis == 0 ? v.x : (axis == 1 ? v.y : v.z); }
+
+// ------------------------------------------------------------------------------------------------ level 0 set-up
+__global__ void init_refs(const float* __restrict__ aabbs, uint32_t n, float4* __restrict__ lo, float4* __restrict__ hi,
+                          int* __restrict__ rootBox, LevelInfo* __restrict__ info) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    int o[6] = {kOrdEmptyLo, kOrdEmptyLo, kOrdEmptyLo, kOrdEmptyHi, kOrdEmptyHi, kOrdEmptyHi};
+    bool neg = false;
+    if (i < n) {
+        const float* a = aabbs + 6 * size_t(i);
+        const float v[6] = {a[0], a[1], a[2], a[3], a[4], a[5]};
+        lo[i] = make_float4(v[0], v[1], v[2], __uint_as_float(i));
+        hi[i] = make_float4(v[3], v[4], v[5], 0.0f);
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            o[k] = ord_from_float(v[k]);
+            neg |= (__float_as_uint(v[k]) == 0x80000000u);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        o[k] = __reduce_min_sync(kFullMask, o[k]);
+        o[3 + k] = __reduce_max_sync(kFullMask, o[3 + k]);
+    }
+    const bool anyNeg = __any_sync(kFullMask, neg);
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            atomicMin(&rootBox[k], o[k]);
+            atomicMax(&rootBox[3 + k], o[3 + k]);
+        }
+        if (anyNeg) atomicOr(&info->negZero, 1u);
+    }
+}
+
+__global__ void make_root(const int* __restrict__ rootBox, uint32_t n, Task* __restrict__ tasks, LevelInfo* __restrict__ info,
+                          RootSplit* __restrict__ root) {
+    Task t;
+    for (int k = 0; k < 3; k++) { t.lo[k] = float_from_ord(rootBox[k]); t.hi[k] = float_from_ord(rootBox[3 + k]); }
+    t.start = 0; t.count = n; t.flatIdx = 0; t.depth = 0;
+    t.kind = kPending; t.axis = -1; t.bin = 0; t.cutoff = 0.0f; t.nFirst = 0; t.leftIsSecond = 0;
+    tasks[0] = t;
+    info->nTasks = 1;
+    info->totalRefs = n;
+    root->minOverlap = __fmul_rn(surface_area(t.lo, t.hi), 10e-6f);   // BVH.cpp:33
+}
+
+// TLAS over a single instance — BVH.cpp:80-88 plus the two-entry refs quirk (:346-349 then :415).
+__global__ void tlas_single(const float* __restrict__ aabbs, float4* __restrict__ nodes, uint32_t* __restrict__ order,
+                            uint8_t* __restrict__ eon) {
+    nodes[0] = make_float4(aabbs[0], aabbs[1], aabbs[2], aabbs[3]);
+    nodes[1] = make_float4(aabbs[4], aabbs[5], 0.0f, 0.0f);
+    nodes[2] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    nodes[3] = make_float4(__int_as_float(~0), __int_as_float(~0), 0.0f, 0.0f);
+    order[0] = 0; order[1] = 0;
+    eon[0] = 0; eon[1] = 1;
+}
+
+// Root turned into a leaf ("last resort", BVH.cpp:303-305; Flatten then emits no node at all).
+__global__ void root_leaf_output(uint32_t n, uint32_t* __restrict__ order, uint8_t* __restrict__ eon) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    order[i] = i;
+    eon[i] = (i == n - 1) ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------- per-level set-up
+__global__ void prepare_level(Task* __restrict__ tasks, LevelInfo* __restrict__ info, uint32_t* __restrict__ chunkBase) {
+    // single CTA: exclusive scan of ceil(count / kChunk) over the level's tasks
+    __shared__ uint32_t carry;
+    __shared__ uint32_t warpSums[32];
+    const uint32_t n = info->nTasks;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n ? (tasks[i].count + kChunk - 1) / kChunk : 0u;
+        uint32_t s = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t o = __shfl_up_sync(kFullMask, s, off);
+            if ((threadIdx.x & 31) >= off) s += o;
+        }
+        if ((threadIdx.x & 31) == 31) warpSums[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = threadIdx.x < (blockDim.x >> 5) ? warpSums[threadIdx.x] : 0u;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t o = __shfl_up_sync(kFullMask, w, off);
+                if (threadIdx.x >= off) w += o;
+            }
+            warpSums[threadIdx.x] = w;   // inclusive
+        }
+        __syncthreads();
+        const uint32_t warpOff = (threadIdx.x >> 5) ? warpSums[(threadIdx.x >> 5) - 1] : 0u;
+        if (i < n) chunkBase[i] = carry + warpOff + s - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry += warpOff + s;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        info->nChunks = carry;
+        info->nNext = 0;
+        info->nMedian = 0;
+    }
+}
+
+__global__ void init_bins(int* __restrict__ bins, const LevelInfo* __restrict__ info, uint32_t binsPerTask3) {
+    const uint64_t total = uint64_t(info->nTasks) * binsPerTask3;
+    for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < total; i += uint64_t(gridDim.x) * blockDim.x)
+        bin_init(bins + i * kBinWords);
+}
+
+// chunk -> (task, offset inside the task)
+__device__ __forceinline__ uint32_t find_task(const uint32_t* __restrict__ chunkBase, uint32_t nTasks, uint32_t chunk) {
+    uint32_t lo = 0, hi = nTasks;   // last task with chunkBase <= chunk
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (chunkBase[mid] <= chunk) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// ------------------------------------------------------------------------------------------ object-split binning
+// FindObjectSplit's hot loop (BVH.cpp:474-482) for all big nodes of a level, all three axes in one pass.
+__global__ void __launch_bounds__(kBigBlock)
+bin_big(const Task* __restrict__ tasks, const LevelInfo* __restrict__ info, const uint32_t* __restrict__ chunkBase,
+        const float4* __restrict__ rlo, const float4* __restrict__ rhi, int* __restrict__ gbins, uint32_t nb) {
+    extern __shared__ int sb[];   // [3][nb][8]
+    __shared__ uint32_t sTask;
+    const uint32_t nChunks = info->nChunks, nTasks = info->nTasks;
+    for (uint32_t c = blockIdx.x; c < nChunks; c += gridDim.x) {
+        if (threadIdx.x == 0) sTask = find_task(chunkBase, nTasks, c);
+        for (uint32_t e = threadIdx.x; e < 3 * nb; e += kBigBlock) bin_init(sb + e * kBinWords);
+        __syncthreads();
+        const uint32_t t = sTask;
+        const Task& tk = tasks[t];
+        const uint32_t off = (c - chunkBase[t]) * kChunk;
+        const uint32_t end = tk.start + tk.count;
+        AxisBins ab[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++) ab[a] = axis_bins(tk.lo[a], tk.hi[a], nb);
+#pragma unroll
+        for (uint32_t r = 0; r < kChunk / kBigBlock; r++) {
+            const uint32_t p = tk.start + off + r * kBigBlock + threadIdx.x;
+            if (p < end) {
+                const float4 l = rlo[p], h = rhi[p];
+                const int ol[3] = {ord_from_float(l.x), ord_from_float(l.y), ord_from_float(l.z)};
+                const int oh[3] = {ord_from_float(h.x), ord_from_float(h.y), ord_from_float(h.z)};
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    if (!ab[a].active) continue;
+                    const uint32_t b = bin_of(bin_centre(comp(l, a), comp(h, a)), ab[a].start, ab[a].inv, nb);
+                    int* rec = sb + (a * nb + b) * kBinWords;
+#pragma unroll
+                    for (int k = 0; k < 3; k++) { atomicMin(rec + k, ol[k]); atomicMax(rec + 3 + k, oh[k]); }
+                    atomicAdd(rec + 6, 1);
+                }
+            }
+        }
+        __syncthreads();
+        int* g = gbins + size_t(t) * 3 * nb * kBinWords;
+        for (uint32_t e = threadIdx.x; e < 3 * nb; e += kBigBlock) {
+            const int* rec = sb + e * kBinWords;
+            if (rec[6] > 0) {
+                int* d = g + e * kBinWords;
+#pragma unroll
+                for (int k = 0; k < 3; k++) { atomicMin(d + k, rec[k]); atomicMax(d + 3 + k, rec[3 + k]); }
+                atomicAdd(d + 6, rec[6]);
+                atomicAdd(d + 7, rec[6]);   // exit == enter == primitiveCount for the object split
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ child creation
+struct Lists {
+    Task* next;
+    SmallTask* small;
+    LevelInfo* info;
+    float4* nodes;
+    uint32_t budget;
+    uint32_t nextBuf;
+};
+
+__device__ __forceinline__ void enqueue_child(const Lists& L, const Box3& box, uint32_t start, uint32_t count,
+                                              uint32_t flatIdx, uint32_t depth) {
+    if (count <= 1u) return;
+    if (count <= kSubtreeMax && bins_at_depth(L.budget, depth) <= kSubtreeBins) {
+        const uint32_t s = atomicAdd(&L.info->nSmall, 1u);
+        SmallTask st;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { st.lo[k] = box.lo[k]; st.hi[k] = box.hi[k]; }
+        st.start = start; st.count = count; st.flatIdx = flatIdx; st.depth = depth; st.buf = L.nextBuf; st.pad = 0;
+        L.small[s] = st;
+    } else {
+        const uint32_t s = atomicAdd(&L.info->nNext, 1u);
+        Task t;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { t.lo[k] = box.lo[k]; t.hi[k] = box.hi[k]; }
+        t.start = start; t.count = count; t.flatIdx = flatIdx; t.depth = depth;
+        t.kind = kPending; t.axis = -1; t.bin = 0; t.cutoff = 0.0f; t.nFirst = 0; t.leftIsSecond = 0;
+        L.next[s] = t;
+    }
+}
+
+// Writes the flattened node of `t` and queues its children. Called by ONE thread. Flatten (BVH.cpp:419-438): the child
+// with the larger surface area goes first (swap iff SA(left) < SA(right)); leaf pointer = ~slot.
+__device__ __forceinline__ void emit_children(const Lists& L, Task& t, const Box3& left, const Box3& right, uint32_t nLeft) {
+    const uint32_t nRight = t.count - nLeft;
+    const bool swapped = surface_area(left) < surface_area(right);
+    const Box3& first = swapped ? right : left;
+    const Box3& second = swapped ? left : right;
+    const uint32_t nFirst = swapped ? nRight : nLeft, nSecond = t.count - nFirst;
+    const int32_t ptr1 = nFirst > 1u ? int32_t(t.flatIdx + 1u) : ~int32_t(t.start);
+    const int32_t ptr2 = nSecond > 1u ? int32_t(t.flatIdx + nFirst) : ~int32_t(t.start + nFirst);
+    float4* N = L.nodes + 4 * size_t(t.flatIdx);
+    N[0] = make_float4(first.lo[0], first.lo[1], first.lo[2], first.hi[0]);
+    N[1] = make_float4(first.hi[1], first.hi[2], second.lo[0], second.lo[1]);
+    N[2] = make_float4(second.lo[2], second.hi[0], second.hi[1], second.hi[2]);
+    N[3] = make_float4(__int_as_float(ptr1), __int_as_float(ptr2), 0.0f, 0.0f);
+    t.nFirst = nFirst;
+    t.leftIsSecond = swapped ? 1u : 0u;
+    enqueue_child(L, first, t.start, nFirst, t.flatIdx + 1u, t.depth + 1u);
+    enqueue_child(L, second, t.start + nFirst, nSecond, t.flatIdx + nFirst, t.depth + 1u);
+}
+
+__device__ __forceinline__ void start_median(Task& t, int* acc, LevelInfo* info) {
+    int axis;
+    float cutoff;
+    median_plane(t.lo, t.hi, axis, cutoff);
+    t.kind = kMedian;
+    t.axis = axis;
+    t.cutoff = cutoff;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { acc[k] = kOrdEmptyLo; acc[3 + k] = kOrdEmptyHi; acc[6 + k] = kOrdEmptyLo; acc[9 + k] = kOrdEmptyHi; }
+    acc[12] = 0;
+    atomicAdd(&info->nMedian, 1u);
+    atomicAdd(&info->stats[3], 1ull);
+}
+
+// ------------------------------------------------------------------------------------------- split selection
+// Build #2 decision (BVH.cpp:351-370) for every big node of the level: one warp per node.
+__global__ void select_big(Task* __restrict__ tasks, LevelInfo* __restrict__ info, const int* __restrict__ gbins,
+                           int* __restrict__ gsfx, int* __restrict__ medAcc, Lists L, uint32_t nb) {
+    const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= info->nTasks) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    Task tk = tasks[t];
+    const int* bins = gbins + size_t(t) * 3 * nb * kBinWords;
+    int* sfx = gsfx + size_t(t) * nb * 6;
+    BestSplit best = best_none();
+    for (int a = 0; a < 3; a++) {
+        const AxisBins ab = axis_bins(tk.lo[a], tk.hi[a], nb);
+        if (!ab.active) continue;
+        warp_sweep_axis(bins + size_t(a) * nb * kBinWords, nb, sfx, tk.count, a, best);
+    }
+    const float nodeCost = __fmul_rn(__uint2float_rn(tk.count), surface_area(tk.lo, tk.hi));   // BVH.cpp:238
+    if (best.axis < 0 || best.cost >= nodeCost) {
+        if (lane == 0) {
+            start_median(tk, medAcc + size_t(t) * 16, info);
+            tasks[t] = tk;
+        }
+        return;
+    }
+    OBox l, r;
+    uint32_t nLeft, nExit;
+    warp_split_boxes(bins + size_t(best.axis) * nb * kBinWords, nb, best.bin, l, r, nLeft, nExit);
+    if (lane == 0) {
+        tk.kind = kObject;
+        tk.axis = best.axis;
+        tk.bin = best.bin;
+        emit_children(L, tk, obox_to_box(l), obox_to_box(r), nLeft);
+        tasks[t] = tk;
+    }
+}
+
+// Build #1, first half (BVH.cpp:258-268): object split of the BLAS root and the "try a spatial split?" test.
+__global__ void select_root_object(Task* __restrict__ tasks, LevelInfo* __restrict__ info, const int* __restrict__ gbins,
+                                   int* __restrict__ gsfx, RootSplit* __restrict__ root, uint32_t nb) {
+    const uint32_t lane = threadIdx.x & 31u;
+    Task tk = tasks[0];
+    BestSplit best = best_none();
+    for (int a = 0; a < 3; a++) {
+        const AxisBins ab = axis_bins(tk.lo[a], tk.hi[a], nb);
+        if (!ab.active) continue;
+        warp_sweep_axis(gbins + size_t(a) * nb * kBinWords, nb, gsfx, tk.count, a, best);
+    }
+    Box3 l = empty_box(), r = empty_box();
+    if (best.axis >= 0) {
+        OBox ol, orr;
+        uint32_t nLeft, nExit;
+        warp_split_boxes(gbins + size_t(best.axis) * nb * kBinWords, nb, best.bin, ol, orr, nLeft, nExit);
+        l = obox_to_box(ol);
+        r = obox_to_box(orr);
+    }
+    if (lane == 0) {
+        root->objCost = best.cost;
+        root->objAxis = best.axis;
+        root->objBin = best.bin;
+        root->spaCost = kFltMax;
+        root->spaAxis = -1;
+        root->spaBin = 0;
+        // overlap = left; overlap.Intersect(right) — AABB.cpp:102-107
+        float olo[3], ohi[3];
+        for (int k = 0; k < 3; k++) { olo[k] = gl_max(l.lo[k], r.lo[k]); ohi[k] = gl_min(l.hi[k], r.hi[k]); }
+        info->rootNeedSpatial = (surface_area(olo, ohi) >= root->minOverlap) ? 1u : 0u;
+    }
+}
+
+// SplitReference — BVH.cpp:760-798. tri = 9 floats; cur = box of the reference being split.
+__device__ inline void split_reference(const float* __restrict__ tri, const Box3& cur, Box3& L, Box3& R, float plane, int axis) {
+    L = empty_box();
+    R = empty_box();
+    float v[3][3];
+#pragma unroll
+    for (int k = 0; k < 9; k++) v[k / 3][k % 3] = tri[k];
+#pragma unroll
+    for (int e = 0; e < 3; e++) {
+        const float* a = v[e];
+        const float* b = v[(e + 1) % 3];
+        const float av = a[axis], bv = b[axis];
+        if ((av < plane && bv > plane) || (av > plane && bv < plane)) {
+            const float off = gl_clamp(__fdiv_rn(__fsub_rn(plane, av), __fsub_rn(bv, av)), 0.0f, 1.0f);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float p = __fadd_rn(a[k], __fmul_rn(off, __fsub_rn(b[k], a[k])));   // glm 0.9.8 mix
+                L.hi[k] = gl_max(p, L.hi[k]); L.lo[k] = gl_min(p, L.lo[k]);               // Grow(vec3): point first
+                R.hi[k] = gl_max(p, R.hi[k]); R.lo[k] = gl_min(p, R.lo[k]);
+            }
+        }
+        if (av <= plane) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) { L.hi[k] = gl_max(a[k], L.hi[k]); L.lo[k] = gl_min(a[k], L.lo[k]); }
+        }
+        if (av >= plane) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) { R.hi[k] = gl_max(a[k], R.hi[k]); R.lo[k] = gl_min(a[k], R.lo[k]); }
+        }
+    }
+    L.hi[axis] = plane;
+    R.lo[axis] = plane;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {   // Intersect(currentRef.aabb)
+        L.lo[k] = gl_max(L.lo[k], cur.lo[k]); L.hi[k] = gl_min(L.hi[k], cur.hi[k]);
+        R.lo[k] = gl_max(R.lo[k], cur.lo[k]); R.hi[k] = gl_min(R.hi[k], cur.hi[k]);
+    }
+}
+
+__device__ __forceinline__ void bin_grow_shared(int* rec, const Box3& b) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { atomicMin(rec + k, ord_from_float(b.lo[k])); atomicMax(rec + 3 + k, ord_from_float(b.hi[k])); }
+}
+
+// FindSpatialSplit's binning (BVH.cpp:589-619) over the root's refs; one ref per thread, bins in shared memory.
+__global__ void __launch_bounds__(kBigBlock)
+spatial_bin_root(const Task* __restrict__ tasks, const float4* __restrict__ rlo, const float4* __restrict__ rhi,
+                 const float* __restrict__ tris, int* __restrict__ gbins, uint32_t nb) {
+    extern __shared__ int sb[];   // [3][nb][8]
+    for (uint32_t e = threadIdx.x; e < 3 * nb; e += kBigBlock) bin_init(sb + e * kBinWords);
+    __syncthreads();
+    const Task& tk = tasks[0];
+    AxisBins ab[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) ab[a] = axis_bins(tk.lo[a], tk.hi[a], nb);
+    for (uint32_t p = blockIdx.x * kBigBlock + threadIdx.x; p < tk.count; p += gridDim.x * kBigBlock) {
+        const float4 l = rlo[p], h = rhi[p];
+        Box3 box;
+        box.lo[0] = l.x; box.lo[1] = l.y; box.lo[2] = l.z;
+        box.hi[0] = h.x; box.hi[1] = h.y; box.hi[2] = h.z;
+        const uint32_t src = __float_as_uint(l.w);
+#pragma unroll 1
+        for (int a = 0; a < 3; a++) {
+            if (!ab[a].active) continue;
+            const uint32_t b0 = bin_of(box.lo[a], ab[a].start, ab[a].inv, nb);
+            const uint32_t b1 = bin_of(box.hi[a], ab[a].start, ab[a].inv, nb);
+            int* base = sb + a * nb * kBinWords;
+            if (b0 == b1) {
+                bin_grow_shared(base + b0 * kBinWords, box);
+                atomicAdd(base + b0 * kBinWords + 6, 1);
+                atomicAdd(base + b0 * kBinWords + 7, 1);
+                continue;
+            }
+            Box3 rest = box;
+            for (uint32_t j = b0; j < b1; j++) {
+                Box3 cl, cr;
+                const float plane = __fadd_rn(ab[a].start, __fmul_rn(__uint2float_rn(j + 1u), ab[a].width));
+                split_reference(tris + 9 * size_t(src), rest, cl, cr, plane, a);
+                bin_grow_shared(base + j * kBinWords, cl);
+                rest = cr;
+            }
+            bin_grow_shared(base + b1 * kBinWords, rest);
+            atomicAdd(base + b0 * kBinWords + 6, 1);
+            atomicAdd(base + b1 * kBinWords + 7, 1);
+        }
+    }
+    __syncthreads();
+    for (uint32_t e = threadIdx.x; e < 3 * nb; e += kBigBlock) {
+        const int* rec = sb + e * kBinWords;
+        int* d = gbins + e * kBinWords;
+        // a bin's box can be grown without its counters changing (chopped interior pieces), so test the box too
+        if (rec[6] | rec[7] | (rec[0] != kOrdEmptyLo) | (rec[3] != kOrdEmptyHi)) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) { atomicMin(d + k, rec[k]); atomicMax(d + 3 + k, rec[3 + k]); }
+            if (rec[6]) atomicAdd(d + 6, rec[6]);
+            if (rec[7]) atomicAdd(d + 7, rec[7]);
+        }
+    }
+}
+
+// Build #1, second half (BVH.cpp:276-301): choose between median, spatial and object split for the BLAS root.
+__global__ void select_root_final(Task* __restrict__ tasks, LevelInfo* __restrict__ info, const int* __restrict__ objBins,
+                                  const int* __restrict__ spaBins, int* __restrict__ gsfx, int* __restrict__ medAcc,
+                                  RootSplit* __restrict__ root, Lists L, uint32_t nb, int trySpatial) {
+    const uint32_t lane = threadIdx.x & 31u;
+    Task tk = tasks[0];
+    BestSplit spa = best_none();
+    if (trySpatial) {
+        for (int a = 0; a < 3; a++) {
+            const AxisBins ab = axis_bins(tk.lo[a], tk.hi[a], nb);
+            if (!ab.active) continue;
+            warp_sweep_axis(spaBins + size_t(a) * nb * kBinWords, nb, gsfx, tk.count, a, spa);
+        }
+    }
+    const float objCost = root->objCost;
+    const int objAxis = root->objAxis;
+    const float nodeCost = __fmul_rn(__uint2float_rn(tk.count), surface_area(tk.lo, tk.hi));   // BVH.cpp:230
+    if ((objAxis < 0 || objCost >= nodeCost) && (spa.axis < 0 || spa.cost >= nodeCost)) {
+        if (lane == 0) {
+            start_median(tk, medAcc, info);
+            tasks[0] = tk;
+            info->rootKind = kMedian;
+        }
+        return;
+    }
+    if (spa.cost < objCost) {
+        OBox l, r;
+        uint32_t nEnter, nExit;
+        warp_split_boxes(spaBins + size_t(spa.axis) * nb * kBinWords, nb, spa.bin, l, r, nEnter, nExit);
+        if (lane == 0) {
+            const AxisBins ab = axis_bins(tk.lo[spa.axis], tk.hi[spa.axis], nb);
+            tk.kind = kSpatial;
+            tk.axis = spa.axis;
+            tk.bin = spa.bin;
+            tasks[0] = tk;
+            root->spaCost = spa.cost;
+            root->spaAxis = spa.axis;
+            root->spaBin = spa.bin;
+            root->spaPos = __fadd_rn(ab.start, __fmul_rn(__uint2float_rn(spa.bin), ab.width));   // BVH.cpp:656
+            for (int k = 0; k < 3; k++) {
+                root->splitBox[k] = l.lo[k]; root->splitBox[3 + k] = l.hi[k];
+                root->splitBox[6 + k] = r.lo[k]; root->splitBox[9 + k] = r.hi[k];
+            }
+            info->rootKind = kSpatial;
+            atomicAdd(&info->stats[1], 1ull);
+        }
+        return;
+    }
+    // objCost <= spaCost
+    OBox l, r;
+    uint32_t nLeft, nExit;
+    warp_split_boxes(objBins + size_t(objAxis) * nb * kBinWords, nb, root->objBin, l, r, nLeft, nExit);
+    if (lane == 0) {
+        tk.kind = kObject;
+        tk.axis = objAxis;
+        tk.bin = root->objBin;
+        emit_children(L, tk, obox_to_box(l), obox_to_box(r), nLeft);
+        tasks[0] = tk;
+        info->rootKind = kObject;
+    }
+}
+
+// --------------------------------------------------------------------------------------------- median split
+// First loop of PerformMedianSplit (BVH.cpp:813-823) for big nodes flagged kMedian: side counts and side boxes.
+__global__ void __launch_bounds__(kBigBlock)
+median_reduce_big(const Task* __restrict__ tasks, const LevelInfo* __restrict__ info, const uint32_t* __restrict__ chunkBase,
+                  const float4* __restrict__ rlo, const float4* __restrict__ rhi, int* __restrict__ medAcc) {
+    __shared__ uint32_t sTask;
+    if (info->nMedian == 0) return;
+    const uint32_t nChunks = info->nChunks, nTasks = info->nTasks;
+    for (uint32_t c = blockIdx.x; c < nChunks; c += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x == 0) sTask = find_task(chunkBase, nTasks, c);
+        __syncthreads();
+        const uint32_t t = sTask;
+        const Task& tk = tasks[t];
+        if (tk.kind != kMedian) continue;
+        const uint32_t off = (c - chunkBase[t]) * kChunk;
+        const uint32_t end = tk.start + tk.count;
+        OBox L = obox_empty(), R = obox_empty();
+        uint32_t nL = 0;
+#pragma unroll
+        for (uint32_t r = 0; r < kChunk / kBigBlock; r++) {
+            const uint32_t p = tk.start + off + r * kBigBlock + threadIdx.x;
+            if (p < end) {
+                const float4 l = rlo[p], h = rhi[p];
+                OBox b;
+                b.lo[0] = ord_from_float(l.x); b.lo[1] = ord_from_float(l.y); b.lo[2] = ord_from_float(l.z);
+                b.hi[0] = ord_from_float(h.x); b.hi[1] = ord_from_float(h.y); b.hi[2] = ord_from_float(h.z);
+                if (median_centre(comp(l, tk.axis), comp(h, tk.axis)) < tk.cutoff) { obox_grow(L, b); nL++; }
+                else obox_grow(R, b);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            L.lo[k] = __reduce_min_sync(kFullMask, L.lo[k]); L.hi[k] = __reduce_max_sync(kFullMask, L.hi[k]);
+            R.lo[k] = __reduce_min_sync(kFullMask, R.lo[k]); R.hi[k] = __reduce_max_sync(kFullMask, R.hi[k]);
+        }
+        nL = __reduce_add_sync(kFullMask, nL);
+        if ((threadIdx.x & 31) == 0) {
+            int* acc = medAcc + size_t(t) * 16;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                atomicMin(acc + k, L.lo[k]); atomicMax(acc + 3 + k, L.hi[k]);
+                atomicMin(acc + 6 + k, R.lo[k]); atomicMax(acc + 9 + k, R.hi[k]);
+            }
+            if (nL) atomicAdd(acc + 12, int(nL));
+        }
+    }
+}
+
+// Rest of PerformMedianSplit for big nodes: either accept the cutoff split, or run the std::sort fallback
+// (BVH.cpp:826-851) on the node's refs. One warp per task; the sort itself is the single-thread libstdc++ restatement.
+__global__ void median_finalize_big(Task* __restrict__ tasks, LevelInfo* __restrict__ info, const int* __restrict__ medAcc,
+                                    float4* __restrict__ curLo, float4* __restrict__ curHi, float4* __restrict__ nxtLo,
+                                    float4* __restrict__ nxtHi, uint32_t* __restrict__ order, uint8_t* __restrict__ eon,
+                                    Lists L, int blasRoot) {
+    if (info->nMedian == 0) return;
+    const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= info->nTasks) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    Task tk = tasks[t];
+    if (tk.kind != kMedian) return;
+    const int* acc = medAcc + size_t(t) * 16;
+    const uint32_t nL = uint32_t(acc[12]);
+    if (nL != 0u && nL != tk.count) {
+        if (lane == 0) {
+            OBox l, r;
+            for (int k = 0; k < 3; k++) { l.lo[k] = acc[k]; l.hi[k] = acc[3 + k]; r.lo[k] = acc[6 + k]; r.hi[k] = acc[9 + k]; }
+            emit_children(L, tk, obox_to_box(l), obox_to_box(r), nL);
+            tasks[t] = tk;
+        }
+        return;
+    }
+    // ---- fallback: sort by extent along the axis, split in the middle
+    if (lane == 0) {
+        atomicAdd(&info->stats[4], 1ull);
+        atomicMax(&info->stats[5], (unsigned long long)tk.count);
+        std_sort_refs(RefArray{curLo + tk.start, curHi + tk.start, tk.axis}, int(tk.count));
+    }
+    __syncwarp();
+    const uint32_t half = tk.count / 2u;
+    if (blasRoot && tk.depth == 0u && half == 0u) {   // Build #1 "last resort": an empty side makes the root a leaf
+        if (lane == 0) { info->rootLeaf = 1u; tk.kind = kDone; tasks[t] = tk; }
+        return;
+    }
+    OBox l = obox_empty(), r = obox_empty();
+    for (uint32_t i = lane; i < tk.count; i += 32u) {
+        const float4 a = curLo[tk.start + i], b = curHi[tk.start + i];
+        OBox x;
+        x.lo[0] = ord_from_float(a.x); x.lo[1] = ord_from_float(a.y); x.lo[2] = ord_from_float(a.z);
+        x.hi[0] = ord_from_float(b.x); x.hi[1] = ord_from_float(b.y); x.hi[2] = ord_from_float(b.z);
+        if (i < half) obox_grow(l, x); else obox_grow(r, x);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        l.lo[k] = __reduce_min_sync(kFullMask, l.lo[k]); l.hi[k] = __reduce_max_sync(kFullMask, l.hi[k]);
+        r.lo[k] = __reduce_min_sync(kFullMask, r.lo[k]); r.hi[k] = __reduce_max_sync(kFullMask, r.hi[k]);
+    }
+    if (lane == 0) {
+        emit_children(L, tk, obox_to_box(l), obox_to_box(r), half);
+        tk.kind = kDone;
+        tasks[t] = tk;
+    }
+    const uint32_t nFirst = __shfl_sync(kFullMask, tk.nFirst, 0);
+    const uint32_t swapped = __shfl_sync(kFullMask, tk.leftIsSecond, 0);
+    // copy the sorted refs into the next buffer in flattened arrangement: [first child | second child]
+    for (uint32_t i = lane; i < tk.count; i += 32u) {
+        const bool isLeft = i < half;
+        const bool first = isLeft != (swapped != 0u);
+        const uint32_t rank = isLeft ? i : i - half;
+        const uint32_t dst = tk.start + (first ? rank : nFirst + rank);
+        const float4 a = curLo[tk.start + i], b = curHi[tk.start + i];
+        nxtLo[dst] = a;
+        nxtHi[dst] = b;
+        const uint32_t childCount = first ? nFirst : tk.count - nFirst;
+        if (childCount == 1u) { order[dst] = __float_as_uint(a.w); eon[dst] = 1; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ partition
+// PerformObjectSplit (BVH.cpp:541-554) / the cutoff loop of PerformMedianSplit (:813-823): which side a ref goes to.
+__device__ __forceinline__ bool goes_left(const Task& tk, const AxisBins& ab, uint32_t nb, const float4& l, const float4& h) {
+    if (tk.kind == kObject) return bin_of(bin_centre(comp(l, tk.axis), comp(h, tk.axis)), ab.start, ab.inv, nb) < tk.bin;
+    return median_centre(comp(l, tk.axis), comp(h, tk.axis)) < tk.cutoff;
+}
+
+__global__ void __launch_bounds__(kBigBlock)
+partition_count(const Task* __restrict__ tasks, const LevelInfo* __restrict__ info, const uint32_t* __restrict__ chunkBase,
+                const float4* __restrict__ rlo, const float4* __restrict__ rhi, uint32_t* __restrict__ chunkFirst, uint32_t nb) {
+    __shared__ uint32_t sTask;
+    __shared__ uint32_t sCount;
+    const uint32_t nChunks = info->nChunks, nTasks = info->nTasks;
+    for (uint32_t c = blockIdx.x; c < nChunks; c += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x == 0) { sTask = find_task(chunkBase, nTasks, c); sCount = 0; }
+        __syncthreads();
+        const uint32_t t = sTask;
+        const Task& tk = tasks[t];
+        if (tk.kind != kObject && tk.kind != kMedian) continue;
+        const AxisBins ab = axis_bins(tk.lo[tk.axis], tk.hi[tk.axis], nb);
+        const uint32_t off = (c - chunkBase[t]) * kChunk;
+        const uint32_t end = tk.start + tk.count;
+        uint32_t mine = 0;
+#pragma unroll
+        for (uint32_t r = 0; r < kChunk / kBigBlock; r++) {
+            const uint32_t p = tk.start + off + r * kBigBlock + threadIdx.x;
+            if (p < end) {
+                const bool first = goes_left(tk, ab, nb, rlo[p], rhi[p]) != (tk.leftIsSecond != 0u);
+                mine += first ? 1u : 0u;
+            }
+        }
+        mine = __reduce_add_sync(kFullMask, mine);
+        if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&sCount, mine);
+        __syncthreads();
+        if (threadIdx.x == 0) chunkFirst[c] = sCount;
+    }
+}
+
+// exclusive scan of chunkFirst inside every task (one warp per task)
+__global__ void partition_scan(const Task* __restrict__ tasks, const LevelInfo* __restrict__ info,
+                               const uint32_t* __restrict__ chunkBase, uint32_t* __restrict__ chunkFirst) {
+    const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= info->nTasks) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    const Task& tk = tasks[t];
+    if (tk.kind != kObject && tk.kind != kMedian) return;
+    const uint32_t base = chunkBase[t], n = (tk.count + kChunk - 1) / kChunk;
+    uint32_t carry = 0;
+    for (uint32_t b = 0; b < n; b += 32u) {
+        const uint32_t i = b + lane;
+        const uint32_t v = i < n ? chunkFirst[base + i] : 0u;
+        uint32_t s = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t o = __shfl_up_sync(kFullMask, s, off);
+            if (lane >= uint32_t(off)) s += o;
+        }
+        if (i < n) chunkFirst[base + i] = carry + s - v;
+        carry += __shfl_sync(kFullMask, s, 31);
+    }
+}
+
+__global__ void __launch_bounds__(kBigBlock)
+partition_scatter(const Task* __restrict__ tasks, const LevelInfo* __restrict__ info, const uint32_t* __restrict__ chunkBase,
+                  const uint32_t* __restrict__ chunkFirst, const float4* __restrict__ rlo, const float4* __restrict__ rhi,
+                  float4* __restrict__ wlo, float4* __restrict__ whi, uint32_t* __restrict__ order, uint8_t* __restrict__ eon,
+                  uint32_t nb) {
+    __shared__ uint32_t sTask;
+    __shared__ uint32_t sWarpFirst[kBigBlock / 32], sWarpSecond[kBigBlock / 32];
+    const uint32_t nChunks = info->nChunks, nTasks = info->nTasks;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t c = blockIdx.x; c < nChunks; c += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x == 0) sTask = find_task(chunkBase, nTasks, c);
+        __syncthreads();
+        const uint32_t t = sTask;
+        const Task& tk = tasks[t];
+        if (tk.kind != kObject && tk.kind != kMedian) continue;
+        const AxisBins ab = axis_bins(tk.lo[tk.axis], tk.hi[tk.axis], nb);
+        const uint32_t off = (c - chunkBase[t]) * kChunk;
+        const uint32_t end = tk.start + tk.count;
+        const uint32_t nFirst = tk.nFirst, nSecond = tk.count - tk.nFirst;
+        uint32_t baseFirst = chunkFirst[c];     // refs of this task before this chunk that go first
+        uint32_t baseSecond = off - baseFirst;  // ... and second
+        for (uint32_t r = 0; r < kChunk / kBigBlock; r++) {
+            const uint32_t p = tk.start + off + r * kBigBlock + threadIdx.x;
+            const bool valid = p < end;
+            float4 l = make_float4(0, 0, 0, 0), h = l;
+            bool first = false;
+            if (valid) {
+                l = rlo[p];
+                h = rhi[p];
+                first = goes_left(tk, ab, nb, l, h) != (tk.leftIsSecond != 0u);
+            }
+            const unsigned bf = __ballot_sync(kFullMask, valid && first);
+            const unsigned bs = __ballot_sync(kFullMask, valid && !first);
+            if (lane == 0) { sWarpFirst[warp] = __popc(bf); sWarpSecond[warp] = __popc(bs); }
+            __syncthreads();
+            uint32_t wf = 0, ws = 0, tf = 0, ts = 0;
+#pragma unroll
+            for (int w = 0; w < kBigBlock / 32; w++) {
+                const uint32_t a = sWarpFirst[w], b = sWarpSecond[w];
+                if (uint32_t(w) < warp) { wf += a; ws += b; }
+                tf += a; ts += b;
+            }
+            if (valid) {
+                const unsigned lt = (1u << lane) - 1u;
+                const uint32_t dst = tk.start + (first ? baseFirst + wf + __popc(bf & lt)
+                                                       : nFirst + baseSecond + ws + __popc(bs & lt));
+                wlo[dst] = l;
+                whi[dst] = h;
+                if ((first ? nFirst : nSecond) == 1u) { order[dst] = __float_as_uint(l.w); eon[dst] = 1; }
+            }
+            baseFirst += tf;
+            baseSecond += ts;
+            __syncthreads();
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------- root spatial split
+// PerformSpatialSplit, first loop (BVH.cpp:680-697): class of every root ref (0 = left, 1 = right, 2 = straddler),
+// per-chunk class counts, and growth of split.leftAABB / rightAABB by the refs that are not straddlers.
+__device__ __forceinline__ int spatial_class(const AxisBins& ab, uint32_t nb, uint32_t splitBin, int axis, const float4& l, const float4& h) {
+    const uint32_t b0 = bin_of(comp(l, axis), ab.start, ab.inv, nb);
+    const uint32_t b1 = bin_of(comp(h, axis), ab.start, ab.inv, nb);
+    if (b1 < splitBin) return 0;
+    if (b0 >= splitBin) return 1;
+    return 2;
+}
+
+__global__ void __launch_bounds__(kBigBlock)
+spatial_count(const Task* __restrict__ tasks, const float4* __restrict__ rlo, const float4* __restrict__ rhi,
+              RootSplit* __restrict__ root, uint32_t* __restrict__ chunkCounts /*[3][nChunks]*/, uint32_t nChunks, uint32_t nb) {
+    __shared__ uint32_t sCount[3];
+    const Task& tk = tasks[0];
+    const AxisBins ab = axis_bins(tk.lo[tk.axis], tk.hi[tk.axis], nb);
+    for (uint32_t c = blockIdx.x; c < nChunks; c += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x < 3) sCount[threadIdx.x] = 0;
+        __syncthreads();
+        OBox L = obox_empty(), R = obox_empty();
+        uint32_t n[3] = {0, 0, 0};
+#pragma unroll
+        for (uint32_t r = 0; r < kChunk / kBigBlock; r++) {
+            const uint32_t p = c * kChunk + r * kBigBlock + threadIdx.x;
+            if (p < tk.count) {
+                const float4 l = rlo[p], h = rhi[p];
+                const int cls = spatial_class(ab, nb, tk.bin, tk.axis, l, h);
+                OBox b;
+                b.lo[0] = ord_from_float(l.x); b.lo[1] = ord_from_float(l.y); b.lo[2] = ord_from_float(l.z);
+                b.hi[0] = ord_from_float(h.x); b.hi[1] = ord_from_float(h.y); b.hi[2] = ord_from_float(h.z);
+                if (cls == 0) { obox_grow(L, b); n[0]++; }
+                else if (cls == 1) { obox_grow(R, b); n[1]++; }
+                else n[2]++;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            L.lo[k] = __reduce_min_sync(kFullMask, L.lo[k]); L.hi[k] = __reduce_max_sync(kFullMask, L.hi[k]);
+            R.lo[k] = __reduce_min_sync(kFullMask, R.lo[k]); R.hi[k] = __reduce_max_sync(kFullMask, R.hi[k]);
+            n[k] = __reduce_add_sync(kFullMask, n[k]);
+        }
+        if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                atomicMin(&root->splitBox[k], L.lo[k]); atomicMax(&root->splitBox[3 + k], L.hi[k]);
+                atomicMin(&root->splitBox[6 + k], R.lo[k]); atomicMax(&root->splitBox[9 + k], R.hi[k]);
+                if (n[k]) atomicAdd(&sCount[k], n[k]);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 3) chunkCounts[threadIdx.x * nChunks + c] = sCount[threadIdx.x];
+    }
+}
+
+// exclusive scans of the three class-count arrays (single CTA, three warps)
+__global__ void spatial_scan(uint32_t* __restrict__ chunkCounts, uint32_t nChunks, LevelInfo* __restrict__ info) {
+    const uint32_t lane = threadIdx.x & 31u, cls = threadIdx.x >> 5;
+    if (cls >= 3) return;
+    uint32_t* a = chunkCounts + cls * nChunks;
+    uint32_t carry = 0;
+    for (uint32_t b = 0; b < nChunks; b += 32u) {
+        const uint32_t i = b + lane;
+        const uint32_t v = i < nChunks ? a[i] : 0u;
+        uint32_t s = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t o = __shfl_up_sync(kFullMask, s, off);
+            if (lane >= uint32_t(off)) s += o;
+        }
+        if (i < nChunks) a[i] = carry + s - v;
+        carry += __shfl_sync(kFullMask, s, 31);
+    }
+    if (lane == 0) {
+        if (cls == 0) info->nL0 = carry;
+        if (cls == 1) info->nR0 = carry;
+        if (cls == 2) info->nStraddle = carry;
+    }
+}
+
+// Stable three-way scatter: left refs -> tmpL, right refs -> tmpR, straddlers -> straddle arrays together with the
+// two clipped boxes SplitReference gives them at the split plane (BVH.cpp:709-711), precomputed in parallel.
+__global__ void __launch_bounds__(kBigBlock)
+spatial_scatter(const Task* __restrict__ tasks, const float4* __restrict__ rlo, const float4* __restrict__ rhi,
+                const float* __restrict__ tris, const RootSplit* __restrict__ root, const uint32_t* __restrict__ chunkCounts,
+                uint32_t nChunks, uint32_t nb, float4* __restrict__ tmpLlo, float4* __restrict__ tmpLhi,
+                float4* __restrict__ tmpRlo, float4* __restrict__ tmpRhi, float4* __restrict__ strad /*[6][cap]*/, uint32_t cap) {
+    __shared__ uint32_t sWarp[3][kBigBlock / 32];
+    const Task& tk = tasks[0];
+    const AxisBins ab = axis_bins(tk.lo[tk.axis], tk.hi[tk.axis], nb);
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const float plane = root->spaPos;
+    for (uint32_t c = blockIdx.x; c < nChunks; c += gridDim.x) {
+        uint32_t base[3] = {chunkCounts[c], chunkCounts[nChunks + c], chunkCounts[2 * nChunks + c]};
+        for (uint32_t r = 0; r < kChunk / kBigBlock; r++) {
+            const uint32_t p = c * kChunk + r * kBigBlock + threadIdx.x;
+            const bool valid = p < tk.count;
+            float4 l = make_float4(0, 0, 0, 0), h = l;
+            int cls = -1;
+            if (valid) { l = rlo[p]; h = rhi[p]; cls = spatial_class(ab, nb, tk.bin, tk.axis, l, h); }
+            unsigned bal[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) bal[k] = __ballot_sync(kFullMask, cls == k);
+            __syncthreads();
+            if (lane == 0) { sWarp[0][warp] = __popc(bal[0]); sWarp[1][warp] = __popc(bal[1]); sWarp[2][warp] = __popc(bal[2]); }
+            __syncthreads();
+            uint32_t before[3] = {0, 0, 0}, total[3] = {0, 0, 0};
+#pragma unroll
+            for (int w = 0; w < kBigBlock / 32; w++) {
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const uint32_t v = sWarp[k][w];
+                    if (uint32_t(w) < warp) before[k] += v;
+                    total[k] += v;
+                }
+            }
+            if (valid) {
+                const unsigned lt = (1u << lane) - 1u;
+                if (cls == 0) { const uint32_t d = base[0] + before[0] + __popc(bal[0] & lt); tmpLlo[d] = l; tmpLhi[d] = h; }
+                else if (cls == 1) { const uint32_t d = base[1] + before[1] + __popc(bal[1] & lt); tmpRlo[d] = l; tmpRhi[d] = h; }
+                else {
+                    const uint32_t d = base[2] + before[2] + __popc(bal[2] & lt);
+                    Box3 box, cl, cr;
+                    box.lo[0] = l.x; box.lo[1] = l.y; box.lo[2] = l.z;
+                    box.hi[0] = h.x; box.hi[1] = h.y; box.hi[2] = h.z;
+                    split_reference(tris + 9 * size_t(__float_as_uint(l.w)), box, cl, cr, plane, tk.axis);
+                    strad[d] = l;
+                    strad[cap + d] = h;
+                    strad[2 * size_t(cap) + d] = make_float4(cl.lo[0], cl.lo[1], cl.lo[2], l.w);
+                    strad[3 * size_t(cap) + d] = make_float4(cl.hi[0], cl.hi[1], cl.hi[2], 0.0f);
+                    strad[4 * size_t(cap) + d] = make_float4(cr.lo[0], cr.lo[1], cr.lo[2], l.w);
+                    strad[5 * size_t(cap) + d] = make_float4(cr.hi[0], cr.hi[1], cr.hi[2], 0.0f);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 3; k++) base[k] += total[k];
+        }
+    }
+}
+
+// PerformSpatialSplit, second loop (BVH.cpp:699-756): order-dependent, so one thread decides while the CTA stages the
+// straddlers' precomputed boxes through shared memory, 128 at a time.
+constexpr int kSeqTile = 128;
+__global__ void __launch_bounds__(kSeqTile)
+spatial_sequential(LevelInfo* __restrict__ info, RootSplit* __restrict__ root, const float4* __restrict__ strad, uint32_t cap,
+                   float4* __restrict__ tmpLlo, float4* __restrict__ tmpLhi, float4* __restrict__ tmpRlo,
+                   float4* __restrict__ tmpRhi) {
+    __shared__ float4 tile[6][kSeqTile];
+    const uint32_t nS = info->nStraddle;
+    uint32_t nL = info->nL0, nR = info->nR0;
+    float L[6], R[6];   // lo.xyz, hi.xyz of split.leftAABB / split.rightAABB
+    unsigned long long dups = 0;
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 6; k++) { L[k] = float_from_ord(root->splitBox[k]); R[k] = float_from_ord(root->splitBox[6 + k]); }
+    }
+    for (uint32_t base = 0; base < nS; base += kSeqTile) {
+        __syncthreads();
+        const uint32_t i = base + threadIdx.x;
+        if (i < nS) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) tile[k][threadIdx.x] = strad[size_t(k) * cap + i];
+        }
+        __syncthreads();
+        if (threadIdx.x != 0) continue;
+        const uint32_t m = min(uint32_t(kSeqTile), nS - base);
+        for (uint32_t s = 0; s < m; s++) {
+            const float4 rl = tile[0][s], rh = tile[1][s], cll = tile[2][s], clh = tile[3][s], crl = tile[4][s], crh = tile[5][s];
+            const float ref[6] = {rl.x, rl.y, rl.z, rh.x, rh.y, rh.z};
+            const float cl[6] = {cll.x, cll.y, cll.z, clh.x, clh.y, clh.z};
+            const float cr[6] = {crl.x, crl.y, crl.z, crh.x, crh.y, crh.z};
+            float uL[6], uR[6], dL[6], dR[6];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {   // Grow(AABB): accumulated value first — AABB.cpp:88-93
+                uL[k] = gl_min(L[k], ref[k]); uL[3 + k] = gl_max(L[3 + k], ref[3 + k]);
+                uR[k] = gl_min(R[k], ref[k]); uR[3 + k] = gl_max(R[3 + k], ref[3 + k]);
+                dL[k] = gl_min(L[k], cl[k]); dL[3 + k] = gl_max(L[3 + k], cl[3 + k]);
+                dR[k] = gl_min(R[k], cr[k]); dR[3 + k] = gl_max(R[3 + k], cr[3 + k]);
+            }
+            const float fl = __uint2float_rn(nL), fr = __uint2float_rn(nR);
+            const float fl1 = __uint2float_rn(nL + 1u), fr1 = __uint2float_rn(nR + 1u);
+            const float sahUL = __fadd_rn(__fmul_rn(surface_area(uL, uL + 3), fl1), __fmul_rn(surface_area(R, R + 3), fr));
+            const float sahUR = __fadd_rn(__fmul_rn(surface_area(L, L + 3), fl), __fmul_rn(surface_area(uR, uR + 3), fr1));
+            const float sahD = __fadd_rn(__fmul_rn(surface_area(dL, dL + 3), fl1), __fmul_rn(surface_area(dR, dR + 3), fr1));
+            const float best = gl_min(sahD, gl_min(sahUR, sahUL));
+            if (best == sahUL) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) L[k] = uL[k];
+                tmpLlo[nL] = rl; tmpLhi[nL] = rh; nL++;
+            } else if (best == sahUR) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) R[k] = uR[k];
+                tmpRlo[nR] = rl; tmpRhi[nR] = rh; nR++;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 6; k++) { L[k] = dL[k]; R[k] = dR[k]; }
+                tmpLlo[nL] = cll; tmpLhi[nL] = clh; nL++;
+                tmpRlo[nR] = crl; tmpRhi[nR] = crh; nR++;
+                dups++;
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 6; k++) { root->finalBox[k] = L[k]; root->finalBox[6 + k] = R[k]; }
+        root->nL = nL;
+        root->nR = nR;
+        info->totalRefs = nL + nR;
+        info->stats[2] = dups;
+    }
+}
+
+// Children of the spatially split root (or the last-resort leaf when a side ended up empty).
+__global__ void spatial_emit(Task* __restrict__ tasks, LevelInfo* __restrict__ info, const RootSplit* __restrict__ root, Lists L) {
+    Task tk = tasks[0];
+    if (root->nL == 0u || root->nR == 0u) {
+        info->rootLeaf = 1u;
+        info->totalRefs = tk.count;
+        return;
+    }
+    Box3 l, r;
+    for (int k = 0; k < 3; k++) { l.lo[k] = root->finalBox[k]; l.hi[k] = root->finalBox[3 + k]; r.lo[k] = root->finalBox[6 + k]; r.hi[k] = root->finalBox[9 + k]; }
+    tk.count = root->nL + root->nR;
+    emit_children(L, tk, l, r, root->nL);
+    tasks[0] = tk;
+}
+
+// copy tmpL / tmpR into the ref buffer in flattened arrangement
+__global__ void spatial_place(const Task* __restrict__ tasks, const RootSplit* __restrict__ root, const float4* __restrict__ tmpLlo,
+                              const float4* __restrict__ tmpLhi, const float4* __restrict__ tmpRlo, const float4* __restrict__ tmpRhi,
+                              float4* __restrict__ wlo, float4* __restrict__ whi, uint32_t* __restrict__ order, uint8_t* __restrict__ eon) {
+    const Task& tk = tasks[0];
+    const uint32_t nL = root->nL, nR = root->nR, total = nL + nR;
+    const bool swapped = tk.leftIsSecond != 0u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const bool isLeft = i < nL;
+        const uint32_t rank = isLeft ? i : i - nL;
+        const bool first = isLeft != swapped;
+        const uint32_t dst = first ? rank : tk.nFirst + rank;
+        const float4 a = isLeft ? tmpLlo[rank] : tmpRlo[rank];
+        const float4 b = isLeft ? tmpLhi[rank] : tmpRhi[rank];
+        wlo[dst] = a;
+        whi[dst] = b;
+        const uint32_t childCount = first ? tk.nFirst : total - tk.nFirst;
+        if (childCount == 1u) { order[dst] = __float_as_uint(a.w); eon[dst] = 1; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------- subtree kernel
+struct SubNode {
+    uint16_t start, count;
+    uint32_t flatIdx;
+    uint32_t boxRef;   // (parent flat index << 1) | isSecondChild, or 0xffffffff for the subtree root
+};
+
+__global__ void __launch_bounds__(kSubBlock)
+build_subtrees(const SmallTask* __restrict__ small, uint32_t nSmall, float4* const lo0, float4* const hi0, float4* const lo1,
+               float4* const hi1, float4* nodes, uint32_t* __restrict__ order, uint8_t* __restrict__ eon,
+               LevelInfo* __restrict__ info, uint32_t budget) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    float4* sLo = reinterpret_cast<float4*>(smemRaw);                      // [2][kSubtreeMax]
+    float4* sHi = sLo + 2 * kSubtreeMax;                                   // [2][kSubtreeMax]
+    SubNode* lists = reinterpret_cast<SubNode*>(sHi + 2 * kSubtreeMax);    // [2][kSubtreeMax / 2]
+    int* wBins = reinterpret_cast<int*>(lists + kSubtreeMax);              // [warps][3][32][8]
+    int* wSfx = wBins + kSubWarps * 3 * kSubtreeBins * kBinWords;          // [warps][32][6]
+    __shared__ uint32_t sNext;
+    __shared__ unsigned long long sStats[3];   // median splits, sort fallbacks, largest fallback
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (blockIdx.x >= nSmall) return;
+    const SmallTask task = small[blockIdx.x];
+    const float4* gLo = task.buf ? lo1 : lo0;
+    const float4* gHi = task.buf ? hi1 : hi0;
+    for (uint32_t i = tid; i < task.count; i += kSubBlock) {
+        sLo[i] = gLo[task.start + i];
+        sHi[i] = gHi[task.start + i];
+    }
+    if (tid == 0) {
+        lists[0] = SubNode{0, uint16_t(task.count), task.flatIdx, 0xffffffffu};
+        sStats[0] = sStats[1] = sStats[2] = 0;
+    }
+    uint32_t nCur = 1, cur = 0, level = 0;
+    int* bins = wBins + warp * 3 * kSubtreeBins * kBinWords;
+    int* sfx = wSfx + warp * kSubtreeBins * 6;
+    __syncthreads();
+
+    while (nCur > 0) {
+        const uint32_t depth = task.depth + level;
+        const uint32_t nb = bins_at_depth(budget, depth);   // <= kSubtreeBins by construction
+        if (tid == 0) sNext = 0;
+        __syncthreads();
+        const SubNode* curList = lists + (level & 1u) * (kSubtreeMax / 2);
+        SubNode* nextList = lists + ((level + 1u) & 1u) * (kSubtreeMax / 2);
+        float4* cLo = sLo + cur * kSubtreeMax;
+        float4* cHi = sHi + cur * kSubtreeMax;
+        float4* nLo = sLo + (cur ^ 1u) * kSubtreeMax;
+        float4* nHi = sHi + (cur ^ 1u) * kSubtreeMax;
+
+        for (uint32_t ni = warp; ni < nCur; ni += kSubWarps) {
+            const SubNode nd = curList[ni];
+            const uint32_t n = nd.count, s = nd.start;
+            // ---- node box: the subtree root's comes with the task, any other from its parent's flattened record
+            float blo[3], bhi[3];
+            if (nd.boxRef == 0xffffffffu) {
+#pragma unroll
+                for (int k = 0; k < 3; k++) { blo[k] = task.lo[k]; bhi[k] = task.hi[k]; }
+            } else {
+                const volatile float4* P = nodes + 4 * size_t(nd.boxRef >> 1);
+                float4 n0, n1, n2;
+                n0.x = P[0].x; n0.y = P[0].y; n0.z = P[0].z; n0.w = P[0].w;
+                n1.x = P[1].x; n1.y = P[1].y; n1.z = P[1].z; n1.w = P[1].w;
+                n2.x = P[2].x; n2.y = P[2].y; n2.z = P[2].z; n2.w = P[2].w;
+                if (nd.boxRef & 1u) { blo[0] = n1.z; blo[1] = n1.w; blo[2] = n2.x; bhi[0] = n2.y; bhi[1] = n2.z; bhi[2] = n2.w; }
+                else { blo[0] = n0.x; blo[1] = n0.y; blo[2] = n0.z; bhi[0] = n0.w; bhi[1] = n1.x; bhi[2] = n1.y; }
+            }
+            AxisBins ab[3];
+#pragma unroll
+            for (int a = 0; a < 3; a++) ab[a] = axis_bins(blo[a], bhi[a], nb);
+            // ---- FindObjectSplit
+            for (uint32_t e = lane; e < 3 * nb; e += 32u) bin_init(bins + e * kBinWords);
+            __syncwarp();
+            for (uint32_t i = lane; i < n; i += 32u) {
+                const float4 l = cLo[s + i], h = cHi[s + i];
+                const int ol[3] = {ord_from_float(l.x), ord_from_float(l.y), ord_from_float(l.z)};
+                const int oh[3] = {ord_from_float(h.x), ord_from_float(h.y), ord_from_float(h.z)};
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    if (!ab[a].active) continue;
+                    const uint32_t b = bin_of(bin_centre(comp(l, a), comp(h, a)), ab[a].start, ab[a].inv, nb);
+                    int* rec = bins + (a * nb + b) * kBinWords;
+#pragma unroll
+                    for (int k = 0; k < 3; k++) { atomicMin(rec + k, ol[k]); atomicMax(rec + 3 + k, oh[k]); }
+                    atomicAdd(rec + 6, 1);
+                    atomicAdd(rec + 7, 1);
+                }
+            }
+            __syncwarp();
+            BestSplit best = best_none();
+            for (int a = 0; a < 3; a++) {
+                if (!ab[a].active) continue;
+                warp_sweep_axis(bins + a * nb * kBinWords, nb, sfx, n, a, best);
+            }
+            const float nodeCost = __fmul_rn(__uint2float_rn(n), surface_area(blo, bhi));
+            // mode: 0 = object split on (axis, bin), 1 = median cutoff, 2 = sorted, split by position
+            int mode, axis = 0;
+            uint32_t splitBin = 0, nLeft = 0;
+            float cutoff = 0.0f;
+            OBox L = obox_empty(), R = obox_empty();
+            if (!(best.axis < 0 || best.cost >= nodeCost)) {
+                mode = 0;
+                axis = best.axis;
+                splitBin = best.bin;
+                uint32_t nExit;
+                warp_split_boxes(bins + axis * nb * kBinWords, nb, splitBin, L, R, nLeft, nExit);
+            } else {
+                mode = 1;
+                median_plane(blo, bhi, axis, cutoff);
+                uint32_t cnt = 0;
+                for (uint32_t i = lane; i < n; i += 32u) {
+                    const float4 l = cLo[s + i], h = cHi[s + i];
+                    OBox b;
+                    b.lo[0] = ord_from_float(l.x); b.lo[1] = ord_from_float(l.y); b.lo[2] = ord_from_float(l.z);
+                    b.hi[0] = ord_from_float(h.x); b.hi[1] = ord_from_float(h.y); b.hi[2] = ord_from_float(h.z);
+                    if (median_centre(comp(l, axis), comp(h, axis)) < cutoff) { obox_grow(L, b); cnt++; } else obox_grow(R, b);
+                }
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    L.lo[k] = __reduce_min_sync(kFullMask, L.lo[k]); L.hi[k] = __reduce_max_sync(kFullMask, L.hi[k]);
+                    R.lo[k] = __reduce_min_sync(kFullMask, R.lo[k]); R.hi[k] = __reduce_max_sync(kFullMask, R.hi[k]);
+                }
+                nLeft = __reduce_add_sync(kFullMask, cnt);
+                if (lane == 0) atomicAdd(&sStats[0], 1ull);
+                if (nLeft == 0u || nLeft == n) {
+                    mode = 2;
+                    if (lane == 0) {
+                        atomicAdd(&sStats[1], 1ull);
+                        atomicMax(&sStats[2], (unsigned long long)n);
+                        std_sort_refs(RefArray{cLo + s, cHi + s, axis}, int(n));
+                    }
+                    __syncwarp();
+                    nLeft = n / 2u;
+                    L = obox_empty();
+                    R = obox_empty();
+                    for (uint32_t i = lane; i < n; i += 32u) {
+                        const float4 l = cLo[s + i], h = cHi[s + i];
+                        OBox b;
+                        b.lo[0] = ord_from_float(l.x); b.lo[1] = ord_from_float(l.y); b.lo[2] = ord_from_float(l.z);
+                        b.hi[0] = ord_from_float(h.x); b.hi[1] = ord_from_float(h.y); b.hi[2] = ord_from_float(h.z);
+                        if (i < nLeft) obox_grow(L, b); else obox_grow(R, b);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        L.lo[k] = __reduce_min_sync(kFullMask, L.lo[k]); L.hi[k] = __reduce_max_sync(kFullMask, L.hi[k]);
+                        R.lo[k] = __reduce_min_sync(kFullMask, R.lo[k]); R.hi[k] = __reduce_max_sync(kFullMask, R.hi[k]);
+                    }
+                }
+            }
+            // ---- Flatten bookkeeping: larger-area child first
+            const Box3 lb = obox_to_box(L), rb = obox_to_box(R);
+            const bool swapped = surface_area(lb) < surface_area(rb);
+            const uint32_t nFirst = swapped ? n - nLeft : nLeft, nSecond = n - nFirst;
+            const uint32_t slot = task.start + s;
+            if (lane == 0) {
+                const Box3& f = swapped ? rb : lb;
+                const Box3& g = swapped ? lb : rb;
+                const int32_t ptr1 = nFirst > 1u ? int32_t(nd.flatIdx + 1u) : ~int32_t(slot);
+                const int32_t ptr2 = nSecond > 1u ? int32_t(nd.flatIdx + nFirst) : ~int32_t(slot + nFirst);
+                float4* N = nodes + 4 * size_t(nd.flatIdx);
+                N[0] = make_float4(f.lo[0], f.lo[1], f.lo[2], f.hi[0]);
+                N[1] = make_float4(f.hi[1], f.hi[2], g.lo[0], g.lo[1]);
+                N[2] = make_float4(g.lo[2], g.hi[0], g.hi[1], g.hi[2]);
+                N[3] = make_float4(__int_as_float(ptr1), __int_as_float(ptr2), 0.0f, 0.0f);
+                if (nFirst > 1u) nextList[atomicAdd(&sNext, 1u)] = SubNode{uint16_t(s), uint16_t(nFirst), nd.flatIdx + 1u, nd.flatIdx << 1};
+                if (nSecond > 1u) nextList[atomicAdd(&sNext, 1u)] = SubNode{uint16_t(s + nFirst), uint16_t(nSecond), nd.flatIdx + nFirst, (nd.flatIdx << 1) | 1u};
+            }
+            // ---- stable partition into the other buffer (or straight to the final slot for one-ref children)
+            uint32_t doneFirst = 0, doneSecond = 0;
+            for (uint32_t b = 0; b < n; b += 32u) {
+                const uint32_t i = b + lane;
+                const bool valid = i < n;
+                float4 l = make_float4(0, 0, 0, 0), h = l;
+                bool first = false;
+                if (valid) {
+                    l = cLo[s + i];
+                    h = cHi[s + i];
+                    bool isLeft;
+                    if (mode == 0) isLeft = bin_of(bin_centre(comp(l, axis), comp(h, axis)), ab[axis].start, ab[axis].inv, nb) < splitBin;
+                    else if (mode == 1) isLeft = median_centre(comp(l, axis), comp(h, axis)) < cutoff;
+                    else isLeft = i < nLeft;
+                    first = isLeft != swapped;
+                }
+                const unsigned bf = __ballot_sync(kFullMask, valid && first);
+                const unsigned bs = __ballot_sync(kFullMask, valid && !first);
+                if (valid) {
+                    const unsigned lt = (1u << lane) - 1u;
+                    const uint32_t dst = first ? doneFirst + __popc(bf & lt) : nFirst + doneSecond + __popc(bs & lt);
+                    if ((first ? nFirst : nSecond) == 1u) {
+                        order[slot + dst] = __float_as_uint(l.w);
+                        eon[slot + dst] = 1;
+                    } else {
+                        nLo[s + dst] = l;
+                        nHi[s + dst] = h;
+                    }
+                }
+                doneFirst += __popc(bf);
+                doneSecond += __popc(bs);
+            }
+        }
+        __syncthreads();
+        nCur = sNext;
+        cur ^= 1u;
+        level++;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        if (sStats[0]) atomicAdd(&info->stats[3], sStats[0]);
+        if (sStats[1]) atomicAdd(&info->stats[4], sStats[1]);
+        if (sStats[2]) atomicMax(&info->stats[5], sStats[2]);
+    }
+}
+
+constexpr size_t kSubtreeSmem = size_t(4) * kSubtreeMax * sizeof(float4) + size_t(kSubtreeMax) * sizeof(SubNode) +
+                                size_t(kSubWarps) * 3 * kSubtreeBins * kBinWords * sizeof(int) +
+                                size_t(kSubWarps) * kSubtreeBins * 6 * sizeof(int);
+
+template <typename T>
+int read_back(atlas_rt_context* ctx, const T* dev, T* host) {
+    static_assert(sizeof(T) <= 4096, "pinned staging too small");
+    ATLAS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, dev, sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    ATLAS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(host, ctx->pinned, sizeof(T));
+    return ATLAS_RT_OK;
+}
+
+}   // namespace
+
+#define ATLAS_TRY(expr)            \
+    do {                           \
+        int rc__ = (expr);         \
+        if (rc__ != ATLAS_RT_OK) { cleanup(); return rc__; } \
+    } while (0)
+#define ATLAS_CUDA_C(ctx, call)                                                          \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess) { cleanup(); return fail((ctx), ATLAS_RT_ERR_CUDA, #call, e__); } \
+    } while (0)
+#define ATLAS_LAUNCHED(ctx)                                                              \
+    do {                                                                                 \
+        (ctx)->launches++;                                                               \
+        cudaError_t e__ = cudaGetLastError();                                            \
+        if (e__ != cudaSuccess) { cleanup(); return fail((ctx), ATLAS_RT_ERR_CUDA, "kernel launch", e__); } \
+    } while (0)
+
+int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, uint64_t count64, bool tlas, atlas_rt_bvh* out) {
+    const uint32_t n = uint32_t(count64);
+    cudaStream_t st = ctx->stream;
+    out->nodeCount = 0;
+    out->refCount = 0;
+    if (n == 0) return ATLAS_RT_OK;   // the reference dereferences a null child for an empty input; we return an empty BVH
+
+    static bool attrSet = false;
+    if (!attrSet) {
+        cudaFuncSetAttribute(build_subtrees, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSubtreeSmem));
+        attrSet = true;
+    }
+
+    if (tlas && n == 1) {
+        ATLAS_CUDA(ctx, dev_alloc(ctx, &out->nodes, 4));
+        ATLAS_CUDA(ctx, dev_alloc(ctx, &out->order, 2));
+        ATLAS_CUDA(ctx, dev_alloc(ctx, &out->endOfNode, 2));
+        tlas_single<<<1, 1, 0, st>>>(dAabbs, out->nodes, out->order, out->endOfNode);
+        ATLAS_LAUNCH_CHECK(ctx);
+        out->nodeCount = 1;
+        out->refCount = 2;
+        return ATLAS_RT_OK;
+    }
+
+    BuildBuffers B;
+    memset(&B, 0, sizeof(B));
+    B.budget = tlas ? 64u : 256u;
+    B.cap = tlas ? n : 2u * n;
+    B.tris = dTris;
+    const uint32_t cap = B.cap;
+    const uint32_t maxTasks = cap / kSubtreeMax + 256u + 2u;
+    const uint32_t maxSmall = cap / 2u + 2u;
+    const uint32_t maxChunks = cap / kChunk + maxTasks + 2u;
+    // bins scratch: the widest level is bounded by min(2^d, maxTasks) * bins(d)
+    uint64_t binRecords = 0;
+    for (uint32_t d = 0; d < 40; d++) {
+        const uint64_t tasksAtDepth = d < 31 ? std::min<uint64_t>(1ull << d, maxTasks) : maxTasks;
+        binRecords = std::max<uint64_t>(binRecords, tasksAtDepth * bins_at_depth(B.budget, d));
+    }
+    float4 *tmpLlo = nullptr, *tmpLhi = nullptr, *tmpRlo = nullptr, *tmpRhi = nullptr, *strad = nullptr;
+    uint32_t* spaCounts = nullptr;
+    auto cleanup = [&]() {
+        for (int k = 0; k < 2; k++) { dev_free(ctx, B.lo[k]); dev_free(ctx, B.hi[k]); dev_free(ctx, B.tasks[k]); }
+        dev_free(ctx, B.small); dev_free(ctx, B.info); dev_free(ctx, B.root); dev_free(ctx, B.bins); dev_free(ctx, B.sfx);
+        dev_free(ctx, B.spaBins); dev_free(ctx, B.medAcc); dev_free(ctx, B.chunkBase); dev_free(ctx, B.chunkFirst);
+        dev_free(ctx, B.rootBox); dev_free(ctx, tmpLlo); dev_free(ctx, tmpLhi); dev_free(ctx, tmpRlo); dev_free(ctx, tmpRhi);
+        dev_free(ctx, strad); dev_free(ctx, spaCounts);
+    };
+    for (int k = 0; k < 2; k++) {
+        ATLAS_CUDA_C(ctx, dev_alloc(ctx, &B.lo[k], cap));
+        ATLAS_CUDA_C(ctx, dev_alloc(ctx, &B.hi[k], cap));
+        ATLAS_CUDA_C(ctx, dev_alloc(ctx, &B.tasks[k], maxTasks));
+    }
+    ATLAS_CUDA_C(ctx, dev_alloc(ctx, &out->nodes, size_t(cap) * 4));
+    ATLAS_CUDA_C(ctx, dev_alloc(ctx, &out->order, cap));
+    ATLAS_CUDA_C(ctx, dev_alloc(ctx, &out->endOfNode, cap));
+    B.nodes = out->nodes; B.order = out->order; B.eon = out->endOfNode;
+    ATLAS_CUDA_C(ctx, dev_alloc(ctx, &B.small, maxSmall));
+    ATLAS_CUDA_C(ctx, dev_alloc(ctx, &B.info, 1));
+    ATLAS_CUDA_C(ctx, dev_alloc(ctx, &B.root, 1));
+    ATLAS_CUDA_C(ctx, dev_alloc(ctx, &B.bins, binRecords * 3 * kBinWords));
+    ATLAS_CUDA_C(ctx, dev_alloc(ctx, &B.sfx, binRecords * 6));
+    ATLAS_CUDA_C(ctx, dev_alloc(ctx, &B.spaBins, size_t(3) * 256 * kBinWords));
+    ATLAS_CUDA_C(ctx, dev_alloc(ctx, &B.medAcc, size_t(maxTasks) * 16));
+    ATLAS_CUDA_C(ctx, dev_alloc(ctx, &B.chunkBase, maxTasks));
+    ATLAS_CUDA_C(ctx, dev_alloc(ctx, &B.chunkFirst, maxChunks));
+    ATLAS_CUDA_C(ctx, dev_alloc(ctx, &B.rootBox, 8));
+    ATLAS_CUDA_C(ctx, cudaMemsetAsync(B.info, 0, sizeof(LevelInfo), st));
+    ATLAS_CUDA_C(ctx, cudaMemsetAsync(B.root, 0, sizeof(RootSplit), st));
+    ATLAS_CUDA_C(ctx, cudaMemsetAsync(out->endOfNode, 0, cap, st));
+    {
+        const int initBox[8] = {kOrdEmptyLo, kOrdEmptyLo, kOrdEmptyLo, kOrdEmptyHi, kOrdEmptyHi, kOrdEmptyHi, 0, 0};
+        memcpy(ctx->pinned, initBox, sizeof(initBox));
+        ATLAS_CUDA_C(ctx, cudaMemcpyAsync(B.rootBox, ctx->pinned, sizeof(initBox), cudaMemcpyHostToDevice, st));
+    }
+    init_refs<<<(n + 255) / 256, 256, 0, st>>>(dAabbs, n, B.lo[0], B.hi[0], B.rootBox, B.info);
+    ATLAS_LAUNCHED(ctx);
+    make_root<<<1, 1, 0, st>>>(B.rootBox, n, B.tasks[0], B.info, B.root);
+    ATLAS_LAUNCHED(ctx);
+
+    const uint32_t persistent = uint32_t(ctx->smCount) * 4u;
+    uint32_t nTasks = 1, cur = 0, levels = 0;
+    LevelInfo info;
+    memset(&info, 0, sizeof(info));
+    bool rootLeaf = false;
+    uint32_t totalRefs = n;
+
+    for (uint32_t depth = 0; nTasks > 0; depth++, levels++) {
+        const uint32_t nb = bins_at_depth(B.budget, depth);
+        const uint32_t chunksBound = std::min<uint32_t>(totalRefs / kChunk + nTasks + 1u, maxChunks);
+        const uint32_t gridChunks = std::max(1u, std::min(chunksBound, persistent));
+        const uint32_t warpGrid = (nTasks * 32u + 127u) / 128u;
+        const size_t binSmem = size_t(3) * nb * kBinWords * sizeof(int);
+        Task* tasks = B.tasks[cur];
+        Lists L{B.tasks[cur ^ 1u], B.small, B.info, B.nodes, B.budget, cur ^ 1u};
+        const float4 *rlo = B.lo[cur], *rhi = B.hi[cur];
+        float4 *wlo = B.lo[cur ^ 1u], *whi = B.hi[cur ^ 1u];
+
+        prepare_level<<<1, 1024, 0, st>>>(tasks, B.info, B.chunkBase);
+        ATLAS_LAUNCHED(ctx);
+        init_bins<<<std::max(1u, std::min<uint32_t>(persistent, (nTasks * 3u * nb + 255u) / 256u)), 256, 0, st>>>(B.bins, B.info, 3u * nb);
+        ATLAS_LAUNCHED(ctx);
+        bin_big<<<gridChunks, kBigBlock, binSmem, st>>>(tasks, B.info, B.chunkBase, rlo, rhi, B.bins, nb);
+        ATLAS_LAUNCHED(ctx);
+
+        bool spatialPath = false;
+        if (depth == 0 && !tlas) {
+            select_root_object<<<1, 32, 0, st>>>(tasks, B.info, B.bins, B.sfx, B.root, nb);
+            ATLAS_LAUNCHED(ctx);
+            ATLAS_TRY(read_back(ctx, B.info, &info));
+            const int trySpatial = info.rootNeedSpatial ? 1 : 0;
+            if (trySpatial) {
+                const int initGrid = 3;
+                init_bins<<<initGrid, 256, 0, st>>>(B.spaBins, B.info, 3u * nb);   // nTasks == 1
+                ATLAS_LAUNCHED(ctx);
+                spatial_bin_root<<<gridChunks, kBigBlock, binSmem, st>>>(tasks, rlo, rhi, B.tris, B.spaBins, nb);
+                ATLAS_LAUNCHED(ctx);
+            }
+            select_root_final<<<1, 32, 0, st>>>(tasks, B.info, B.bins, B.spaBins, B.sfx, B.medAcc, B.root, L, nb, trySpatial);
+            ATLAS_LAUNCHED(ctx);
+            ATLAS_TRY(read_back(ctx, B.info, &info));
+            out->stats[0] = trySpatial;
+            spatialPath = info.rootKind == uint32_t(kSpatial);
+        } else {
+            select_big<<<warpGrid, 128, 0, st>>>(tasks, B.info, B.bins, B.sfx, B.medAcc, L, nb);
+            ATLAS_LAUNCHED(ctx);
+        }
+
+        if (spatialPath) {
+            const uint32_t nChunks = (n + kChunk - 1) / kChunk;
+            ATLAS_CUDA_C(ctx, dev_alloc(ctx, &tmpLlo, n));
+            ATLAS_CUDA_C(ctx, dev_alloc(ctx, &tmpLhi, n));
+            ATLAS_CUDA_C(ctx, dev_alloc(ctx, &tmpRlo, n));
+            ATLAS_CUDA_C(ctx, dev_alloc(ctx, &tmpRhi, n));
+            ATLAS_CUDA_C(ctx, dev_alloc(ctx, &strad, size_t(6) * n));
+            ATLAS_CUDA_C(ctx, dev_alloc(ctx, &spaCounts, size_t(3) * nChunks));
+            spatial_count<<<gridChunks, kBigBlock, 0, st>>>(tasks, rlo, rhi, B.root, spaCounts, nChunks, nb);
+            ATLAS_LAUNCHED(ctx);
+            spatial_scan<<<1, 96, 0, st>>>(spaCounts, nChunks, B.info);
+            ATLAS_LAUNCHED(ctx);
+            spatial_scatter<<<gridChunks, kBigBlock, 0, st>>>(tasks, rlo, rhi, B.tris, B.root, spaCounts, nChunks, nb, tmpLlo, tmpLhi,
+                                                              tmpRlo, tmpRhi, strad, n);
+            ATLAS_LAUNCHED(ctx);
+            spatial_sequential<<<1, kSeqTile, 0, st>>>(B.info, B.root, strad, n, tmpLlo, tmpLhi, tmpRlo, tmpRhi);
+            ATLAS_LAUNCHED(ctx);
+            spatial_emit<<<1, 1, 0, st>>>(tasks, B.info, B.root, L);
+            ATLAS_LAUNCHED(ctx);
+            spatial_place<<<gridChunks, 256, 0, st>>>(tasks, B.root, tmpLlo, tmpLhi, tmpRlo, tmpRhi, wlo, whi, B.order, B.eon);
+            ATLAS_LAUNCHED(ctx);
+        } else {
+            median_reduce_big<<<gridChunks, kBigBlock, 0, st>>>(tasks, B.info, B.chunkBase, rlo, rhi, B.medAcc);
+            ATLAS_LAUNCHED(ctx);
+            median_finalize_big<<<warpGrid, 128, 0, st>>>(tasks, B.info, B.medAcc, B.lo[cur], B.hi[cur], wlo, whi, B.order, B.eon, L,
+                                                          (!tlas && depth == 0) ? 1 : 0);
+            ATLAS_LAUNCHED(ctx);
+            partition_count<<<gridChunks, kBigBlock, 0, st>>>(tasks, B.info, B.chunkBase, rlo, rhi, B.chunkFirst, nb);
+            ATLAS_LAUNCHED(ctx);
+            partition_scan<<<warpGrid, 128, 0, st>>>(tasks, B.info, B.chunkBase, B.chunkFirst);
+            ATLAS_LAUNCHED(ctx);
+            partition_scatter<<<gridChunks, kBigBlock, 0, st>>>(tasks, B.info, B.chunkBase, B.chunkFirst, rlo, rhi, wlo, whi, B.order,
+                                                                B.eon, nb);
+            ATLAS_LAUNCHED(ctx);
+        }
+        ATLAS_TRY(read_back(ctx, B.info, &info));
+        totalRefs = info.totalRefs;
+        if (info.rootLeaf) { rootLeaf = true; break; }
+        if (info.nNext > maxTasks || info.nSmall > maxSmall) { cleanup(); return fail(ctx, ATLAS_RT_ERR_UNSUPPORTED, "task list overflow"); }
+        // next level
+        nTasks = info.nNext;
+        cur ^= 1u;
+        if (nTasks) {
+            // nTasks for the next level lives in info->nTasks
+            ATLAS_CUDA_C(ctx, cudaMemcpyAsync(&B.info->nTasks, &B.info->nNext, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        }
+    }
+
+    if (rootLeaf) {
+        root_leaf_output<<<(n + 255) / 256, 256, 0, st>>>(n, B.order, B.eon);
+        ATLAS_LAUNCHED(ctx);
+        out->nodeCount = 0;
+        out->refCount = n;
+    } else {
+        if (info.nSmall) {
+            build_subtrees<<<info.nSmall, kSubBlock, kSubtreeSmem, st>>>(B.small, info.nSmall, B.lo[0], B.hi[0], B.lo[1], B.hi[1], B.nodes,
+                                                                         B.order, B.eon, B.info, B.budget);
+            ATLAS_LAUNCHED(ctx);
+            ATLAS_TRY(read_back(ctx, B.info, &info));
+        }
+        out->refCount = totalRefs;
+        out->nodeCount = totalRefs - 1u;
+    }
+    out->stats[1] = info.stats[1];
+    out->stats[2] = info.stats[2];
+    out->stats[3] = info.stats[3];
+    out->stats[4] = info.stats[4];
+    out->stats[5] = info.stats[5];
+    out->stats[6] = levels;
+    out->stats[7] = info.negZero;
+    cleanup();
+    return ATLAS_RT_OK;
+}
+
+}   // namespace atlas

@@ -1,0 +1,147 @@
+// common.cuh — shared definitions of the CUDA implementation behind include/atlas_rt.h (sm_100a only).
+//
+// Arithmetic contract of every kernel in this directory: IEEE fp32, round-to-nearest, NO fused multiply-add on any
+// value that feeds a split decision, a node box, a visit-order decision or a reported hit. The library is compiled
+// with -fmad=false and without fast-math; where it matters the __f*_rn intrinsics are used as well so that a future
+// flag change cannot silently contract them. min/max follow glm 0.9.8 / GLSL comparison forms (see gl_min/gl_max).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/atlas_rt.h"
+#include "layouts.h"
+
+namespace atlas {
+
+constexpr float kFltMax = 3.402823466e+38f;
+
+// glm::min / glm::max (glm 0.9.8 func_common.inl) and GLSL min/max: result is the FIRST argument unless the
+// comparison holds, which also pins what happens with NaN and with -0 vs +0.
+__host__ __device__ __forceinline__ float gl_min(float x, float y) { return (y < x) ? y : x; }
+__host__ __device__ __forceinline__ float gl_max(float x, float y) { return (x < y) ? y : x; }
+__host__ __device__ __forceinline__ float gl_clamp(float x, float lo, float hi) { return gl_min(gl_max(x, lo), hi); }
+
+// Order-preserving map float -> int32 so that integer atomicMin/atomicMax reduce floats exactly and independently of
+// the order of operations (-0 sorts below +0; NaN is outside the contract).
+__host__ __device__ __forceinline__ int ord_from_float(float f) {
+#ifdef __CUDA_ARCH__
+    int i = __float_as_int(f);
+#else
+    int i;
+    memcpy(&i, &f, 4);
+#endif
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__host__ __device__ __forceinline__ float float_from_ord(int i) {
+    int b = i >= 0 ? i : i ^ 0x7fffffff;
+#ifdef __CUDA_ARCH__
+    return __int_as_float(b);
+#else
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+#endif
+}
+
+struct Box3 {
+    float lo[3], hi[3];
+};
+
+__host__ __device__ __forceinline__ Box3 empty_box() {
+    Box3 b;
+    b.lo[0] = b.lo[1] = b.lo[2] = kFltMax;
+    b.hi[0] = b.hi[1] = b.hi[2] = -kFltMax;
+    return b;
+}
+
+// AABB::GetSurfaceArea — src/engine/volume/AABB.cpp:109-115: 2 * ((dx*dy + dy*dz) + dz*dx), no clamping.
+__device__ __forceinline__ float surface_area(const float lo[3], const float hi[3]) {
+    const float dx = __fsub_rn(hi[0], lo[0]), dy = __fsub_rn(hi[1], lo[1]), dz = __fsub_rn(hi[2], lo[2]);
+    return __fmul_rn(2.0f, __fadd_rn(__fadd_rn(__fmul_rn(dx, dy), __fmul_rn(dy, dz)), __fmul_rn(dz, dx)));
+}
+__device__ __forceinline__ float surface_area(const Box3& b) { return surface_area(b.lo, b.hi); }
+
+}   // namespace atlas
+
+// ------------------------------------------------------------------------------------------------ host objects
+struct atlas_rt_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool ownStream = false;
+    int smCount = 148;
+    uint64_t launches = 0;
+    std::string error;
+    unsigned long long* dCounters = nullptr;   // 8 x u64 traversal counters / flags
+    void* pinned = nullptr;                    // small pinned staging area for read-backs
+    size_t pinnedBytes = 0;
+};
+
+struct atlas_rt_bvh {
+    atlas_rt_context* ctx = nullptr;
+    uint64_t nodeCount = 0, refCount = 0;
+    float4* nodes = nullptr;      // GPUBVHNode, 4 x float4 each
+    uint32_t* order = nullptr;    // source index per flattened slot
+    uint8_t* endOfNode = nullptr;
+    uint64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+struct atlas_rt_mesh {
+    atlas_rt_context* ctx = nullptr;
+    const atlas_rt_bvh* blas = nullptr;
+    uint64_t triCount = 0;
+    float4* tris = nullptr;       // GPUBVHTriangle, 3 x float4 each
+};
+
+struct atlas_rt_scene {
+    atlas_rt_context* ctx = nullptr;
+    const atlas_rt_bvh* tlas = nullptr;
+    uint64_t instanceCount = 0;   // == tlas->refCount
+    uint32_t meshCount = 0;
+    float4* instances = nullptr;             // reordered GPUBVHInstance, 4 x float4 each
+    const float4** blasNodes = nullptr;      // device array [meshCount]
+    const float4** bvhTris = nullptr;        // device array [meshCount]
+};
+
+namespace atlas {
+
+int fail(atlas_rt_context* ctx, int status, const char* what, cudaError_t e = cudaSuccess);
+
+#define ATLAS_CUDA(ctx, call)                                                          \
+    do {                                                                               \
+        cudaError_t e__ = (call);                                                      \
+        if (e__ != cudaSuccess) return atlas::fail((ctx), ATLAS_RT_ERR_CUDA, #call, e__); \
+    } while (0)
+
+#define ATLAS_LAUNCH_CHECK(ctx)                                                        \
+    do {                                                                               \
+        (ctx)->launches++;                                                             \
+        cudaError_t e__ = cudaGetLastError();                                          \
+        if (e__ != cudaSuccess) return atlas::fail((ctx), ATLAS_RT_ERR_CUDA, "kernel launch", e__); \
+    } while (0)
+
+// Stream-ordered allocation from the device's default pool (kept warm: release threshold = max).
+template <typename T>
+inline cudaError_t dev_alloc(atlas_rt_context* ctx, T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    return cudaMallocAsync(reinterpret_cast<void**>(p), count * sizeof(T), ctx->stream);
+}
+inline void dev_free(atlas_rt_context* ctx, const void* p) {
+    if (p) cudaFreeAsync(const_cast<void*>(p), ctx->stream);
+}
+
+// Copy count*bytes from src (host or device according to `device`) into device memory on the context stream.
+cudaError_t copy_in(atlas_rt_context* ctx, void* dst, const void* src, size_t bytes, bool srcDevice);
+cudaError_t copy_out(atlas_rt_context* ctx, void* dst, const void* src, size_t bytes, bool dstDevice);
+
+// builder entry points (build.cu)
+int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, uint64_t count, bool tlas, atlas_rt_bvh* out);
+
+// traversal entry points (trace.cu)
+int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float4* dIn, float4* dOut, uint64_t count,
+                 uint32_t cullMask, float tMin, float tMax, bool any, bool perRayTMax, bool counters);
+
+}   // namespace atlas

@@ -1,0 +1,213 @@
+/*
+ * atlas_rt.h — C ABI of the B200-native (CUDA, sm_100a) replacement for Atlas Engine's software ray-tracing
+ * acceleration path: BLAS/TLAS build, flatten + pack into the engine's GPU layouts, closest-hit / any-hit traversal,
+ * and the path tracer's ray-gen / diffuse-bounce loop.
+ *
+ * This header is the drop-in boundary. The reference has no FFI for this path (it is plain C++ classes), so every
+ * entry point cites the reference interface it stands behind (paths relative to the reference repository root);
+ * atlas_engine_b200/host/ holds C++ classes with the reference's own names that forward to these functions, and
+ * INTEGRATION.md shows the patch a maintainer applies.
+ *
+ * Conventions
+ *   - Every function returns ATLAS_RT_OK (0) or a negative atlas_rt_status; nothing throws across the boundary.
+ *     atlas_rt_last_error(ctx) returns a human-readable message for the most recent failure on that context.
+ *   - Plain pointers and sizes only. A pointer argument is HOST memory unless the matching ATLAS_RT_DEVICE_* bit is
+ *     set in `flags`, in which case it is a CUDA device pointer valid on the context's device.
+ *   - All work for a context is issued on the context's CUDA stream. Calls are synchronous on return (like the
+ *     reference's constructors) unless ATLAS_RT_ASYNC is set, in which case the caller synchronises the stream
+ *     (atlas_rt_context_synchronize) before touching outputs. Device outputs stay valid until the owning object is freed.
+ *   - Contexts are independent: one per host thread / stream makes concurrent builds re-entrant, as the reference
+ *     requires (meshes are built concurrently from job-system workers, src/tests/App.cpp:362-370).
+ *   - There is no CPU fallback: if no CUDA device is usable the functions fail with ATLAS_RT_ERR_CUDA.
+ *
+ * Layouts (all little-endian, 4-byte words; asserted in atlas_engine_b200/csrc/layouts.h)
+ *   AABB            24 B  min.xyz, max.xyz                                 src/engine/volume/AABB.h:102-103
+ *   triangle        36 B  v0.xyz, v1.xyz, v2.xyz                           src/engine/volume/BVH.h:26-33 (vertices only)
+ *   BVHNode         56 B  leftAABB, rightAABB, leftPtr, rightPtr           src/engine/volume/BVH.h:14-24
+ *   GPUBVHNode      64 B  BVHNode + 2 pad ints                             src/engine/raytracing/RTStructures.h:95-103
+ *   GPUBVHTriangle  48 B  v0.xyz,endOfNode?1:-1; v1.xyz,bits(material); v2.xyz,opacity   RTStructures.h:23-27, mesh/MeshData.cpp:242-247
+ *   GPUBVHInstance  64 B  mat3x4 inverseMatrix; meshOffset, materialOffset, nextInstance, mask   RTStructures.h:85-93
+ *   PackedRay       48 B  origin.xyz,bits(ID); direction.xyz,[u]; t,bits(hitID),bits(hitInstanceID),[v]
+ *                         data/shader/raytracer/structures.hsh:9-13, common.hsh:46-73. The two lanes the GLSL PackRay
+ *                         leaves unwritten (direction.w, hit.w) carry the barycentrics (sol.y, sol.z) of the accepted hit.
+ *   ptr encoding    ptr >= 0: inner-node index; ptr < 0: leaf, ~ptr = first triangle / instance slot.
+ */
+#ifndef ATLAS_RT_H
+#define ATLAS_RT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ATLAS_RT_VERSION 1
+
+typedef enum atlas_rt_status {
+    ATLAS_RT_OK = 0,
+    ATLAS_RT_ERR_INVALID = -1,      /* null pointer, mismatched sizes, object from another context */
+    ATLAS_RT_ERR_CUDA = -2,         /* a CUDA call failed or no device */
+    ATLAS_RT_ERR_OOM = -3,          /* device or host allocation failed */
+    ATLAS_RT_ERR_UNSUPPORTED = -4,  /* input outside the documented contract (e.g. > 2^31-2 references) */
+    ATLAS_RT_ERR_STACK = -5         /* a ray needed more than ATLAS_RT_STACK_SIZE stack entries (UB in the reference) */
+} atlas_rt_status;
+
+/* flags */
+#define ATLAS_RT_DEVICE_INPUT  (1u << 0)   /* input pointers are device memory */
+#define ATLAS_RT_DEVICE_OUTPUT (1u << 1)   /* output pointers are device memory */
+#define ATLAS_RT_ASYNC         (1u << 2)   /* do not synchronise the stream before returning */
+#define ATLAS_RT_PER_RAY_TMAX  (1u << 3)   /* trace_any: take tMax from each ray's hit.x instead of the argument */
+#define ATLAS_RT_COUNTERS      (1u << 4)   /* trace_*: also count visited nodes / triangles (slower; for parity + roofline) */
+
+/* Instance cull masks — InstanceCullMasks, src/engine/raytracing/RTStructures.h:9-12; common.hsh:14-15. */
+#define ATLAS_RT_MASK_ALL    (1u << 7)
+#define ATLAS_RT_MASK_SHADOW (1u << 6)
+
+#define ATLAS_RT_STACK_SIZE 32             /* STACK_SIZE, data/shader/raytracer/bvh.hsh:16 */
+#define ATLAS_RT_INF 1000000000000.0f      /* INF, data/shader/raytracer/common.hsh:8 */
+
+typedef struct atlas_rt_context atlas_rt_context;
+typedef struct atlas_rt_bvh atlas_rt_bvh;
+typedef struct atlas_rt_mesh atlas_rt_mesh;
+typedef struct atlas_rt_scene atlas_rt_scene;
+
+/* ------------------------------------------------------------------------------------------------ context ---- */
+/* device: CUDA ordinal. stream: a cudaStream_t owned by the caller (e.g. torch's current stream), or NULL to let the
+ * context create and own a non-blocking stream. Replaces the reference's implicit globals (Graphics::GraphicsDevice::
+ * DefaultDevice + the JobSystem pools used by BVH.cpp:36-38). */
+int atlas_rt_context_create(int device, void* stream, atlas_rt_context** out_ctx);
+void atlas_rt_context_destroy(atlas_rt_context* ctx);
+int atlas_rt_context_synchronize(atlas_rt_context* ctx);
+const char* atlas_rt_last_error(const atlas_rt_context* ctx);
+/* Number of CUDA kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t atlas_rt_kernel_launches(const atlas_rt_context* ctx);
+int atlas_rt_version(void);
+
+/* -------------------------------------------------------------------------------------------------- build ---- */
+/* BLAS build + flatten. Replaces Atlas::Volume::BVH::BVH(const std::vector<AABB>&, const std::vector<BVHTriangle>&,
+ * bool) — src/engine/volume/BVH.cpp:14-56 — including the root SBVH spatial split, 256 bins, one primitive per leaf,
+ * median fallback and the larger-area-child-first flatten (BVH.cpp:249-441).
+ * aabbs: count x 6 floats. tris: count x 9 floats (v0,v1,v2 of triangle i; its BVHTriangle::idx is i).
+ * The result holds nodes, the flattened order (source index per slot, duplicates possible) and endOfNode flags. */
+int atlas_rt_build_blas(atlas_rt_context* ctx, const float* aabbs, const float* tris, uint64_t count, uint32_t flags,
+                        atlas_rt_bvh** out_bvh);
+
+/* TLAS build + flatten. Replaces Atlas::Volume::BVH::BVH(const std::vector<AABB>&, bool) — BVH.cpp:58-101 (64 bins,
+ * object/median splits only, the count == 1 special node and its two-entry refs quirk). */
+int atlas_rt_build_tlas(atlas_rt_context* ctx, const float* aabbs, uint64_t count, uint32_t flags,
+                        atlas_rt_bvh** out_bvh);
+
+/* Wrap an already flattened tree (host BVHNode 56 B layout + order + flags), e.g. one built by the reference, so it
+ * can be packed and traversed. Mirrors assigning BVH::nodes / data / refs directly (BVH.h:132-136). */
+int atlas_rt_bvh_upload(atlas_rt_context* ctx, const void* nodes56, uint64_t node_count, const uint32_t* order,
+                        const uint8_t* end_of_node, uint64_t ref_count, atlas_rt_bvh** out_bvh);
+
+/* nodes.size() and data.size()/refs.size() of the reference object. */
+int atlas_rt_bvh_counts(const atlas_rt_bvh* bvh, uint64_t* node_count, uint64_t* ref_count);
+
+/* Copy out in the reference's host layout: BVH::nodes (56 B each), data[i].idx / refs[i].idx, endOfNode.
+ * Any pointer may be NULL to skip it. Honours ATLAS_RT_DEVICE_OUTPUT. */
+int atlas_rt_bvh_download(const atlas_rt_bvh* bvh, void* nodes56, uint32_t* order, uint8_t* end_of_node, uint32_t flags);
+
+/* Device pointers owned by the bvh: GPUBVHNode array (64 B each), order (u32), endOfNode (u8). */
+int atlas_rt_bvh_device_ptrs(const atlas_rt_bvh* bvh, const void** gpu_nodes64, const uint32_t** order,
+                             const uint8_t** end_of_node);
+
+/* Build statistics: out[0] = 1 if the root spatial split was evaluated, [1] = 1 if chosen, [2] = duplicated
+ * references, [3] = median splits, [4] = sort fallbacks, [5] = largest sort fallback, [6] = levels processed,
+ * [7] = 1 if the input contained -0.0 (node boxes may then differ from the reference in the sign of zero only). */
+int atlas_rt_bvh_stats(const atlas_rt_bvh* bvh, uint64_t out[8]);
+
+void atlas_rt_bvh_free(atlas_rt_bvh* bvh);
+
+/* --------------------------------------------------------------------------------------------------- pack ---- */
+/* Gather triangles into flattened order and emit GPUBVHTriangle records + keep the GPUBVHNode array. Replaces the
+ * packing half of Atlas::Mesh::MeshData::BuildBVH — src/engine/mesh/MeshData.cpp:172-269 (traversal payload only:
+ * v0..v2, endOfNode, material index, opacity) — and the uploads of Mesh::BuildBVH, mesh/Mesh.cpp:97-108.
+ * tris: the same count x 9 array the BLAS was built from. material_idx / opacity: per-triangle arrays (count entries,
+ * source order) or NULL for 0 / 1.0f. */
+int atlas_rt_pack_mesh(atlas_rt_context* ctx, const atlas_rt_bvh* blas, const float* tris, uint64_t count,
+                       const int32_t* material_idx, const float* opacity, uint32_t flags, atlas_rt_mesh** out_mesh);
+int atlas_rt_mesh_counts(const atlas_rt_mesh* mesh, uint64_t* node_count, uint64_t* triangle_count);
+/* Copy out gpuBvhNodes (64 B each) and gpuBvhTriangles (48 B each); either may be NULL. */
+int atlas_rt_mesh_download(const atlas_rt_mesh* mesh, void* gpu_nodes64, void* gpu_bvh_triangles48, uint32_t flags);
+void atlas_rt_mesh_free(atlas_rt_mesh* mesh);
+
+/* -------------------------------------------------------------------------------------------------- scene ---- */
+/* Assemble the two-level scene. Replaces RayTracingWorld::UpdateForSoftwareRayTracing — src/engine/raytracing/
+ * RayTracingWorld.cpp:267-307: instances (64 B GPUBVHInstance each, SOURCE order, meshOffset indexing `meshes`) are
+ * permuted by the TLAS order and nextInstance is set to endOfNode ? -1 : slot + 1; TLAS nodes go to the GPUBVHNode
+ * layout. The meshes and the tlas must outlive the scene. */
+int atlas_rt_scene_create(atlas_rt_context* ctx, const atlas_rt_mesh* const* meshes, uint32_t mesh_count,
+                          const void* instances64, uint64_t instance_count, const atlas_rt_bvh* tlas, uint32_t flags,
+                          atlas_rt_scene** out_scene);
+/* Reordered instance records (tlas ref_count x 64 B) and TLAS nodes (64 B each); either may be NULL. */
+int atlas_rt_scene_download(const atlas_rt_scene* scene, void* instances64, void* tlas_nodes64, uint32_t flags);
+void atlas_rt_scene_free(atlas_rt_scene* scene);
+
+/* -------------------------------------------------------------------------------------------------- trace ---- */
+/* Closest hit for a batch of PackedRay (48 B). Replaces the traceClosest.csh dispatch issued by
+ * RayTracingHelper::DispatchHitClosest (src/engine/renderer/helper/RayTracingHelper.cpp:346-364) = HitClosest,
+ * data/shader/raytracer/bvh.hsh:191-273: rays with ID < 0 are passed through with hitID = -1, t = 0; otherwise
+ * t = tMax and hitID = -1 on a miss. rays_out may alias rays_in. */
+int atlas_rt_trace_closest(atlas_rt_context* ctx, const atlas_rt_scene* scene, const void* rays_in, uint64_t count,
+                           uint32_t cull_mask, float t_min, float t_max, void* rays_out, uint32_t flags);
+
+/* Any hit (shadow rays). HitAny, bvh.hsh:359-441, as called inline by the reference's hit shaders
+ * (data/shader/pathtracer/rayHit.csh:327-337). Output hitID >= 0 iff something was hit in (tMin, tMax). */
+int atlas_rt_trace_any(atlas_rt_context* ctx, const atlas_rt_scene* scene, const void* rays_in, uint64_t count,
+                       uint32_t cull_mask, float t_min, float t_max, void* rays_out, uint32_t flags);
+
+/* Traversal work counters of the last trace call on this context that passed ATLAS_RT_COUNTERS, summed over rays:
+ * out = tlasNodes, instances entered, blasNodes, triangles tested, max stack depth, rays that overflowed the stack.
+ * These are the visit counts SURVEY.md 8(d) turns into algorithmic bytes. */
+int atlas_rt_trace_counters(atlas_rt_context* ctx, uint64_t out[6]);
+
+/* ------------------------------------------------------------------------------------------- path tracer ---- */
+typedef struct atlas_rt_camera {
+    float eye[3];      /* globalData.cameraLocation */
+    float origin[3];   /* near-plane upper-left corner  (PathTracingRenderer.cpp:157-162) */
+    float right[3];    /* upper-right - upper-left */
+    float bottom[3];   /* lower-left - upper-left */
+} atlas_rt_camera;
+
+/* Primary rays. Replaces pathtracer/rayGen.csh:25-91 as dispatched by PathTracingRenderer::Render
+ * (src/engine/renderer/PathTracingRenderer.cpp:146-155): width x height x samples rays, ID = (y*w+x)*samples + s,
+ * stored in the shader's 8x8-tile order. jitter = per-sample sub-pixel offset in [0,1)^2 (2 floats per sample).
+ * rays_out: width*height*samples PackedRay, device memory if ATLAS_RT_DEVICE_OUTPUT. */
+int atlas_rt_generate_primary_rays(atlas_rt_context* ctx, const atlas_rt_camera* camera, uint32_t width,
+                                   uint32_t height, uint32_t samples, const float* jitter, void* rays_out, uint32_t flags);
+
+typedef struct atlas_rt_bounce_params {
+    float light_dir[3];     /* direction TO the directional light (normalised) */
+    float light_radiance[3];
+    float albedo[3];        /* Lambertian base colour of every surface */
+    float sky_radiance[3];  /* constant environment */
+    float seed;             /* Uniforms.seed of this bounce */
+    uint32_t bounce;        /* Uniforms.bounceCount */
+    uint32_t max_bounces;   /* Uniforms.maxBounces */
+    uint32_t samples;       /* Uniforms.samplesPerFrame */
+} atlas_rt_bounce_params;
+
+/* One bounce of the diffuse path: closest-hit trace of `count` rays, then per ray: environment on a miss, one shadow
+ * any-hit ray towards the light (origin = P + N*0.1, cull mask MaskShadow), cosine-weighted next direction from the
+ * reference's hash RNG keyed by (ray.ID, seed), Russian roulette, and compaction of the surviving rays. Replaces one
+ * iteration of the loop in PathTracingRenderer.cpp:177-192 = traceClosest.csh + the diffuse / shadow-ray parts of
+ * pathtracer/rayHit.csh:160-337. rays / payload are device buffers of capacity `count` (payload: 2 x float4 per ray:
+ * radiance.rgb, throughput.rgb); accum: width*height*4 floats (rgb sum, sample count) indexed by ray.ID / samples.
+ * out_count receives the number of surviving rays, which are compacted to the front of rays_out / payload_out. */
+int atlas_rt_pathtrace_bounce(atlas_rt_context* ctx, const atlas_rt_scene* scene, const atlas_rt_bounce_params* params,
+                              const void* rays_in, const void* payload_in, uint64_t count, void* rays_out,
+                              void* payload_out, float* accum, uint64_t* out_count, uint32_t flags);
+
+/* ---------------------------------------------------------------------------------------------- multi-GPU ---- */
+/* Contiguous share of `count` rays for `rank` of `world`, aligned to `align` rays (64 keeps rayGen's 8x8 tiles whole).
+ * The scene is replicated per GPU (one process and one context per GPU); ranks trace their share and the caller
+ * gathers hit buffers with one NCCL all-gather (see atlas_engine_b200/sharding.py). */
+int atlas_rt_shard_range(uint64_t count, uint32_t rank, uint32_t world, uint32_t align, uint64_t* begin, uint64_t* end);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ATLAS_RT_H */
