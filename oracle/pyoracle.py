@@ -22,7 +22,7 @@ _u64, _u32, _i32, _f32, _vp = C.c_uint64, C.c_uint32, C.c_int32, C.c_float, C.c_
 def build(force=False):
     """Compile libatlas_oracle.so always, and _ref/libatlas_ref.so when /root/reference is present."""
     args = ["make", "-C", _HERE, "-s"] + (["-B"] if force else []) + ["all"]
-    subprocess.run(args, check=True, stdout=subprocess.DEVNULL)
+    subprocess.run(args, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 
 
 def _ptr(a):
