@@ -1,5 +1,7 @@
 // api.cu — C ABI glue (include/atlas_rt.h): contexts, object lifetime, host<->device staging, pack and scene kernels.
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -80,6 +82,16 @@ __global__ void reorder_instances(const float4* __restrict__ src, const uint32_t
     dst[4 * i + 3] = last;
 }
 
+// A BLAS whose root became a leaf has no nodes at all (Flatten emits none); the reference shader would then read
+// blasNodes[..].data[0] out of bounds. We give such a BLAS one node with two empty boxes so that rays entering the
+// instance simply miss.
+__global__ void write_empty_node(float4* node) {
+    node[0] = make_float4(kFltMax, kFltMax, kFltMax, -kFltMax);
+    node[1] = make_float4(-kFltMax, -kFltMax, kFltMax, kFltMax);
+    node[2] = make_float4(kFltMax, -kFltMax, -kFltMax, -kFltMax);
+    node[3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+
 int sync_unless_async(atlas_rt_context* ctx, uint32_t flags) {
     if (flags & ATLAS_RT_ASYNC) return ATLAS_RT_OK;
     ATLAS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -87,6 +99,15 @@ int sync_unless_async(atlas_rt_context* ctx, uint32_t flags) {
 }
 
 }   // namespace
+
+int ensure_node_storage(atlas_rt_context* ctx, atlas_rt_bvh* bvh) {
+    if (bvh->nodeCount != 0) return ATLAS_RT_OK;
+    if (!bvh->nodes) ATLAS_CUDA(ctx, dev_alloc(ctx, &bvh->nodes, 4));
+    write_empty_node<<<1, 1, 0, ctx->stream>>>(bvh->nodes);
+    ATLAS_LAUNCH_CHECK(ctx);
+    return ATLAS_RT_OK;
+}
+
 }   // namespace atlas
 
 using namespace atlas;
@@ -111,6 +132,9 @@ int atlas_rt_context_create(int device, void* stream, atlas_rt_context** out_ctx
         ctx->ownStream = true;
     }
     cudaDeviceGetAttribute(&ctx->smCount, cudaDevAttrMultiProcessorCount, device);
+    if (const char* e = getenv("ATLAS_RT_TRACE_LEAF_THRESHOLD")) ctx->traceLeafThreshold = std::max(1, std::min(32, atoi(e)));
+    if (const char* e = getenv("ATLAS_RT_TRACE_REFILL_THRESHOLD")) ctx->traceRefillThreshold = std::max(1, std::min(32, atoi(e)));
+    if (const char* e = getenv("ATLAS_RT_TRACE_BLOCKS_PER_SM")) ctx->traceBlocksPerSM = std::max(1, std::min(6, atoi(e)));
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t keep = ~0ull;
@@ -164,6 +188,7 @@ static int build_common(atlas_rt_context* ctx, const float* aabbs, const float* 
     if (!bvh) return fail(ctx, ATLAS_RT_ERR_OOM, "host allocation");
     bvh->ctx = ctx;
     int rc = build_bvh(ctx, dev ? aabbs : dA, tlas ? nullptr : (dev ? tris : dT), count, tlas, bvh);
+    if (rc == ATLAS_RT_OK) rc = ensure_node_storage(ctx, bvh);
     if (!dev) { dev_free(ctx, dA); dev_free(ctx, dT); }
     if (rc != ATLAS_RT_OK) { atlas_rt_bvh_free(bvh); return rc; }
     rc = sync_unless_async(ctx, flags);
@@ -192,7 +217,7 @@ int atlas_rt_bvh_upload(atlas_rt_context* ctx, const void* nodes56, uint64_t nod
     bvh->nodeCount = node_count;
     bvh->refCount = ref_count;
     uint32_t* staging = nullptr;
-    ATLAS_CUDA(ctx, dev_alloc(ctx, &bvh->nodes, node_count * 4));
+    ATLAS_CUDA(ctx, dev_alloc(ctx, &bvh->nodes, (node_count ? node_count : 1) * 4));
     ATLAS_CUDA(ctx, dev_alloc(ctx, &bvh->order, ref_count));
     ATLAS_CUDA(ctx, dev_alloc(ctx, &bvh->endOfNode, ref_count));
     ATLAS_CUDA(ctx, dev_alloc(ctx, &staging, node_count * 14));
@@ -204,6 +229,7 @@ int atlas_rt_bvh_upload(atlas_rt_context* ctx, const void* nodes56, uint64_t nod
         ATLAS_LAUNCH_CHECK(ctx);
     }
     dev_free(ctx, staging);
+    { int rcn = ensure_node_storage(ctx, bvh); if (rcn != ATLAS_RT_OK) { atlas_rt_bvh_free(bvh); return rcn; } }
     ATLAS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *out_bvh = bvh;
     return ATLAS_RT_OK;
@@ -331,12 +357,17 @@ int atlas_rt_scene_create(atlas_rt_context* ctx, const atlas_rt_mesh* const* mes
     scene->meshCount = mesh_count;
     scene->instanceCount = tlas->refCount;
     std::vector<const float4*> nodePtrs(mesh_count), triPtrs(mesh_count);
+    std::vector<uint32_t> nodeCounts(mesh_count);
     for (uint32_t m = 0; m < mesh_count; m++) {
         if (!meshes[m] || meshes[m]->ctx != ctx) { delete scene; return fail(ctx, ATLAS_RT_ERR_INVALID, "mesh from another context"); }
         nodePtrs[m] = meshes[m]->blas->nodes;
         triPtrs[m] = meshes[m]->tris;
+        nodeCounts[m] = uint32_t(meshes[m]->blas->nodeCount);
     }
     float4* dSrc = nullptr;
+    uint32_t* dNodeCounts = nullptr;
+    ATLAS_CUDA(ctx, dev_alloc(ctx, &dNodeCounts, mesh_count));
+    ATLAS_CUDA(ctx, cudaMemcpyAsync(dNodeCounts, nodeCounts.data(), mesh_count * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     ATLAS_CUDA(ctx, dev_alloc(ctx, &scene->blasNodes, mesh_count));
     ATLAS_CUDA(ctx, dev_alloc(ctx, &scene->bvhTris, mesh_count));
     ATLAS_CUDA(ctx, dev_alloc(ctx, &scene->instances, scene->instanceCount * 4));
@@ -344,6 +375,11 @@ int atlas_rt_scene_create(atlas_rt_context* ctx, const atlas_rt_mesh* const* mes
     ATLAS_CUDA(ctx, cudaMemcpyAsync(scene->blasNodes, nodePtrs.data(), mesh_count * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
     ATLAS_CUDA(ctx, cudaMemcpyAsync(scene->bvhTris, triPtrs.data(), mesh_count * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
     ATLAS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the std::vectors die at scope exit
+    {
+        int rcf = scene_fast_flag(ctx, scene, dNodeCounts);
+        dev_free(ctx, dNodeCounts);
+        if (rcf != ATLAS_RT_OK) { atlas_rt_scene_free(scene); return rcf; }
+    }
     const float4* src = static_cast<const float4*>(instances64);
     if (!dev) {
         ATLAS_CUDA(ctx, dev_alloc(ctx, &dSrc, instance_count * 4));

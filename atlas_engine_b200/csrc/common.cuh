@@ -77,6 +77,10 @@ struct atlas_rt_context {
     unsigned long long* dCounters = nullptr;   // 8 x u64 traversal counters / flags
     void* pinned = nullptr;                    // small pinned staging area for read-backs
     size_t pinnedBytes = 0;
+    // scheduling knobs of the persistent traversal kernel (trace.cu); ATLAS_RT_TRACE_* environment variables override
+    int traceLeafThreshold = 8;     // lanes waiting at a leaf before the warp runs a leaf round
+    int traceRefillThreshold = 6;   // idle lanes before the warp fetches new rays
+    int traceBlocksPerSM = 6;
 };
 
 struct atlas_rt_bvh {
@@ -103,6 +107,7 @@ struct atlas_rt_scene {
     float4* instances = nullptr;             // reordered GPUBVHInstance, 4 x float4 each
     const float4** blasNodes = nullptr;      // device array [meshCount]
     const float4** bvhTris = nullptr;        // device array [meshCount]
+    int fastDivision = 0;                    // all scene coordinates below 2^60: slab tests may use div_by_rcp (trace.cu)
 };
 
 namespace atlas {
@@ -137,10 +142,13 @@ inline void dev_free(atlas_rt_context* ctx, const void* p) {
 cudaError_t copy_in(atlas_rt_context* ctx, void* dst, const void* src, size_t bytes, bool srcDevice);
 cudaError_t copy_out(atlas_rt_context* ctx, void* dst, const void* src, size_t bytes, bool dstDevice);
 
+int ensure_node_storage(atlas_rt_context* ctx, atlas_rt_bvh* bvh);
+
 // builder entry points (build.cu)
 int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, uint64_t count, bool tlas, atlas_rt_bvh* out);
 
 // traversal entry points (trace.cu)
+int scene_fast_flag(atlas_rt_context* ctx, atlas_rt_scene* scene, const uint32_t* dNodeCounts);
 int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float4* dIn, float4* dOut, uint64_t count,
                  uint32_t cullMask, float tMin, float tMax, bool any, bool perRayTMax, bool counters);
 

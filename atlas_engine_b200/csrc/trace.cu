@@ -9,6 +9,9 @@
 // Data movement: a node is 64 B = 4 x LDG.128 through the read-only path, a triangle 48 B = 3 x LDG.128, an instance
 // 64 B = 4 x LDG.128; rays are read and written once as 3 x 128-bit each. The per-ray stack (32 node pointers, the
 // reference's STACK_SIZE) lives in shared memory laid out [entry][lane] so a warp's accesses never bank-conflict.
+#include <algorithm>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace atlas {
@@ -16,6 +19,7 @@ namespace atlas {
 namespace {
 
 constexpr int kTraceBlock = 128;
+constexpr unsigned kFull = 0xffffffffu;
 constexpr uint32_t kStack = ATLAS_RT_STACK_SIZE;
 constexpr uint32_t kTlasInvalid = kStack + 2;   // TLAS_INVALID, bvh.hsh:17
 
@@ -68,169 +72,312 @@ __device__ __forceinline__ bool tri_test(const float o[3], const float d[3], con
     return sol[0] >= 0.0f && sol[1] >= 0.0f && sol[2] >= 0.0f && __fadd_rn(sol[1], sol[2]) <= 1.0f;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Exact division by a per-ray precomputed reciprocal. rc = __frcp_rn(d) is the correctly rounded reciprocal; q0 =
+// RN(x * rc) is then a faithful quotient and one FMA residual + one FMA correction (Markstein's theorem) give the
+// correctly rounded x / d — three fma-pipe instructions and nothing on the XU (MUFU) pipe, which the 12 IEEE divisions
+// per node otherwise saturate (profiles/trace_r1.md: XU pipe 58 % busy in the first version).
+// Valid while nothing over/underflows: the caller only takes this path for rays whose direction components lie in
+// [2^-64, 2^64] and whose origin / scene coordinates are below 2^60 (`fast` flag); all other rays use __fdiv_rn.
+// tools/divcheck.cu compared this sequence with __fdiv_rn on 3.2e11 operand pairs (uniform and adversarial
+// mantissas, exponents over the whole admitted range) on a B200: 0 mismatches.
+__device__ __forceinline__ float div_by_rcp(float x, float d, float rc) {
+    const float q = __fmul_rn(x, rc);
+    const float e = __fmaf_rn(-d, q, x);
+    return __fmaf_rn(e, rc, q);
+}
+
+// IntersectAABB on the fast path. No operand can be NaN here (finite boxes, finite non-zero direction), so
+// fminf/fmaxf (one FMNMX each) agree with the GLSL comparison forms up to the sign of zero, which no later comparison
+// can observe.
+__device__ __forceinline__ bool slab_fast(const float o[3], const float d[3], const float rc[3], const float lo[3],
+                                          const float hi[3], float tmin, float tmax, float& dist) {
+    float ts[3], tb[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const float t0 = div_by_rcp(__fsub_rn(lo[a], o[a]), d[a], rc[a]);
+        const float t1 = div_by_rcp(__fsub_rn(hi[a], o[a]), d[a], rc[a]);
+        ts[a] = fminf(t0, t1);
+        tb[a] = fmaxf(t0, t1);
+    }
+    const float tminf = fmaxf(fmaxf(tmin, ts[0]), fmaxf(ts[1], ts[2]));
+    const float tmaxf = fminf(fminf(tmax, tb[0]), fminf(tb[1], tb[2]));
+    const bool hit = tminf <= tmaxf;
+    dist = hit ? tminf : tmax;
+    return hit;
+}
+
+constexpr float kDirLo = 5.421010862427522e-20f;   // 2^-64
+constexpr float kDirHi = 1.8446744073709552e19f;   // 2^64
+constexpr float kPosHi = 1.152921504606847e18f;    // 2^60
+
+__device__ __forceinline__ bool fast_ok(const float o[3], const float d[3]) {
+    bool ok = true;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const float ad = fabsf(d[a]);
+        ok = ok && (ad >= kDirLo) && (ad <= kDirHi) && (fabsf(o[a]) <= kPosHi);
+    }
+    return ok;
+}
+
+constexpr int kBlocksPerSM = 6;
+
+// Persistent-thread traversal. Each warp owns 32 ray slots and refills finished slots from a global ray counter, so
+// lanes do not idle while the longest ray of a static batch finishes (the one-thread-per-ray kernel ran at 8.5 of 32
+// active lanes). Within a warp every round is warp-uniform: either the lanes standing at an inner node take one
+// traversal step, or — once enough lanes wait at a leaf / instance — those lanes process it. A ray's own visit order is
+// exactly the reference's; only the interleaving between different rays changes.
 template <bool ANY, bool COUNT>
-__global__ void __launch_bounds__(kTraceBlock)
-trace_kernel(SceneDev sc, const float4* __restrict__ in, float4* __restrict__ out, uint32_t count, uint32_t cullMask,
-             float tMin, float tMaxArg, int perRayTMax, unsigned long long* __restrict__ counters) {
+__global__ void __launch_bounds__(kTraceBlock, kBlocksPerSM)
+trace_kernel(SceneDev sc, const float4* in, float4* out, uint32_t count, uint32_t cullMask, float tMin, float tMaxArg,
+             int perRayTMax, int sceneFast, int kLeafThreshold, int kRefillThreshold, unsigned int* __restrict__ rayCounter,
+             unsigned long long* __restrict__ counters) {
     __shared__ int stack[kStack][kTraceBlock];
-    const uint32_t tid = threadIdx.x;
-    const uint32_t i = blockIdx.x * kTraceBlock + tid;
-    if (i >= count) return;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const unsigned ltMask = (1u << lane) - 1u;
 
-    const float4 r0 = in[3 * size_t(i)], r1 = in[3 * size_t(i) + 1], r2 = in[3 * size_t(i) + 2];
-    const int id = __float_as_int(r0.w);
-    const float o0[3] = {r0.x, r0.y, r0.z}, d0[3] = {r1.x, r1.y, r1.z};
-
-    // traceClosest.csh:24-25
-    int hitID = -1, hitInst = __float_as_int(r2.z);
-    float hitT = 0.0f, baryU = 0.0f, baryV = 0.0f;
+    bool alive = false, fast = false, moreRays = true, overflow = false;
+    uint32_t ray = 0, sp = 0, tlasIndex = kTlasInvalid;
+    int nodePtr = 0, curInst = 0, hitID = -1, hitInst = 0;
+    float o[3] = {0, 0, 0}, d[3] = {1, 1, 1}, rc[3] = {1, 1, 1};
+    float tMax = tMaxArg, hitT = 0.0f, baryU = 0.0f, baryV = 0.0f;
+    const float4* nodes = sc.tlasNodes;
+    const float4* tris = nullptr;
     uint32_t cTlas = 0, cInst = 0, cBlas = 0, cTri = 0, cMaxSp = 1;
-    bool overflow = false;
 
-    if (id >= 0) {
-        const float tMax = (ANY && perRayTMax) ? r2.x : tMaxArg;
-        hitT = tMax;   // HitClosest: ray.hitDistance = tMax (bvh.hsh:202); any-hit reports tMax on a miss
-        const bool nanDir = (d0[0] != d0[0]) || (d0[1] != d0[1]) || (d0[2] != d0[2]);   // isnan3, bvh.hsh:204
-        if (!nanDir) {
-            uint32_t sp = 1u, tlasIndex = kTlasInvalid;
-            int nodePtr = 0, curInst = 0;
-            float o[3] = {o0[0], o0[1], o0[2]}, d[3] = {d0[0], d0[1], d0[2]};
-            const float4* __restrict__ nodes = sc.tlasNodes;
-            const float4* __restrict__ tris = nullptr;
-            bool hit = false;
-            stack[0][tid] = 0;
-            while (sp != 0u && !(ANY && hit)) {
-                const bool inTlas = sp < tlasIndex;
-                if (inTlas) {
-                    o[0] = o0[0]; o[1] = o0[1]; o[2] = o0[2];
-                    d[0] = d0[0]; d[1] = d0[1]; d[2] = d0[2];
-                    tlasIndex = kTlasInvalid;
-                    nodes = sc.tlasNodes;
-                }
-                if (nodePtr < 0) {
-                    if (inTlas) {
-                        // CheckInstance, bvh.hsh:172-189: vec4(o,1) * M and vec4(d,0) * M, no renormalisation.
-                        const int inst = ~nodePtr;
-                        const float4* I = sc.instances + 4 * size_t(inst);
-                        const float4 c0 = __ldg(I), c1 = __ldg(I + 1), c2 = __ldg(I + 2), c3 = __ldg(I + 3);
-                        if (COUNT) cInst++;
-                        float no[3], nd[3];
-                        no[0] = __fadd_rn(dot3(o[0], o[1], o[2], c0.x, c0.y, c0.z), __fmul_rn(1.0f, c0.w));
-                        no[1] = __fadd_rn(dot3(o[0], o[1], o[2], c1.x, c1.y, c1.z), __fmul_rn(1.0f, c1.w));
-                        no[2] = __fadd_rn(dot3(o[0], o[1], o[2], c2.x, c2.y, c2.z), __fmul_rn(1.0f, c2.w));
-                        nd[0] = __fadd_rn(dot3(d[0], d[1], d[2], c0.x, c0.y, c0.z), __fmul_rn(0.0f, c0.w));
-                        nd[1] = __fadd_rn(dot3(d[0], d[1], d[2], c1.x, c1.y, c1.z), __fmul_rn(0.0f, c1.w));
-                        nd[2] = __fadd_rn(dot3(d[0], d[1], d[2], c2.x, c2.y, c2.z), __fmul_rn(0.0f, c2.w));
-                        o[0] = no[0]; o[1] = no[1]; o[2] = no[2];
-                        d[0] = nd[0]; d[1] = nd[1]; d[2] = nd[2];
-                        curInst = inst;
-                        const int meshPtr = __float_as_int(c3.x);
-                        const uint32_t mask = uint32_t(__float_as_int(c3.w));
-                        nodePtr = 0;
-                        if ((mask & cullMask) > 0u) {
-                            tlasIndex = sp;
-                            nodes = sc.blasNodes[meshPtr];
-                            tris = sc.bvhTris[meshPtr];
-                        } else {
-                            nodePtr = stack[--sp][tid];
-                        }
+    auto finish = [&]() {   // PackRay, common.hsh:61-73 (+ barycentrics in the two lanes GLSL leaves unwritten)
+        const float4 r0 = in[3 * size_t(ray)], r1 = in[3 * size_t(ray) + 1];
+        out[3 * size_t(ray)] = r0;
+        out[3 * size_t(ray) + 1] = make_float4(r1.x, r1.y, r1.z, baryU);
+        out[3 * size_t(ray) + 2] = make_float4(hitT, __int_as_float(hitID), __int_as_float(hitInst), baryV);
+        alive = false;
+    };
+    auto set_ray = [&](const float oo[3], const float dd[3]) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) { o[a] = oo[a]; d[a] = dd[a]; }
+        fast = sceneFast && fast_ok(o, d);
+#pragma unroll
+        for (int a = 0; a < 3; a++) rc[a] = fast ? __frcp_rn(d[a]) : 0.0f;
+    };
+    auto back_to_tlas = [&]() {   // bvh.hsh:217-220: restore the world-space ray when the stack drops below tlasIndex
+        const float4 r0 = in[3 * size_t(ray)], r1 = in[3 * size_t(ray) + 1];
+        const float oo[3] = {r0.x, r0.y, r0.z}, dd[3] = {r1.x, r1.y, r1.z};
+        set_ray(oo, dd);
+        tlasIndex = kTlasInvalid;
+        nodes = sc.tlasNodes;
+    };
+    auto pop = [&]() {
+        nodePtr = stack[--sp][tid];
+        if (sp == 0u) finish();
+        else if (sp < tlasIndex && tlasIndex != kTlasInvalid) back_to_tlas();
+    };
+
+    while (true) {
+        const bool inner = alive && nodePtr >= 0;
+        const bool leafy = alive && nodePtr < 0;
+        const unsigned mI = __ballot_sync(kFull, inner), mL = __ballot_sync(kFull, leafy);
+        const int nI = __popc(mI), nL = __popc(mL), nDead = 32 - nI - nL;
+
+        if (moreRays && (nDead >= kRefillThreshold || nI + nL == 0)) {
+            // ---- fetch new rays for the idle lanes (traceClosest.csh:18-30)
+            const unsigned mDead = ~(mI | mL);
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(rayCounter, unsigned(nDead));
+            base = __shfl_sync(kFull, base, 0);
+            if (base >= count || base + unsigned(nDead) >= count) moreRays = false;
+            if (!alive) {
+                const unsigned idx = base + __popc(mDead & ltMask);
+                if (idx < count && idx >= base) {
+                    ray = idx;
+                    const float4 r0 = in[3 * size_t(ray)], r1 = in[3 * size_t(ray) + 1], r2 = in[3 * size_t(ray) + 2];
+                    const int id = __float_as_int(r0.w);
+                    hitID = -1;
+                    hitInst = __float_as_int(r2.z);
+                    hitT = 0.0f;
+                    baryU = baryV = 0.0f;
+                    alive = true;
+                    if (id < 0) {
+                        finish();
                     } else {
-                        // CheckLeafClosest (bvh.hsh:44-72) / CheckLeaf (:74-104)
-                        int triPtr = ~nodePtr;
-                        bool end = false;
-                        const float tmaxLeaf = ANY ? tMax : hitT;
-                        while (!end && !(ANY && hit)) {
-                            const float4* T = tris + 3 * size_t(triPtr);
-                            const float4 a = __ldg(T), b = __ldg(T + 1), c = __ldg(T + 2);
-                            end = a.w > 0.0f;
-                            if (COUNT) cTri++;
-                            float sol[3];
-                            const bool inside = tri_test(o, d, a, b, c, sol);
-                            if (inside && sol[0] > tMin && sol[0] < tmaxLeaf) {
-                                if (ANY || sol[0] < hitT) {
-                                    hitT = sol[0];
-                                    hitID = triPtr;
-                                    hitInst = curInst;
-                                    baryU = sol[1];
-                                    baryV = sol[2];
-                                    if (ANY) hit = true;
-                                }
-                            }
-                            triPtr++;
+                        tMax = (ANY && perRayTMax) ? r2.x : tMaxArg;
+                        hitT = tMax;   // HitClosest: ray.hitDistance = tMax (bvh.hsh:202); any-hit reports tMax on a miss
+                        if ((r1.x != r1.x) || (r1.y != r1.y) || (r1.z != r1.z)) {   // isnan3, bvh.hsh:204
+                            finish();
+                        } else {
+                            const float oo[3] = {r0.x, r0.y, r0.z}, dd[3] = {r1.x, r1.y, r1.z};
+                            set_ray(oo, dd);
+                            sp = 1u;
+                            tlasIndex = kTlasInvalid;
+                            nodePtr = 0;
+                            curInst = 0;
+                            nodes = sc.tlasNodes;
+                            stack[0][tid] = 0;
                         }
-                        nodePtr = stack[--sp][tid];
+                    }
+                }
+            }
+            continue;
+        }
+        if (nI + nL == 0) break;
+
+        if (nL >= kLeafThreshold || nI == 0) {
+            if (leafy) {
+                if (sp < tlasIndex) {
+                    // CheckInstance, bvh.hsh:172-189: vec4(o,1) * M and vec4(d,0) * M, no renormalisation.
+                    const int inst = ~nodePtr;
+                    const float4* I = sc.instances + 4 * size_t(inst);
+                    const float4 c0 = __ldg(I), c1 = __ldg(I + 1), c2 = __ldg(I + 2), c3 = __ldg(I + 3);
+                    if (COUNT) cInst++;
+                    float no[3], nd[3];
+                    no[0] = __fadd_rn(dot3(o[0], o[1], o[2], c0.x, c0.y, c0.z), __fmul_rn(1.0f, c0.w));
+                    no[1] = __fadd_rn(dot3(o[0], o[1], o[2], c1.x, c1.y, c1.z), __fmul_rn(1.0f, c1.w));
+                    no[2] = __fadd_rn(dot3(o[0], o[1], o[2], c2.x, c2.y, c2.z), __fmul_rn(1.0f, c2.w));
+                    nd[0] = __fadd_rn(dot3(d[0], d[1], d[2], c0.x, c0.y, c0.z), __fmul_rn(0.0f, c0.w));
+                    nd[1] = __fadd_rn(dot3(d[0], d[1], d[2], c1.x, c1.y, c1.z), __fmul_rn(0.0f, c1.w));
+                    nd[2] = __fadd_rn(dot3(d[0], d[1], d[2], c2.x, c2.y, c2.z), __fmul_rn(0.0f, c2.w));
+                    curInst = inst;
+                    const int meshPtr = __float_as_int(c3.x);
+                    const uint32_t mask = uint32_t(__float_as_int(c3.w));
+                    nodePtr = 0;
+                    if ((mask & cullMask) > 0u) {
+                        set_ray(no, nd);
+                        tlasIndex = sp;
+                        nodes = sc.blasNodes[meshPtr];
+                        tris = sc.bvhTris[meshPtr];
+                    } else {
+                        pop();   // the transformed ray is discarded: the TLAS branch restores the original anyway
                     }
                 } else {
-                    // inner node of the TLAS or the current BLAS — UnpackNode, bvh.hsh:21-37
-                    const float4* N = nodes + 4 * size_t(nodePtr);
-                    const float4 n0 = __ldg(N), n1 = __ldg(N + 1), n2 = __ldg(N + 2), n3 = __ldg(N + 3);
-                    if (COUNT) { if (inTlas) cTlas++; else cBlas++; }
-                    const float llo[3] = {n0.x, n0.y, n0.z}, lhi[3] = {n0.w, n1.x, n1.y};
-                    const float rlo[3] = {n1.z, n1.w, n2.x}, rhi[3] = {n2.y, n2.z, n2.w};
-                    const int leftPtr = __float_as_int(n3.x), rightPtr = __float_as_int(n3.y);
-                    const float tfar = ANY ? tMax : hitT;
-                    float hitL = 0.0f, hitR = 0.0f;
-                    const bool iL = slab(o, d, llo, lhi, tMin, tfar, hitL);
-                    const bool iR = slab(o, d, rlo, rhi, tMin, tfar, hitR);
-                    int pushPtr;
-                    if (!ANY) {
-                        const bool leftFirst = hitL <= hitR;
-                        nodePtr = leftFirst ? leftPtr : rightPtr;
-                        pushPtr = leftFirst ? rightPtr : leftPtr;
-                    } else {
-                        nodePtr = iL ? leftPtr : rightPtr;
-                        pushPtr = rightPtr;
+                    // CheckLeafClosest (bvh.hsh:44-72) / CheckLeaf (:74-104)
+                    int triPtr = ~nodePtr;
+                    bool end = false, hit = false;
+                    const float tmaxLeaf = ANY ? tMax : hitT;
+                    while (!end && !(ANY && hit)) {
+                        const float4* T = tris + 3 * size_t(triPtr);
+                        const float4 a = __ldg(T), b = __ldg(T + 1), c = __ldg(T + 2);
+                        end = a.w > 0.0f;
+                        if (COUNT) cTri++;
+                        float sol[3];
+                        const bool inside = tri_test(o, d, a, b, c, sol);
+                        if (inside && sol[0] > tMin && sol[0] < tmaxLeaf) {
+                            if (ANY || sol[0] < hitT) {
+                                hitT = sol[0];
+                                hitID = triPtr;
+                                hitInst = curInst;
+                                baryU = sol[1];
+                                baryV = sol[2];
+                                if (ANY) hit = true;
+                            }
+                        }
+                        triPtr++;
                     }
-                    if (!iL && !iR) nodePtr = stack[--sp][tid];
-                    if (iL && iR) {
-                        if (sp < kStack) stack[sp][tid] = pushPtr; else overflow = true;
-                        sp++;
-                        if (sp > kStack) { sp = kStack; }   // entry dropped; flagged as ATLAS_RT_ERR_STACK
-                    }
-                    if (COUNT && sp > cMaxSp) cMaxSp = sp;
+                    if (ANY && hit) finish(); else pop();
                 }
+            }
+        } else if (inner) {
+            // inner node of the TLAS or of the current BLAS — UnpackNode, bvh.hsh:21-37
+            const float4* N = nodes + 4 * size_t(nodePtr);
+            const float4 n0 = __ldg(N), n1 = __ldg(N + 1), n2 = __ldg(N + 2), n3 = __ldg(N + 3);
+            if (COUNT) { if (sp < tlasIndex) cTlas++; else cBlas++; }
+            const float llo[3] = {n0.x, n0.y, n0.z}, lhi[3] = {n0.w, n1.x, n1.y};
+            const float rlo[3] = {n1.z, n1.w, n2.x}, rhi[3] = {n2.y, n2.z, n2.w};
+            const int leftPtr = __float_as_int(n3.x), rightPtr = __float_as_int(n3.y);
+            const float tfar = ANY ? tMax : hitT;
+            float hitL = 0.0f, hitR = 0.0f;
+            bool iL, iR;
+            if (fast) {
+                iL = slab_fast(o, d, rc, llo, lhi, tMin, tfar, hitL);
+                iR = slab_fast(o, d, rc, rlo, rhi, tMin, tfar, hitR);
+            } else {
+                iL = slab(o, d, llo, lhi, tMin, tfar, hitL);
+                iR = slab(o, d, rlo, rhi, tMin, tfar, hitR);
+            }
+            int pushPtr;
+            if (!ANY) {
+                const bool leftFirst = hitL <= hitR;
+                nodePtr = leftFirst ? leftPtr : rightPtr;
+                pushPtr = leftFirst ? rightPtr : leftPtr;
+            } else {
+                nodePtr = iL ? leftPtr : rightPtr;
+                pushPtr = rightPtr;
+            }
+            if (iL && iR) {
+                if (sp < kStack) { stack[sp][tid] = pushPtr; sp++; } else overflow = true;   // entry dropped -> ATLAS_RT_ERR_STACK
+                if (COUNT && sp > cMaxSp) cMaxSp = sp;
+            } else if (!iL && !iR) {
+                pop();
             }
         }
     }
 
-    // PackRay, common.hsh:61-73 (+ barycentrics in the two lanes GLSL leaves unwritten)
-    out[3 * size_t(i)] = r0;
-    out[3 * size_t(i) + 1] = make_float4(r1.x, r1.y, r1.z, baryU);
-    out[3 * size_t(i) + 2] = make_float4(hitT, __int_as_float(hitID), __int_as_float(hitInst), baryV);
-
     if (overflow) atomicAdd(&counters[5], 1ull);
     if (COUNT) {
-        // warp-aggregate before the global atomics
-        const unsigned m = __activemask();
-        unsigned long long v[4] = {cTlas, cInst, cBlas, cTri};
+        const unsigned v[4] = {cTlas, cInst, cBlas, cTri};
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            unsigned s = unsigned(v[k]);
-            s = __reduce_add_sync(m, s);
-            if ((tid & 31u) == (__ffs(m) - 1)) atomicAdd(&counters[k], (unsigned long long)s);
+            // per-lane counts fit 32 bits; the warp sum may not, so add in two halves
+            const unsigned lo16 = __reduce_add_sync(kFull, v[k] & 0xffffu), hi16 = __reduce_add_sync(kFull, v[k] >> 16);
+            if (lane == 0) atomicAdd(&counters[k], (unsigned long long)lo16 + ((unsigned long long)hi16 << 16));
         }
-        const unsigned mx = __reduce_max_sync(m, cMaxSp);
-        if ((tid & 31u) == (__ffs(m) - 1)) atomicMax(&counters[4], (unsigned long long)mx);
+        const unsigned mx = __reduce_max_sync(kFull, cMaxSp);
+        if (lane == 0) atomicMax(&counters[4], (unsigned long long)mx);
     }
+}
+
+// Largest coordinate magnitude of the scene: node 0 of the TLAS and of every BLAS bounds everything below it.
+__global__ void scene_bounds(const float4* __restrict__ tlasNodes, uint32_t tlasNodeCount, const float4* const* __restrict__ blasNodes,
+                             const uint32_t* __restrict__ blasNodeCounts, uint32_t meshCount, unsigned int* __restrict__ maxAbsBits) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > meshCount) return;
+    const float4* N = nullptr;
+    if (i == meshCount) { if (tlasNodeCount) N = tlasNodes; }
+    else if (blasNodeCounts[i]) N = blasNodes[i];
+    if (!N) return;
+    const float4 a = N[0], b = N[1], c = N[2];
+    const float v[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+    float m = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 12; k++) m = fmaxf(m, fabsf(v[k]));
+    if (!(m == m)) m = __int_as_float(0x7f800000);
+    atomicMax(maxAbsBits, __float_as_uint(m));   // non-negative floats order like their bit patterns
 }
 
 }   // namespace
 
+int scene_fast_flag(atlas_rt_context* ctx, atlas_rt_scene* scene, const uint32_t* dNodeCounts) {
+    unsigned int* dMax = reinterpret_cast<unsigned int*>(ctx->dCounters + 7);
+    ATLAS_CUDA(ctx, cudaMemsetAsync(dMax, 0, sizeof(unsigned int), ctx->stream));
+    scene_bounds<<<(scene->meshCount + 1 + 127) / 128, 128, 0, ctx->stream>>>(scene->tlas->nodes, uint32_t(scene->tlas->nodeCount), scene->blasNodes,
+                                                                               dNodeCounts, scene->meshCount, dMax);
+    ATLAS_LAUNCH_CHECK(ctx);
+    ATLAS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, dMax, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+    ATLAS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    unsigned int bits = 0;
+    memcpy(&bits, ctx->pinned, sizeof(bits));
+    float m;
+    memcpy(&m, &bits, sizeof(m));
+    scene->fastDivision = (m <= kPosHi) ? 1 : 0;
+    return ATLAS_RT_OK;
+}
+
 int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float4* dIn, float4* dOut, uint64_t count,
                  uint32_t cullMask, float tMin, float tMax, bool any, bool perRayTMax, bool counters) {
     if (count == 0) return ATLAS_RT_OK;
-    if (count > 0xffffffffull) return fail(ctx, ATLAS_RT_ERR_UNSUPPORTED, "more than 2^32-1 rays in one batch");
+    if (count > 0x7fffffffull) return fail(ctx, ATLAS_RT_ERR_UNSUPPORTED, "more than 2^31-1 rays in one batch");
     SceneDev sc{scene->tlas->nodes, scene->instances, scene->blasNodes, scene->bvhTris};
     const uint32_t n = uint32_t(count);
-    const uint32_t grid = (n + kTraceBlock - 1) / kTraceBlock;
-    ATLAS_CUDA(ctx, cudaMemsetAsync(ctx->dCounters, 0, 8 * sizeof(unsigned long long), ctx->stream));
-    const int pr = perRayTMax ? 1 : 0;
+    const uint32_t grid = std::min<uint32_t>((n + kTraceBlock - 1) / kTraceBlock, uint32_t(ctx->smCount) * uint32_t(ctx->traceBlocksPerSM));
+    const int lt = ctx->traceLeafThreshold, rt = ctx->traceRefillThreshold;
+    ATLAS_CUDA(ctx, cudaMemsetAsync(ctx->dCounters, 0, 7 * sizeof(unsigned long long), ctx->stream));
+    unsigned int* rayCounter = reinterpret_cast<unsigned int*>(ctx->dCounters + 6);
+    const int pr = perRayTMax ? 1 : 0, sf = scene->fastDivision;
     if (any) {
-        if (counters) trace_kernel<true, true><<<grid, kTraceBlock, 0, ctx->stream>>>(sc, dIn, dOut, n, cullMask, tMin, tMax, pr, ctx->dCounters);
-        else trace_kernel<true, false><<<grid, kTraceBlock, 0, ctx->stream>>>(sc, dIn, dOut, n, cullMask, tMin, tMax, pr, ctx->dCounters);
+        if (counters) trace_kernel<true, true><<<grid, kTraceBlock, 0, ctx->stream>>>(sc, dIn, dOut, n, cullMask, tMin, tMax, pr, sf, lt, rt, rayCounter, ctx->dCounters);
+        else trace_kernel<true, false><<<grid, kTraceBlock, 0, ctx->stream>>>(sc, dIn, dOut, n, cullMask, tMin, tMax, pr, sf, lt, rt, rayCounter, ctx->dCounters);
     } else {
-        if (counters) trace_kernel<false, true><<<grid, kTraceBlock, 0, ctx->stream>>>(sc, dIn, dOut, n, cullMask, tMin, tMax, pr, ctx->dCounters);
-        else trace_kernel<false, false><<<grid, kTraceBlock, 0, ctx->stream>>>(sc, dIn, dOut, n, cullMask, tMin, tMax, pr, ctx->dCounters);
+        if (counters) trace_kernel<false, true><<<grid, kTraceBlock, 0, ctx->stream>>>(sc, dIn, dOut, n, cullMask, tMin, tMax, pr, sf, lt, rt, rayCounter, ctx->dCounters);
+        else trace_kernel<false, false><<<grid, kTraceBlock, 0, ctx->stream>>>(sc, dIn, dOut, n, cullMask, tMin, tMax, pr, sf, lt, rt, rayCounter, ctx->dCounters);
     }
     ATLAS_LAUNCH_CHECK(ctx);
     return ATLAS_RT_OK;

@@ -164,3 +164,20 @@ def test_primary_rays_match_numpy_recipe(ctx):
             first = ids[:64]
             assert set((first // w).tolist()) == set(range(8)) and set((first % w).tolist()) == set(range(8))
             assert np.all((ids[full:] % w >= (w // 8) * 8) | (ids[full:] // w >= (h // 8) * 8))
+
+
+def test_leaf_root_blas_is_traversable(ctx, oracle):
+    """A BLAS whose root stayed a leaf has zero nodes (Flatten emits none); the reference shader would read out of
+    bounds there. The library gives it one empty node so rays simply miss; the tree itself must still equal the oracle."""
+    tri = np.array([[0, 0, 0, 0, 0, 0, 0, 0, 0]], dtype=np.float32)     # degenerate: nothing to split
+    boxes = W.tri_boxes(tri)
+    b = ctx.build_blas(boxes, tri)
+    nodes, order, eon = b.download()
+    o = oracle.build_blas(boxes, tri)
+    assert nodes.shape == o.nodes.shape and np.array_equal(order, o.order) and np.array_equal(eon, o.end_of_node)
+    if nodes.shape[0] == 0:
+        mesh = ctx.pack_mesh(b, tri)
+        tl = ctx.build_tlas(np.array([[-1, -1, -1, 1, 1, 1]], dtype=np.float32))
+        sc = ctx.create_scene([mesh], W.identity_instance(), tl)
+        out = ctx.trace(sc, W.random_rays(1000, [-2, -2, -2], [2, 2, 2], seed=1))
+        assert np.all(out[:, 9].view(np.int32) == -1)
