@@ -82,14 +82,16 @@ __global__ void reorder_instances(const float4* __restrict__ src, const uint32_t
     dst[4 * i + 3] = last;
 }
 
-// A BLAS whose root became a leaf has no nodes at all (Flatten emits none); the reference shader would then read
-// blasNodes[..].data[0] out of bounds. We give such a BLAS one node with two empty boxes so that rays entering the
-// instance simply miss.
-__global__ void write_empty_node(float4* node) {
-    node[0] = make_float4(kFltMax, kFltMax, kFltMax, -kFltMax);
-    node[1] = make_float4(-kFltMax, -kFltMax, kFltMax, kFltMax);
-    node[2] = make_float4(kFltMax, -kFltMax, -kFltMax, -kFltMax);
-    node[3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+// A BLAS whose root became a leaf has no nodes at all (Flatten emits none, BVH.cpp:411-417); the reference shader would
+// then read blasNodes[..].data[0] out of bounds. Device storage for such a BLAS gets one synthetic node that is NOT part
+// of the reported tree (nodeCount stays 0): its left child is the leaf starting at slot 0 inside a box that every ray
+// hits, its right child a point box at +FLT_MAX that no ray hits. Rays entering the instance therefore test the leaf's
+// triangles (up to endOfNode) and return correct hits instead of undefined behaviour.
+__global__ void write_root_leaf_node(float4* node) {
+    node[0] = make_float4(-kFltMax, -kFltMax, -kFltMax, kFltMax);
+    node[1] = make_float4(kFltMax, kFltMax, kFltMax, kFltMax);
+    node[2] = make_float4(kFltMax, kFltMax, kFltMax, kFltMax);
+    node[3] = make_float4(__int_as_float(~0), __int_as_float(~0), 0.0f, 0.0f);
 }
 
 int sync_unless_async(atlas_rt_context* ctx, uint32_t flags) {
@@ -103,7 +105,7 @@ int sync_unless_async(atlas_rt_context* ctx, uint32_t flags) {
 int ensure_node_storage(atlas_rt_context* ctx, atlas_rt_bvh* bvh) {
     if (bvh->nodeCount != 0) return ATLAS_RT_OK;
     if (!bvh->nodes) ATLAS_CUDA(ctx, dev_alloc(ctx, &bvh->nodes, 4));
-    write_empty_node<<<1, 1, 0, ctx->stream>>>(bvh->nodes);
+    write_root_leaf_node<<<1, 1, 0, ctx->stream>>>(bvh->nodes);
     ATLAS_LAUNCH_CHECK(ctx);
     return ATLAS_RT_OK;
 }
@@ -134,7 +136,7 @@ int atlas_rt_context_create(int device, void* stream, atlas_rt_context** out_ctx
     cudaDeviceGetAttribute(&ctx->smCount, cudaDevAttrMultiProcessorCount, device);
     if (const char* e = getenv("ATLAS_RT_TRACE_LEAF_THRESHOLD")) ctx->traceLeafThreshold = std::max(1, std::min(32, atoi(e)));
     if (const char* e = getenv("ATLAS_RT_TRACE_REFILL_THRESHOLD")) ctx->traceRefillThreshold = std::max(1, std::min(32, atoi(e)));
-    if (const char* e = getenv("ATLAS_RT_TRACE_BLOCKS_PER_SM")) ctx->traceBlocksPerSM = std::max(1, std::min(6, atoi(e)));
+    if (const char* e = getenv("ATLAS_RT_TRACE_BLOCKS_PER_SM")) ctx->traceBlocksPerSM = std::max(1, std::min(9, atoi(e)));
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t keep = ~0ull;

@@ -1070,6 +1070,152 @@ struct SubNode {
     uint32_t boxRef;   // (parent flat index << 1) | isSecondChild, or 0xffffffff for the subtree root
 };
 
+constexpr uint32_t kTinyMax = 4;   // nodes with at most this many refs are handled by ONE lane (32 nodes per warp)
+
+// One lane builds one node with 2..kTinyMax refs. Same decisions as the warp path, evaluated without bins: with n refs
+// at most n-1 bin boundaries separate them, and every other candidate j of BVH.cpp:496-522 repeats the partition (and
+// hence the cost) of the nearest boundary below it, so scanning only the boundaries in ascending j and keeping strictly
+// smaller costs selects the same (axis, j). Boxes are reduced on the ordered-int image like everywhere else.
+__device__ inline void build_tiny_node(const SubNode nd, const SmallTask& task, uint32_t depth, uint32_t budget,
+                                       const float4* __restrict__ cLo, const float4* __restrict__ cHi, float4* __restrict__ nLo,
+                                       float4* __restrict__ nHi, float4* nodes, uint32_t* __restrict__ order, uint8_t* __restrict__ eon,
+                                       SubNode* nextList, uint32_t* sNext, unsigned long long* sStats) {
+    const uint32_t n = nd.count, s = nd.start;
+    const uint32_t nb = bins_at_depth(budget, depth);
+    float blo[3], bhi[3];
+    if (nd.boxRef == 0xffffffffu) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { blo[k] = task.lo[k]; bhi[k] = task.hi[k]; }
+    } else {
+        const volatile float4* P = nodes + 4 * size_t(nd.boxRef >> 1);
+        float4 n0, n1, n2;
+        n0.x = P[0].x; n0.y = P[0].y; n0.z = P[0].z; n0.w = P[0].w;
+        n1.x = P[1].x; n1.y = P[1].y; n1.z = P[1].z; n1.w = P[1].w;
+        n2.x = P[2].x; n2.y = P[2].y; n2.z = P[2].z; n2.w = P[2].w;
+        if (nd.boxRef & 1u) { blo[0] = n1.z; blo[1] = n1.w; blo[2] = n2.x; bhi[0] = n2.y; bhi[1] = n2.z; bhi[2] = n2.w; }
+        else { blo[0] = n0.x; blo[1] = n0.y; blo[2] = n0.z; bhi[0] = n0.w; bhi[1] = n1.x; bhi[2] = n1.y; }
+    }
+    float4 rl[kTinyMax], rh[kTinyMax];
+    OBox rb[kTinyMax];
+#pragma unroll
+    for (uint32_t i = 0; i < kTinyMax; i++) {
+        if (i < n) { rl[i] = cLo[s + i]; rh[i] = cHi[s + i]; }
+        else { rl[i] = make_float4(kFltMax, kFltMax, kFltMax, 0.0f); rh[i] = make_float4(-kFltMax, -kFltMax, -kFltMax, 0.0f); }
+        rb[i].lo[0] = ord_from_float(rl[i].x); rb[i].lo[1] = ord_from_float(rl[i].y); rb[i].lo[2] = ord_from_float(rl[i].z);
+        rb[i].hi[0] = ord_from_float(rh[i].x); rb[i].hi[1] = ord_from_float(rh[i].y); rb[i].hi[2] = ord_from_float(rh[i].z);
+    }
+    // ---- FindObjectSplit over the bin boundaries that actually separate refs
+    float bestCost = kFltMax;
+    int bestAxis = -1;
+    uint32_t bestJ = 0;
+#pragma unroll 1
+    for (int a = 0; a < 3; a++) {
+        const AxisBins ab = axis_bins(blo[a], bhi[a], nb);
+        if (!ab.active) continue;
+        uint32_t b[kTinyMax];
+#pragma unroll
+        for (uint32_t i = 0; i < kTinyMax; i++) b[i] = i < n ? bin_of(bin_centre(comp(rl[i], a), comp(rh[i], a)), ab.start, ab.inv, nb) : 0xffffffffu;
+        uint32_t prevJ = 0;
+#pragma unroll 1
+        for (uint32_t c = 0; c + 1 < n; c++) {
+            uint32_t j = 0xffffffffu;
+#pragma unroll
+            for (uint32_t i = 0; i < kTinyMax; i++) if (i < n && b[i] + 1u > prevJ && b[i] + 1u < j) j = b[i] + 1u;
+            if (j == 0xffffffffu) break;
+            prevJ = j;
+            OBox L = obox_empty(), R = obox_empty();
+            uint32_t nL = 0, nR = 0;
+#pragma unroll
+            for (uint32_t i = 0; i < kTinyMax; i++) {
+                if (i < n) { if (b[i] < j) { obox_grow(L, rb[i]); nL++; } else { obox_grow(R, rb[i]); nR++; } }
+            }
+            if (nL == 0u || nR == 0u) continue;
+            const float cost = __fadd_rn(__fmul_rn(obox_area(L), __uint2float_rn(nL)), __fmul_rn(obox_area(R), __uint2float_rn(nR)));
+            if (cost < bestCost) { bestCost = cost; bestAxis = a; bestJ = j; }
+        }
+    }
+    const float nodeCost = __fmul_rn(__uint2float_rn(n), surface_area(blo, bhi));
+    bool isLeft[kTinyMax];
+    if (!(bestAxis < 0 || bestCost >= nodeCost)) {
+        const AxisBins ab = axis_bins(blo[bestAxis], bhi[bestAxis], nb);
+#pragma unroll
+        for (uint32_t i = 0; i < kTinyMax; i++)
+            isLeft[i] = i < n && bin_of(bin_centre(comp(rl[i], bestAxis), comp(rh[i], bestAxis)), ab.start, ab.inv, nb) < bestJ;
+    } else {
+        // ---- PerformMedianSplit
+        int axis;
+        float cutoff;
+        median_plane(blo, bhi, axis, cutoff);
+        atomicAdd(&sStats[0], 1ull);
+        uint32_t nL = 0;
+#pragma unroll
+        for (uint32_t i = 0; i < kTinyMax; i++) {
+            isLeft[i] = i < n && median_centre(comp(rl[i], axis), comp(rh[i], axis)) < cutoff;
+            nL += isLeft[i] ? 1u : 0u;
+        }
+        if (nL == 0u || nL == n) {
+            // std::sort on <= 16 elements is a plain insertion sort, i.e. THE stable order by key (extent on the axis)
+            atomicAdd(&sStats[1], 1ull);
+            atomicMax(&sStats[2], (unsigned long long)n);
+            float key[kTinyMax];
+#pragma unroll
+            for (uint32_t i = 0; i < kTinyMax; i++) key[i] = i < n ? __fsub_rn(comp(rh[i], axis), comp(rl[i], axis)) : 0.0f;
+#pragma unroll
+            for (uint32_t i = 1; i < kTinyMax; i++) {
+#pragma unroll
+                for (uint32_t k = i; k > 0; k--) {
+                    if (i < n && key[k] < key[k - 1]) {
+                        const float tk = key[k]; key[k] = key[k - 1]; key[k - 1] = tk;
+                        const float4 tl = rl[k]; rl[k] = rl[k - 1]; rl[k - 1] = tl;
+                        const float4 th = rh[k]; rh[k] = rh[k - 1]; rh[k - 1] = th;
+                        const OBox tb = rb[k]; rb[k] = rb[k - 1]; rb[k - 1] = tb;
+                    }
+                }
+            }
+            const uint32_t half = n / 2u;
+#pragma unroll
+            for (uint32_t i = 0; i < kTinyMax; i++) isLeft[i] = i < half;
+        }
+    }
+    OBox L = obox_empty(), R = obox_empty();
+    uint32_t nLeft = 0;
+#pragma unroll
+    for (uint32_t i = 0; i < kTinyMax; i++) {
+        if (i < n) { if (isLeft[i]) { obox_grow(L, rb[i]); nLeft++; } else obox_grow(R, rb[i]); }
+    }
+    // ---- Flatten bookkeeping + stable placement
+    const Box3 lb = obox_to_box(L), rbx = obox_to_box(R);
+    const bool swapped = surface_area(lb) < surface_area(rbx);
+    const uint32_t nFirst = swapped ? n - nLeft : nLeft, nSecond = n - nFirst;
+    const uint32_t slot = task.start + s;
+    const Box3& f = swapped ? rbx : lb;
+    const Box3& g = swapped ? lb : rbx;
+    const int32_t ptr1 = nFirst > 1u ? int32_t(nd.flatIdx + 1u) : ~int32_t(slot);
+    const int32_t ptr2 = nSecond > 1u ? int32_t(nd.flatIdx + nFirst) : ~int32_t(slot + nFirst);
+    float4* N = nodes + 4 * size_t(nd.flatIdx);
+    N[0] = make_float4(f.lo[0], f.lo[1], f.lo[2], f.hi[0]);
+    N[1] = make_float4(f.hi[1], f.hi[2], g.lo[0], g.lo[1]);
+    N[2] = make_float4(g.lo[2], g.hi[0], g.hi[1], g.hi[2]);
+    N[3] = make_float4(__int_as_float(ptr1), __int_as_float(ptr2), 0.0f, 0.0f);
+    if (nFirst > 1u) nextList[atomicAdd(sNext, 1u)] = SubNode{uint16_t(s), uint16_t(nFirst), nd.flatIdx + 1u, nd.flatIdx << 1};
+    if (nSecond > 1u) nextList[atomicAdd(sNext, 1u)] = SubNode{uint16_t(s + nFirst), uint16_t(nSecond), nd.flatIdx + nFirst, (nd.flatIdx << 1) | 1u};
+    uint32_t doneFirst = 0, doneSecond = 0;
+#pragma unroll
+    for (uint32_t i = 0; i < kTinyMax; i++) {
+        if (i < n) {
+            const bool first = isLeft[i] != swapped;
+            const uint32_t dst = first ? doneFirst++ : nFirst + doneSecond++;
+            if ((first ? nFirst : nSecond) == 1u) {
+                order[slot + dst] = __float_as_uint(rl[i].w);
+                eon[slot + dst] = 1;
+            } else {
+                nLo[s + dst] = rl[i];
+                nHi[s + dst] = rh[i];
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kSubBlock)
 build_subtrees(const SmallTask* __restrict__ small, uint32_t nSmall, float4* const lo0, float4* const hi0, float4* const lo1,
                float4* const hi1, float4* nodes, uint32_t* __restrict__ order, uint8_t* __restrict__ eon,
@@ -1113,9 +1259,17 @@ build_subtrees(const SmallTask* __restrict__ small, uint32_t nSmall, float4* con
         float4* nLo = sLo + (cur ^ 1u) * kSubtreeMax;
         float4* nHi = sHi + (cur ^ 1u) * kSubtreeMax;
 
+        // tiny nodes: one lane each
+        for (uint32_t ni = tid; ni < nCur; ni += kSubBlock) {
+            const SubNode nd = curList[ni];
+            if (nd.count <= kTinyMax)
+                build_tiny_node(nd, task, depth, budget, cLo, cHi, nLo, nHi, nodes, order, eon, nextList, &sNext, sStats);
+        }
+        // everything else: one warp per node
         for (uint32_t ni = warp; ni < nCur; ni += kSubWarps) {
             const SubNode nd = curList[ni];
             const uint32_t n = nd.count, s = nd.start;
+            if (n <= kTinyMax) continue;
             // ---- node box: the subtree root's comes with the task, any other from its parent's flattened record
             float blo[3], bhi[3];
             if (nd.boxRef == 0xffffffffu) {

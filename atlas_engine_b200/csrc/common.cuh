@@ -80,7 +80,7 @@ struct atlas_rt_context {
     // scheduling knobs of the persistent traversal kernel (trace.cu); ATLAS_RT_TRACE_* environment variables override
     int traceLeafThreshold = 8;     // lanes waiting at a leaf before the warp runs a leaf round
     int traceRefillThreshold = 6;   // idle lanes before the warp fetches new rays
-    int traceBlocksPerSM = 6;
+    int traceBlocksPerSM = 9;
 };
 
 struct atlas_rt_bvh {

@@ -121,7 +121,7 @@ __device__ __forceinline__ bool fast_ok(const float o[3], const float d[3]) {
     return ok;
 }
 
-constexpr int kBlocksPerSM = 6;
+constexpr int kBlocksPerSM = 9;
 
 // Persistent-thread traversal. Each warp owns 32 ray slots and refills finished slots from a global ray counter, so
 // lanes do not idle while the longest ray of a static batch finishes (the one-thread-per-ray kernel ran at 8.5 of 32
@@ -333,6 +333,7 @@ __global__ void scene_bounds(const float4* __restrict__ tlasNodes, uint32_t tlas
     const float4* N = nullptr;
     if (i == meshCount) { if (tlasNodeCount) N = tlasNodes; }
     else if (blasNodeCounts[i]) N = blasNodes[i];
+    else atomicMax(maxAbsBits, 0x7f800000u);   // root-leaf BLAS: its synthetic node holds +-FLT_MAX boxes, keep such scenes on __fdiv_rn
     if (!N) return;
     const float4 a = N[0], b = N[1], c = N[2];
     const float v[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};

@@ -168,16 +168,27 @@ def test_primary_rays_match_numpy_recipe(ctx):
 
 def test_leaf_root_blas_is_traversable(ctx, oracle):
     """A BLAS whose root stayed a leaf has zero nodes (Flatten emits none); the reference shader would read out of
-    bounds there. The library gives it one empty node so rays simply miss; the tree itself must still equal the oracle."""
+    bounds there. The tree must still equal the oracle's, and the library's synthetic root-leaf node must make rays
+    test the leaf's triangles: hits equal a brute-force loop over the triangles."""
     tri = np.array([[0, 0, 0, 0, 0, 0, 0, 0, 0]], dtype=np.float32)     # degenerate: nothing to split
-    boxes = W.tri_boxes(tri)
-    b = ctx.build_blas(boxes, tri)
-    nodes, order, eon = b.download()
-    o = oracle.build_blas(boxes, tri)
-    assert nodes.shape == o.nodes.shape and np.array_equal(order, o.order) and np.array_equal(eon, o.end_of_node)
-    if nodes.shape[0] == 0:
-        mesh = ctx.pack_mesh(b, tri)
-        tl = ctx.build_tlas(np.array([[-1, -1, -1, 1, 1, 1]], dtype=np.float32))
-        sc = ctx.create_scene([mesh], W.identity_instance(), tl)
-        out = ctx.trace(sc, W.random_rays(1000, [-2, -2, -2], [2, 2, 2], seed=1))
-        assert np.all(out[:, 9].view(np.int32) == -1)
+    for tris in (tri, ):
+        boxes = W.tri_boxes(tris)
+        b = ctx.build_blas(boxes, tris)
+        nodes, order, eon = b.download()
+        o = oracle.build_blas(boxes, tris)
+        assert nodes.shape == o.nodes.shape and np.array_equal(order, o.order) and np.array_equal(eon, o.end_of_node)
+        b.free()
+    # a hand-made root-leaf BLAS over real triangles (what Flatten produces when the "last resort" fires)
+    tris = W.uv_sphere(8, 4)
+    n = len(tris)
+    b = ctx.upload_bvh(np.zeros((0, 14), np.uint32), np.arange(n, dtype=np.uint32), np.r_[np.zeros(n - 1, np.uint8), np.uint8(1)])
+    mesh = ctx.pack_mesh(b, tris)
+    tl = ctx.build_tlas(np.array([[-1, -1, -1, 1, 1, 1]], dtype=np.float32))
+    sc = ctx.create_scene([mesh], W.identity_instance(), tl)
+    rays = W.random_rays(2000, [-2, -2, -2], [2, 2, 2], seed=1)
+    out = ctx.trace(sc, rays)
+    packed = W.pack_bvh_triangles(tris, np.arange(n), np.r_[np.zeros(n - 1), 1])
+    osc = OScene(np.zeros((1, 16), np.float32), W.identity_instance(), [np.zeros((1, 16), np.float32)], [packed])
+    bt, btri, _ = oracle.brute_force(osc, rays)
+    assert np.array_equal(out[:, 8], bt) and np.array_equal(out[:, 9].view(np.int32), btri)
+    assert (btri >= 0).mean() > 0.05
