@@ -72,6 +72,17 @@ class AtlasError(RuntimeError):
     pass
 
 
+class Camera(C.Structure):
+    """atlas_rt_camera"""
+    _fields_ = [("eye", _f32 * 3), ("origin", _f32 * 3), ("right", _f32 * 3), ("bottom", _f32 * 3)]
+
+
+class BounceParams(C.Structure):
+    """atlas_rt_bounce_params"""
+    _fields_ = [("light_dir", _f32 * 3), ("light_radiance", _f32 * 3), ("albedo", _f32 * 3), ("sky_radiance", _f32 * 3),
+                ("seed", _f32), ("bounce", _u32), ("max_bounces", _u32), ("samples", _u32)]
+
+
 def _addr(x):
     """Pointer value of a numpy array (host), an int (device pointer) or None."""
     if x is None:
@@ -180,6 +191,26 @@ class Context:
         res = np.empty_like(rays) if out is None else out
         self.check(fn(self.h, scene.h, _addr(rays), rays.shape[0], cull_mask, t_min, t_max, _addr(res), flags))
         return res
+
+    # ------------------------------------------------------------------------------------------ path tracer
+    def generate_primary_rays(self, eye, origin, right, bottom, width, height, samples=1, jitter=None, out=None):
+        """rayGen.csh. out: device pointer / CUDA tensor of width*height*samples PackedRay, or None for a host array."""
+        cam = Camera((_f32 * 3)(*eye), (_f32 * 3)(*origin), (_f32 * 3)(*right), (_f32 * 3)(*bottom))
+        jit = None if jitter is None else np.ascontiguousarray(jitter, dtype=np.float32)
+        if out is None:
+            res = np.zeros((width * height * samples, 12), dtype=np.float32)
+            self.check(self.L.atlas_rt_generate_primary_rays(self.h, C.byref(cam), width, height, samples, _addr(jit), _addr(res), 0))
+            return res
+        self.check(self.L.atlas_rt_generate_primary_rays(self.h, C.byref(cam), width, height, samples, _addr(jit), _addr(out), DEVICE_OUTPUT))
+        return out
+
+    def pathtrace_bounce(self, scene, params, rays_in, payload_in, count, rays_out, payload_out, accum):
+        """One diffuse bounce on device buffers; returns the number of surviving rays (compacted into rays_out)."""
+        n = _u64()
+        self.check(self.L.atlas_rt_pathtrace_bounce(self.h, scene.h, C.byref(params), _addr(rays_in), _addr(payload_in), count,
+                                                    _addr(rays_out), _addr(payload_out), _addr(accum), C.byref(n),
+                                                    DEVICE_INPUT | DEVICE_OUTPUT))
+        return int(n.value)
 
     def trace_counters(self):
         out = np.zeros(6, dtype=np.uint64)

@@ -106,21 +106,30 @@ __device__ __forceinline__ void load_box(const Task& t, float lo[3], float hi[3]
 __device__ __forceinline__ float comp(const float4& v, int axis) { return axis == 0 ? v.x : (axis == 1 ? v.y : v.z); }
 
 // ------------------------------------------------------------------------------------------------ level 0 set-up
-__global__ void init_refs(const float* __restrict__ aabbs, uint32_t n, float4* __restrict__ lo, float4* __restrict__ hi,
-                          int* __restrict__ rootBox, LevelInfo* __restrict__ info) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+init_refs(const float* __restrict__ aabbs, uint32_t n, float4* __restrict__ lo, float4* __restrict__ hi,
+          int* __restrict__ rootBox, LevelInfo* __restrict__ info) {
+    // refs[i] = {idx = i, aabb = aabbs[i]} and the root box (BVH.cpp:21-31); grid-stride so that only one set of
+    // atomics per CTA reaches the six root-box words.
+    __shared__ int sBox[6];
+    __shared__ int sNeg;
+    if (threadIdx.x < 6) sBox[threadIdx.x] = threadIdx.x < 3 ? kOrdEmptyLo : kOrdEmptyHi;
+    if (threadIdx.x == 6) sNeg = 0;
+    __syncthreads();
     int o[6] = {kOrdEmptyLo, kOrdEmptyLo, kOrdEmptyLo, kOrdEmptyHi, kOrdEmptyHi, kOrdEmptyHi};
     bool neg = false;
-    if (i < n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float* a = aabbs + 6 * size_t(i);
         const float v[6] = {a[0], a[1], a[2], a[3], a[4], a[5]};
         lo[i] = make_float4(v[0], v[1], v[2], __uint_as_float(i));
         hi[i] = make_float4(v[3], v[4], v[5], 0.0f);
 #pragma unroll
-        for (int k = 0; k < 6; k++) {
-            o[k] = ord_from_float(v[k]);
-            neg |= (__float_as_uint(v[k]) == 0x80000000u);
+        for (int k = 0; k < 3; k++) {
+            o[k] = min(o[k], ord_from_float(v[k]));
+            o[3 + k] = max(o[3 + k], ord_from_float(v[3 + k]));
         }
+#pragma unroll
+        for (int k = 0; k < 6; k++) neg |= (__float_as_uint(v[k]) == 0x80000000u);
     }
 #pragma unroll
     for (int k = 0; k < 3; k++) {
@@ -130,12 +139,13 @@ __global__ void init_refs(const float* __restrict__ aabbs, uint32_t n, float4* _
     const bool anyNeg = __any_sync(kFullMask, neg);
     if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
-            atomicMin(&rootBox[k], o[k]);
-            atomicMax(&rootBox[3 + k], o[3 + k]);
-        }
-        if (anyNeg) atomicOr(&info->negZero, 1u);
+        for (int k = 0; k < 3; k++) { atomicMin(&sBox[k], o[k]); atomicMax(&sBox[3 + k], o[3 + k]); }
+        if (anyNeg) sNeg = 1;
     }
+    __syncthreads();
+    if (threadIdx.x < 3) atomicMin(&rootBox[threadIdx.x], sBox[threadIdx.x]);
+    else if (threadIdx.x < 6) atomicMax(&rootBox[threadIdx.x], sBox[threadIdx.x]);
+    else if (threadIdx.x == 6 && sNeg) atomicOr(&info->negZero, 1u);
 }
 
 __global__ void make_root(const int* __restrict__ rootBox, uint32_t n, Task* __restrict__ tasks, LevelInfo* __restrict__ info,
@@ -1537,7 +1547,7 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
         memcpy(ctx->pinned, initBox, sizeof(initBox));
         ATLAS_CUDA_C(ctx, cudaMemcpyAsync(B.rootBox, ctx->pinned, sizeof(initBox), cudaMemcpyHostToDevice, st));
     }
-    init_refs<<<(n + 255) / 256, 256, 0, st>>>(dAabbs, n, B.lo[0], B.hi[0], B.rootBox, B.info);
+    init_refs<<<std::max(1u, std::min<uint32_t>((n + 255) / 256, uint32_t(ctx->smCount) * 8u)), 256, 0, st>>>(dAabbs, n, B.lo[0], B.hi[0], B.rootBox, B.info);
     ATLAS_LAUNCHED(ctx);
     make_root<<<1, 1, 0, st>>>(B.rootBox, n, B.tasks[0], B.info, B.root);
     ATLAS_LAUNCHED(ctx);

@@ -194,9 +194,14 @@ typedef struct atlas_rt_bounce_params {
  * any-hit ray towards the light (origin = P + N*0.1, cull mask MaskShadow), cosine-weighted next direction from the
  * reference's hash RNG keyed by (ray.ID, seed), Russian roulette, and compaction of the surviving rays. Replaces one
  * iteration of the loop in PathTracingRenderer.cpp:177-192 = traceClosest.csh + the diffuse / shadow-ray parts of
- * pathtracer/rayHit.csh:160-337. rays / payload are device buffers of capacity `count` (payload: 2 x float4 per ray:
- * radiance.rgb, throughput.rgb); accum: width*height*4 floats (rgb sum, sample count) indexed by ray.ID / samples.
- * out_count receives the number of surviving rays, which are compacted to the front of rays_out / payload_out. */
+ * pathtracer/rayHit.csh:160-337 for Lambertian, opaque, untextured, two-sided surfaces lit by one directional light
+ * and a constant sky (materials, textures and light sampling are shading inputs outside this path's scope).
+ * All buffers are DEVICE memory (flags must carry ATLAS_RT_DEVICE_INPUT | ATLAS_RT_DEVICE_OUTPUT):
+ *   rays_in      count PackedRay; updated IN PLACE with the closest hits (the shader's write to the other buffer half)
+ *   payload_in   2 x float4 per ray (radiance.rgb, throughput.rgb); ignored when params->bounce == 0
+ *   rays_out / payload_out   capacity count; receive the surviving rays compacted to the front; must not alias the inputs
+ *   accum        width*height x 4 floats (rgb sum, finished-path count), indexed by ray.ID / samples, updated atomically
+ * out_count (host) receives the number of surviving rays; the call synchronises the stream to read it. */
 int atlas_rt_pathtrace_bounce(atlas_rt_context* ctx, const atlas_rt_scene* scene, const atlas_rt_bounce_params* params,
                               const void* rays_in, const void* payload_in, uint64_t count, void* rays_out,
                               void* payload_out, float* accum, uint64_t* out_count, uint32_t flags);
