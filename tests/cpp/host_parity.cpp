@@ -1,0 +1,165 @@
+// Drives the C++ drop-in classes (atlas_engine_b200/host/AtlasRT.h) the way the engine drives the originals and
+// compares with the reference through its C bridge (oracle/_ref/libatlas_ref.so, dlopen'ed — test infrastructure).
+// Also builds several meshes from concurrent threads, as the engine's job system does (src/tests/App.cpp:362-370).
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <thread>
+#include <vector>
+
+#include "../../atlas_engine_b200/host/AtlasRT.h"
+
+using namespace Atlas;
+
+typedef void* (*ref_build_blas_t)(const float*, const float*, uint64_t, int);
+typedef void* (*ref_build_tlas_t)(const float*, uint64_t, int);
+typedef uint64_t (*ref_count_t)(void*);
+typedef void (*ref_copy_nodes_t)(void*, void*);
+typedef void (*ref_copy_order_t)(void*, uint32_t*, uint8_t*);
+typedef void (*ref_free_t)(void*);
+typedef int (*ref_void_t)();
+
+static std::vector<Volume::BVHTriangle> soup(size_t n, unsigned seed, float extent) {
+    std::mt19937 rng(seed);
+    std::uniform_real_distribution<float> u(0.0f, 1.0f);
+    std::vector<Volume::BVHTriangle> t(n);
+    for (size_t i = 0; i < n; i++) {
+        const vec3 c(u(rng), u(rng), u(rng));
+        vec3* v[3] = {&t[i].v0, &t[i].v1, &t[i].v2};
+        for (auto* p : v) *p = vec3(c.x + (u(rng) - 0.5f) * extent, c.y + (u(rng) - 0.5f) * extent, c.z + (u(rng) - 0.5f) * extent);
+        t[i].idx = uint32_t(i);
+    }
+    return t;
+}
+
+static std::vector<Volume::AABB> boxes_of(const std::vector<Volume::BVHTriangle>& t) {
+    std::vector<Volume::AABB> b(t.size());
+    for (size_t i = 0; i < t.size(); i++) {
+        for (int c = 0; c < 3; c++) {
+            b[i].min[c] = std::min(t[i].v0[c], std::min(t[i].v1[c], t[i].v2[c]));
+            b[i].max[c] = std::max(t[i].v0[c], std::max(t[i].v1[c], t[i].v2[c]));
+        }
+    }
+    return b;
+}
+
+int main(int argc, char** argv) {
+    const char* refPath = argc > 1 ? argv[1] : "oracle/_ref/libatlas_ref.so";
+    void* lib = dlopen(refPath, RTLD_NOW);
+    if (!lib) { printf("SKIP: cannot load %s\n", refPath); return 77; }
+    auto ref_build_blas = (ref_build_blas_t)dlsym(lib, "ref_build_blas");
+    auto ref_build_tlas = (ref_build_tlas_t)dlsym(lib, "ref_build_tlas");
+    auto ref_nodes = (ref_count_t)dlsym(lib, "ref_bvh_node_count");
+    auto ref_refs = (ref_count_t)dlsym(lib, "ref_bvh_ref_count");
+    auto ref_copy_nodes = (ref_copy_nodes_t)dlsym(lib, "ref_bvh_copy_nodes");
+    auto ref_copy_order = (ref_copy_order_t)dlsym(lib, "ref_bvh_copy_order");
+    auto ref_free = (ref_free_t)dlsym(lib, "ref_bvh_free");
+    auto ref_shutdown = (ref_void_t)dlsym(lib, "ref_shutdown");
+    int failures = 0;
+
+    // ---- BLAS through Volume::BVH(aabbs, data), several meshes concurrently
+    const size_t sizes[4] = {1000, 20000, 7, 50000};
+    const float extents[4] = {0.05f, 0.01f, 0.5f, 0.3f};
+    std::vector<Volume::BVH> built(4);
+    std::vector<std::vector<Volume::BVHTriangle>> tris(4);
+    std::vector<std::vector<Volume::AABB>> boxes(4);
+    for (int k = 0; k < 4; k++) { tris[k] = soup(sizes[k], 100 + k, extents[k]); boxes[k] = boxes_of(tris[k]); }
+    std::vector<std::thread> workers;
+    for (int k = 0; k < 4; k++) workers.emplace_back([&, k] { built[k] = Volume::BVH(boxes[k], tris[k], true); });
+    for (auto& w : workers) w.join();
+    for (int k = 0; k < 4; k++) {
+        std::vector<float> flat(sizes[k] * 9);
+        for (size_t i = 0; i < sizes[k]; i++) {
+            const float v[9] = {tris[k][i].v0.x, tris[k][i].v0.y, tris[k][i].v0.z, tris[k][i].v1.x, tris[k][i].v1.y, tris[k][i].v1.z,
+                                tris[k][i].v2.x, tris[k][i].v2.y, tris[k][i].v2.z};
+            memcpy(&flat[9 * i], v, sizeof(v));
+        }
+        void* r = ref_build_blas(reinterpret_cast<const float*>(boxes[k].data()), flat.data(), sizes[k], 1);
+        std::vector<Volume::BVHNode> rn(ref_nodes(r));
+        std::vector<uint32_t> ro(ref_refs(r));
+        std::vector<uint8_t> rf(ref_refs(r));
+        ref_copy_nodes(r, rn.data());
+        ref_copy_order(r, ro.data(), rf.data());
+        ref_free(r);
+        bool ok = rn.size() == built[k].nodes.size() && ro.size() == built[k].data.size() &&
+                  (rn.empty() || memcmp(rn.data(), built[k].nodes.data(), rn.size() * sizeof(Volume::BVHNode)) == 0);
+        for (size_t i = 0; ok && i < ro.size(); i++)
+            ok = built[k].data[i].idx == ro[i] && built[k].data[i].endOfNode == (rf[i] != 0) &&
+                 memcmp(&built[k].aabbs[i], &boxes[k][ro[i]], sizeof(Volume::AABB)) == 0;
+        ok = ok && built[k].refs.empty();
+        printf("BLAS %zu tris: nodes %zu refs %zu %s\n", sizes[k], built[k].nodes.size(), built[k].data.size(), ok ? "== reference" : "MISMATCH");
+        failures += ok ? 0 : 1;
+    }
+    // size mismatch => silently empty (BVH.cpp:18-19)
+    {
+        std::vector<Volume::AABB> fewer(boxes[0].begin(), boxes[0].begin() + 10);
+        Volume::BVH bad(fewer, tris[0]);
+        const bool ok = bad.nodes.empty() && bad.data.empty();
+        printf("size mismatch: %s\n", ok ? "empty BVH" : "MISMATCH");
+        failures += ok ? 0 : 1;
+    }
+    // ---- TLAS through Volume::BVH(aabbs)
+    for (size_t m : {size_t(1), size_t(2), size_t(300)}) {
+        std::vector<Volume::AABB> ib(boxes[3].begin(), boxes[3].begin() + m);
+        Volume::BVH tl(ib);
+        void* r = ref_build_tlas(reinterpret_cast<const float*>(ib.data()), m, 1);
+        std::vector<Volume::BVHNode> rn(ref_nodes(r));
+        std::vector<uint32_t> ro(ref_refs(r));
+        std::vector<uint8_t> rf(ref_refs(r));
+        ref_copy_nodes(r, rn.data());
+        ref_copy_order(r, ro.data(), rf.data());
+        ref_free(r);
+        bool ok = rn.size() == tl.nodes.size() && ro.size() == tl.refs.size() && memcmp(rn.data(), tl.nodes.data(), rn.size() * sizeof(Volume::BVHNode)) == 0;
+        for (size_t i = 0; ok && i < ro.size(); i++) ok = tl.refs[i].idx == ro[i] && tl.refs[i].endOfNode == (rf[i] != 0);
+        printf("TLAS %zu instances: nodes %zu refs %zu %s\n", m, tl.nodes.size(), tl.refs.size(), ok ? "== reference" : "MISMATCH");
+        failures += ok ? 0 : 1;
+    }
+    // ---- MeshData::BuildBVH + UpdateForSoftwareRayTracing + trace, end to end through the mirrors
+    {
+        std::vector<vec3> verts;
+        std::vector<uint32_t> idx;
+        const int g = 40;
+        for (int z = 0; z <= g; z++) for (int x = 0; x <= g; x++) verts.push_back(vec3(float(x), 2.0f * sinf(0.3f * x) * cosf(0.2f * z), float(z)));
+        for (int z = 0; z < g; z++) for (int x = 0; x < g; x++) {
+            const uint32_t a = z * (g + 1) + x, b = a + 1, c = a + g + 1, d = c + 1;
+            for (uint32_t v : {a, b, d, a, d, c}) idx.push_back(v);
+        }
+        RayTracing::MeshBVH mesh;
+        bool ok = RayTracing::BuildMeshBVH(verts, idx, 3, 1.0f, mesh) && mesh.IsBVHBuilt() && mesh.gpuBvhNodes.size() + 1 == mesh.gpuBvhTriangles.size();
+        std::vector<GPUBVHInstance> inst(2);
+        std::vector<Volume::AABB> actor(2);
+        for (int k = 0; k < 2; k++) {
+            const float dx = 100.0f * k;   // instance k is the mesh translated by (dx, 0, 0): inverse translates back
+            inst[k].inverseMatrix[0] = vec4(1, 0, 0, -dx); inst[k].inverseMatrix[1] = vec4(0, 1, 0, 0); inst[k].inverseMatrix[2] = vec4(0, 0, 1, 0);
+            inst[k].meshOffset = 0; inst[k].mask = MaskAll | MaskShadow;
+            actor[k] = Volume::AABB(vec3(dx, -2.0f, 0.0f), vec3(dx + g, 2.0f, float(g)));
+        }
+        RayTracing::World world;
+        ok = ok && RayTracing::UpdateForSoftwareRayTracing(inst, actor, {&mesh}, world) && world.tlasNodes.size() == 1 && inst.size() == 2;
+        std::vector<PackedRay> rays(2), out;
+        for (int k = 0; k < 2; k++) {
+            int id = k;
+            rays[k].origin = vec4(100.0f * k + 20.3f, 50.0f, 20.7f, 0.0f);
+            memcpy(&rays[k].origin.w, &id, 4);
+            rays[k].direction = vec4(0.001f, -1.0f, 0.002f, 0.0f);
+        }
+        ok = ok && RayTracing::Tracer::HitClosest(world, rays, out);
+        int hitInst[2] = {-1, -1};
+        for (int k = 0; ok && k < 2; k++) {
+            int hitID;
+            memcpy(&hitID, &out[k].hit.y, 4);
+            memcpy(&hitInst[k], &out[k].hit.z, 4);
+            ok = hitID >= 0 && out[k].hit.x > 45.0f && out[k].hit.x < 55.0f;
+        }
+        ok = ok && hitInst[0] != hitInst[1] && out[0].hit.x == out[1].hit.x;   // same mesh, same local ray => same t
+        printf("mesh + world + trace through the mirrors: %s (%s)\n", ok ? "ok" : "MISMATCH", RayTracing::LastError().c_str());
+        failures += ok ? 0 : 1;
+        world.Release();
+        mesh.Release();
+    }
+    if (ref_shutdown) ref_shutdown();
+    printf(failures ? "FAILED %d\n" : "ALL OK\n", failures);
+    return failures ? 1 : 0;
+}
