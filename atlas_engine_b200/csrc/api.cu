@@ -136,6 +136,8 @@ int atlas_rt_context_create(int device, void* stream, atlas_rt_context** out_ctx
     cudaDeviceGetAttribute(&ctx->smCount, cudaDevAttrMultiProcessorCount, device);
     if (const char* e = getenv("ATLAS_RT_TRACE_LEAF_THRESHOLD")) ctx->traceLeafThreshold = std::max(1, std::min(32, atoi(e)));
     if (const char* e = getenv("ATLAS_RT_TRACE_REFILL_THRESHOLD")) ctx->traceRefillThreshold = std::max(1, std::min(32, atoi(e)));
+    if (const char* e = getenv("ATLAS_RT_TRACE_RAYS_PER_WARP")) ctx->traceRaysPerWarp = std::max(1, atoi(e));
+    if (const char* e = getenv("ATLAS_RT_TRACE_LONGEST_FIRST")) ctx->traceLongestFirst = atoi(e);
     if (const char* e = getenv("ATLAS_RT_TRACE_BLOCKS_PER_SM")) ctx->traceBlocksPerSM = std::max(1, std::min(9, atoi(e)));
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -146,6 +148,10 @@ int atlas_rt_context_create(int device, void* stream, atlas_rt_context** out_ctx
     cudaMemset(ctx->dCounters, 0, 8 * sizeof(unsigned long long));
     ctx->pinnedBytes = 4096;
     if (cudaMallocHost(&ctx->pinned, ctx->pinnedBytes) != cudaSuccess) { cudaFree(ctx->dCounters); delete ctx; return ATLAS_RT_ERR_OOM; }
+    if (cudaStreamCreateWithFlags(&ctx->copyIn, cudaStreamNonBlocking) != cudaSuccess) ctx->copyIn = nullptr;
+    if (cudaStreamCreateWithFlags(&ctx->copyOut, cudaStreamNonBlocking) != cudaSuccess) ctx->copyOut = nullptr;
+    for (auto& ev : ctx->pipeEvents)
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { ev = nullptr; ctx->copyIn = nullptr; }
     *out_ctx = ctx;
     return ATLAS_RT_OK;
 }
@@ -154,6 +160,9 @@ void atlas_rt_context_destroy(atlas_rt_context* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (auto& ev : ctx->pipeEvents) if (ev) cudaEventDestroy(ev);
+    if (ctx->copyIn) cudaStreamDestroy(ctx->copyIn);
+    if (ctx->copyOut) cudaStreamDestroy(ctx->copyOut);
     cudaFree(ctx->dCounters);
     cudaFreeHost(ctx->pinned);
     if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
@@ -429,18 +438,51 @@ static int trace_common(atlas_rt_context* ctx, const atlas_rt_scene* scene, cons
     float4* out = static_cast<float4*>(rays_out);
     if (!devIn) {
         ATLAS_CUDA(ctx, dev_alloc(ctx, &dIn, count * 3));
-        ATLAS_CUDA(ctx, copy_in(ctx, dIn, rays_in, count * 48, false));
         in = dIn;
     }
     if (!devOut) {
         if (dIn) out = dIn;   // in-place on the staging buffer
         else { ATLAS_CUDA(ctx, dev_alloc(ctx, &dOut, count * 3)); out = dOut; }
     }
-    int rc = launch_trace(ctx, scene, in, out, count, cull_mask, t_min, t_max, any, (flags & ATLAS_RT_PER_RAY_TMAX) != 0,
-                          (flags & ATLAS_RT_COUNTERS) != 0);
-    if (rc == ATLAS_RT_OK && !devOut) {
-        cudaError_t e = copy_out(ctx, rays_out, out, count * 48, false);
-        if (e != cudaSuccess) rc = fail(ctx, ATLAS_RT_ERR_CUDA, "copy_out", e);
+    const bool perRay = (flags & ATLAS_RT_PER_RAY_TMAX) != 0, counters = (flags & ATLAS_RT_COUNTERS) != 0;
+    int rc = ATLAS_RT_OK;
+    const uint64_t kPipeMin = 262144;
+    if (!devIn && !devOut && count >= kPipeMin && ctx->copyIn && ctx->copyOut) {
+        // Host buffers on both sides: split the batch and overlap H2D of chunk i+1, the trace of chunk i and D2H of
+        // chunk i-1 on the two copy engines (pays off with pinned host memory; pageable memory still works).
+        uint32_t chunks = count >= 16 * kPipeMin ? 4u : 2u;   // every launch pays the latency of its longest ray: keep chunks large
+        if (const char* e = getenv("ATLAS_RT_PIPE_CHUNKS")) chunks = uint32_t(std::max(1, std::min(8, atoi(e))));
+        cudaEvent_t* ev = ctx->pipeEvents;   // [0] staging ready, [1+c] chunk c uploaded, [9+c] chunk c traced, [19] all downloaded
+        cudaError_t e = cudaEventRecord(ev[0], ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copyIn, ev[0], 0);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copyOut, ev[0], 0);
+        for (uint32_t c = 0; c < chunks && e == cudaSuccess && rc == ATLAS_RT_OK; c++) {
+            const uint64_t b = (count * c / chunks) & ~uint64_t(31), end = c + 1 == chunks ? count : ((count * (c + 1) / chunks) & ~uint64_t(31));
+            const char* hIn = static_cast<const char*>(rays_in) + 48 * b;
+            char* hOut = static_cast<char*>(rays_out) + 48 * b;
+            e = cudaMemcpyAsync(dIn + 3 * b, hIn, 48 * (end - b), cudaMemcpyHostToDevice, ctx->copyIn);
+            if (e == cudaSuccess) e = cudaEventRecord(ev[1 + c], ctx->copyIn);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev[1 + c], 0);
+            if (e != cudaSuccess) break;
+            rc = launch_trace(ctx, scene, dIn + 3 * b, dIn + 3 * b, end - b, cull_mask, t_min, t_max, any, perRay, counters, c == 0);
+            if (rc != ATLAS_RT_OK) break;
+            e = cudaEventRecord(ev[9 + c], ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copyOut, ev[9 + c], 0);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(hOut, dIn + 3 * b, 48 * (end - b), cudaMemcpyDeviceToHost, ctx->copyOut);
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(ev[19], ctx->copyOut);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev[19], 0);   // the context stream now orders after the downloads
+        if (e != cudaSuccess && rc == ATLAS_RT_OK) rc = fail(ctx, ATLAS_RT_ERR_CUDA, "pipelined trace", e);
+    } else {
+        if (!devIn) {
+            cudaError_t e = copy_in(ctx, dIn, rays_in, count * 48, false);
+            if (e != cudaSuccess) rc = fail(ctx, ATLAS_RT_ERR_CUDA, "copy_in", e);
+        }
+        if (rc == ATLAS_RT_OK) rc = launch_trace(ctx, scene, in, out, count, cull_mask, t_min, t_max, any, perRay, counters);
+        if (rc == ATLAS_RT_OK && !devOut) {
+            cudaError_t e = copy_out(ctx, rays_out, out, count * 48, false);
+            if (e != cudaSuccess) rc = fail(ctx, ATLAS_RT_ERR_CUDA, "copy_out", e);
+        }
     }
     dev_free(ctx, dIn);
     dev_free(ctx, dOut);

@@ -245,11 +245,36 @@ bin_big(const Task* __restrict__ tasks, const LevelInfo* __restrict__ info, cons
     extern __shared__ int sb[];   // [3][nb][8]
     __shared__ uint32_t sTask;
     const uint32_t nChunks = info->nChunks, nTasks = info->nTasks;
-    for (uint32_t c = blockIdx.x; c < nChunks; c += gridDim.x) {
+    // every CTA takes a contiguous run of chunks and keeps accumulating in shared memory while the run stays inside one
+    // node, so the shared bins are merged into the node's global bins once per (CTA, node) instead of once per chunk
+    const uint32_t perCta = (nChunks + gridDim.x - 1) / gridDim.x;
+    const uint32_t c0 = blockIdx.x * perCta, c1 = min(nChunks, c0 + perCta);
+    uint32_t cur = 0xffffffffu;
+    auto flush = [&](uint32_t t) {
+        __syncthreads();
+        int* g = gbins + size_t(t) * 3 * nb * kBinWords;
+        for (uint32_t e = threadIdx.x; e < 3 * nb; e += kBigBlock) {
+            const int* rec = sb + e * kBinWords;
+            if (rec[6] > 0) {
+                int* d = g + e * kBinWords;
+#pragma unroll
+                for (int k = 0; k < 3; k++) { atomicMin(d + k, rec[k]); atomicMax(d + 3 + k, rec[3 + k]); }
+                atomicAdd(d + 6, rec[6]);
+                atomicAdd(d + 7, rec[6]);   // exit == enter == primitiveCount for the object split
+            }
+        }
+        __syncthreads();
+    };
+    for (uint32_t c = c0; c < c1; c++) {
         if (threadIdx.x == 0) sTask = find_task(chunkBase, nTasks, c);
-        for (uint32_t e = threadIdx.x; e < 3 * nb; e += kBigBlock) bin_init(sb + e * kBinWords);
         __syncthreads();
         const uint32_t t = sTask;
+        if (t != cur) {
+            if (cur != 0xffffffffu) flush(cur);
+            for (uint32_t e = threadIdx.x; e < 3 * nb; e += kBigBlock) bin_init(sb + e * kBinWords);
+            cur = t;
+            __syncthreads();
+        }
         const Task& tk = tasks[t];
         const uint32_t off = (c - chunkBase[t]) * kChunk;
         const uint32_t end = tk.start + tk.count;
@@ -274,20 +299,9 @@ bin_big(const Task* __restrict__ tasks, const LevelInfo* __restrict__ info, cons
                 }
             }
         }
-        __syncthreads();
-        int* g = gbins + size_t(t) * 3 * nb * kBinWords;
-        for (uint32_t e = threadIdx.x; e < 3 * nb; e += kBigBlock) {
-            const int* rec = sb + e * kBinWords;
-            if (rec[6] > 0) {
-                int* d = g + e * kBinWords;
-#pragma unroll
-                for (int k = 0; k < 3; k++) { atomicMin(d + k, rec[k]); atomicMax(d + 3 + k, rec[3 + k]); }
-                atomicAdd(d + 6, rec[6]);
-                atomicAdd(d + 7, rec[6]);   // exit == enter == primitiveCount for the object split
-            }
-        }
-        __syncthreads();
+        __syncthreads();   // sTask is rewritten at the top of the next iteration
     }
+    if (cur != 0xffffffffu) flush(cur);
 }
 
 // ------------------------------------------------------------------------------------------------ child creation
@@ -1574,7 +1588,8 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
         ATLAS_LAUNCHED(ctx);
         init_bins<<<std::max(1u, std::min<uint32_t>(persistent, (nTasks * 3u * nb + 255u) / 256u)), 256, 0, st>>>(B.bins, B.info, 3u * nb);
         ATLAS_LAUNCHED(ctx);
-        bin_big<<<gridChunks, kBigBlock, binSmem, st>>>(tasks, B.info, B.chunkBase, rlo, rhi, B.bins, nb);
+        const uint32_t gridBin = std::max(1u, std::min(chunksBound, uint32_t(ctx->smCount) * 2u));
+        bin_big<<<gridBin, kBigBlock, binSmem, st>>>(tasks, B.info, B.chunkBase, rlo, rhi, B.bins, nb);
         ATLAS_LAUNCHED(ctx);
 
         bool spatialPath = false;
@@ -1587,7 +1602,7 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
                 const int initGrid = 3;
                 init_bins<<<initGrid, 256, 0, st>>>(B.spaBins, B.info, 3u * nb);   // nTasks == 1
                 ATLAS_LAUNCHED(ctx);
-                spatial_bin_root<<<gridChunks, kBigBlock, binSmem, st>>>(tasks, rlo, rhi, B.tris, B.spaBins, nb);
+                spatial_bin_root<<<gridBin, kBigBlock, binSmem, st>>>(tasks, rlo, rhi, B.tris, B.spaBins, nb);
                 ATLAS_LAUNCHED(ctx);
             }
             select_root_final<<<1, 32, 0, st>>>(tasks, B.info, B.bins, B.spaBins, B.sfx, B.medAcc, B.root, L, nb, trySpatial);

@@ -77,10 +77,16 @@ struct atlas_rt_context {
     unsigned long long* dCounters = nullptr;   // 8 x u64 traversal counters / flags
     void* pinned = nullptr;                    // small pinned staging area for read-backs
     size_t pinnedBytes = 0;
+    // copy engines used to overlap H2D / trace / D2H when a trace call is given host buffers (api.cu)
+    cudaStream_t copyIn = nullptr, copyOut = nullptr;
+    cudaEvent_t pipeEvents[20] = {};
     // scheduling knobs of the persistent traversal kernel (trace.cu); ATLAS_RT_TRACE_* environment variables override
     int traceLeafThreshold = 8;     // lanes waiting at a leaf before the warp runs a leaf round
     int traceRefillThreshold = 6;   // idle lanes before the warp fetches new rays
     int traceBlocksPerSM = 9;
+    int traceLongestFirst = 1;      // fetch rays longest-estimated-path first (hides the drain of the longest rays)
+    int traceLongestFirstMin = 65536;
+    int traceRaysPerWarp = 96;      // small batches use fewer persistent warps so each warp still sees this many rays
 };
 
 struct atlas_rt_bvh {
@@ -150,6 +156,6 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
 // traversal entry points (trace.cu)
 int scene_fast_flag(atlas_rt_context* ctx, atlas_rt_scene* scene, const uint32_t* dNodeCounts);
 int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float4* dIn, float4* dOut, uint64_t count,
-                 uint32_t cullMask, float tMin, float tMax, bool any, bool perRayTMax, bool counters);
+                 uint32_t cullMask, float tMin, float tMax, bool any, bool perRayTMax, bool counters, bool resetCounters = true);
 
 }   // namespace atlas
