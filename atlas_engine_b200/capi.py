@@ -11,7 +11,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libatlas_rt.so")
 
-DEVICE_INPUT, DEVICE_OUTPUT, ASYNC, PER_RAY_TMAX, COUNTERS = 1, 2, 4, 8, 16
+DEVICE_INPUT, DEVICE_OUTPUT, ASYNC, PER_RAY_TMAX, COUNTERS, OPACITY = 1, 2, 4, 8, 16, 32
 MASK_ALL, MASK_SHADOW = 1 << 7, 1 << 6
 INF = 1e12
 STATUS = {0: "OK", -1: "ERR_INVALID", -2: "ERR_CUDA", -3: "ERR_OOM", -4: "ERR_UNSUPPORTED", -5: "ERR_STACK"}
@@ -35,6 +35,8 @@ SIGNATURES = {
     "atlas_rt_bvh_stats": (_i32, [_vp, _vp]),
     "atlas_rt_bvh_free": (None, [_vp]),
     "atlas_rt_pack_mesh": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _u32, C.POINTER(_vp)]),
+    "atlas_rt_mesh_pack_shading": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _u32]),
+    "atlas_rt_mesh_download_shading": (_i32, [_vp, _vp, _u32]),
     "atlas_rt_mesh_counts": (_i32, [_vp, C.POINTER(_u64), C.POINTER(_u64)]),
     "atlas_rt_mesh_download": (_i32, [_vp, _vp, _vp, _u32]),
     "atlas_rt_mesh_free": (None, [_vp]),
@@ -261,6 +263,21 @@ class Mesh:
         tris = np.zeros((m.value, 12), dtype=np.float32)
         self.ctx.check(self.ctx.L.atlas_rt_mesh_download(self.h, _addr(nodes), _addr(tris), 0))
         return nodes, tris
+
+    def pack_shading(self, tris, material_idx=None, opacity=None, payload11=None):
+        """Adds the 96-byte GPUTriangle array the opacity-aware traversal variants read."""
+        tris = np.ascontiguousarray(tris, dtype=np.float32)
+        m = None if material_idx is None else np.ascontiguousarray(material_idx, dtype=np.int32)
+        o = None if opacity is None else np.ascontiguousarray(opacity, dtype=np.float32)
+        p = None if payload11 is None else np.ascontiguousarray(payload11, dtype=np.uint32)
+        self.ctx.check(self.ctx.L.atlas_rt_mesh_pack_shading(self.ctx.h, self.h, _addr(tris), tris.shape[0], _addr(m), _addr(o), _addr(p), 0))
+
+    def download_shading(self):
+        n, m = _u64(), _u64()
+        self.ctx.check(self.ctx.L.atlas_rt_mesh_counts(self.h, C.byref(n), C.byref(m)))
+        out = np.zeros((m.value, 24), dtype=np.float32)
+        self.ctx.check(self.ctx.L.atlas_rt_mesh_download_shading(self.h, _addr(out), 0))
+        return out
 
     def free(self):
         if self.h:

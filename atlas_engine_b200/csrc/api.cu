@@ -68,6 +68,29 @@ __global__ void pack_bvh_triangles(const float* __restrict__ tris, const uint32_
     out[3 * i + 2] = make_float4(t[6], t[7], t[8], op);
 }
 
+// GPUTriangle records in flattened order — mesh/MeshData.cpp:230-239; the 11 shading words per triangle are the
+// engine's own packed values and are only moved.
+__global__ void pack_shading_triangles(const float* __restrict__ tris, const uint32_t* __restrict__ order,
+                                       const uint8_t* __restrict__ endOfNode, const int32_t* __restrict__ material,
+                                       const float* __restrict__ opacity, const uint32_t* __restrict__ payload,
+                                       float4* __restrict__ out, uint64_t refs) {
+    const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if (i >= refs) return;
+    const uint32_t src = order[i];
+    const float* t = tris + 9 * size_t(src);
+    uint32_t p[11];
+#pragma unroll
+    for (int k = 0; k < 11; k++) p[k] = payload ? payload[11 * size_t(src) + k] : 0u;
+    const int32_t mat = material ? material[src] : 0;
+    const float op = opacity ? opacity[src] : 1.0f;
+    out[6 * i + 0] = make_float4(t[0], t[1], t[2], __uint_as_float(p[0]));
+    out[6 * i + 1] = make_float4(t[3], t[4], t[5], __uint_as_float(p[1]));
+    out[6 * i + 2] = make_float4(t[6], t[7], t[8], __uint_as_float(p[2]));
+    out[6 * i + 3] = make_float4(__uint_as_float(p[3]), __uint_as_float(p[4]), __uint_as_float(p[5]), __int_as_float(mat));
+    out[6 * i + 4] = make_float4(__uint_as_float(p[6]), __uint_as_float(p[7]), endOfNode[i] ? 1.0f : -1.0f, 0.0f);
+    out[6 * i + 5] = make_float4(__uint_as_float(p[8]), __uint_as_float(p[9]), __uint_as_float(p[10]), op);
+}
+
 // Instance permutation of RayTracingWorld.cpp:287-295.
 __global__ void reorder_instances(const float4* __restrict__ src, const uint32_t* __restrict__ order,
                                   const uint8_t* __restrict__ endOfNode, float4* __restrict__ dst, uint64_t refs) {
@@ -329,6 +352,42 @@ int atlas_rt_pack_mesh(atlas_rt_context* ctx, const atlas_rt_bvh* blas, const fl
     return ATLAS_RT_OK;
 }
 
+int atlas_rt_mesh_pack_shading(atlas_rt_context* ctx, atlas_rt_mesh* mesh, const float* tris, uint64_t count,
+                               const int32_t* material_idx, const float* opacity, const uint32_t* payload11, uint32_t flags) {
+    if (!ctx || !mesh || mesh->ctx != ctx || (count && !tris)) return fail(ctx, ATLAS_RT_ERR_INVALID, "bad argument");
+    ATLAS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const bool dev = flags & ATLAS_RT_DEVICE_INPUT;
+    float* dT = nullptr;
+    int32_t* dM = nullptr;
+    float* dO = nullptr;
+    uint32_t* dP = nullptr;
+    if (!dev) {
+        ATLAS_CUDA(ctx, dev_alloc(ctx, &dT, count * 9));
+        ATLAS_CUDA(ctx, copy_in(ctx, dT, tris, count * 36, false));
+        if (material_idx) { ATLAS_CUDA(ctx, dev_alloc(ctx, &dM, count)); ATLAS_CUDA(ctx, copy_in(ctx, dM, material_idx, count * 4, false)); }
+        if (opacity) { ATLAS_CUDA(ctx, dev_alloc(ctx, &dO, count)); ATLAS_CUDA(ctx, copy_in(ctx, dO, opacity, count * 4, false)); }
+        if (payload11) { ATLAS_CUDA(ctx, dev_alloc(ctx, &dP, count * 11)); ATLAS_CUDA(ctx, copy_in(ctx, dP, payload11, count * 44, false)); }
+    }
+    if (!mesh->tris96) ATLAS_CUDA(ctx, dev_alloc(ctx, &mesh->tris96, mesh->triCount * 6));
+    if (mesh->triCount) {
+        pack_shading_triangles<<<grid_for(mesh->triCount), kBlock, 0, ctx->stream>>>(
+            dev ? tris : dT, mesh->blas->order, mesh->blas->endOfNode, dev ? material_idx : dM, dev ? opacity : dO, dev ? payload11 : dP,
+            mesh->tris96, mesh->triCount);
+        ATLAS_LAUNCH_CHECK(ctx);
+    }
+    if (!dev) { dev_free(ctx, dT); dev_free(ctx, dM); dev_free(ctx, dO); dev_free(ctx, dP); }
+    return sync_unless_async(ctx, flags);
+}
+
+int atlas_rt_mesh_download_shading(const atlas_rt_mesh* mesh, void* gpu_triangles96, uint32_t flags) {
+    if (!mesh || !gpu_triangles96) return ATLAS_RT_ERR_INVALID;
+    atlas_rt_context* ctx = mesh->ctx;
+    if (!mesh->tris96) return fail(ctx, ATLAS_RT_ERR_INVALID, "atlas_rt_mesh_pack_shading has not been called for this mesh");
+    ATLAS_CUDA(ctx, cudaSetDevice(ctx->device));
+    ATLAS_CUDA(ctx, copy_out(ctx, gpu_triangles96, mesh->tris96, mesh->triCount * 96, (flags & ATLAS_RT_DEVICE_OUTPUT) != 0));
+    return sync_unless_async(ctx, flags);
+}
+
 int atlas_rt_mesh_counts(const atlas_rt_mesh* mesh, uint64_t* node_count, uint64_t* triangle_count) {
     if (!mesh) return ATLAS_RT_ERR_INVALID;
     if (node_count) *node_count = mesh->blas->nodeCount;
@@ -350,6 +409,7 @@ void atlas_rt_mesh_free(atlas_rt_mesh* mesh) {
     if (!mesh) return;
     cudaSetDevice(mesh->ctx->device);
     dev_free(mesh->ctx, mesh->tris);
+    dev_free(mesh->ctx, mesh->tris96);
     delete mesh;
 }
 
@@ -367,12 +427,15 @@ int atlas_rt_scene_create(atlas_rt_context* ctx, const atlas_rt_mesh* const* mes
     scene->tlas = tlas;
     scene->meshCount = mesh_count;
     scene->instanceCount = tlas->refCount;
-    std::vector<const float4*> nodePtrs(mesh_count), triPtrs(mesh_count);
+    std::vector<const float4*> nodePtrs(mesh_count), triPtrs(mesh_count), tri96Ptrs(mesh_count);
     std::vector<uint32_t> nodeCounts(mesh_count);
+    scene->allShading = true;
     for (uint32_t m = 0; m < mesh_count; m++) {
         if (!meshes[m] || meshes[m]->ctx != ctx) { delete scene; return fail(ctx, ATLAS_RT_ERR_INVALID, "mesh from another context"); }
         nodePtrs[m] = meshes[m]->blas->nodes;
         triPtrs[m] = meshes[m]->tris;
+        tri96Ptrs[m] = meshes[m]->tris96;
+        scene->allShading = scene->allShading && meshes[m]->tris96 != nullptr;
         nodeCounts[m] = uint32_t(meshes[m]->blas->nodeCount);
     }
     float4* dSrc = nullptr;
@@ -381,10 +444,12 @@ int atlas_rt_scene_create(atlas_rt_context* ctx, const atlas_rt_mesh* const* mes
     ATLAS_CUDA(ctx, cudaMemcpyAsync(dNodeCounts, nodeCounts.data(), mesh_count * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     ATLAS_CUDA(ctx, dev_alloc(ctx, &scene->blasNodes, mesh_count));
     ATLAS_CUDA(ctx, dev_alloc(ctx, &scene->bvhTris, mesh_count));
+    ATLAS_CUDA(ctx, dev_alloc(ctx, &scene->triangles, mesh_count));
     ATLAS_CUDA(ctx, dev_alloc(ctx, &scene->instances, scene->instanceCount * 4));
     // pointer tables are tiny: plain synchronous copies from pageable memory are fine here
     ATLAS_CUDA(ctx, cudaMemcpyAsync(scene->blasNodes, nodePtrs.data(), mesh_count * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
     ATLAS_CUDA(ctx, cudaMemcpyAsync(scene->bvhTris, triPtrs.data(), mesh_count * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
+    ATLAS_CUDA(ctx, cudaMemcpyAsync(scene->triangles, tri96Ptrs.data(), mesh_count * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
     ATLAS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the std::vectors die at scope exit
     {
         int rcf = scene_fast_flag(ctx, scene, dNodeCounts);
@@ -424,6 +489,7 @@ void atlas_rt_scene_free(atlas_rt_scene* scene) {
     dev_free(scene->ctx, scene->instances);
     dev_free(scene->ctx, scene->blasNodes);
     dev_free(scene->ctx, scene->bvhTris);
+    dev_free(scene->ctx, scene->triangles);
     delete scene;
 }
 
@@ -445,6 +511,12 @@ static int trace_common(atlas_rt_context* ctx, const atlas_rt_scene* scene, cons
         else { ATLAS_CUDA(ctx, dev_alloc(ctx, &dOut, count * 3)); out = dOut; }
     }
     const bool perRay = (flags & ATLAS_RT_PER_RAY_TMAX) != 0, counters = (flags & ATLAS_RT_COUNTERS) != 0;
+    const bool opacity = (flags & ATLAS_RT_OPACITY) != 0;
+    if (opacity && !scene->allShading) {
+        dev_free(ctx, dIn);
+        dev_free(ctx, dOut);
+        return fail(ctx, ATLAS_RT_ERR_INVALID, "ATLAS_RT_OPACITY needs atlas_rt_mesh_pack_shading on every mesh of the scene (before atlas_rt_scene_create)");
+    }
     int rc = ATLAS_RT_OK;
     const uint64_t kPipeMin = 262144;
     if (!devIn && !devOut && count >= kPipeMin && ctx->copyIn && ctx->copyOut) {
@@ -464,7 +536,7 @@ static int trace_common(atlas_rt_context* ctx, const atlas_rt_scene* scene, cons
             if (e == cudaSuccess) e = cudaEventRecord(ev[1 + c], ctx->copyIn);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev[1 + c], 0);
             if (e != cudaSuccess) break;
-            rc = launch_trace(ctx, scene, dIn + 3 * b, dIn + 3 * b, end - b, cull_mask, t_min, t_max, any, perRay, counters, c == 0);
+            rc = launch_trace(ctx, scene, dIn + 3 * b, dIn + 3 * b, end - b, cull_mask, t_min, t_max, any, perRay, counters, c == 0, opacity);
             if (rc != ATLAS_RT_OK) break;
             e = cudaEventRecord(ev[9 + c], ctx->stream);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copyOut, ev[9 + c], 0);
@@ -478,7 +550,7 @@ static int trace_common(atlas_rt_context* ctx, const atlas_rt_scene* scene, cons
             cudaError_t e = copy_in(ctx, dIn, rays_in, count * 48, false);
             if (e != cudaSuccess) rc = fail(ctx, ATLAS_RT_ERR_CUDA, "copy_in", e);
         }
-        if (rc == ATLAS_RT_OK) rc = launch_trace(ctx, scene, in, out, count, cull_mask, t_min, t_max, any, perRay, counters);
+        if (rc == ATLAS_RT_OK) rc = launch_trace(ctx, scene, in, out, count, cull_mask, t_min, t_max, any, perRay, counters, true, opacity);
         if (rc == ATLAS_RT_OK && !devOut) {
             cudaError_t e = copy_out(ctx, rays_out, out, count * 48, false);
             if (e != cudaSuccess) rc = fail(ctx, ATLAS_RT_ERR_CUDA, "copy_out", e);

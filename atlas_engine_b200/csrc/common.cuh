@@ -103,6 +103,7 @@ struct atlas_rt_mesh {
     const atlas_rt_bvh* blas = nullptr;
     uint64_t triCount = 0;
     float4* tris = nullptr;       // GPUBVHTriangle, 3 x float4 each
+    float4* tris96 = nullptr;     // GPUTriangle, 6 x float4 each (only after atlas_rt_mesh_pack_shading)
 };
 
 struct atlas_rt_scene {
@@ -113,6 +114,8 @@ struct atlas_rt_scene {
     float4* instances = nullptr;             // reordered GPUBVHInstance, 4 x float4 each
     const float4** blasNodes = nullptr;      // device array [meshCount]
     const float4** bvhTris = nullptr;        // device array [meshCount]
+    const float4** triangles = nullptr;      // device array [meshCount] of 96-byte triangle arrays (entries may be null)
+    bool allShading = false;                 // every mesh has its 96-byte array: the opacity-aware variants may run
     int fastDivision = 0;                    // all scene coordinates below 2^60: slab tests may use div_by_rcp (trace.cu)
 };
 
@@ -156,6 +159,7 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
 // traversal entry points (trace.cu)
 int scene_fast_flag(atlas_rt_context* ctx, atlas_rt_scene* scene, const uint32_t* dNodeCounts);
 int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float4* dIn, float4* dOut, uint64_t count,
-                 uint32_t cullMask, float tMin, float tMax, bool any, bool perRayTMax, bool counters, bool resetCounters = true);
+                 uint32_t cullMask, float tMin, float tMax, bool any, bool perRayTMax, bool counters, bool resetCounters = true,
+                 bool opacity = false);
 
 }   // namespace atlas

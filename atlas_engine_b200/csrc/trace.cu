@@ -28,6 +28,7 @@ struct SceneDev {
     const float4* instances;
     const float4* const* blasNodes;
     const float4* const* bvhTris;
+    const float4* const* triangles;   // 96-byte GPUTriangle arrays (opacity-aware variants)
 };
 
 // IntersectAABB (intersections.hsh:19-34): true division by the direction, GLSL min/max forms.
@@ -128,7 +129,7 @@ constexpr int kBlocksPerSM = 9;
 // active lanes). Within a warp every round is warp-uniform: either the lanes standing at an inner node take one
 // traversal step, or — once enough lanes wait at a leaf / instance — those lanes process it. A ray's own visit order is
 // exactly the reference's; only the interleaving between different rays changes.
-template <bool ANY, bool COUNT>
+template <bool ANY, bool COUNT, bool OPACITY>
 __global__ void __launch_bounds__(kTraceBlock, kBlocksPerSM)
 trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restrict__ perm, uint32_t count, uint32_t cullMask, float tMin,
              float tMaxArg,
@@ -143,6 +144,7 @@ trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restr
     int nodePtr = 0, curInst = 0, hitID = -1, hitInst = 0;
     float o[3] = {0, 0, 0}, d[3] = {1, 1, 1}, rc[3] = {1, 1, 1};
     float tMax = tMaxArg, hitT = 0.0f, baryU = 0.0f, baryV = 0.0f;
+    float transparency = 1.0f;   // HitAnyTransparency's accumulator; reported in direction.w
     const float4* nodes = sc.tlasNodes;
     const float4* tris = nullptr;
     uint32_t cTlas = 0, cInst = 0, cBlas = 0, cTri = 0, cMaxSp = 1;
@@ -150,7 +152,7 @@ trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restr
     auto finish = [&]() {   // PackRay, common.hsh:61-73 (+ barycentrics in the two lanes GLSL leaves unwritten)
         const float4 r0 = in[3 * size_t(ray)], r1 = in[3 * size_t(ray) + 1];
         out[3 * size_t(ray)] = r0;
-        out[3 * size_t(ray) + 1] = make_float4(r1.x, r1.y, r1.z, baryU);
+        out[3 * size_t(ray) + 1] = make_float4(r1.x, r1.y, r1.z, (ANY && OPACITY) ? transparency : baryU);
         out[3 * size_t(ray) + 2] = make_float4(hitT, __int_as_float(hitID), __int_as_float(hitInst), baryV);
         alive = false;
     };
@@ -197,6 +199,7 @@ trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restr
                     hitInst = __float_as_int(r2.z);
                     hitT = 0.0f;
                     baryU = baryV = 0.0f;
+                    transparency = 1.0f;
                     alive = true;
                     if (id < 0) {
                         finish();
@@ -245,24 +248,41 @@ trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restr
                         set_ray(no, nd);
                         tlasIndex = sp;
                         nodes = sc.blasNodes[meshPtr];
-                        tris = sc.bvhTris[meshPtr];
+                        tris = OPACITY ? sc.triangles[meshPtr] : sc.bvhTris[meshPtr];
                     } else {
                         pop();   // the transformed ray is discarded: the TLAS branch restores the original anyway
                     }
                 } else {
-                    // CheckLeafClosest (bvh.hsh:44-72) / CheckLeaf (:74-104)
+                    // CheckLeafClosest (bvh.hsh:44-72) / CheckLeaf (:74-104); with OPACITY CheckLeafClosestTransparency
+                    // (:106-135) / CheckLeafTransparency (:137-170) over the 96-byte triangles
                     int triPtr = ~nodePtr;
                     bool end = false, hit = false;
                     const float tmaxLeaf = ANY ? tMax : hitT;
-                    while (!end && !(ANY && hit)) {
-                        const float4* T = tris + 3 * size_t(triPtr);
-                        const float4 a = __ldg(T), b = __ldg(T + 1), c = __ldg(T + 2);
-                        end = a.w > 0.0f;
+                    float leafTransparency = transparency;
+                    while (!end && !(ANY && !OPACITY && hit)) {
+                        float4 a, b, c;
+                        float triOpacity = 1.0f;
+                        if (OPACITY) {
+                            const float4* T = tris + 6 * size_t(triPtr);
+                            a = __ldg(T); b = __ldg(T + 1); c = __ldg(T + 2);
+                            const float4 d1 = __ldg(T + 4), d2 = __ldg(T + 5);
+                            end = d1.z > 0.0f;
+                            triOpacity = d2.w < 0.0f ? 1.0f : d2.w;   // textured opacity is outside this path
+                        } else {
+                            const float4* T = tris + 3 * size_t(triPtr);
+                            a = __ldg(T); b = __ldg(T + 1); c = __ldg(T + 2);
+                            end = a.w > 0.0f;
+                        }
                         if (COUNT) cTri++;
                         float sol[3];
                         const bool inside = tri_test(o, d, a, b, c, sol);
                         if (inside && sol[0] > tMin && sol[0] < tmaxLeaf) {
-                            if (ANY || sol[0] < hitT) {
+                            if (OPACITY && ANY) {
+                                hitT = sol[0];
+                                hitID = triPtr;
+                                hitInst = curInst;
+                                leafTransparency = __fmul_rn(leafTransparency, __fsub_rn(1.0f, triOpacity));
+                            } else if (ANY || (sol[0] < hitT && (!OPACITY || triOpacity > 0.0f))) {
                                 hitT = sol[0];
                                 hitID = triPtr;
                                 hitInst = curInst;
@@ -272,6 +292,11 @@ trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restr
                             }
                         }
                         triPtr++;
+                    }
+                    if (ANY && OPACITY) {   // bvh.hsh:489-492: transparency *= CheckLeafTransparency(..., transparency)
+                        transparency = __fmul_rn(transparency, leafTransparency);
+                        if (transparency < 0.000001f) transparency = 0.0f;
+                        hit = !(transparency > 0.0f);
                     }
                     if (ANY && hit) finish(); else pop();
                 }
@@ -459,10 +484,10 @@ int scene_fast_flag(atlas_rt_context* ctx, atlas_rt_scene* scene, const uint32_t
 }
 
 int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float4* dIn, float4* dOut, uint64_t count,
-                 uint32_t cullMask, float tMin, float tMax, bool any, bool perRayTMax, bool counters, bool resetCounters) {
+                 uint32_t cullMask, float tMin, float tMax, bool any, bool perRayTMax, bool counters, bool resetCounters, bool opacity) {
     if (count == 0) return ATLAS_RT_OK;
     if (count > 0x7fffffffull) return fail(ctx, ATLAS_RT_ERR_UNSUPPORTED, "more than 2^31-1 rays in one batch");
-    SceneDev sc{scene->tlas->nodes, scene->instances, scene->blasNodes, scene->bvhTris};
+    SceneDev sc{scene->tlas->nodes, scene->instances, scene->blasNodes, scene->bvhTris, scene->triangles};
     const uint32_t n = uint32_t(count);
     // small batches get fewer persistent warps so that each still refills its lanes many times (>= traceRaysPerWarp rays per warp)
     const uint32_t wantBlocks = std::max<uint32_t>(uint32_t(ctx->smCount) * 2u, n / (uint32_t(ctx->traceRaysPerWarp) * (kTraceBlock / 32)));
@@ -490,13 +515,16 @@ int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float
         ATLAS_LAUNCH_CHECK(ctx);
     }
     const int pr = perRayTMax ? 1 : 0, sf = scene->fastDivision;
-    if (any) {
-        if (counters) trace_kernel<true, true><<<grid, kTraceBlock, 0, ctx->stream>>>(sc, dIn, dOut, perm, n, cullMask, tMin, tMax, pr, sf, lt, rt, rayCounter, ctx->dCounters);
-        else trace_kernel<true, false><<<grid, kTraceBlock, 0, ctx->stream>>>(sc, dIn, dOut, perm, n, cullMask, tMin, tMax, pr, sf, lt, rt, rayCounter, ctx->dCounters);
+#define ATLAS_TRACE_LAUNCH(A, C, O) \
+    trace_kernel<A, C, O><<<grid, kTraceBlock, 0, ctx->stream>>>(sc, dIn, dOut, perm, n, cullMask, tMin, tMax, pr, sf, lt, rt, rayCounter, ctx->dCounters)
+    if (opacity) {
+        if (any) { if (counters) ATLAS_TRACE_LAUNCH(true, true, true); else ATLAS_TRACE_LAUNCH(true, false, true); }
+        else { if (counters) ATLAS_TRACE_LAUNCH(false, true, true); else ATLAS_TRACE_LAUNCH(false, false, true); }
     } else {
-        if (counters) trace_kernel<false, true><<<grid, kTraceBlock, 0, ctx->stream>>>(sc, dIn, dOut, perm, n, cullMask, tMin, tMax, pr, sf, lt, rt, rayCounter, ctx->dCounters);
-        else trace_kernel<false, false><<<grid, kTraceBlock, 0, ctx->stream>>>(sc, dIn, dOut, perm, n, cullMask, tMin, tMax, pr, sf, lt, rt, rayCounter, ctx->dCounters);
+        if (any) { if (counters) ATLAS_TRACE_LAUNCH(true, true, false); else ATLAS_TRACE_LAUNCH(true, false, false); }
+        else { if (counters) ATLAS_TRACE_LAUNCH(false, true, false); else ATLAS_TRACE_LAUNCH(false, false, false); }
     }
+#undef ATLAS_TRACE_LAUNCH
     dev_free(ctx, perm);
     dev_free(ctx, bucketOf);
     dev_free(ctx, hist);

@@ -59,6 +59,7 @@ struct mat3x4 {   // 3 columns of vec4, as glm::mat3x4 / the std430 `mat3x4 inve
 enum InstanceCullMasks { MaskAll = 1 << 7, MaskShadow = 1 << 6 };   // RTStructures.h:9-12
 
 struct GPUAABB { vec3 min; vec3 max; };
+struct GPUTriangle { vec4 v0; vec4 v1; vec4 v2; vec4 d0; vec4 d1; vec4 d2; };   // RTStructures.h:14-21
 struct GPUBVHTriangle { vec4 v0; vec4 v1; vec4 v2; };
 struct GPUBVHInstance {
     mat3x4 inverseMatrix;
@@ -77,7 +78,7 @@ struct GPUBVHNode {
 };
 struct PackedRay { vec4 origin; vec4 direction; vec4 hit; };   // data/shader/raytracer/structures.hsh:9-13
 
-static_assert(sizeof(GPUBVHTriangle) == 48 && sizeof(GPUBVHInstance) == 64 && sizeof(GPUBVHNode) == 64 && sizeof(PackedRay) == 48, "GPU layouts");
+static_assert(sizeof(GPUTriangle) == 96 && sizeof(GPUBVHTriangle) == 48 && sizeof(GPUBVHInstance) == 64 && sizeof(GPUBVHNode) == 64 && sizeof(PackedRay) == 48, "GPU layouts");
 
 namespace RayTracing {
 
@@ -226,6 +227,7 @@ namespace RayTracing {
 // and mesh are kept (handles) so the scene can be traced without re-uploading; gpuBvhTriangles / gpuBvhNodes are the
 // host copies Mesh::BuildBVH would upload (mesh/Mesh.cpp:97-108).
 struct MeshBVH {
+    std::vector<GPUTriangle> gpuTriangles;        // filled by PackShadingTriangles
     std::vector<GPUBVHTriangle> gpuBvhTriangles;
     std::vector<GPUBVHNode> gpuBvhNodes;
     atlas_rt_bvh* blas = nullptr;
@@ -268,6 +270,32 @@ inline bool BuildMeshBVH(const std::vector<vec3>& vertices, const std::vector<ui
         out.gpuBvhNodes.resize(nodes);
         out.gpuBvhTriangles.resize(refs);
         if (!detail::Check(atlas_rt_mesh_download(out.mesh, out.gpuBvhNodes.data(), out.gpuBvhTriangles.data(), 0))) return false;
+    }
+    return true;
+}
+
+// The GPUTriangle half of MeshData::BuildBVH (mesh/MeshData.cpp:176-239): `packed` holds, per SOURCE triangle, the 11
+// words the engine already computes there (pn0, pn1, pn2, puv0, puv1, puv2, pt, pbt, pc0, pc1, pc2); they are gathered
+// into flattened order next to the vertices, material index, endOfNode flag and opacity. Needed by the opacity-aware
+// traversal (ATLAS_RT_OPACITY) and by the engine's hit shaders.
+inline bool PackShadingTriangles(MeshBVH& mesh, const std::vector<vec3>& vertices, const std::vector<uint32_t>& indices,
+                                 const std::vector<int32_t>& materialIdx, const std::vector<float>& opacity,
+                                 const std::vector<uint32_t>& packed, bool keepHostCopy = true) {
+    atlas_rt_context* ctx = detail::Context();
+    if (!ctx || !mesh.mesh) return false;
+    const size_t n = indices.size() / 3;
+    if (materialIdx.size() != n || opacity.size() != n || (!packed.empty() && packed.size() != 11 * n)) return false;
+    std::vector<float> tris(n * 9);
+    for (size_t k = 0; k < n; k++)
+        for (int v = 0; v < 3; v++)
+            for (int c = 0; c < 3; c++) tris[9 * k + 3 * v + c] = vertices[indices[3 * k + v]][c];
+    if (!detail::Check(atlas_rt_mesh_pack_shading(ctx, mesh.mesh, tris.data(), n, materialIdx.data(), opacity.data(),
+                                                  packed.empty() ? nullptr : packed.data(), 0))) return false;
+    if (keepHostCopy) {
+        uint64_t nodes = 0, refs = 0;
+        atlas_rt_mesh_counts(mesh.mesh, &nodes, &refs);
+        mesh.gpuTriangles.resize(refs);
+        return detail::Check(atlas_rt_mesh_download_shading(mesh.mesh, mesh.gpuTriangles.data(), 0));
     }
     return true;
 }

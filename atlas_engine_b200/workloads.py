@@ -264,3 +264,24 @@ def pack_bvh_triangles(tris, order, end_of_node, material_idx=0, opacity=1.0):
     out[:, 8:11] = t[:, 6:9]
     out[:, 11] = np.float32(opacity)
     return out
+
+
+def pack_shading_triangles(tris, order, end_of_node, material_idx=None, opacity=None, payload11=None):
+    """GPUTriangle rows (24 float32) as MeshData.cpp:230-239 lays them out; payload11 = the engine's packed shading
+    words per SOURCE triangle (n0,n1,n2,uv0,uv1,uv2,t,bt,c0,c1,c2), moved verbatim. numpy mirror of the CUDA pack."""
+    order = np.asarray(order, dtype=np.int64)
+    t = np.asarray(tris, dtype=np.float32).reshape(-1, 9)[order]
+    n = t.shape[0]
+    p = np.zeros((n, 11), dtype=np.uint32) if payload11 is None else np.asarray(payload11, dtype=np.uint32)[order]
+    mat = np.zeros(n, dtype=np.int32) if material_idx is None else np.asarray(material_idx, dtype=np.int32)[order]
+    op = np.ones(n, dtype=np.float32) if opacity is None else np.asarray(opacity, dtype=np.float32)[order]
+    out = np.zeros((n, 24), dtype=np.uint32)
+    tv = t.view(np.uint32)
+    out[:, 0:3], out[:, 3] = tv[:, 0:3], p[:, 0]
+    out[:, 4:7], out[:, 7] = tv[:, 3:6], p[:, 1]
+    out[:, 8:11], out[:, 11] = tv[:, 6:9], p[:, 2]
+    out[:, 12:15], out[:, 15] = p[:, 3:6], mat.view(np.uint32)
+    out[:, 16:18] = p[:, 6:8]
+    out[:, 18] = np.where(np.asarray(end_of_node) != 0, np.float32(1.0), np.float32(-1.0)).astype(np.float32).view(np.uint32)
+    out[:, 20:23], out[:, 23] = p[:, 8:11], op.view(np.uint32)
+    return out.view(np.float32)

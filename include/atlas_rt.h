@@ -58,6 +58,7 @@ typedef enum atlas_rt_status {
 #define ATLAS_RT_DEVICE_OUTPUT (1u << 1)   /* output pointers are device memory */
 #define ATLAS_RT_ASYNC         (1u << 2)   /* do not synchronise the stream before returning */
 #define ATLAS_RT_PER_RAY_TMAX  (1u << 3)   /* trace_any: take tMax from each ray's hit.x instead of the argument */
+#define ATLAS_RT_OPACITY       (1u << 5)   /* trace_*: the *Transparency variants over the 96-byte triangles (needs atlas_rt_mesh_pack_shading) */
 #define ATLAS_RT_COUNTERS      (1u << 4)   /* trace_*: also count visited nodes / triangles (slower; for parity + roofline) */
 
 /* Instance cull masks — InstanceCullMasks, src/engine/raytracing/RTStructures.h:9-12; common.hsh:14-15. */
@@ -129,6 +130,17 @@ void atlas_rt_bvh_free(atlas_rt_bvh* bvh);
  * source order) or NULL for 0 / 1.0f. */
 int atlas_rt_pack_mesh(atlas_rt_context* ctx, const atlas_rt_bvh* blas, const float* tris, uint64_t count,
                        const int32_t* material_idx, const float* opacity, uint32_t flags, atlas_rt_mesh** out_mesh);
+/* Adds the 96-byte GPUTriangle array ("triangles[]", RTStructures.h:14-21) that the opacity-aware traversal variants
+ * and the hit shaders read — the other half of mesh/MeshData.cpp:172-239. Per flattened slot i (source triangle
+ * k = order[i]): v0 = (tris[k].v0, p[0]), v1 = (.., p[1]), v2 = (.., p[2]), d0 = (p[3], p[4], p[5], bits(material_idx[k])),
+ * d1 = (p[6], p[7], endOfNode ? 1 : -1, 0), d2 = (p[8], p[9], p[10], opacity[k]) where p = payload11 + 11*k are the
+ * engine's already packed shading words (normals 10-10-10-2, uv half2, tangent, bitangent, colours unorm8 — produced by
+ * Common::Packing / glm on the engine side exactly as today; they are opaque to this library). payload11 may be NULL
+ * (zeros). opacity < 0 marks a textured-opacity triangle (MeshData.cpp:136). */
+int atlas_rt_mesh_pack_shading(atlas_rt_context* ctx, atlas_rt_mesh* mesh, const float* tris, uint64_t count,
+                               const int32_t* material_idx, const float* opacity, const uint32_t* payload11, uint32_t flags);
+/* Copy out the GPUTriangle array (96 B each). */
+int atlas_rt_mesh_download_shading(const atlas_rt_mesh* mesh, void* gpu_triangles96, uint32_t flags);
 int atlas_rt_mesh_counts(const atlas_rt_mesh* mesh, uint64_t* node_count, uint64_t* triangle_count);
 /* Copy out gpuBvhNodes (64 B each) and gpuBvhTriangles (48 B each); either may be NULL. */
 int atlas_rt_mesh_download(const atlas_rt_mesh* mesh, void* gpu_nodes64, void* gpu_bvh_triangles48, uint32_t flags);
@@ -155,7 +167,16 @@ int atlas_rt_trace_closest(atlas_rt_context* ctx, const atlas_rt_scene* scene, c
                            uint32_t cull_mask, float t_min, float t_max, void* rays_out, uint32_t flags);
 
 /* Any hit (shadow rays). HitAny, bvh.hsh:359-441, as called inline by the reference's hit shaders
- * (data/shader/pathtracer/rayHit.csh:327-337). Output hitID >= 0 iff something was hit in (tMin, tMax). */
+ * (data/shader/pathtracer/rayHit.csh:327-337). Output hitID >= 0 iff something was hit in (tMin, tMax).
+ *
+ * With ATLAS_RT_OPACITY both calls run the shader's *Transparency variants over the 96-byte triangles instead
+ * (what the path tracer actually dispatches: traceClosest.csh with OPACITY_CHECK, rayHit.csh:331):
+ *   closest  HitClosestTransparency, bvh.hsh:275-357: a triangle is only accepted if its opacity is > 0;
+ *   any      HitAnyTransparency, bvh.hsh:443-524: walks on until the accumulated transparency reaches 0; the returned
+ *            transparency is written to direction.w, and t / hitID / instanceID hold the LAST triangle intersected
+ *            (exactly what the shader leaves in the ray), including the shader's `transparency *= leaf(transparency)` form.
+ * Triangles with textured opacity (opacity < 0) would need the material and texture tables (GetOpacity,
+ * surface.hsh:147-160), which are shading inputs outside this path: they count as opacity 1. */
 int atlas_rt_trace_any(atlas_rt_context* ctx, const atlas_rt_scene* scene, const void* rays_in, uint64_t count,
                        uint32_t cull_mask, float t_min, float t_max, void* rays_out, uint32_t flags);
 

@@ -471,6 +471,7 @@ struct SceneView {
     const float* instances;          // 16 words per instance (GPUBVHInstance, RTStructures.h:85-93)
     const float* const* blasNodes;   // per mesh: 16 floats per node
     const float* const* bvhTris;     // per mesh: 12 floats per triangle (GPUBVHTriangle, RTStructures.h:23-27)
+    const float* const* triangles;   // per mesh: 24 floats per triangle (GPUTriangle, RTStructures.h:14-21); only for the *Transparency variants
 };
 
 struct Counters {
@@ -482,6 +483,7 @@ struct RayState {
     float hitDistance;
     int32_t hitID, hitInstanceID, currentInstanceID;
     float baryU, baryV;
+    float transparency;
 };
 
 // IntersectAABB with distance — intersections.hsh:19-34 (divides by the direction, no reciprocal).
@@ -518,8 +520,11 @@ constexpr uint32_t kStackLimit = 32;                 // STACK_SIZE, bvh.hsh:16
 constexpr uint32_t kTlasInvalid = kStackLimit + 2;   // TLAS_INVALID, bvh.hsh:17
 constexpr uint32_t kOracleStack = 4096;              // the oracle never overflows; it reports depth > 32 instead
 
-// HitClosest (bvh.hsh:191-273) when ANY == false, HitAny (bvh.hsh:359-441) when ANY == true.
-template <bool ANY>
+// HitClosest (bvh.hsh:191-273) when ANY == false, HitAny (bvh.hsh:359-441) when ANY == true. With OPACITY the
+// *Transparency variants (bvh.hsh:275-357, :443-524) with CheckLeafClosestTransparency (:106-135) / CheckLeafTransparency
+// (:137-170): they read the 96-byte triangles[] array and consult tri.opacity. Textured opacity (tri.opacity < 0 ->
+// GetOpacity, surface.hsh:147-160) needs the material/texture tables, which are outside this path: it counts as 1.0.
+template <bool ANY, bool OPACITY = false>
 bool traverse(const SceneView& sc, RayState& ray, uint32_t cullMask, float tMin, float tMax, Counters& ct) {
     if (std::isnan(ray.d[0]) || std::isnan(ray.d[1]) || std::isnan(ray.d[2])) {
         if (!ANY) ray.hitDistance = tMax;
@@ -535,7 +540,8 @@ bool traverse(const SceneView& sc, RayState& ray, uint32_t cullMask, float tMin,
     bool hit = false;
     uint64_t localMax = 1;
     // In the closest-hit loop the slab interval is [tMin, ray.hitDistance]; in the any-hit loop [tMin, tMax].
-    while (sp != 0u && !(ANY && hit)) {
+    if (ANY && OPACITY) ray.transparency = 1.0f;
+    while (sp != 0u && !(ANY && !OPACITY && hit) && !(ANY && OPACITY && !(ray.transparency > 0.0f))) {
         const bool inTlas = sp < tlasIndex;
         if (inTlas) {
             // HitClosest restores unconditionally (bvh.hsh:218-220); HitAny only when leaving a BLAS (:387-390) —
@@ -566,18 +572,30 @@ bool traverse(const SceneView& sc, RayState& ray, uint32_t cullMask, float tMin,
             continue;
         }
         if (!inTlas && nodePtr < 0) {
-            // CheckLeafClosest (bvh.hsh:44-72) / CheckLeaf (:74-104).
+            // CheckLeafClosest (bvh.hsh:44-72) / CheckLeaf (:74-104) / the two *Transparency leaf loops.
             int32_t triPtr = ~nodePtr;
             bool end = false;
             const float tmaxLeaf = ANY ? tMax : ray.hitDistance;   // captured at call time (by-value parameter)
-            while (!end && !(ANY && hit)) {
-                const float* T = sc.bvhTris[meshPtr] + 12 * size_t(triPtr);
-                end = T[3] > 0.0f;
+            float leafTransparency = ray.transparency;              // CheckLeafTransparency's by-value parameter
+            while (!end && !(ANY && !OPACITY && hit)) {
+                const float* T = OPACITY ? sc.triangles[meshPtr] + 24 * size_t(triPtr) : sc.bvhTris[meshPtr] + 12 * size_t(triPtr);
+                end = OPACITY ? (T[18] > 0.0f) : (T[3] > 0.0f);     // d1.z / v0.w
                 float sol[3];
                 ct.triangles++;
                 const bool in = tri_test(ray, T, T + 4, T + 8, sol);
                 if (in && sol[0] > tMin && sol[0] < tmaxLeaf) {
-                    if (ANY || sol[0] < ray.hitDistance) {
+                    if (OPACITY) {
+                        const float triOpacity = T[23] < 0.0f ? 1.0f : T[23];   // d2.w
+                        if (!ANY) {
+                            if (sol[0] < ray.hitDistance && triOpacity > 0.0f) {
+                                ray.hitDistance = sol[0]; ray.hitID = triPtr; ray.hitInstanceID = ray.currentInstanceID;
+                                ray.baryU = sol[1]; ray.baryV = sol[2];
+                            }
+                        } else {
+                            ray.hitDistance = sol[0]; ray.hitID = triPtr; ray.hitInstanceID = ray.currentInstanceID;
+                            leafTransparency *= (1.0f - triOpacity);
+                        }
+                    } else if (ANY || sol[0] < ray.hitDistance) {
                         ray.hitDistance = sol[0];
                         ray.hitID = triPtr;
                         ray.hitInstanceID = ray.currentInstanceID;
@@ -587,6 +605,10 @@ bool traverse(const SceneView& sc, RayState& ray, uint32_t cullMask, float tMin,
                     }
                 }
                 triPtr++;
+            }
+            if (ANY && OPACITY) {   // bvh.hsh:489-492: transparency *= CheckLeafTransparency(..., transparency)
+                ray.transparency *= leafTransparency;
+                if (ray.transparency < 0.000001f) ray.transparency = 0.0f;
             }
             nodePtr = stack[--sp];
             continue;
@@ -715,8 +737,9 @@ void oracle_tree_free(void* h) { delete static_cast<OracleTree*>(h); }
 // counters (6 x u64): tlasNodes, instances, blasNodes, triangles, maxStack, raysWithStack>32.
 void oracle_trace(const float* tlasNodes, const float* instances, const float* const* blasNodes,
                   const float* const* bvhTris, const float* rays, uint64_t n, uint32_t cullMask, float tMin,
-                  float tMax, int any, int perRayTMax, float* out, uint64_t* counters, int nthreads) {
-    SceneView sc{tlasNodes, instances, blasNodes, bvhTris};
+                  float tMax, int any, int perRayTMax, float* out, uint64_t* counters, int nthreads,
+                  const float* const* triangles96, int opacity) {
+    SceneView sc{tlasNodes, instances, blasNodes, bvhTris, triangles96};
     std::vector<Counters> perThread(size_t(std::max(nthreads, 1)));
     parallel_for(n, nthreads, [&](uint64_t b, uint64_t e, int tid) {
         Counters& ct = perThread[size_t(tid)];
@@ -732,18 +755,21 @@ void oracle_trace(const float* tlasNodes, const float* instances, const float* c
             r.hitID = -1;
             r.hitDistance = 0.0f;
             r.baryU = r.baryV = 0.0f;
+            r.transparency = 1.0f;
             if (id >= 0) {
                 if (any) {
                     const float tm = perRayTMax ? in[8] : tMax;
                     r.hitDistance = tm;   // HitAny does not reset hitDistance; report tMax on a miss
-                    traverse<true>(sc, r, cullMask, tMin, tm, ct);
+                    if (opacity) traverse<true, true>(sc, r, cullMask, tMin, tm, ct);
+                    else traverse<true>(sc, r, cullMask, tMin, tm, ct);
                 } else {
-                    traverse<false>(sc, r, cullMask, tMin, tMax, ct);
+                    if (opacity) traverse<false, true>(sc, r, cullMask, tMin, tMax, ct);
+                    else traverse<false>(sc, r, cullMask, tMin, tMax, ct);
                 }
             }
             for (int a = 0; a < 3; a++) { o[a] = r.o[a]; o[4 + a] = r.d[a]; }
             std::memcpy(o + 3, &id, 4);
-            o[7] = r.baryU;
+            o[7] = (any && opacity) ? r.transparency : r.baryU;   // HitAnyTransparency's return value travels in direction.w
             o[8] = r.hitDistance;
             std::memcpy(o + 9, &r.hitID, 4);
             std::memcpy(o + 10, &r.hitInstanceID, 4);

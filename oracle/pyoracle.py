@@ -142,7 +142,7 @@ COUNTER_NAMES = ("tlas_nodes", "instances", "blas_nodes", "triangles", "max_stac
 class Scene:
     """Host-side flattened scene in the GPU layouts, as the traversal restatement consumes it."""
 
-    def __init__(self, tlas_nodes, instances, blas_nodes, bvh_tris):
+    def __init__(self, tlas_nodes, instances, blas_nodes, bvh_tris, triangles96=None):
         self.tlas_nodes = _f32c(tlas_nodes).reshape(-1, 16)
         self.instances = np.ascontiguousarray(instances).view(np.float32).reshape(-1, 16)
         self.blas_nodes = [_f32c(b).reshape(-1, 16) for b in blas_nodes]
@@ -151,6 +151,8 @@ class Scene:
         self._node_ptrs = (C.c_void_p * m)(*[b.ctypes.data for b in self.blas_nodes])
         self._tri_ptrs = (C.c_void_p * m)(*[t.ctypes.data for t in self.bvh_tris])
         self.tri_counts = np.array([t.shape[0] for t in self.bvh_tris], dtype=np.uint32)
+        self.triangles96 = None if triangles96 is None else [_f32c(t).reshape(-1, 24) for t in triangles96]
+        self._tri96_ptrs = None if triangles96 is None else (C.c_void_p * m)(*[t.ctypes.data for t in self.triangles96])
 
 
 class Oracle:
@@ -171,7 +173,7 @@ class Oracle:
         L.oracle_tree_copy_order.argtypes = [_vp, _vp, _vp]
         L.oracle_tree_stats.argtypes = [_vp, _vp]
         L.oracle_tree_free.argtypes = [_vp]
-        L.oracle_trace.argtypes = [_vp, _vp, _vp, _vp, _vp, _u64, _u32, _f32, _f32, C.c_int, C.c_int, _vp, _vp, C.c_int]
+        L.oracle_trace.argtypes = [_vp, _vp, _vp, _vp, _vp, _u64, _u32, _f32, _f32, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, C.c_int]
         L.oracle_brute_force.argtypes = [_vp, _u32, _vp, _vp, _vp, _u64, _u32, _f32, _f32, _vp, _vp, _vp, C.c_int]
 
     def _collect(self, h):
@@ -195,14 +197,14 @@ class Oracle:
         return self._collect(self.lib.oracle_build_tlas(_ptr(aabbs), aabbs.shape[0]))
 
     def trace(self, scene, rays, cull_mask=1 << 7, t_min=0.0, t_max=1e12, any_hit=False, per_ray_tmax=False,
-              nthreads=1):
+              nthreads=1, opacity=False):
         """rays (n, 12) float32 PackedRay. Returns (out rays (n, 12), counters dict)."""
         rays = _f32c(rays).reshape(-1, 12)
         out = np.zeros_like(rays)
         ct = np.zeros(6, dtype=np.uint64)
         self.lib.oracle_trace(_ptr(scene.tlas_nodes), _ptr(scene.instances), scene._node_ptrs, scene._tri_ptrs,
                               _ptr(rays), rays.shape[0], cull_mask, t_min, t_max, int(any_hit), int(per_ray_tmax),
-                              _ptr(out), _ptr(ct), nthreads)
+                              _ptr(out), _ptr(ct), nthreads, scene._tri96_ptrs if opacity else None, int(opacity))
         return out, dict(zip(COUNTER_NAMES, (int(x) for x in ct)))
 
     def brute_force(self, scene, rays, cull_mask=1 << 7, t_min=0.0, t_max=1e12, nthreads=1):
