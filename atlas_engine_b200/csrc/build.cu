@@ -1240,6 +1240,170 @@ __device__ inline void build_tiny_node(const SubNode nd, const SmallTask& task, 
     }
 }
 
+__device__ __forceinline__ OBox obox_of_ref(const float4& l, const float4& h) {
+    OBox b;
+    b.lo[0] = ord_from_float(l.x); b.lo[1] = ord_from_float(l.y); b.lo[2] = ord_from_float(l.z);
+    b.hi[0] = ord_from_float(h.x); b.hi[1] = ord_from_float(h.y); b.hi[2] = ord_from_float(h.z);
+    return b;
+}
+
+// A group of G lanes (a warp, or a half warp for nodes with at most 16 refs) builds one node of a subtree: Build #2
+// (BVH.cpp:343-406) = FindObjectSplit else PerformMedianSplit, then the flattened node record and the stable partition.
+// The three axes are binned and swept one after the other in the group's single-axis bin array.
+template <int G>
+__device__ inline void build_group_node(const SubNode nd, const SmallTask& task, uint32_t depth, uint32_t budget, float4* cLo, float4* cHi,
+                                        float4* __restrict__ nLo, float4* __restrict__ nHi, float4* nodes, uint32_t* __restrict__ order,
+                                        uint8_t* __restrict__ eon, SubNode* nextList, uint32_t* sNext, unsigned long long* sStats,
+                                        int* bins /*[32][8]*/, int* sfx /*[32][6]*/) {
+    const LaneGroup<G> g;
+    const uint32_t lane = g.lane;
+    const uint32_t n = nd.count, s = nd.start;
+    const uint32_t nb = bins_at_depth(budget, depth);   // <= kSubtreeBins by construction
+    // ---- node box: the subtree root's comes with the task, any other from its parent's flattened record
+    float blo[3], bhi[3];
+    if (nd.boxRef == 0xffffffffu) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { blo[k] = task.lo[k]; bhi[k] = task.hi[k]; }
+    } else {
+        const volatile float4* P = nodes + 4 * size_t(nd.boxRef >> 1);
+        float4 n0, n1, n2;
+        n0.x = P[0].x; n0.y = P[0].y; n0.z = P[0].z; n0.w = P[0].w;
+        n1.x = P[1].x; n1.y = P[1].y; n1.z = P[1].z; n1.w = P[1].w;
+        n2.x = P[2].x; n2.y = P[2].y; n2.z = P[2].z; n2.w = P[2].w;
+        if (nd.boxRef & 1u) { blo[0] = n1.z; blo[1] = n1.w; blo[2] = n2.x; bhi[0] = n2.y; bhi[1] = n2.z; bhi[2] = n2.w; }
+        else { blo[0] = n0.x; blo[1] = n0.y; blo[2] = n0.z; bhi[0] = n0.w; bhi[1] = n1.x; bhi[2] = n1.y; }
+    }
+    AxisBins ab[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) ab[a] = axis_bins(blo[a], bhi[a], nb);
+    // ---- FindObjectSplit, one axis at a time
+    BestSplit best = best_none();
+    OBox objL = obox_empty(), objR = obox_empty();
+    uint32_t objLeft = 0;
+#pragma unroll 1
+    for (int a = 0; a < 3; a++) {
+        if (!ab[a].active) continue;
+        for (uint32_t e = lane; e < nb; e += G) bin_init(bins + e * kBinWords);
+        g.sync();
+        for (uint32_t i = lane; i < n; i += G) {
+            const float4 l = cLo[s + i], h = cHi[s + i];
+            const uint32_t b = bin_of(bin_centre(comp(l, a), comp(h, a)), ab[a].start, ab[a].inv, nb);
+            int* rec = bins + b * kBinWords;
+            atomicMin(rec + 0, ord_from_float(l.x)); atomicMin(rec + 1, ord_from_float(l.y)); atomicMin(rec + 2, ord_from_float(l.z));
+            atomicMax(rec + 3, ord_from_float(h.x)); atomicMax(rec + 4, ord_from_float(h.y)); atomicMax(rec + 5, ord_from_float(h.z));
+            atomicAdd(rec + 6, 1);
+            atomicAdd(rec + 7, 1);
+        }
+        g.sync();
+        if (group_sweep_axis<G, true>(g, bins, nb, sfx, n, a, best)) {
+            // this axis holds the best split so far: its boxes are the prefix stored at bins[j-1] and the suffix sfx[j]
+            g.sync();
+            const int* pl = bins + (best.bin - 1u) * kBinWords;
+            const int* pr = sfx + best.bin * 6;
+#pragma unroll
+            for (int w = 0; w < 3; w++) { objL.lo[w] = pl[w]; objL.hi[w] = pl[3 + w]; objR.lo[w] = pr[w]; objR.hi[w] = pr[3 + w]; }
+            objLeft = uint32_t(pl[6]);
+        }
+        g.sync();
+    }
+    const float nodeCost = __fmul_rn(__uint2float_rn(n), surface_area(blo, bhi));
+    // mode: 0 = object split on (axis, bin), 1 = median cutoff, 2 = sorted, split by position
+    int mode, axis = 0;
+    uint32_t splitBin = 0, nLeft = 0;
+    float cutoff = 0.0f;
+    OBox L = obox_empty(), R = obox_empty();
+    if (!(best.axis < 0 || best.cost >= nodeCost)) {
+        mode = 0;
+        axis = best.axis;
+        splitBin = best.bin;
+        L = objL;
+        R = objR;
+        nLeft = objLeft;
+    } else {
+        mode = 1;
+        median_plane(blo, bhi, axis, cutoff);
+        uint32_t cnt = 0;
+        for (uint32_t i = lane; i < n; i += G) {
+            const float4 l = cLo[s + i], h = cHi[s + i];
+            if (median_centre(comp(l, axis), comp(h, axis)) < cutoff) { obox_grow(L, obox_of_ref(l, h)); cnt++; } else obox_grow(R, obox_of_ref(l, h));
+        }
+        g.reduce(L);
+        g.reduce(R);
+        nLeft = g.radd(cnt);
+    }
+    if (mode == 1) {
+        if (lane == 0) atomicAdd(&sStats[0], 1ull);
+        if (nLeft == 0u || nLeft == n) {
+            mode = 2;
+            if (lane == 0) {
+                atomicAdd(&sStats[1], 1ull);
+                atomicMax(&sStats[2], (unsigned long long)n);
+                std_sort_refs(RefArray{cLo + s, cHi + s, axis}, int(n));
+            }
+            g.sync();
+            nLeft = n / 2u;
+            L = obox_empty();
+            R = obox_empty();
+            for (uint32_t i = lane; i < n; i += G) {
+                const OBox b = obox_of_ref(cLo[s + i], cHi[s + i]);
+                if (i < nLeft) obox_grow(L, b); else obox_grow(R, b);
+            }
+            g.reduce(L);
+            g.reduce(R);
+        }
+    }
+    // ---- Flatten bookkeeping: larger-area child first
+    const Box3 lb = obox_to_box(L), rb = obox_to_box(R);
+    const bool swapped = surface_area(lb) < surface_area(rb);
+    const uint32_t nFirst = swapped ? n - nLeft : nLeft, nSecond = n - nFirst;
+    const uint32_t slot = task.start + s;
+    if (lane == 0) {
+        const Box3& f = swapped ? rb : lb;
+        const Box3& h2 = swapped ? lb : rb;
+        const int32_t ptr1 = nFirst > 1u ? int32_t(nd.flatIdx + 1u) : ~int32_t(slot);
+        const int32_t ptr2 = nSecond > 1u ? int32_t(nd.flatIdx + nFirst) : ~int32_t(slot + nFirst);
+        float4* N = nodes + 4 * size_t(nd.flatIdx);
+        N[0] = make_float4(f.lo[0], f.lo[1], f.lo[2], f.hi[0]);
+        N[1] = make_float4(f.hi[1], f.hi[2], h2.lo[0], h2.lo[1]);
+        N[2] = make_float4(h2.lo[2], h2.hi[0], h2.hi[1], h2.hi[2]);
+        N[3] = make_float4(__int_as_float(ptr1), __int_as_float(ptr2), 0.0f, 0.0f);
+        if (nFirst > 1u) nextList[atomicAdd(sNext, 1u)] = SubNode{uint16_t(s), uint16_t(nFirst), nd.flatIdx + 1u, nd.flatIdx << 1};
+        if (nSecond > 1u) nextList[atomicAdd(sNext, 1u)] = SubNode{uint16_t(s + nFirst), uint16_t(nSecond), nd.flatIdx + nFirst, (nd.flatIdx << 1) | 1u};
+    }
+    // ---- stable partition into the other buffer (or straight to the final slot for one-ref children)
+    uint32_t doneFirst = 0, doneSecond = 0;
+    for (uint32_t b = 0; b < n; b += G) {
+        const uint32_t i = b + lane;
+        const bool valid = i < n;
+        float4 l = make_float4(0, 0, 0, 0), h = l;
+        bool first = false;
+        if (valid) {
+            l = cLo[s + i];
+            h = cHi[s + i];
+            bool isLeft;
+            if (mode == 0) isLeft = bin_of(bin_centre(comp(l, axis), comp(h, axis)), ab[axis].start, ab[axis].inv, nb) < splitBin;
+            else if (mode == 1) isLeft = median_centre(comp(l, axis), comp(h, axis)) < cutoff;
+            else isLeft = i < nLeft;
+            first = isLeft != swapped;
+        }
+        const unsigned bf = g.ballot(valid && first);
+        const unsigned bs = g.ballot(valid && !first);
+        if (valid) {
+            const unsigned lt = (1u << lane) - 1u;
+            const uint32_t dst = first ? doneFirst + __popc(bf & lt) : nFirst + doneSecond + __popc(bs & lt);
+            if ((first ? nFirst : nSecond) == 1u) {
+                order[slot + dst] = __float_as_uint(l.w);
+                eon[slot + dst] = 1;
+            } else {
+                nLo[s + dst] = l;
+                nHi[s + dst] = h;
+            }
+        }
+        doneFirst += __popc(bf);
+        doneSecond += __popc(bs);
+    }
+}
+
 __global__ void __launch_bounds__(kSubBlock)
 build_subtrees(const SmallTask* __restrict__ small, uint32_t nSmall, float4* const lo0, float4* const hi0, float4* const lo1,
                float4* const hi1, float4* nodes, uint32_t* __restrict__ order, uint8_t* __restrict__ eon,
@@ -1248,9 +1412,11 @@ build_subtrees(const SmallTask* __restrict__ small, uint32_t nSmall, float4* con
     float4* sLo = reinterpret_cast<float4*>(smemRaw);                      // [2][kSubtreeMax]
     float4* sHi = sLo + 2 * kSubtreeMax;                                   // [2][kSubtreeMax]
     SubNode* lists = reinterpret_cast<SubNode*>(sHi + 2 * kSubtreeMax);    // [2][kSubtreeMax / 2]
-    int* wBins = reinterpret_cast<int*>(lists + kSubtreeMax);              // [warps][3][32][8]
-    int* wSfx = wBins + kSubWarps * 3 * kSubtreeBins * kBinWords;          // [warps][32][6]
+    int* wBins = reinterpret_cast<int*>(lists + kSubtreeMax);              // [warps][2 half-warp groups][32][8]
+    int* wSfx = wBins + kSubWarps * 2 * kSubtreeBins * kBinWords;          // [warps][2][32][6]
+    uint16_t* clsIdx = reinterpret_cast<uint16_t*>(wSfx + kSubWarps * 2 * kSubtreeBins * 6);   // [3][kSubtreeMax / 2]
     __shared__ uint32_t sNext;
+    __shared__ uint32_t sCls[3];               // nodes of the level by size class: <= kTinyMax, <= 16, larger
     __shared__ unsigned long long sStats[3];   // median splits, sort fallbacks, largest fallback
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -1267,14 +1433,17 @@ build_subtrees(const SmallTask* __restrict__ small, uint32_t nSmall, float4* con
         sStats[0] = sStats[1] = sStats[2] = 0;
     }
     uint32_t nCur = 1, cur = 0, level = 0;
-    int* bins = wBins + warp * 3 * kSubtreeBins * kBinWords;
-    int* sfx = wSfx + warp * kSubtreeBins * 6;
+    const uint32_t half = lane >> 4;
+    int* binsW = wBins + (warp * 2) * kSubtreeBins * kBinWords;   // the warp's first group area (a whole-warp group uses it alone)
+    int* sfxW = wSfx + (warp * 2) * kSubtreeBins * 6;
+    int* binsH = binsW + half * kSubtreeBins * kBinWords;         // this lane's half-warp group area
+    int* sfxH = sfxW + half * kSubtreeBins * 6;
     __syncthreads();
 
     while (nCur > 0) {
         const uint32_t depth = task.depth + level;
-        const uint32_t nb = bins_at_depth(budget, depth);   // <= kSubtreeBins by construction
         if (tid == 0) sNext = 0;
+        if (tid < 3) sCls[tid] = 0;
         __syncthreads();
         const SubNode* curList = lists + (level & 1u) * (kSubtreeMax / 2);
         SubNode* nextList = lists + ((level + 1u) & 1u) * (kSubtreeMax / 2);
@@ -1283,164 +1452,26 @@ build_subtrees(const SmallTask* __restrict__ small, uint32_t nSmall, float4* con
         float4* nLo = sLo + (cur ^ 1u) * kSubtreeMax;
         float4* nHi = sHi + (cur ^ 1u) * kSubtreeMax;
 
-        // tiny nodes: one lane each
+        // sort the level's nodes into size classes so that lanes / half warps / warps each get a dense run of work
         for (uint32_t ni = tid; ni < nCur; ni += kSubBlock) {
-            const SubNode nd = curList[ni];
-            if (nd.count <= kTinyMax)
-                build_tiny_node(nd, task, depth, budget, cLo, cHi, nLo, nHi, nodes, order, eon, nextList, &sNext, sStats);
+            const uint32_t c = curList[ni].count;
+            const uint32_t k = c <= kTinyMax ? 0u : (c <= 16u ? 1u : 2u);
+            clsIdx[k * (kSubtreeMax / 2) + atomicAdd(&sCls[k], 1u)] = uint16_t(ni);
         }
-        // everything else: one warp per node
-        for (uint32_t ni = warp; ni < nCur; ni += kSubWarps) {
-            const SubNode nd = curList[ni];
-            const uint32_t n = nd.count, s = nd.start;
-            if (n <= kTinyMax) continue;
-            // ---- node box: the subtree root's comes with the task, any other from its parent's flattened record
-            float blo[3], bhi[3];
-            if (nd.boxRef == 0xffffffffu) {
-#pragma unroll
-                for (int k = 0; k < 3; k++) { blo[k] = task.lo[k]; bhi[k] = task.hi[k]; }
-            } else {
-                const volatile float4* P = nodes + 4 * size_t(nd.boxRef >> 1);
-                float4 n0, n1, n2;
-                n0.x = P[0].x; n0.y = P[0].y; n0.z = P[0].z; n0.w = P[0].w;
-                n1.x = P[1].x; n1.y = P[1].y; n1.z = P[1].z; n1.w = P[1].w;
-                n2.x = P[2].x; n2.y = P[2].y; n2.z = P[2].z; n2.w = P[2].w;
-                if (nd.boxRef & 1u) { blo[0] = n1.z; blo[1] = n1.w; blo[2] = n2.x; bhi[0] = n2.y; bhi[1] = n2.z; bhi[2] = n2.w; }
-                else { blo[0] = n0.x; blo[1] = n0.y; blo[2] = n0.z; bhi[0] = n0.w; bhi[1] = n1.x; bhi[2] = n1.y; }
-            }
-            AxisBins ab[3];
-#pragma unroll
-            for (int a = 0; a < 3; a++) ab[a] = axis_bins(blo[a], bhi[a], nb);
-            // ---- FindObjectSplit
-            for (uint32_t e = lane; e < 3 * nb; e += 32u) bin_init(bins + e * kBinWords);
-            __syncwarp();
-            for (uint32_t i = lane; i < n; i += 32u) {
-                const float4 l = cLo[s + i], h = cHi[s + i];
-                const int ol[3] = {ord_from_float(l.x), ord_from_float(l.y), ord_from_float(l.z)};
-                const int oh[3] = {ord_from_float(h.x), ord_from_float(h.y), ord_from_float(h.z)};
-#pragma unroll
-                for (int a = 0; a < 3; a++) {
-                    if (!ab[a].active) continue;
-                    const uint32_t b = bin_of(bin_centre(comp(l, a), comp(h, a)), ab[a].start, ab[a].inv, nb);
-                    int* rec = bins + (a * nb + b) * kBinWords;
-#pragma unroll
-                    for (int k = 0; k < 3; k++) { atomicMin(rec + k, ol[k]); atomicMax(rec + 3 + k, oh[k]); }
-                    atomicAdd(rec + 6, 1);
-                    atomicAdd(rec + 7, 1);
-                }
-            }
-            __syncwarp();
-            BestSplit best = best_none();
-            for (int a = 0; a < 3; a++) {
-                if (!ab[a].active) continue;
-                warp_sweep_axis(bins + a * nb * kBinWords, nb, sfx, n, a, best);
-            }
-            const float nodeCost = __fmul_rn(__uint2float_rn(n), surface_area(blo, bhi));
-            // mode: 0 = object split on (axis, bin), 1 = median cutoff, 2 = sorted, split by position
-            int mode, axis = 0;
-            uint32_t splitBin = 0, nLeft = 0;
-            float cutoff = 0.0f;
-            OBox L = obox_empty(), R = obox_empty();
-            if (!(best.axis < 0 || best.cost >= nodeCost)) {
-                mode = 0;
-                axis = best.axis;
-                splitBin = best.bin;
-                uint32_t nExit;
-                warp_split_boxes(bins + axis * nb * kBinWords, nb, splitBin, L, R, nLeft, nExit);
-            } else {
-                mode = 1;
-                median_plane(blo, bhi, axis, cutoff);
-                uint32_t cnt = 0;
-                for (uint32_t i = lane; i < n; i += 32u) {
-                    const float4 l = cLo[s + i], h = cHi[s + i];
-                    OBox b;
-                    b.lo[0] = ord_from_float(l.x); b.lo[1] = ord_from_float(l.y); b.lo[2] = ord_from_float(l.z);
-                    b.hi[0] = ord_from_float(h.x); b.hi[1] = ord_from_float(h.y); b.hi[2] = ord_from_float(h.z);
-                    if (median_centre(comp(l, axis), comp(h, axis)) < cutoff) { obox_grow(L, b); cnt++; } else obox_grow(R, b);
-                }
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    L.lo[k] = __reduce_min_sync(kFullMask, L.lo[k]); L.hi[k] = __reduce_max_sync(kFullMask, L.hi[k]);
-                    R.lo[k] = __reduce_min_sync(kFullMask, R.lo[k]); R.hi[k] = __reduce_max_sync(kFullMask, R.hi[k]);
-                }
-                nLeft = __reduce_add_sync(kFullMask, cnt);
-                if (lane == 0) atomicAdd(&sStats[0], 1ull);
-                if (nLeft == 0u || nLeft == n) {
-                    mode = 2;
-                    if (lane == 0) {
-                        atomicAdd(&sStats[1], 1ull);
-                        atomicMax(&sStats[2], (unsigned long long)n);
-                        std_sort_refs(RefArray{cLo + s, cHi + s, axis}, int(n));
-                    }
-                    __syncwarp();
-                    nLeft = n / 2u;
-                    L = obox_empty();
-                    R = obox_empty();
-                    for (uint32_t i = lane; i < n; i += 32u) {
-                        const float4 l = cLo[s + i], h = cHi[s + i];
-                        OBox b;
-                        b.lo[0] = ord_from_float(l.x); b.lo[1] = ord_from_float(l.y); b.lo[2] = ord_from_float(l.z);
-                        b.hi[0] = ord_from_float(h.x); b.hi[1] = ord_from_float(h.y); b.hi[2] = ord_from_float(h.z);
-                        if (i < nLeft) obox_grow(L, b); else obox_grow(R, b);
-                    }
-#pragma unroll
-                    for (int k = 0; k < 3; k++) {
-                        L.lo[k] = __reduce_min_sync(kFullMask, L.lo[k]); L.hi[k] = __reduce_max_sync(kFullMask, L.hi[k]);
-                        R.lo[k] = __reduce_min_sync(kFullMask, R.lo[k]); R.hi[k] = __reduce_max_sync(kFullMask, R.hi[k]);
-                    }
-                }
-            }
-            // ---- Flatten bookkeeping: larger-area child first
-            const Box3 lb = obox_to_box(L), rb = obox_to_box(R);
-            const bool swapped = surface_area(lb) < surface_area(rb);
-            const uint32_t nFirst = swapped ? n - nLeft : nLeft, nSecond = n - nFirst;
-            const uint32_t slot = task.start + s;
-            if (lane == 0) {
-                const Box3& f = swapped ? rb : lb;
-                const Box3& g = swapped ? lb : rb;
-                const int32_t ptr1 = nFirst > 1u ? int32_t(nd.flatIdx + 1u) : ~int32_t(slot);
-                const int32_t ptr2 = nSecond > 1u ? int32_t(nd.flatIdx + nFirst) : ~int32_t(slot + nFirst);
-                float4* N = nodes + 4 * size_t(nd.flatIdx);
-                N[0] = make_float4(f.lo[0], f.lo[1], f.lo[2], f.hi[0]);
-                N[1] = make_float4(f.hi[1], f.hi[2], g.lo[0], g.lo[1]);
-                N[2] = make_float4(g.lo[2], g.hi[0], g.hi[1], g.hi[2]);
-                N[3] = make_float4(__int_as_float(ptr1), __int_as_float(ptr2), 0.0f, 0.0f);
-                if (nFirst > 1u) nextList[atomicAdd(&sNext, 1u)] = SubNode{uint16_t(s), uint16_t(nFirst), nd.flatIdx + 1u, nd.flatIdx << 1};
-                if (nSecond > 1u) nextList[atomicAdd(&sNext, 1u)] = SubNode{uint16_t(s + nFirst), uint16_t(nSecond), nd.flatIdx + nFirst, (nd.flatIdx << 1) | 1u};
-            }
-            // ---- stable partition into the other buffer (or straight to the final slot for one-ref children)
-            uint32_t doneFirst = 0, doneSecond = 0;
-            for (uint32_t b = 0; b < n; b += 32u) {
-                const uint32_t i = b + lane;
-                const bool valid = i < n;
-                float4 l = make_float4(0, 0, 0, 0), h = l;
-                bool first = false;
-                if (valid) {
-                    l = cLo[s + i];
-                    h = cHi[s + i];
-                    bool isLeft;
-                    if (mode == 0) isLeft = bin_of(bin_centre(comp(l, axis), comp(h, axis)), ab[axis].start, ab[axis].inv, nb) < splitBin;
-                    else if (mode == 1) isLeft = median_centre(comp(l, axis), comp(h, axis)) < cutoff;
-                    else isLeft = i < nLeft;
-                    first = isLeft != swapped;
-                }
-                const unsigned bf = __ballot_sync(kFullMask, valid && first);
-                const unsigned bs = __ballot_sync(kFullMask, valid && !first);
-                if (valid) {
-                    const unsigned lt = (1u << lane) - 1u;
-                    const uint32_t dst = first ? doneFirst + __popc(bf & lt) : nFirst + doneSecond + __popc(bs & lt);
-                    if ((first ? nFirst : nSecond) == 1u) {
-                        order[slot + dst] = __float_as_uint(l.w);
-                        eon[slot + dst] = 1;
-                    } else {
-                        nLo[s + dst] = l;
-                        nHi[s + dst] = h;
-                    }
-                }
-                doneFirst += __popc(bf);
-                doneSecond += __popc(bs);
-            }
-        }
+        __syncthreads();
+        const uint32_t nTiny = sCls[0], nHalf = sCls[1], nWarp = sCls[2];
+        // tiny nodes: one lane each
+        for (uint32_t k = tid; k < nTiny; k += kSubBlock)
+            build_tiny_node(curList[clsIdx[k]], task, depth, budget, cLo, cHi, nLo, nHi, nodes, order, eon, nextList, &sNext, sStats);
+        // 5..16 refs: one half warp each
+        for (uint32_t k = warp * 2u + half; k < nHalf; k += kSubWarps * 2u)
+            build_group_node<16>(curList[clsIdx[(kSubtreeMax / 2) + k]], task, depth, budget, cLo, cHi, nLo, nHi, nodes, order, eon, nextList,
+                                 &sNext, sStats, binsH, sfxH);
+        __syncwarp();
+        // larger nodes: one warp each
+        for (uint32_t k = warp; k < nWarp; k += kSubWarps)
+            build_group_node<32>(curList[clsIdx[2 * (kSubtreeMax / 2) + k]], task, depth, budget, cLo, cHi, nLo, nHi, nodes, order, eon, nextList,
+                                 &sNext, sStats, binsW, sfxW);
         __syncthreads();
         nCur = sNext;
         cur ^= 1u;
@@ -1455,8 +1486,8 @@ build_subtrees(const SmallTask* __restrict__ small, uint32_t nSmall, float4* con
 }
 
 constexpr size_t kSubtreeSmem = size_t(4) * kSubtreeMax * sizeof(float4) + size_t(kSubtreeMax) * sizeof(SubNode) +
-                                size_t(kSubWarps) * 3 * kSubtreeBins * kBinWords * sizeof(int) +
-                                size_t(kSubWarps) * kSubtreeBins * 6 * sizeof(int);
+                                size_t(kSubWarps) * 2 * kSubtreeBins * kBinWords * sizeof(int) +
+                                size_t(kSubWarps) * 2 * kSubtreeBins * 6 * sizeof(int) + size_t(3) * (kSubtreeMax / 2) * sizeof(uint16_t);
 
 template <typename T>
 int read_back(atlas_rt_context* ctx, const T* dev, T* host) {

@@ -113,49 +113,101 @@ struct BestSplit {
 };
 __device__ __forceinline__ BestSplit best_none() { return BestSplit{kFltMax, -1, 0u}; }
 
-// Warp-cooperative SAH sweep over the bins of ONE axis (BVH.cpp:484-522 object, :621-661 spatial). `bins` = nb
+// A group of G consecutive lanes of a warp (G = 32: the whole warp, G = 16: a half warp) working on one node. All
+// cross-lane operations take the group's own member mask, so the two halves of a warp can build two different nodes
+// in the same instruction stream.
+template <int G>
+struct LaneGroup {
+    static constexpr unsigned kBits = (G == 32) ? 0xffffffffu : ((1u << (G & 31)) - 1u);
+    unsigned shift, mask, lane;
+    __device__ __forceinline__ LaneGroup() {
+        const unsigned l = threadIdx.x & 31u;
+        shift = l & ~(unsigned(G) - 1u);
+        mask = kBits << shift;
+        lane = l & (unsigned(G) - 1u);
+    }
+    __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(mask, p) >> shift) & kBits; }
+    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+    __device__ __forceinline__ int up(int v, int off) const { return __shfl_up_sync(mask, v, off, G); }
+    __device__ __forceinline__ unsigned up(unsigned v, int off) const { return __shfl_up_sync(mask, v, off, G); }
+    __device__ __forceinline__ int down(int v, int off) const { return __shfl_down_sync(mask, v, off, G); }
+    __device__ __forceinline__ int bcast(int v, int src) const { return __shfl_sync(mask, v, src, G); }
+    __device__ __forceinline__ unsigned bcast(unsigned v, int src) const { return __shfl_sync(mask, v, src, G); }
+    __device__ __forceinline__ float bxor(float v, int off) const { return __shfl_xor_sync(mask, v, off, G); }
+    __device__ __forceinline__ unsigned bxor(unsigned v, int off) const { return __shfl_xor_sync(mask, v, off, G); }
+    // Group reductions. The whole-warp group uses REDUX with the constant full mask; a half-warp group uses a shuffle
+    // butterfly, because REDUX with a run-time mask compiles to a MATCH.ANY loop and branching to two constant-mask
+    // REDUX instructions makes the two halves diverge (measured: slower than the butterfly).
+    __device__ __forceinline__ int rmin(int v) const {
+        if (G == 32) return __reduce_min_sync(0xffffffffu, v);
+#pragma unroll
+        for (int off = G / 2; off > 0; off >>= 1) v = min(v, __shfl_xor_sync(mask, v, off, G));
+        return v;
+    }
+    __device__ __forceinline__ int rmax(int v) const {
+        if (G == 32) return __reduce_max_sync(0xffffffffu, v);
+#pragma unroll
+        for (int off = G / 2; off > 0; off >>= 1) v = max(v, __shfl_xor_sync(mask, v, off, G));
+        return v;
+    }
+    __device__ __forceinline__ unsigned radd(unsigned v) const {
+        if (G == 32) return __reduce_add_sync(0xffffffffu, v);
+#pragma unroll
+        for (int off = G / 2; off > 0; off >>= 1) v += __shfl_xor_sync(mask, v, off, G);
+        return v;
+    }
+    __device__ __forceinline__ void reduce(OBox& b) const {
+#pragma unroll
+        for (int w = 0; w < 3; w++) { b.lo[w] = rmin(b.lo[w]); b.hi[w] = rmax(b.hi[w]); }
+    }
+};
+
+// Group-cooperative SAH sweep over the bins of ONE axis (BVH.cpp:484-522 object, :621-661 spatial). `bins` = nb
 // records of kBinWords ints in shared or global memory, `sfx` = scratch for nb suffix boxes (6 ints each) in the same
-// kind of memory, private to this warp. All 32 lanes must call; every lane returns the same updated `best`.
+// kind of memory, private to this group. All G lanes must call; every lane returns the same updated `best`.
 // Candidate j in [1, nb): left = bins[0..j-1], right = bins[j..nb-1], nLeft = sum enter[0..j-1],
 // nRight = total - sum exit[0..j-1]; skipped when either is 0; cost = SA(left)*float(nLeft) + SA(right)*float(nRight);
 // strictly smaller cost wins, i.e. the lowest (axis, j) among equal costs.
-__device__ inline void warp_sweep_axis(const int* bins, uint32_t nb, int* sfx, uint32_t total, int axis, BestSplit& best) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t chunks = (nb + 31u) / 32u;
+// With STORE_PREFIX the forward pass overwrites bins[k] with the prefix union / prefix enter count of bins[0..k], so that
+// the caller can read the winning split's boxes as bins[j-1] and sfx[j] without another pass. Returns true when this
+// axis improved `best`.
+template <int G, bool STORE_PREFIX, typename BinPtr>
+__device__ inline bool group_sweep_axis(const LaneGroup<G>& g, BinPtr bins, uint32_t nb, int* sfx, uint32_t total, int axis,
+                                        BestSplit& best) {
+    const uint32_t lane = g.lane;
+    const uint32_t chunks = (nb + G - 1u) / G;
     // ---- backward pass: sfx[k] = union of bins[k..nb-1]
     OBox carry = obox_empty();
     for (int c = int(chunks) - 1; c >= 0; c--) {
-        const uint32_t k = uint32_t(c) * 32u + lane;
+        const uint32_t k = uint32_t(c) * G + lane;
         OBox b = obox_empty();
         if (k < nb) {
 #pragma unroll
             for (int w = 0; w < 3; w++) { b.lo[w] = bins[k * kBinWords + w]; b.hi[w] = bins[k * kBinWords + 3 + w]; }
         }
 #pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
+        for (int off = 1; off < G; off <<= 1) {
             OBox o;
 #pragma unroll
-            for (int w = 0; w < 3; w++) {
-                o.lo[w] = __shfl_down_sync(kFullMask, b.lo[w], off);
-                o.hi[w] = __shfl_down_sync(kFullMask, b.hi[w], off);
-            }
-            if (lane + off < 32u) obox_grow(b, o);
+            for (int w = 0; w < 3; w++) { o.lo[w] = g.down(b.lo[w], off); o.hi[w] = g.down(b.hi[w], off); }
+            if (lane + off < uint32_t(G)) obox_grow(b, o);
         }
         obox_grow(b, carry);
         if (k < nb) {
 #pragma unroll
             for (int w = 0; w < 3; w++) { sfx[k * 6 + w] = b.lo[w]; sfx[k * 6 + 3 + w] = b.hi[w]; }
         }
-        carry = obox_shfl(b, 0);
+#pragma unroll
+        for (int w = 0; w < 3; w++) { carry.lo[w] = g.bcast(b.lo[w], 0); carry.hi[w] = g.bcast(b.hi[w], 0); }
     }
-    __syncwarp();
+    g.sync();
     // ---- forward pass
     OBox pcarry = obox_empty();
     uint32_t ecarry = 0, xcarry = 0;
     float myCost = kFltMax;
     uint32_t myBin = 0xffffffffu;
     for (uint32_t c = 0; c < chunks; c++) {
-        const uint32_t k = c * 32u + lane;
+        const uint32_t k = c * G + lane;
         OBox b = obox_empty();
         uint32_t en = 0, ex = 0;
         if (k < nb) {
@@ -165,19 +217,22 @@ __device__ inline void warp_sweep_axis(const int* bins, uint32_t nb, int* sfx, u
             ex = uint32_t(bins[k * kBinWords + 7]);
         }
 #pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
+        for (int off = 1; off < G; off <<= 1) {
             OBox o;
 #pragma unroll
-            for (int w = 0; w < 3; w++) {
-                o.lo[w] = __shfl_up_sync(kFullMask, b.lo[w], off);
-                o.hi[w] = __shfl_up_sync(kFullMask, b.hi[w], off);
-            }
-            const uint32_t oe = __shfl_up_sync(kFullMask, en, off), ox = __shfl_up_sync(kFullMask, ex, off);
+            for (int w = 0; w < 3; w++) { o.lo[w] = g.up(b.lo[w], off); o.hi[w] = g.up(b.hi[w], off); }
+            const uint32_t oe = g.up(en, off), ox = g.up(ex, off);
             if (lane >= uint32_t(off)) { obox_grow(b, o); en += oe; ex += ox; }
         }
         obox_grow(b, pcarry);
         en += ecarry;
         ex += xcarry;
+        if (STORE_PREFIX && k < nb) {
+            int* rec = const_cast<int*>(bins) + k * kBinWords;
+#pragma unroll
+            for (int w = 0; w < 3; w++) { rec[w] = b.lo[w]; rec[3 + w] = b.hi[w]; }
+            rec[6] = int(en);
+        }
         const uint32_t j = k + 1u;   // split after bin k
         if (j < nb) {
             const uint32_t nLeft = en, nRight = total - ex;
@@ -190,23 +245,31 @@ __device__ inline void warp_sweep_axis(const int* bins, uint32_t nb, int* sfx, u
                 if (cost < myCost) { myCost = cost; myBin = j; }   // ascending j within a lane: first wins ties
             }
         }
-        pcarry = obox_shfl(b, 31);
-        ecarry = __shfl_sync(kFullMask, en, 31);
-        xcarry = __shfl_sync(kFullMask, ex, 31);
-    }
-    __syncwarp();
-    // ---- warp arg-min on (cost, j); NaN costs never satisfy cost < x and so never win (as in the reference)
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const float oc = __shfl_xor_sync(kFullMask, myCost, off);
-        const uint32_t ob = __shfl_xor_sync(kFullMask, myBin, off);
+        for (int w = 0; w < 3; w++) { pcarry.lo[w] = g.bcast(b.lo[w], G - 1); pcarry.hi[w] = g.bcast(b.hi[w], G - 1); }
+        ecarry = g.bcast(en, G - 1);
+        xcarry = g.bcast(ex, G - 1);
+    }
+    g.sync();
+    // ---- group arg-min on (cost, j); NaN costs never satisfy cost < x and so never win (as in the reference)
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) {
+        const float oc = g.bxor(myCost, off);
+        const uint32_t ob = g.bxor(myBin, off);
         if (oc < myCost || (oc == myCost && ob < myBin)) { myCost = oc; myBin = ob; }
     }
     if (myBin != 0xffffffffu && myCost < best.cost) {
         best.cost = myCost;
         best.axis = axis;
         best.bin = myBin;
+        return true;
     }
+    return false;
+}
+
+__device__ inline void warp_sweep_axis(const int* bins, uint32_t nb, int* sfx, uint32_t total, int axis, BestSplit& best) {
+    const LaneGroup<32> g;
+    group_sweep_axis<32, false>(g, bins, nb, sfx, total, axis, best);
 }
 
 // leftAABB / rightAABB / primitivesLeft of the chosen split, recomputed from the bins of the winning axis.
