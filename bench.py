@@ -100,7 +100,7 @@ def make_inputs(rank):
     return tris, boxes, root, rays
 
 
-def reference_arm(args, rank):
+def reference_arm(args, rank, out):
     """The reference's own CPU implementation on the host cores: Atlas::Volume::BVH built by the unmodified
     src/engine/volume/BVH.cpp (oracle/_ref) and BVH::GetIntersection over it, rays split over all hardware threads."""
     if rank != 0:
@@ -152,10 +152,20 @@ def reference_arm(args, rank):
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: everything else any library prints to fd 1 (NCCL's version banner, make) is
+    sent to stderr. Returns a file object for the real stdout."""
+    real = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    return real
 
 
 def main():
+    real_stdout = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -170,7 +180,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        reference_arm(args, rank)
+        reference_arm(args, rank, real_stdout)
         return
 
     import torch
@@ -262,9 +272,10 @@ def main():
     clocks = clk.summary()
 
     # ---- end to end with HOST ray buffers (pinned): H2D + trace + (gather) + D2H inside the timed region.
-    # N == 1: one atlas_rt_trace_closest call with host pointers (the library stages and copies). N > 1: the same copies
-    # issued from torch around the device-pointer call so the all-gather can run on the device-resident hits.
-    h_gath = torch.empty((world * N_RAYS, 4), dtype=torch.float32).pin_memory() if world > 1 else None
+    # N == 1: one atlas_rt_trace_closest call with host pointers (the library stages, pipelines and copies). N > 1: the
+    # same copies issued from torch around the device-pointer call so the all-gather can run on the device-resident
+    # hits; every rank then reads back its own 16 B/ray share of the gathered hit records.
+    h_hits = torch.empty((N_RAYS, 4), dtype=torch.float32).pin_memory() if world > 1 else None
 
     def e2e_step():
         if world == 1:
@@ -273,7 +284,7 @@ def main():
             d_rays.copy_(h_rays, non_blocking=True)
             ctx.trace(scene, d_rays, N_RAYS, out=d_out, flags=capi.ASYNC)
             sharding.gather_hits(d_out, gathered)
-            h_gath.copy_(gathered, non_blocking=True)
+            h_hits.copy_(gathered[rank * N_RAYS:(rank + 1) * N_RAYS], non_blocking=True)   # this rank's share of the gathered hits
             stream.synchronize()
     for _ in range(args.warmup):
         e2e_step()
@@ -328,7 +339,7 @@ def main():
         "config": {"workload": WORKLOAD, "rays_per_gpu": N_RAYS, "triangles": N_TRIS, "bvh": "replicated per GPU",
                    "l2": "flushed between timed iterations (256 MiB memset)", "gather": "nccl all_gather of 16 B hit records" if world > 1 else "none"},
         "clocks": clocks,
-        "e2e": {"value": world * N_RAYS / e2e_ms / 1e3, "unit": "Mrays/s", "h2d_bytes_per_step": 48 * N_RAYS, "d2h_bytes_per_step": 48 * N_RAYS if world == 1 else 16 * N_RAYS * world,
+        "e2e": {"value": world * N_RAYS / e2e_ms / 1e3, "unit": "Mrays/s", "h2d_bytes_per_step": 48 * N_RAYS, "d2h_bytes_per_step": 48 * N_RAYS if world == 1 else 16 * N_RAYS,
                 "ms_per_step": e2e_ms},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "trace_kernel<closest>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -350,7 +361,7 @@ def main():
             line["build"]["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                                          "algorithmic_bytes": b_build, "traffic": None}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
