@@ -98,11 +98,6 @@ struct BuildBuffers {
     uint32_t cap;
 };
 
-__device__ __forceinline__ void load_box(const Task& t, float lo[3], float hi[3]) {
-#pragma unroll
-    for (int k = 0; k < 3; k++) { lo[k] = t.lo[k]; hi[k] = t.hi[k]; }
-}
-
 __device__ __forceinline__ float comp(const float4& v, int axis) { return axis == 0 ? v.x : (axis == 1 ? v.y : v.z); }
 
 // ------------------------------------------------------------------------------------------------ level 0 set-up

@@ -81,15 +81,6 @@ __device__ __forceinline__ void obox_grow(OBox& a, const OBox& b) {
         a.hi[k] = max(a.hi[k], b.hi[k]);
     }
 }
-__device__ __forceinline__ OBox obox_shfl(const OBox& b, int srcLane) {
-    OBox r;
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        r.lo[k] = __shfl_sync(kFullMask, b.lo[k], srcLane);
-        r.hi[k] = __shfl_sync(kFullMask, b.hi[k], srcLane);
-    }
-    return r;
-}
 __device__ __forceinline__ float obox_area(const OBox& b) {
     const float lo[3] = {float_from_ord(b.lo[0]), float_from_ord(b.lo[1]), float_from_ord(b.lo[2])};
     const float hi[3] = {float_from_ord(b.hi[0]), float_from_ord(b.hi[1]), float_from_ord(b.hi[2])};

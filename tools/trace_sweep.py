@@ -14,9 +14,9 @@ dev = torch.device("cuda", 0)
 stream = torch.cuda.Stream(device=dev); torch.cuda.set_stream(stream)
 d_rays = torch.from_numpy(rays).to(dev); d_out = torch.empty_like(d_rays)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-grid = [(8, 8, b, p) for b in (6, 7, 8, 9) for p in (0, 1, 2)]
+grid = [(8, 6, 9, 1), (8, 6, 9, 0), (4, 6, 9, 1), (12, 6, 9, 1), (8, 6, 8, 1)]
 for (l, r, b, p) in grid:
-    os.environ["ATLAS_RT_TRACE_LEAF_THRESHOLD"] = str(l); os.environ["ATLAS_RT_TRACE_REFILL_THRESHOLD"] = str(r); os.environ["ATLAS_RT_TRACE_BLOCKS_PER_SM"] = str(b); os.environ["ATLAS_RT_TRACE_PREFETCH"] = str(p)
+    os.environ["ATLAS_RT_TRACE_LEAF_THRESHOLD"] = str(l); os.environ["ATLAS_RT_TRACE_REFILL_THRESHOLD"] = str(r); os.environ["ATLAS_RT_TRACE_BLOCKS_PER_SM"] = str(b); os.environ["ATLAS_RT_TRACE_LONGEST_FIRST"] = str(p)
     ctx = capi.Context(0, stream.cuda_stream)
     blas = ctx.build_blas(boxes, tris); tlas = ctx.build_tlas(root); mesh = ctx.pack_mesh(blas, tris)
     scene = ctx.create_scene([mesh], W.identity_instance(), tlas)
@@ -26,6 +26,6 @@ for (l, r, b, p) in grid:
         a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream); ctx.trace(scene, d_rays, N, out=d_out, flags=capi.ASYNC); e.record(stream)
         torch.cuda.synchronize(); ts.append(a.elapsed_time(e))
-    print(f"leaf={l:2d} refill={r:2d} blocks={b} prefetch={p} ms={np.median(ts[2:]):.3f}", flush=True)
+    print(f"leaf={l:2d} refill={r:2d} blocks={b} longest_first={p} ms={np.median(ts[2:]):.3f}", flush=True)
     for o in (scene, mesh, tlas, blas): o.free()
     ctx.close()
