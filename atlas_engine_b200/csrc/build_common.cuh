@@ -130,22 +130,31 @@ struct LaneGroup {
     // butterfly, because REDUX with a run-time mask compiles to a MATCH.ANY loop and branching to two constant-mask
     // REDUX instructions makes the two halves diverge (measured: slower than the butterfly).
     __device__ __forceinline__ int rmin(int v) const {
-        if (G == 32) return __reduce_min_sync(0xffffffffu, v);
+        if constexpr (G == 32) {
+            return __reduce_min_sync(0xffffffffu, v);
+        } else {
 #pragma unroll
-        for (int off = G / 2; off > 0; off >>= 1) v = min(v, __shfl_xor_sync(mask, v, off, G));
-        return v;
+            for (int off = G / 2; off > 0; off >>= 1) v = min(v, __shfl_xor_sync(mask, v, off, G));
+            return v;
+        }
     }
     __device__ __forceinline__ int rmax(int v) const {
-        if (G == 32) return __reduce_max_sync(0xffffffffu, v);
+        if constexpr (G == 32) {
+            return __reduce_max_sync(0xffffffffu, v);
+        } else {
 #pragma unroll
-        for (int off = G / 2; off > 0; off >>= 1) v = max(v, __shfl_xor_sync(mask, v, off, G));
-        return v;
+            for (int off = G / 2; off > 0; off >>= 1) v = max(v, __shfl_xor_sync(mask, v, off, G));
+            return v;
+        }
     }
     __device__ __forceinline__ unsigned radd(unsigned v) const {
-        if (G == 32) return __reduce_add_sync(0xffffffffu, v);
+        if constexpr (G == 32) {
+            return __reduce_add_sync(0xffffffffu, v);
+        } else {
 #pragma unroll
-        for (int off = G / 2; off > 0; off >>= 1) v += __shfl_xor_sync(mask, v, off, G);
-        return v;
+            for (int off = G / 2; off > 0; off >>= 1) v += __shfl_xor_sync(mask, v, off, G);
+            return v;
+        }
     }
     __device__ __forceinline__ void reduce(OBox& b) const {
 #pragma unroll
