@@ -82,7 +82,7 @@ struct atlas_rt_context {
     cudaEvent_t pipeEvents[20] = {};
     // scheduling knobs of the persistent traversal kernel (trace.cu); ATLAS_RT_TRACE_* environment variables override
     int traceLeafThreshold = 8;     // lanes waiting at a leaf before the warp runs a leaf round
-    int traceRefillThreshold = 6;   // idle lanes before the warp fetches new rays
+    int traceRefillThreshold = 16;  // idle lanes before the warp fetches new rays (swept with the longest-first order: 16-20 is best)
     int traceBlocksPerSM = 9;
     int traceLongestFirst = 1;      // fetch rays longest-estimated-path first (hides the drain of the longest rays)
     int traceLongestFirstMin = 65536;
