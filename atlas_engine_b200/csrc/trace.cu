@@ -6,8 +6,9 @@
 // Visit order is part of the contract: ties in t are resolved by "first visited wins" (strict < in bvh.hsh:62-63), so
 // one ray's node/triangle sequence must never be reordered; parallelism is across rays only.
 //
-// Data movement: a node is 64 B = 4 x LDG.128 through the read-only path, a triangle 48 B = 3 x LDG.128, an instance
-// 64 B = 4 x LDG.128; rays are read and written once as 3 x 128-bit each. The per-ray stack (32 node pointers, the
+// Data movement: a node is 64 B = 2 x LDG.256 through the read-only path (sm_100's 256-bit loads halve the L1TEX
+// wavefronts per visit), an instance 64 B = 2 x LDG.256, a triangle 48 B = 3 x LDG.128 (96 B = 3 x LDG.256 for the
+// opacity-aware variants); rays are read and written once as 3 x 128-bit each. The per-ray stack (32 node pointers, the
 // reference's STACK_SIZE) lives in shared memory laid out [entry][lane] so a warp's accesses never bank-conflict.
 #include <algorithm>
 #include <cstring>
@@ -30,6 +31,19 @@ struct SceneDev {
     const float4* const* bvhTris;
     const float4* const* triangles;   // 96-byte GPUTriangle arrays (opacity-aware variants)
 };
+
+// 256-bit read-only load (sm_100: LDG.E.256). A 64-byte node or instance record is two of these instead of four
+// 128-bit loads, which halves the L1TEX wavefronts per visit — the unit the traversal saturates (profiles/: l1tex
+// throughput 90 % with 128-bit loads). p must be 32-byte aligned (nodes and instances are 64-byte records in
+// cudaMalloc'ed arrays).
+struct alignas(32) Float8 { float4 a, b; };
+__device__ __forceinline__ Float8 ldg256(const float4* p) {
+    Float8 r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w)
+                 : "l"(p));
+    return r;
+}
 
 // IntersectAABB (intersections.hsh:19-34): true division by the direction, GLSL min/max forms.
 __device__ __forceinline__ bool slab(const float o[3], const float d[3], const float lo[3], const float hi[3],
@@ -231,7 +245,8 @@ trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restr
                     // CheckInstance, bvh.hsh:172-189: vec4(o,1) * M and vec4(d,0) * M, no renormalisation.
                     const int inst = ~nodePtr;
                     const float4* I = sc.instances + 4 * size_t(inst);
-                    const float4 c0 = __ldg(I), c1 = __ldg(I + 1), c2 = __ldg(I + 2), c3 = __ldg(I + 3);
+                    const Float8 iA = ldg256(I), iB = ldg256(I + 2);
+                    const float4 c0 = iA.a, c1 = iA.b, c2 = iB.a, c3 = iB.b;
                     if (COUNT) cInst++;
                     float no[3], nd[3];
                     no[0] = __fadd_rn(dot3(o[0], o[1], o[2], c0.x, c0.y, c0.z), __fmul_rn(1.0f, c0.w));
@@ -263,9 +278,10 @@ trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restr
                         float4 a, b, c;
                         float triOpacity = 1.0f;
                         if (OPACITY) {
-                            const float4* T = tris + 6 * size_t(triPtr);
-                            a = __ldg(T); b = __ldg(T + 1); c = __ldg(T + 2);
-                            const float4 d1 = __ldg(T + 4), d2 = __ldg(T + 5);
+                            const float4* T = tris + 6 * size_t(triPtr);   // 96-byte records: three 256-bit loads
+                            const Float8 tA = ldg256(T), tB = ldg256(T + 2), tC = ldg256(T + 4);
+                            a = tA.a; b = tA.b; c = tB.a;
+                            const float4 d1 = tC.a, d2 = tC.b;
                             end = d1.z > 0.0f;
                             triOpacity = d2.w < 0.0f ? 1.0f : d2.w;   // textured opacity is outside this path
                         } else {
@@ -304,7 +320,8 @@ trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restr
         } else if (inner) {
             // inner node of the TLAS or of the current BLAS — UnpackNode, bvh.hsh:21-37
             const float4* N = nodes + 4 * size_t(nodePtr);
-            const float4 n0 = __ldg(N), n1 = __ldg(N + 1), n2 = __ldg(N + 2), n3 = __ldg(N + 3);
+            const Float8 nA = ldg256(N), nB = ldg256(N + 2);
+            const float4 n0 = nA.a, n1 = nA.b, n2 = nB.a, n3 = nB.b;
             if (COUNT) { if (sp < tlasIndex) cTlas++; else cBlas++; }
             const float llo[3] = {n0.x, n0.y, n0.z}, lhi[3] = {n0.w, n1.x, n1.y};
             const float rlo[3] = {n1.z, n1.w, n2.x}, rhi[3] = {n2.y, n2.z, n2.w};

@@ -14,7 +14,7 @@ dev = torch.device("cuda", 0)
 stream = torch.cuda.Stream(device=dev); torch.cuda.set_stream(stream)
 d_rays = torch.from_numpy(rays).to(dev); d_out = torch.empty_like(d_rays)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-grid = [(8, r, 9, 1) for r in (16, 20, 24, 28, 32)] + [(6, 24, 9, 1), (10, 24, 9, 1)]
+grid = [(8, 16, 9, 1), (8, 16, 9, 1), (8, 16, 8, 1)]
 for (l, r, b, p) in grid:
     os.environ["ATLAS_RT_TRACE_LEAF_THRESHOLD"] = str(l); os.environ["ATLAS_RT_TRACE_REFILL_THRESHOLD"] = str(r); os.environ["ATLAS_RT_TRACE_BLOCKS_PER_SM"] = str(b); os.environ["ATLAS_RT_TRACE_LONGEST_FIRST"] = str(p)
     ctx = capi.Context(0, stream.cuda_stream)
