@@ -169,8 +169,11 @@ int atlas_rt_context_create(int device, void* stream, atlas_rt_context** out_ctx
     }
     if (cudaMalloc(&ctx->dCounters, 8 * sizeof(unsigned long long)) != cudaSuccess) { delete ctx; return ATLAS_RT_ERR_OOM; }
     cudaMemset(ctx->dCounters, 0, 8 * sizeof(unsigned long long));
-    ctx->pinnedBytes = 4096;
+    ctx->pinnedBytes = 8192;
     if (cudaMallocHost(&ctx->pinned, ctx->pinnedBytes) != cudaSuccess) { cudaFree(ctx->dCounters); delete ctx; return ATLAS_RT_ERR_OOM; }
+    ctx->levelSlots = static_cast<char*>(ctx->pinned) + 4096;
+    for (auto& ev : ctx->levelEvents)
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { cudaFreeHost(ctx->pinned); cudaFree(ctx->dCounters); delete ctx; return ATLAS_RT_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&ctx->copyIn, cudaStreamNonBlocking) != cudaSuccess) ctx->copyIn = nullptr;
     if (cudaStreamCreateWithFlags(&ctx->copyOut, cudaStreamNonBlocking) != cudaSuccess) ctx->copyOut = nullptr;
     for (auto& ev : ctx->pipeEvents)
@@ -184,6 +187,7 @@ void atlas_rt_context_destroy(atlas_rt_context* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto& ev : ctx->pipeEvents) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->levelEvents) if (ev) cudaEventDestroy(ev);
     if (ctx->copyIn) cudaStreamDestroy(ctx->copyIn);
     if (ctx->copyOut) cudaStreamDestroy(ctx->copyOut);
     cudaFree(ctx->dCounters);

@@ -61,7 +61,7 @@ struct SmallTask {   // root of a shared-memory subtree (48 B)
 
 struct LevelInfo {   // device-resident, read back once per level
     uint32_t nTasks, nChunks, nNext, nSmall, nMedian, rootNeedSpatial, rootKind, rootLeaf;
-    uint32_t totalRefs, negZero, nStraddle, nL0, nR0, pad0, pad1, pad2;
+    uint32_t totalRefs, negZero, nStraddle, nL0, nR0, levels, overflow, pad2;
     unsigned long long stats[8];   // [2] duplicates [3] median splits [4] sort fallbacks [5] largest sort fallback
 };
 
@@ -175,13 +175,20 @@ __global__ void root_leaf_output(uint32_t n, uint32_t* __restrict__ order, uint8
 }
 
 // ---------------------------------------------------------------------------------------------- per-level set-up
-__global__ void prepare_level(Task* __restrict__ tasks, LevelInfo* __restrict__ info, uint32_t* __restrict__ chunkBase) {
-    // single CTA: exclusive scan of ceil(count / kChunk) over the level's tasks
+__global__ void prepare_level(Task* __restrict__ tasks, LevelInfo* __restrict__ info, uint32_t* __restrict__ chunkBase, int advance) {
+    // single CTA: the level's task count (the previous level's nNext when `advance`), then an exclusive scan of
+    // ceil(count / kChunk) over the level's tasks
     __shared__ uint32_t carry;
     __shared__ uint32_t warpSums[32];
-    const uint32_t n = info->nTasks;
-    if (threadIdx.x == 0) carry = 0;
+    __shared__ uint32_t sN;
+    if (threadIdx.x == 0) {
+        if (advance) info->nTasks = min(info->nNext, 0x7fffffffu);
+        sN = info->nTasks;
+        if (sN) info->levels++;
+        carry = 0;
+    }
     __syncthreads();
+    const uint32_t n = sN;
     for (uint32_t base = 0; base < n; base += blockDim.x) {
         const uint32_t i = base + threadIdx.x;
         const uint32_t v = i < n ? (tasks[i].count + kChunk - 1) / kChunk : 0u;
@@ -307,6 +314,7 @@ struct Lists {
     float4* nodes;
     uint32_t budget;
     uint32_t nextBuf;
+    uint32_t maxTasks, maxSmall;
 };
 
 __device__ __forceinline__ void enqueue_child(const Lists& L, const Box3& box, uint32_t start, uint32_t count,
@@ -314,6 +322,7 @@ __device__ __forceinline__ void enqueue_child(const Lists& L, const Box3& box, u
     if (count <= 1u) return;
     if (count <= kSubtreeMax && bins_at_depth(L.budget, depth) <= kSubtreeBins) {
         const uint32_t s = atomicAdd(&L.info->nSmall, 1u);
+        if (s >= L.maxSmall) { L.info->overflow = 1u; return; }
         SmallTask st;
 #pragma unroll
         for (int k = 0; k < 3; k++) { st.lo[k] = box.lo[k]; st.hi[k] = box.hi[k]; }
@@ -321,6 +330,7 @@ __device__ __forceinline__ void enqueue_child(const Lists& L, const Box3& box, u
         L.small[s] = st;
     } else {
         const uint32_t s = atomicAdd(&L.info->nNext, 1u);
+        if (s >= L.maxTasks) { L.info->overflow = 1u; return; }
         Task t;
 #pragma unroll
         for (int k = 0; k < 3; k++) { t.lo[k] = box.lo[k]; t.hi[k] = box.hi[k]; }
@@ -1593,26 +1603,45 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
     ATLAS_LAUNCHED(ctx);
 
     const uint32_t persistent = uint32_t(ctx->smCount) * 4u;
-    uint32_t nTasks = 1, cur = 0, levels = 0;
+    uint32_t cur = 0;
     LevelInfo info;
     memset(&info, 0, sizeof(info));
     bool rootLeaf = false;
     uint32_t totalRefs = n;
+    // The level loop is enqueued WITHOUT waiting for the device: grids are sized from upper bounds, the kernels read the
+    // real task / chunk counts from device memory and fall through when a level is empty. After each level the 128-byte
+    // level record is copied to a pinned slot; the host only looks at records that are kLookahead levels old (or already
+    // complete) to learn that the tree is finished, so host latency never stalls the GPU. Only the BLAS root, whose
+    // outcome decides which kernels run and what must be allocated, is read back synchronously.
+    constexpr uint32_t kLookahead = 3;
+    LevelInfo* slots = static_cast<LevelInfo*>(ctx->levelSlots);
 
-    for (uint32_t depth = 0; nTasks > 0; depth++, levels++) {
+    for (uint32_t depth = 0; depth < 100000u; depth++) {
+        if (depth > 0) {
+            bool finished = false;
+            const uint32_t oldest = depth > kLookahead ? depth - kLookahead - 1u : 0u;
+            for (uint32_t k = oldest; k < depth && !finished; k++) {
+                if (k == oldest && depth > kLookahead) ATLAS_CUDA_C(ctx, cudaEventSynchronize(ctx->levelEvents[k % 32u]));
+                else if (cudaEventQuery(ctx->levelEvents[k % 32u]) != cudaSuccess) break;
+                if (slots[k % 32u].nNext == 0u) finished = true;
+            }
+            (void)cudaGetLastError();   // cudaEventQuery's cudaErrorNotReady is not an error
+            if (finished) break;
+        }
         const uint32_t nb = bins_at_depth(B.budget, depth);
-        const uint32_t chunksBound = std::min<uint32_t>(totalRefs / kChunk + nTasks + 1u, maxChunks);
+        const uint32_t tasksBound = depth == 0 ? 1u : std::min<uint32_t>(depth < 31u ? (1u << depth) : maxTasks, maxTasks);
+        const uint32_t chunksBound = std::min<uint32_t>(totalRefs / kChunk + tasksBound + 1u, maxChunks);
         const uint32_t gridChunks = std::max(1u, std::min(chunksBound, persistent));
-        const uint32_t warpGrid = (nTasks * 32u + 127u) / 128u;
+        const uint32_t warpGrid = (tasksBound * 32u + 127u) / 128u;
         const size_t binSmem = size_t(3) * nb * kBinWords * sizeof(int);
         Task* tasks = B.tasks[cur];
-        Lists L{B.tasks[cur ^ 1u], B.small, B.info, B.nodes, B.budget, cur ^ 1u};
+        Lists L{B.tasks[cur ^ 1u], B.small, B.info, B.nodes, B.budget, cur ^ 1u, maxTasks, maxSmall};
         const float4 *rlo = B.lo[cur], *rhi = B.hi[cur];
         float4 *wlo = B.lo[cur ^ 1u], *whi = B.hi[cur ^ 1u];
 
-        prepare_level<<<1, 1024, 0, st>>>(tasks, B.info, B.chunkBase);
+        prepare_level<<<1, 1024, 0, st>>>(tasks, B.info, B.chunkBase, depth > 0 ? 1 : 0);
         ATLAS_LAUNCHED(ctx);
-        init_bins<<<std::max(1u, std::min<uint32_t>(persistent, (nTasks * 3u * nb + 255u) / 256u)), 256, 0, st>>>(B.bins, B.info, 3u * nb);
+        init_bins<<<std::max(1u, std::min<uint32_t>(persistent, (tasksBound * 3u * nb + 255u) / 256u)), 256, 0, st>>>(B.bins, B.info, 3u * nb);
         ATLAS_LAUNCHED(ctx);
         const uint32_t gridBin = std::max(1u, std::min(chunksBound, uint32_t(ctx->smCount) * 2u));
         bin_big<<<gridBin, kBigBlock, binSmem, st>>>(tasks, B.info, B.chunkBase, rlo, rhi, B.bins, nb);
@@ -1676,18 +1705,21 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
                                                                 B.eon, nb);
             ATLAS_LAUNCHED(ctx);
         }
-        ATLAS_TRY(read_back(ctx, B.info, &info));
-        totalRefs = info.totalRefs;
-        if (info.rootLeaf) { rootLeaf = true; break; }
-        if (info.nNext > maxTasks || info.nSmall > maxSmall) { cleanup(); return fail(ctx, ATLAS_RT_ERR_UNSUPPORTED, "task list overflow"); }
-        // next level
-        nTasks = info.nNext;
-        cur ^= 1u;
-        if (nTasks) {
-            // nTasks for the next level lives in info->nTasks
-            ATLAS_CUDA_C(ctx, cudaMemcpyAsync(&B.info->nTasks, &B.info->nNext, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        ATLAS_CUDA_C(ctx, cudaMemcpyAsync(&slots[depth % 32u], B.info, sizeof(LevelInfo), cudaMemcpyDeviceToHost, st));
+        ATLAS_CUDA_C(ctx, cudaEventRecord(ctx->levelEvents[depth % 32u], st));
+        if (depth == 0 && !tlas) {
+            // the root's outcome (spatial duplicates, a root that stayed a leaf) sizes everything that follows
+            ATLAS_CUDA_C(ctx, cudaEventSynchronize(ctx->levelEvents[0]));
+            info = slots[0];
+            totalRefs = info.totalRefs;
+            if (info.rootLeaf) { rootLeaf = true; break; }
         }
+        cur ^= 1u;
     }
+    ATLAS_TRY(read_back(ctx, B.info, &info));
+    if (info.overflow) { cleanup(); return fail(ctx, ATLAS_RT_ERR_UNSUPPORTED, "task list overflow"); }
+    totalRefs = info.totalRefs;
+    const uint32_t levels = info.levels;
 
     if (rootLeaf) {
         root_leaf_output<<<(n + 255) / 256, 256, 0, st>>>(n, B.order, B.eon);

@@ -80,6 +80,8 @@ struct atlas_rt_context {
     // copy engines used to overlap H2D / trace / D2H when a trace call is given host buffers (api.cu)
     cudaStream_t copyIn = nullptr, copyOut = nullptr;
     cudaEvent_t pipeEvents[20] = {};
+    cudaEvent_t levelEvents[32] = {};          // builder: one per in-flight level read-back (build.cu)
+    void* levelSlots = nullptr;                // pinned, 32 x 128 B level read-back slots
     // scheduling knobs of the persistent traversal kernel (trace.cu); ATLAS_RT_TRACE_* environment variables override
     int traceLeafThreshold = 8;     // lanes waiting at a leaf before the warp runs a leaf round
     int traceRefillThreshold = 16;  // idle lanes before the warp fetches new rays (swept with the longest-first order: 16-20 is best)

@@ -145,13 +145,16 @@ constexpr int kBlocksPerSM = 9;
 // exactly the reference's; only the interleaving between different rays changes.
 template <bool ANY, bool COUNT, bool OPACITY>
 __global__ void __launch_bounds__(kTraceBlock, kBlocksPerSM)
-trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restrict__ perm, uint32_t count, uint32_t cullMask, float tMin,
-             float tMaxArg,
+trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restrict__ permIn, const unsigned int* __restrict__ usePerm,
+             uint32_t count, uint32_t cullMask, float tMin, float tMaxArg,
              int perRayTMax, int sceneFast, int kLeafThreshold, int kRefillThreshold, unsigned int* __restrict__ rayCounter,
              unsigned long long* __restrict__ counters) {
     __shared__ int stack[kStack][kTraceBlock];
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     const unsigned ltMask = (1u << lane) - 1u;
+    const uint32_t* __restrict__ perm = (permIn && *usePerm) ? permIn : nullptr;
+    // batches kept in their own (coherent) order refill eagerly; reordered ones do better refilling half a warp at a time
+    if (!perm) kRefillThreshold = min(kRefillThreshold, 6);
 
     bool alive = false, fast = false, moreRays = true, overflow = false;
     uint32_t ray = 0, sp = 0, tlasIndex = kTlasInvalid;
@@ -407,27 +410,47 @@ __device__ __forceinline__ void scene_box(const float4* __restrict__ tlasNodes, 
 __global__ void __launch_bounds__(kSortBlock)
 ray_cost_histogram(const float4* __restrict__ rays, uint32_t count, const float4* __restrict__ tlasNodes, uint8_t* __restrict__ bucketOf,
                    unsigned int* __restrict__ hist) {
-    __shared__ unsigned int sh[kCostBuckets];
-    if (threadIdx.x < kCostBuckets) sh[threadIdx.x] = 0;
+    __shared__ unsigned int sh[kCostBuckets + 1];   // [kCostBuckets] = pairs of neighbouring rays that are coherent
+    if (threadIdx.x <= kCostBuckets) sh[threadIdx.x] = 0;
     __syncthreads();
     float lo[3], hi[3], invDiag;
     scene_box(tlasNodes, lo, hi, invDiag);
     const uint32_t base = blockIdx.x * (kSortBlock * kSortPerThread);
+    unsigned coherent = 0;
 #pragma unroll
     for (int k = 0; k < kSortPerThread; k++) {
         const uint32_t i = base + k * kSortBlock + threadIdx.x;
+        float4 r0 = make_float4(0, 0, 0, 0), r1 = r0;
         if (i < count) {
-            const uint32_t b = ray_cost_bucket(rays[3 * size_t(i)], rays[3 * size_t(i) + 1], lo, hi, invDiag);
+            r0 = rays[3 * size_t(i)];
+            r1 = rays[3 * size_t(i) + 1];
+            const uint32_t b = ray_cost_bucket(r0, r1, lo, hi, invDiag);
             bucketOf[i] = uint8_t(b);
             atomicAdd(&sh[b], 1u);
         }
+        // is the next ray in the buffer (the next lane) a near copy of this one? (same origin within 1 % of the scene
+        // diagonal, directions within ~18 degrees) — true for rayGen's pixel tiles, false for random or bounced rays
+        const float nox = __shfl_down_sync(kFull, r0.x, 1), noy = __shfl_down_sync(kFull, r0.y, 1), noz = __shfl_down_sync(kFull, r0.z, 1);
+        const float ndx = __shfl_down_sync(kFull, r1.x, 1), ndy = __shfl_down_sync(kFull, r1.y, 1), ndz = __shfl_down_sync(kFull, r1.z, 1);
+        if ((threadIdx.x & 31) != 31 && i + 1 < count) {
+            const float dx = nox - r0.x, dy = noy - r0.y, dz = noz - r0.z;
+            const float dd = r1.x * ndx + r1.y * ndy + r1.z * ndz;
+            const float l0 = r1.x * r1.x + r1.y * r1.y + r1.z * r1.z, l1 = ndx * ndx + ndy * ndy + ndz * ndz;
+            const bool near = (dx * dx + dy * dy + dz * dz) * invDiag * invDiag <= 1.0e-4f;
+            coherent += (near && dd > 0.0f && dd * dd >= 0.9f * l0 * l1) ? 1u : 0u;
+        }
     }
+    coherent = __reduce_add_sync(kFull, coherent);
+    if ((threadIdx.x & 31) == 0 && coherent) atomicAdd(&sh[kCostBuckets], coherent);
     __syncthreads();
-    if (threadIdx.x < kCostBuckets && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+    if (threadIdx.x <= kCostBuckets && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
 }
 
-__global__ void ray_cost_offsets(unsigned int* __restrict__ hist) {   // exclusive prefix over 64 buckets, in place (one warp)
+__global__ void ray_cost_offsets(unsigned int* __restrict__ hist, uint32_t count) {   // exclusive prefix over 64 buckets, in place (one warp)
     const unsigned lane = threadIdx.x;
+    // hist[kCostBuckets + 1] = 1 when the batch should be reordered: coherent batches (most neighbours are near copies)
+    // keep their own order, which is worth more than starting the long rays first
+    if (lane == 0) hist[kCostBuckets + 1] = (2ull * hist[kCostBuckets] < uint64_t(count) * 31ull / 32ull) ? 1u : 0u;
     const unsigned a = hist[lane], b = hist[32 + lane];
     unsigned sa = a, sb = b;
 #pragma unroll
@@ -443,6 +466,7 @@ __global__ void ray_cost_offsets(unsigned int* __restrict__ hist) {   // exclusi
 __global__ void __launch_bounds__(kSortBlock)
 ray_cost_scatter(const uint8_t* __restrict__ bucketOf, uint32_t count, unsigned int* __restrict__ offsets, uint32_t* __restrict__ perm) {
     __shared__ unsigned int cnt[kCostBuckets], base[kCostBuckets];
+    if (offsets[kCostBuckets + 1] == 0u) return;   // coherent batch: the trace kernel ignores the permutation
     if (threadIdx.x < kCostBuckets) cnt[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t first = blockIdx.x * (kSortBlock * kSortPerThread);
@@ -521,19 +545,19 @@ int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float
     if (ctx->traceLongestFirst && n >= uint32_t(ctx->traceLongestFirstMin) && scene->tlas->nodeCount > 0) {
         ATLAS_CUDA(ctx, dev_alloc(ctx, &perm, n));
         ATLAS_CUDA(ctx, dev_alloc(ctx, &bucketOf, n));
-        ATLAS_CUDA(ctx, dev_alloc(ctx, &hist, kCostBuckets));
-        ATLAS_CUDA(ctx, cudaMemsetAsync(hist, 0, kCostBuckets * sizeof(unsigned int), ctx->stream));
+        ATLAS_CUDA(ctx, dev_alloc(ctx, &hist, kCostBuckets + 2));
+        ATLAS_CUDA(ctx, cudaMemsetAsync(hist, 0, (kCostBuckets + 2) * sizeof(unsigned int), ctx->stream));
         const uint32_t sortGrid = (n + kSortBlock * kSortPerThread - 1) / (kSortBlock * kSortPerThread);
         ray_cost_histogram<<<sortGrid, kSortBlock, 0, ctx->stream>>>(dIn, n, scene->tlas->nodes, bucketOf, hist);
         ATLAS_LAUNCH_CHECK(ctx);
-        ray_cost_offsets<<<1, 32, 0, ctx->stream>>>(hist);
+        ray_cost_offsets<<<1, 32, 0, ctx->stream>>>(hist, n);
         ATLAS_LAUNCH_CHECK(ctx);
         ray_cost_scatter<<<sortGrid, kSortBlock, 0, ctx->stream>>>(bucketOf, n, hist, perm);
         ATLAS_LAUNCH_CHECK(ctx);
     }
     const int pr = perRayTMax ? 1 : 0, sf = scene->fastDivision;
 #define ATLAS_TRACE_LAUNCH(A, C, O) \
-    trace_kernel<A, C, O><<<grid, kTraceBlock, 0, ctx->stream>>>(sc, dIn, dOut, perm, n, cullMask, tMin, tMax, pr, sf, lt, rt, rayCounter, ctx->dCounters)
+    trace_kernel<A, C, O><<<grid, kTraceBlock, 0, ctx->stream>>>(sc, dIn, dOut, perm, hist ? hist + kCostBuckets + 1 : nullptr, n, cullMask, tMin, tMax, pr, sf, lt, rt, rayCounter, ctx->dCounters)
     if (opacity) {
         if (any) { if (counters) ATLAS_TRACE_LAUNCH(true, true, true); else ATLAS_TRACE_LAUNCH(true, false, true); }
         else { if (counters) ATLAS_TRACE_LAUNCH(false, true, true); else ATLAS_TRACE_LAUNCH(false, false, true); }
