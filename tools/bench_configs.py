@@ -105,6 +105,30 @@ if "C1" in which:
     rays = ctx.generate_primary_rays(eye, origin, right, bottom, 1920, 1080, 1)
     st, out = trace_stats(scene, rays)
     okb, okt = oracle_check(None, [tris], root[None], W.identity_instance(), rays, out, [blas])
+    # the RTAO caller (data/shader/ao/rtao.csh:97-100): short any-hit rays from every primary hit, cosine
+    # distributed around the geometric normal, tMax = radius
+    hit = out[:, 9].view(np.int32) >= 0
+    P = (out[:, 0:3] + out[:, 4:7] * out[:, 8:9])[hit]
+    order = blas.download()[1]
+    T = tris[order[out[hit, 9].view(np.int32)]].reshape(-1, 3, 3)
+    Ng = np.cross(T[:, 0] - T[:, 1], T[:, 0] - T[:, 2])
+    Ng /= np.maximum(np.linalg.norm(Ng, axis=1, keepdims=True), 1e-30)
+    Ng *= np.where((Ng * out[hit, 4:7]).sum(1, keepdims=True) > 0, -1.0, 1.0)
+    rng = np.random.default_rng(11)
+    ao = []
+    for s4 in range(4):
+        u0, u1 = rng.random(len(P)), rng.random(len(P))
+        r_, phi = np.sqrt(u0), 2 * np.pi * u1
+        up = np.where((np.abs(Ng[:, 2]) < 0.999)[:, None], [0.0, 0.0, 1.0], [1.0, 0.0, 0.0])
+        tg = np.cross(up, Ng); tg /= np.linalg.norm(tg, axis=1, keepdims=True)
+        bt = np.cross(Ng, tg)
+        d_ = tg * (r_ * np.cos(phi))[:, None] + bt * (r_ * np.sin(phi))[:, None] + Ng * np.sqrt(1 - u0)[:, None]
+        ao.append(W.pack_rays((P + Ng * 0.01).astype(np.float32), d_.astype(np.float32), t=np.full(len(P), 1.5, np.float32)))
+    ao = np.concatenate(ao)
+    st_ao, out_ao = trace_stats(scene, ao, any_hit=True, mask=capi.MASK_SHADOW, per_ray=True)
+    _, ok_ao = oracle_check(None, [tris], root[None], W.identity_instance(), ao, out_ao, [blas], any_hit=True, per_ray_tmax=True, cull_mask=capi.MASK_SHADOW)
+    emit("F1 RTAO-style caller on the C1 scene: 4 short any-hit rays (tMax 1.5) per primary hit", rays=len(ao), any=st_ao,
+         hits_equal_oracle_100k=ok_ao)
     emit("C1 atrium stand-in for sponza, 1920x1080 primaries", triangles=len(tris), refs=blas.counts()[1], build_ms=build_ms,
          build_mtris=len(tris) / build_ms / 1e3, stats=blas.stats(), closest=st, build_equals_oracle=okb, hits_equal_oracle_100k=okt)
 
