@@ -29,6 +29,7 @@ SIGNATURES = {
     "atlas_rt_build_blas": (_i32, [_vp, _vp, _vp, _u64, _u32, C.POINTER(_vp)]),
     "atlas_rt_build_tlas": (_i32, [_vp, _vp, _u64, _u32, C.POINTER(_vp)]),
     "atlas_rt_bvh_upload": (_i32, [_vp, _vp, _u64, _vp, _vp, _u64, C.POINTER(_vp)]),
+    "atlas_rt_bvh_import": (_i32, [_vp, _vp, _u64, _vp, _vp, _u64, _u32, C.POINTER(_vp)]),
     "atlas_rt_bvh_counts": (_i32, [_vp, C.POINTER(_u64), C.POINTER(_u64)]),
     "atlas_rt_bvh_download": (_i32, [_vp, _vp, _vp, _vp, _u32]),
     "atlas_rt_bvh_device_ptrs": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
@@ -159,6 +160,13 @@ class Context:
         self.check(self.L.atlas_rt_bvh_upload(self.h, _addr(nodes56), nodes56.shape[0], _addr(order), _addr(end_of_node), order.shape[0], C.byref(h)))
         return BVH(self, h)
 
+    def import_bvh_device(self, nodes56, order, end_of_node):
+        """Wrap a flattened tree whose arrays are CUDA tensors on this device (int32 (n,14), int32 (m,), uint8 (m,))."""
+        h = _vp()
+        self.check(self.L.atlas_rt_bvh_import(self.h, _addr(nodes56), nodes56.shape[0], _addr(order), _addr(end_of_node), order.shape[0],
+                                              DEVICE_INPUT, C.byref(h)))
+        return BVH(self, h)
+
     def pack_mesh(self, blas, tris, count=None, material_idx=None, opacity=None, flags=0):
         dev = _is_device(tris)
         if not dev:
@@ -237,6 +245,18 @@ class BVH:
         order = np.zeros(m, dtype=np.uint32)
         flags = np.zeros(m, dtype=np.uint8)
         self.ctx.check(self.ctx.L.atlas_rt_bvh_download(self.h, _addr(nodes), _addr(order), _addr(flags), 0))
+        return nodes, order, flags
+
+    def download_device(self):
+        """(nodes (n,14) int32, order (m,) int32, end_of_node (m,) uint8) as CUDA tensors on the context's device."""
+        import torch
+        n, m = self.counts()
+        dev = torch.device("cuda", self.ctx.device)
+        nodes = torch.empty((n, 14), dtype=torch.int32, device=dev)
+        order = torch.empty(m, dtype=torch.int32, device=dev)
+        flags = torch.empty(m, dtype=torch.uint8, device=dev)
+        self.ctx.check(self.ctx.L.atlas_rt_bvh_download(self.h, _addr(nodes) if n else None, _addr(order) if m else None,
+                                                        _addr(flags) if m else None, DEVICE_OUTPUT))
         return nodes, order, flags
 
     def stats(self):

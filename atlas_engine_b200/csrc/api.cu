@@ -244,11 +244,12 @@ int atlas_rt_build_tlas(atlas_rt_context* ctx, const float* aabbs, uint64_t coun
     return build_common(ctx, aabbs, nullptr, count, flags, true, out_bvh);
 }
 
-int atlas_rt_bvh_upload(atlas_rt_context* ctx, const void* nodes56, uint64_t node_count, const uint32_t* order,
-                        const uint8_t* end_of_node, uint64_t ref_count, atlas_rt_bvh** out_bvh) {
+int atlas_rt_bvh_import(atlas_rt_context* ctx, const void* nodes56, uint64_t node_count, const uint32_t* order,
+                        const uint8_t* end_of_node, uint64_t ref_count, uint32_t flags, atlas_rt_bvh** out_bvh) {
     if (!ctx || !out_bvh || (node_count && !nodes56) || (ref_count && (!order || !end_of_node))) return fail(ctx, ATLAS_RT_ERR_INVALID, "null argument");
     *out_bvh = nullptr;
     ATLAS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const bool dev = flags & ATLAS_RT_DEVICE_INPUT;
     auto* bvh = new (std::nothrow) atlas_rt_bvh;
     if (!bvh) return fail(ctx, ATLAS_RT_ERR_OOM, "host allocation");
     bvh->ctx = ctx;
@@ -259,9 +260,9 @@ int atlas_rt_bvh_upload(atlas_rt_context* ctx, const void* nodes56, uint64_t nod
     ATLAS_CUDA(ctx, dev_alloc(ctx, &bvh->order, ref_count));
     ATLAS_CUDA(ctx, dev_alloc(ctx, &bvh->endOfNode, ref_count));
     ATLAS_CUDA(ctx, dev_alloc(ctx, &staging, node_count * 14));
-    ATLAS_CUDA(ctx, copy_in(ctx, staging, nodes56, node_count * 56, false));
-    ATLAS_CUDA(ctx, copy_in(ctx, bvh->order, order, ref_count * 4, false));
-    ATLAS_CUDA(ctx, copy_in(ctx, bvh->endOfNode, end_of_node, ref_count, false));
+    ATLAS_CUDA(ctx, copy_in(ctx, staging, nodes56, node_count * 56, dev));
+    ATLAS_CUDA(ctx, copy_in(ctx, bvh->order, order, ref_count * 4, dev));
+    ATLAS_CUDA(ctx, copy_in(ctx, bvh->endOfNode, end_of_node, ref_count, dev));
     if (node_count) {
         nodes56_to_64<<<grid_for(node_count * 16), kBlock, 0, ctx->stream>>>(staging, reinterpret_cast<uint32_t*>(bvh->nodes), node_count);
         ATLAS_LAUNCH_CHECK(ctx);
@@ -271,6 +272,11 @@ int atlas_rt_bvh_upload(atlas_rt_context* ctx, const void* nodes56, uint64_t nod
     ATLAS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *out_bvh = bvh;
     return ATLAS_RT_OK;
+}
+
+int atlas_rt_bvh_upload(atlas_rt_context* ctx, const void* nodes56, uint64_t node_count, const uint32_t* order,
+                        const uint8_t* end_of_node, uint64_t ref_count, atlas_rt_bvh** out_bvh) {
+    return atlas_rt_bvh_import(ctx, nodes56, node_count, order, end_of_node, ref_count, 0, out_bvh);
 }
 
 int atlas_rt_bvh_counts(const atlas_rt_bvh* bvh, uint64_t* node_count, uint64_t* ref_count) {

@@ -55,3 +55,61 @@ def gather_hits_ragged(rays_out, count, align=64):
     out = torch.empty((world * biggest, 4), dtype=hits.dtype, device=hits.device)
     dist.all_gather_into_tensor(out, padded)
     return torch.cat([out[r * biggest: r * biggest + (e - b)] for r, (b, e) in enumerate(sizes)], dim=0)
+
+
+# --------------------------------------------------------------------------------------- instance sets across GPUs
+def exchange_flat_trees(local, count, device):
+    """Every rank ends up with all `count` flattened trees. `local` maps tree index -> (nodes (n,14) int32,
+    order (m,) int32, end_of_node (m,) uint8) tensors on `device` for the trees this rank built (blas_owner). Sizes are
+    exchanged first (one all_reduce), then each tree is broadcast from its owner. Backend-agnostic (NCCL / gloo)."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if world == 1:
+        return [local[k] for k in range(count)]
+    sizes = torch.zeros((count, 2), dtype=torch.int64, device=device)
+    for k, (nodes, order, _) in local.items():
+        sizes[k, 0], sizes[k, 1] = nodes.shape[0], order.shape[0]
+    dist.all_reduce(sizes)
+    sizes = sizes.cpu()
+    out = []
+    for k in range(count):
+        n, m = int(sizes[k, 0]), int(sizes[k, 1])
+        if k in local:
+            nodes, order, eon = local[k]
+        else:
+            nodes = torch.empty((n, 14), dtype=torch.int32, device=device)
+            order = torch.empty(m, dtype=torch.int32, device=device)
+            eon = torch.empty(m, dtype=torch.uint8, device=device)
+        src = blas_owner(k, world)
+        for t in (nodes, order, eon):
+            if t.numel():
+                dist.broadcast(t, src=src)
+        out.append((nodes, order, eon))
+    return out
+
+
+def build_scene_sharded(ctx, mesh_tris, inst_boxes, inst_records):
+    """SURVEY.md 8(e): the BLASes of an instanced scene are independent, so rank r builds meshes r, r+world, ...;
+    the flattened trees are exchanged over NCCL and imported on the other ranks (atlas_rt_bvh_import); the TLAS is built
+    on rank 0 and broadcast. Every rank returns an identical, complete scene. Returns (scene, keepalive objects)."""
+    from . import workloads as W
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    device = torch.device("cuda", ctx.device)
+    built, local = {}, {}
+    for k, tris in enumerate(mesh_tris):
+        if blas_owner(k, world) == rank:
+            built[k] = ctx.build_blas(W.tri_boxes(tris), tris)
+            local[k] = built[k].download_device()
+    trees = exchange_flat_trees(local, len(mesh_tris), device)
+    blas = [built[k] if k in built else ctx.import_bvh_device(*trees[k]) for k in range(len(mesh_tris))]
+    meshes = [ctx.pack_mesh(b, t) for b, t in zip(blas, mesh_tris)]
+    tl_local = {}
+    tlas = None
+    if rank == 0:
+        tlas = ctx.build_tlas(inst_boxes)
+        tl_local[0] = tlas.download_device()
+    tl_tree = exchange_flat_trees(tl_local, 1, device)[0]
+    if tlas is None:
+        tlas = ctx.import_bvh_device(*tl_tree)
+    scene = ctx.create_scene(meshes, inst_records, tlas)
+    return scene, (blas, meshes, tlas)

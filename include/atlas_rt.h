@@ -104,6 +104,12 @@ int atlas_rt_build_tlas(atlas_rt_context* ctx, const float* aabbs, uint64_t coun
 int atlas_rt_bvh_upload(atlas_rt_context* ctx, const void* nodes56, uint64_t node_count, const uint32_t* order,
                         const uint8_t* end_of_node, uint64_t ref_count, atlas_rt_bvh** out_bvh);
 
+/* Same as atlas_rt_bvh_upload but honouring ATLAS_RT_DEVICE_INPUT: the three arrays may already live on the context's
+ * device (e.g. a BLAS another GPU built and sent over NCCL — instance sets are built round-robin across GPUs and
+ * exchanged, atlas_engine_b200/sharding.py). */
+int atlas_rt_bvh_import(atlas_rt_context* ctx, const void* nodes56, uint64_t node_count, const uint32_t* order,
+                        const uint8_t* end_of_node, uint64_t ref_count, uint32_t flags, atlas_rt_bvh** out_bvh);
+
 /* nodes.size() and data.size()/refs.size() of the reference object. */
 int atlas_rt_bvh_counts(const atlas_rt_bvh* bvh, uint64_t* node_count, uint64_t* ref_count);
 
