@@ -1093,11 +1093,19 @@ __global__ void spatial_place(const Task* __restrict__ tasks, const RootSplit* _
 }
 
 // ------------------------------------------------------------------------------------------- subtree kernel
-struct SubNode {
-    uint16_t start, count;
-    uint32_t flatIdx;
-    uint32_t boxRef;   // (parent flat index << 1) | isSecondChild, or 0xffffffff for the subtree root
+struct alignas(16) SubNode {   // a node of the current level inside a subtree CTA (32 B)
+    uint16_t start, count;     // ref range inside the CTA's buffers
+    uint16_t rel, pad;         // flattened index relative to the subtree root's
+    float lo[3], hi[3];        // the node's box = the child box its parent recorded (BVH.cpp:399-400)
 };
+
+__device__ __forceinline__ SubNode make_subnode(uint32_t start, uint32_t count, uint32_t rel, const Box3& b) {
+    SubNode n;
+    n.start = uint16_t(start); n.count = uint16_t(count); n.rel = uint16_t(rel); n.pad = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { n.lo[k] = b.lo[k]; n.hi[k] = b.hi[k]; }
+    return n;
+}
 
 constexpr uint32_t kTinyMax = 4;   // nodes with at most this many refs are handled by ONE lane (32 nodes per warp)
 
@@ -1111,19 +1119,10 @@ __device__ inline void build_tiny_node(const SubNode nd, const SmallTask& task, 
                                        SubNode* nextList, uint32_t* sNext, unsigned long long* sStats) {
     const uint32_t n = nd.count, s = nd.start;
     const uint32_t nb = bins_at_depth(budget, depth);
+    const uint32_t flatIdx = task.flatIdx + nd.rel;
     float blo[3], bhi[3];
-    if (nd.boxRef == 0xffffffffu) {
 #pragma unroll
-        for (int k = 0; k < 3; k++) { blo[k] = task.lo[k]; bhi[k] = task.hi[k]; }
-    } else {
-        const volatile float4* P = nodes + 4 * size_t(nd.boxRef >> 1);
-        float4 n0, n1, n2;
-        n0.x = P[0].x; n0.y = P[0].y; n0.z = P[0].z; n0.w = P[0].w;
-        n1.x = P[1].x; n1.y = P[1].y; n1.z = P[1].z; n1.w = P[1].w;
-        n2.x = P[2].x; n2.y = P[2].y; n2.z = P[2].z; n2.w = P[2].w;
-        if (nd.boxRef & 1u) { blo[0] = n1.z; blo[1] = n1.w; blo[2] = n2.x; bhi[0] = n2.y; bhi[1] = n2.z; bhi[2] = n2.w; }
-        else { blo[0] = n0.x; blo[1] = n0.y; blo[2] = n0.z; bhi[0] = n0.w; bhi[1] = n1.x; bhi[2] = n1.y; }
-    }
+    for (int k = 0; k < 3; k++) { blo[k] = nd.lo[k]; bhi[k] = nd.hi[k]; }
     float4 rl[kTinyMax], rh[kTinyMax];
     OBox rb[kTinyMax];
 #pragma unroll
@@ -1219,15 +1218,15 @@ __device__ inline void build_tiny_node(const SubNode nd, const SmallTask& task, 
     const uint32_t slot = task.start + s;
     const Box3& f = swapped ? rbx : lb;
     const Box3& g = swapped ? lb : rbx;
-    const int32_t ptr1 = nFirst > 1u ? int32_t(nd.flatIdx + 1u) : ~int32_t(slot);
-    const int32_t ptr2 = nSecond > 1u ? int32_t(nd.flatIdx + nFirst) : ~int32_t(slot + nFirst);
-    float4* N = nodes + 4 * size_t(nd.flatIdx);
+    const int32_t ptr1 = nFirst > 1u ? int32_t(flatIdx + 1u) : ~int32_t(slot);
+    const int32_t ptr2 = nSecond > 1u ? int32_t(flatIdx + nFirst) : ~int32_t(slot + nFirst);
+    float4* N = nodes + 4 * size_t(flatIdx);
     N[0] = make_float4(f.lo[0], f.lo[1], f.lo[2], f.hi[0]);
     N[1] = make_float4(f.hi[1], f.hi[2], g.lo[0], g.lo[1]);
     N[2] = make_float4(g.lo[2], g.hi[0], g.hi[1], g.hi[2]);
     N[3] = make_float4(__int_as_float(ptr1), __int_as_float(ptr2), 0.0f, 0.0f);
-    if (nFirst > 1u) nextList[atomicAdd(sNext, 1u)] = SubNode{uint16_t(s), uint16_t(nFirst), nd.flatIdx + 1u, nd.flatIdx << 1};
-    if (nSecond > 1u) nextList[atomicAdd(sNext, 1u)] = SubNode{uint16_t(s + nFirst), uint16_t(nSecond), nd.flatIdx + nFirst, (nd.flatIdx << 1) | 1u};
+    if (nFirst > 1u) nextList[atomicAdd(sNext, 1u)] = make_subnode(s, nFirst, nd.rel + 1u, f);
+    if (nSecond > 1u) nextList[atomicAdd(sNext, 1u)] = make_subnode(s + nFirst, nSecond, nd.rel + nFirst, g);
     uint32_t doneFirst = 0, doneSecond = 0;
 #pragma unroll
     for (uint32_t i = 0; i < kTinyMax; i++) {
@@ -1252,32 +1251,23 @@ __device__ __forceinline__ OBox obox_of_ref(const float4& l, const float4& h) {
     return b;
 }
 
-// A group of G lanes (a warp, or a half warp for nodes with at most 16 refs) builds one node of a subtree: Build #2
-// (BVH.cpp:343-406) = FindObjectSplit else PerformMedianSplit, then the flattened node record and the stable partition.
-// The three axes are binned and swept one after the other in the group's single-axis bin array.
+// A group of G lanes (a warp, or a half warp for nodes with at most 16 refs once the level has at most 16 bins) builds
+// one node of a subtree: Build #2 (BVH.cpp:343-406) = FindObjectSplit else PerformMedianSplit, then the flattened node
+// record and the stable partition. The three axes are binned one after the other in the group's single-axis bin array
+// (shared-memory atomics on the ordered-int image) and swept with one bin per lane (group_sweep_single).
 template <int G>
 __device__ inline void build_group_node(const SubNode nd, const SmallTask& task, uint32_t depth, uint32_t budget, float4* cLo, float4* cHi,
                                         float4* __restrict__ nLo, float4* __restrict__ nHi, float4* nodes, uint32_t* __restrict__ order,
                                         uint8_t* __restrict__ eon, SubNode* nextList, uint32_t* sNext, unsigned long long* sStats,
-                                        int* bins /*[32][8]*/, int* sfx /*[32][6]*/) {
+                                        int* bins /*[32][kSubBinWords]*/) {
     const LaneGroup<G> g;
     const uint32_t lane = g.lane;
     const uint32_t n = nd.count, s = nd.start;
-    const uint32_t nb = bins_at_depth(budget, depth);   // <= kSubtreeBins by construction
-    // ---- node box: the subtree root's comes with the task, any other from its parent's flattened record
+    const uint32_t nb = bins_at_depth(budget, depth);   // <= kSubtreeBins by construction, <= 16 for a half warp
+    const uint32_t flatIdx = task.flatIdx + nd.rel;
     float blo[3], bhi[3];
-    if (nd.boxRef == 0xffffffffu) {
 #pragma unroll
-        for (int k = 0; k < 3; k++) { blo[k] = task.lo[k]; bhi[k] = task.hi[k]; }
-    } else {
-        const volatile float4* P = nodes + 4 * size_t(nd.boxRef >> 1);
-        float4 n0, n1, n2;
-        n0.x = P[0].x; n0.y = P[0].y; n0.z = P[0].z; n0.w = P[0].w;
-        n1.x = P[1].x; n1.y = P[1].y; n1.z = P[1].z; n1.w = P[1].w;
-        n2.x = P[2].x; n2.y = P[2].y; n2.z = P[2].z; n2.w = P[2].w;
-        if (nd.boxRef & 1u) { blo[0] = n1.z; blo[1] = n1.w; blo[2] = n2.x; bhi[0] = n2.y; bhi[1] = n2.z; bhi[2] = n2.w; }
-        else { blo[0] = n0.x; blo[1] = n0.y; blo[2] = n0.z; bhi[0] = n0.w; bhi[1] = n1.x; bhi[2] = n1.y; }
-    }
+    for (int k = 0; k < 3; k++) { blo[k] = nd.lo[k]; bhi[k] = nd.hi[k]; }
     AxisBins ab[3];
 #pragma unroll
     for (int a = 0; a < 3; a++) ab[a] = axis_bins(blo[a], bhi[a], nb);
@@ -1288,26 +1278,22 @@ __device__ inline void build_group_node(const SubNode nd, const SmallTask& task,
 #pragma unroll 1
     for (int a = 0; a < 3; a++) {
         if (!ab[a].active) continue;
-        for (uint32_t e = lane; e < nb; e += G) bin_init(bins + e * kBinWords);
+        for (uint32_t e = lane; e < nb; e += G) sub_bin_init(bins + e * kSubBinWords);
         g.sync();
         for (uint32_t i = lane; i < n; i += G) {
             const float4 l = cLo[s + i], h = cHi[s + i];
             const uint32_t b = bin_of(bin_centre(comp(l, a), comp(h, a)), ab[a].start, ab[a].inv, nb);
-            int* rec = bins + b * kBinWords;
+            int* rec = bins + b * kSubBinWords;
             atomicMin(rec + 0, ord_from_float(l.x)); atomicMin(rec + 1, ord_from_float(l.y)); atomicMin(rec + 2, ord_from_float(l.z));
             atomicMax(rec + 3, ord_from_float(h.x)); atomicMax(rec + 4, ord_from_float(h.y)); atomicMax(rec + 5, ord_from_float(h.z));
             atomicAdd(rec + 6, 1);
-            atomicAdd(rec + 7, 1);
         }
         g.sync();
-        if (group_sweep_axis<G, true>(g, bins, nb, sfx, n, a, best)) {
-            // this axis holds the best split so far: its boxes are the prefix stored at bins[j-1] and the suffix sfx[j]
-            g.sync();
-            const int* pl = bins + (best.bin - 1u) * kBinWords;
-            const int* pr = sfx + best.bin * 6;
-#pragma unroll
-            for (int w = 0; w < 3; w++) { objL.lo[w] = pl[w]; objL.hi[w] = pl[3 + w]; objR.lo[w] = pr[w]; objR.hi[w] = pr[3 + w]; }
-            objLeft = uint32_t(pl[6]);
+        if constexpr (G == 32) {
+            if (nb <= 16u) group_sweep_single<32, true>(g, bins, nb, n, a, best, objL, objR, objLeft);
+            else group_sweep_single<32, false>(g, bins, nb, n, a, best, objL, objR, objLeft);
+        } else {
+            group_sweep_single<G, false>(g, bins, nb, n, a, best, objL, objR, objLeft);
         }
         g.sync();
     }
@@ -1365,15 +1351,15 @@ __device__ inline void build_group_node(const SubNode nd, const SmallTask& task,
     if (lane == 0) {
         const Box3& f = swapped ? rb : lb;
         const Box3& h2 = swapped ? lb : rb;
-        const int32_t ptr1 = nFirst > 1u ? int32_t(nd.flatIdx + 1u) : ~int32_t(slot);
-        const int32_t ptr2 = nSecond > 1u ? int32_t(nd.flatIdx + nFirst) : ~int32_t(slot + nFirst);
-        float4* N = nodes + 4 * size_t(nd.flatIdx);
+        const int32_t ptr1 = nFirst > 1u ? int32_t(flatIdx + 1u) : ~int32_t(slot);
+        const int32_t ptr2 = nSecond > 1u ? int32_t(flatIdx + nFirst) : ~int32_t(slot + nFirst);
+        float4* N = nodes + 4 * size_t(flatIdx);
         N[0] = make_float4(f.lo[0], f.lo[1], f.lo[2], f.hi[0]);
         N[1] = make_float4(f.hi[1], f.hi[2], h2.lo[0], h2.lo[1]);
         N[2] = make_float4(h2.lo[2], h2.hi[0], h2.hi[1], h2.hi[2]);
         N[3] = make_float4(__int_as_float(ptr1), __int_as_float(ptr2), 0.0f, 0.0f);
-        if (nFirst > 1u) nextList[atomicAdd(sNext, 1u)] = SubNode{uint16_t(s), uint16_t(nFirst), nd.flatIdx + 1u, nd.flatIdx << 1};
-        if (nSecond > 1u) nextList[atomicAdd(sNext, 1u)] = SubNode{uint16_t(s + nFirst), uint16_t(nSecond), nd.flatIdx + nFirst, (nd.flatIdx << 1) | 1u};
+        if (nFirst > 1u) nextList[atomicAdd(sNext, 1u)] = make_subnode(s, nFirst, nd.rel + 1u, f);
+        if (nSecond > 1u) nextList[atomicAdd(sNext, 1u)] = make_subnode(s + nFirst, nSecond, nd.rel + nFirst, h2);
     }
     // ---- stable partition into the other buffer (or straight to the final slot for one-ref children)
     uint32_t doneFirst = 0, doneSecond = 0;
@@ -1409,6 +1395,11 @@ __device__ inline void build_group_node(const SubNode nd, const SmallTask& task,
     }
 }
 
+constexpr uint32_t kSubNodes = kSubtreeMax / 2;   // most nodes one level of a subtree can hold (each has >= 2 refs)
+constexpr size_t kSubtreeSmem = size_t(4) * kSubtreeMax * sizeof(float4) + size_t(2) * kSubNodes * sizeof(SubNode) +
+                                size_t(kSubWarps) * 2 * kSubtreeBins * kSubBinWords * sizeof(int) + size_t(2) * kSubNodes * sizeof(uint16_t);
+static_assert(2 * (kSubtreeSmem + 1024 + 128) <= 228 * 1024, "two subtree CTAs must fit one SM");
+
 __global__ void __launch_bounds__(kSubBlock)
 build_subtrees(const SmallTask* __restrict__ small, uint32_t nSmall, float4* const lo0, float4* const hi0, float4* const lo1,
                float4* const hi1, float4* nodes, uint32_t* __restrict__ order, uint8_t* __restrict__ eon,
@@ -1416,12 +1407,12 @@ build_subtrees(const SmallTask* __restrict__ small, uint32_t nSmall, float4* con
     extern __shared__ __align__(16) unsigned char smemRaw[];
     float4* sLo = reinterpret_cast<float4*>(smemRaw);                      // [2][kSubtreeMax]
     float4* sHi = sLo + 2 * kSubtreeMax;                                   // [2][kSubtreeMax]
-    SubNode* lists = reinterpret_cast<SubNode*>(sHi + 2 * kSubtreeMax);    // [2][kSubtreeMax / 2]
-    int* wBins = reinterpret_cast<int*>(lists + kSubtreeMax);              // [warps][2 half-warp groups][32][8]
-    int* wSfx = wBins + kSubWarps * 2 * kSubtreeBins * kBinWords;          // [warps][2][32][6]
-    uint16_t* clsIdx = reinterpret_cast<uint16_t*>(wSfx + kSubWarps * 2 * kSubtreeBins * 6);   // [3][kSubtreeMax / 2]
+    SubNode* lists = reinterpret_cast<SubNode*>(sHi + 2 * kSubtreeMax);    // [2][kSubNodes]
+    int* wBins = reinterpret_cast<int*>(lists + 2 * kSubNodes);            // [warps][2 half-warp groups][32][kSubBinWords]
+    uint16_t* clsA = reinterpret_cast<uint16_t*>(wBins + kSubWarps * 2 * kSubtreeBins * kSubBinWords);   // tiny nodes from the front, warp nodes from the back
+    uint16_t* clsB = clsA + kSubNodes;                                     // half-warp nodes
     __shared__ uint32_t sNext;
-    __shared__ uint32_t sCls[3];               // nodes of the level by size class: <= kTinyMax, <= 16, larger
+    __shared__ uint32_t sCls[3];               // nodes of the level by size class: <= kTinyMax, half warp, warp
     __shared__ unsigned long long sStats[3];   // median splits, sort fallbacks, largest fallback
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -1434,24 +1425,26 @@ build_subtrees(const SmallTask* __restrict__ small, uint32_t nSmall, float4* con
         sHi[i] = gHi[task.start + i];
     }
     if (tid == 0) {
-        lists[0] = SubNode{0, uint16_t(task.count), task.flatIdx, 0xffffffffu};
+        Box3 rootBox;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { rootBox.lo[k] = task.lo[k]; rootBox.hi[k] = task.hi[k]; }
+        lists[0] = make_subnode(0, task.count, 0, rootBox);
         sStats[0] = sStats[1] = sStats[2] = 0;
     }
     uint32_t nCur = 1, cur = 0, level = 0;
     const uint32_t half = lane >> 4;
-    int* binsW = wBins + (warp * 2) * kSubtreeBins * kBinWords;   // the warp's first group area (a whole-warp group uses it alone)
-    int* sfxW = wSfx + (warp * 2) * kSubtreeBins * 6;
-    int* binsH = binsW + half * kSubtreeBins * kBinWords;         // this lane's half-warp group area
-    int* sfxH = sfxW + half * kSubtreeBins * 6;
+    int* binsW = wBins + (warp * 2) * kSubtreeBins * kSubBinWords;   // the warp's first group area (a whole-warp group uses it alone)
+    int* binsH = binsW + half * kSubtreeBins * kSubBinWords;         // this lane's half-warp group area
     __syncthreads();
 
     while (nCur > 0) {
         const uint32_t depth = task.depth + level;
+        const bool halfOk = bins_at_depth(budget, depth) <= 16u;   // a half warp sweeps one bin per lane
         if (tid == 0) sNext = 0;
         if (tid < 3) sCls[tid] = 0;
         __syncthreads();
-        const SubNode* curList = lists + (level & 1u) * (kSubtreeMax / 2);
-        SubNode* nextList = lists + ((level + 1u) & 1u) * (kSubtreeMax / 2);
+        const SubNode* curList = lists + (level & 1u) * kSubNodes;
+        SubNode* nextList = lists + ((level + 1u) & 1u) * kSubNodes;
         float4* cLo = sLo + cur * kSubtreeMax;
         float4* cHi = sHi + cur * kSubtreeMax;
         float4* nLo = sLo + (cur ^ 1u) * kSubtreeMax;
@@ -1460,23 +1453,23 @@ build_subtrees(const SmallTask* __restrict__ small, uint32_t nSmall, float4* con
         // sort the level's nodes into size classes so that lanes / half warps / warps each get a dense run of work
         for (uint32_t ni = tid; ni < nCur; ni += kSubBlock) {
             const uint32_t c = curList[ni].count;
-            const uint32_t k = c <= kTinyMax ? 0u : (c <= 16u ? 1u : 2u);
-            clsIdx[k * (kSubtreeMax / 2) + atomicAdd(&sCls[k], 1u)] = uint16_t(ni);
+            if (c <= kTinyMax) clsA[atomicAdd(&sCls[0], 1u)] = uint16_t(ni);
+            else if (c <= 16u && halfOk) clsB[atomicAdd(&sCls[1], 1u)] = uint16_t(ni);
+            else clsA[kSubNodes - 1u - atomicAdd(&sCls[2], 1u)] = uint16_t(ni);
         }
         __syncthreads();
         const uint32_t nTiny = sCls[0], nHalf = sCls[1], nWarp = sCls[2];
         // tiny nodes: one lane each
         for (uint32_t k = tid; k < nTiny; k += kSubBlock)
-            build_tiny_node(curList[clsIdx[k]], task, depth, budget, cLo, cHi, nLo, nHi, nodes, order, eon, nextList, &sNext, sStats);
+            build_tiny_node(curList[clsA[k]], task, depth, budget, cLo, cHi, nLo, nHi, nodes, order, eon, nextList, &sNext, sStats);
         // 5..16 refs: one half warp each
         for (uint32_t k = warp * 2u + half; k < nHalf; k += kSubWarps * 2u)
-            build_group_node<16>(curList[clsIdx[(kSubtreeMax / 2) + k]], task, depth, budget, cLo, cHi, nLo, nHi, nodes, order, eon, nextList,
-                                 &sNext, sStats, binsH, sfxH);
+            build_group_node<16>(curList[clsB[k]], task, depth, budget, cLo, cHi, nLo, nHi, nodes, order, eon, nextList, &sNext, sStats, binsH);
         __syncwarp();
         // larger nodes: one warp each
         for (uint32_t k = warp; k < nWarp; k += kSubWarps)
-            build_group_node<32>(curList[clsIdx[2 * (kSubtreeMax / 2) + k]], task, depth, budget, cLo, cHi, nLo, nHi, nodes, order, eon, nextList,
-                                 &sNext, sStats, binsW, sfxW);
+            build_group_node<32>(curList[clsA[kSubNodes - 1u - k]], task, depth, budget, cLo, cHi, nLo, nHi, nodes, order, eon, nextList, &sNext,
+                                 sStats, binsW);
         __syncthreads();
         nCur = sNext;
         cur ^= 1u;
@@ -1489,10 +1482,6 @@ build_subtrees(const SmallTask* __restrict__ small, uint32_t nSmall, float4* con
         if (sStats[2]) atomicMax(&info->stats[5], sStats[2]);
     }
 }
-
-constexpr size_t kSubtreeSmem = size_t(4) * kSubtreeMax * sizeof(float4) + size_t(kSubtreeMax) * sizeof(SubNode) +
-                                size_t(kSubWarps) * 2 * kSubtreeBins * kBinWords * sizeof(int) +
-                                size_t(kSubWarps) * 2 * kSubtreeBins * 6 * sizeof(int) + size_t(3) * (kSubtreeMax / 2) * sizeof(uint16_t);
 
 template <typename T>
 int read_back(atlas_rt_context* ctx, const T* dev, T* host) {

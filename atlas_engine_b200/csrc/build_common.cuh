@@ -267,6 +267,106 @@ __device__ inline bool group_sweep_axis(const LaneGroup<G>& g, BinPtr bins, uint
     return false;
 }
 
+// Shared-memory subtree kernel: one bin = 7 ints (ord lo.xyz, ord hi.xyz, primitiveCount). The odd stride keeps the
+// lane-per-bin loads of the sweep and the atomics of neighbouring bins in different banks.
+constexpr int kSubBinWords = 7;
+
+__device__ __forceinline__ void sub_bin_init(int* b) {
+    b[0] = b[1] = b[2] = kOrdEmptyLo;
+    b[3] = b[4] = b[5] = kOrdEmptyHi;
+    b[6] = 0;
+}
+
+// Object-split sweep of ONE axis whose nb bins fit the group (nb <= G): every bin lives in a lane, prefix and suffix
+// boxes are scanned with shuffles only, and the boxes / left count of the winning candidate are handed back from the
+// lanes that hold them. Same candidates, costs and tie rule as group_sweep_axis.
+// REV (whole warp, nb <= 16): lanes 0..15 hold bins 0..15, lanes 16..31 hold the bins in reverse order, so ONE
+// width-16 up-scan produces the prefix boxes in the low half and the suffix boxes in the high half.
+template <int G, bool REV>
+__device__ __forceinline__ bool group_sweep_single(const LaneGroup<G>& g, const int* bins, uint32_t nb, uint32_t total, int axis,
+                                                   BestSplit& best, OBox& outL, OBox& outR, uint32_t& outLeft) {
+    static_assert(!REV || G == 32, "the reversed layout needs a whole warp");
+    const uint32_t lane = g.lane;
+    OBox pre = obox_empty();
+    OBox right;          // suffix box of candidate j = lane + 1
+    OBox suf;            // !REV: suffix box starting at this lane's bin
+    uint32_t en = 0;
+    if constexpr (REV) {
+        const uint32_t m = lane & 15u;
+        const uint32_t k = lane < 16u ? m : nb - 1u - m;
+        if (m < nb) {
+            const int* rec = bins + k * kSubBinWords;
+#pragma unroll
+            for (int w = 0; w < 3; w++) { pre.lo[w] = rec[w]; pre.hi[w] = rec[3 + w]; }
+            en = uint32_t(rec[6]);
+        }
+#pragma unroll
+        for (int off = 1; off < 16; off <<= 1) {
+            OBox o;
+#pragma unroll
+            for (int w = 0; w < 3; w++) { o.lo[w] = __shfl_up_sync(kFullMask, pre.lo[w], off, 16); o.hi[w] = __shfl_up_sync(kFullMask, pre.hi[w], off, 16); }
+            const uint32_t oe = __shfl_up_sync(kFullMask, en, off, 16);
+            if (m >= uint32_t(off)) { obox_grow(pre, o); en += oe; }
+        }
+        // suffix over bins [j, nb) sits in lane 16 + (nb - 1 - j)
+        const int src = 16 + int((nb - 2u - lane) & 15u);
+#pragma unroll
+        for (int w = 0; w < 3; w++) { right.lo[w] = __shfl_sync(kFullMask, pre.lo[w], src); right.hi[w] = __shfl_sync(kFullMask, pre.hi[w], src); }
+        suf = pre;
+    } else {
+        if (lane < nb) {
+            const int* rec = bins + lane * kSubBinWords;
+#pragma unroll
+            for (int w = 0; w < 3; w++) { pre.lo[w] = rec[w]; pre.hi[w] = rec[3 + w]; }
+            en = uint32_t(rec[6]);
+        }
+        suf = pre;
+#pragma unroll
+        for (int off = 1; off < G; off <<= 1) {
+            OBox o, p;
+#pragma unroll
+            for (int w = 0; w < 3; w++) {
+                o.lo[w] = g.up(pre.lo[w], off); o.hi[w] = g.up(pre.hi[w], off);
+                p.lo[w] = g.down(suf.lo[w], off); p.hi[w] = g.down(suf.hi[w], off);
+            }
+            const uint32_t oe = g.up(en, off);
+            if (lane >= uint32_t(off)) { obox_grow(pre, o); en += oe; }
+            if (lane + off < uint32_t(G)) obox_grow(suf, p);
+        }
+#pragma unroll
+        for (int w = 0; w < 3; w++) { right.lo[w] = g.down(suf.lo[w], 1); right.hi[w] = g.down(suf.hi[w], 1); }
+    }
+    float myCost = kFltMax;
+    uint32_t myBin = 0xffffffffu;
+    const uint32_t j = lane + 1u;   // split after bin `lane`
+    if (j < nb && (!REV || lane < 16u)) {
+        const uint32_t nLeft = en, nRight = total - en;
+        if (nLeft != 0u && nRight != 0u) {
+            const float cost = __fadd_rn(__fmul_rn(obox_area(pre), __uint2float_rn(nLeft)), __fmul_rn(obox_area(right), __uint2float_rn(nRight)));
+            if (cost < kFltMax) { myCost = cost; myBin = j; }   // NaN / inf never beat the initial best (BVH.cpp:519)
+        }
+    }
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) {
+        const float oc = g.bxor(myCost, off);
+        const uint32_t ob = g.bxor(myBin, off);
+        if (oc < myCost || (oc == myCost && ob < myBin)) { myCost = oc; myBin = ob; }   // lanes without a candidate hold (FLT_MAX, ~0)
+    }
+    if (myBin == 0xffffffffu || !(myCost < best.cost)) return false;
+    best.cost = myCost;
+    best.axis = axis;
+    best.bin = myBin;
+    const int lsrc = int(myBin) - 1;
+    const int rsrc = REV ? 16 + int(nb - 1u - myBin) : int(myBin);
+#pragma unroll
+    for (int w = 0; w < 3; w++) {
+        outL.lo[w] = g.bcast(pre.lo[w], lsrc); outL.hi[w] = g.bcast(pre.hi[w], lsrc);
+        outR.lo[w] = g.bcast(suf.lo[w], rsrc); outR.hi[w] = g.bcast(suf.hi[w], rsrc);
+    }
+    outLeft = g.bcast(en, lsrc);
+    return true;
+}
+
 __device__ inline void warp_sweep_axis(const int* bins, uint32_t nb, int* sfx, uint32_t total, int axis, BestSplit& best) {
     const LaneGroup<32> g;
     group_sweep_axis<32, false>(g, bins, nb, sfx, total, axis, best);
