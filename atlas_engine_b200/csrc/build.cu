@@ -38,6 +38,7 @@ namespace {
 
 constexpr uint32_t kSubtreeMax = 1024;   // refs a shared-memory subtree CTA can hold
 constexpr uint32_t kSubtreeBins = 32;    // ... and the bin count it supports (one bin per lane)
+constexpr int kSmemBin = 9;              // stride of a bin record in SHARED memory: odd, so lanes on different bins hit different banks
 constexpr uint32_t kChunk = 1024;        // refs per CTA pass in the big-node kernels
 constexpr int kBigBlock = 256;
 constexpr int kSubBlock = 256;
@@ -76,6 +77,12 @@ struct RootSplit {   // state of the BLAS root decision (Build #1)
     uint32_t nL, nR;
 };
 
+// chunk -> (task, first ref, refs in the chunk, offset of the chunk inside the task); written once per level so that the
+// chunk kernels start their loads after a single dependent read
+struct ChunkInfo {
+    uint32_t task, refStart, nValid, off;
+};
+
 struct BuildBuffers {
     float4* lo[2];
     float4* hi[2];
@@ -92,6 +99,7 @@ struct BuildBuffers {
     int* medAcc;        // [task][16]
     uint32_t* chunkBase;    // [task]
     uint32_t* chunkFirst;   // [chunk]
+    ChunkInfo* chunkInfo;   // [chunk]
     int* rootBox;       // 6 ord ints
     const float* tris;
     uint32_t budget;
@@ -175,23 +183,39 @@ __global__ void root_leaf_output(uint32_t n, uint32_t* __restrict__ order, uint8
 }
 
 // ---------------------------------------------------------------------------------------------- per-level set-up
-__global__ void prepare_level(Task* __restrict__ tasks, LevelInfo* __restrict__ info, uint32_t* __restrict__ chunkBase, int advance) {
+__device__ __forceinline__ void fill_chunk(ChunkInfo* __restrict__ chunkInfo, uint32_t* __restrict__ chunkFirst, uint32_t c, uint32_t task,
+                                           uint32_t start, uint32_t count, uint32_t k) {
+    ChunkInfo ci;
+    ci.task = task;
+    ci.off = k * kChunk;
+    ci.refStart = start + ci.off;
+    ci.nValid = min(kChunk, count - ci.off);
+    chunkInfo[c] = ci;
+    chunkFirst[c] = 0u;
+}
+
+__global__ void prepare_level(Task* __restrict__ tasks, LevelInfo* __restrict__ info, uint32_t* __restrict__ chunkBase,
+                              ChunkInfo* __restrict__ chunkInfo, uint32_t* __restrict__ chunkFirst, int advance) {
     // single CTA: the level's task count (the previous level's nNext when `advance`), then an exclusive scan of
-    // ceil(count / kChunk) over the level's tasks
+    // ceil(count / kChunk) over the level's tasks, and the chunk table
     __shared__ uint32_t carry;
     __shared__ uint32_t warpSums[32];
-    __shared__ uint32_t sN;
+    __shared__ uint32_t sN, sBigN;
+    __shared__ uint32_t sBig[1024];   // tasks of this pass with many chunks: filled by the whole CTA
     if (threadIdx.x == 0) {
         if (advance) info->nTasks = min(info->nNext, 0x7fffffffu);
         sN = info->nTasks;
         if (sN) info->levels++;
         carry = 0;
+        sBigN = 0;
     }
     __syncthreads();
     const uint32_t n = sN;
     for (uint32_t base = 0; base < n; base += blockDim.x) {
         const uint32_t i = base + threadIdx.x;
-        const uint32_t v = i < n ? (tasks[i].count + kChunk - 1) / kChunk : 0u;
+        uint32_t tStart = 0, tCount = 0;
+        if (i < n) { tStart = tasks[i].start; tCount = tasks[i].count; }
+        const uint32_t v = (tCount + kChunk - 1) / kChunk;
         uint32_t s = v;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
@@ -211,9 +235,26 @@ __global__ void prepare_level(Task* __restrict__ tasks, LevelInfo* __restrict__ 
         }
         __syncthreads();
         const uint32_t warpOff = (threadIdx.x >> 5) ? warpSums[(threadIdx.x >> 5) - 1] : 0u;
-        if (i < n) chunkBase[i] = carry + warpOff + s - v;
+        const uint32_t myBase = carry + warpOff + s - v;
+        if (i < n) {
+            chunkBase[i] = myBase;
+            if (v <= 8u) {
+                for (uint32_t k = 0; k < v; k++) fill_chunk(chunkInfo, chunkFirst, myBase + k, i, tStart, tCount, k);
+            } else {
+                sBig[atomicAdd(&sBigN, 1u)] = i;
+            }
+        }
         __syncthreads();
+        const uint32_t nBig = sBigN;
+        for (uint32_t b = 0; b < nBig; b++) {
+            const uint32_t t = sBig[b];
+            const uint32_t bStart = tasks[t].start, bCount = tasks[t].count, bBase = chunkBase[t];
+            const uint32_t bv = (bCount + kChunk - 1) / kChunk;
+            for (uint32_t k = threadIdx.x; k < bv; k += blockDim.x) fill_chunk(chunkInfo, chunkFirst, bBase + k, t, bStart, bCount, k);
+        }
         if (threadIdx.x == blockDim.x - 1) carry += warpOff + s;
+        __syncthreads();
+        if (threadIdx.x == 0) sBigN = 0;
         __syncthreads();
     }
     if (threadIdx.x == 0) {
@@ -229,34 +270,24 @@ __global__ void init_bins(int* __restrict__ bins, const LevelInfo* __restrict__ 
         bin_init(bins + i * kBinWords);
 }
 
-// chunk -> (task, offset inside the task)
-__device__ __forceinline__ uint32_t find_task(const uint32_t* __restrict__ chunkBase, uint32_t nTasks, uint32_t chunk) {
-    uint32_t lo = 0, hi = nTasks;   // last task with chunkBase <= chunk
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (chunkBase[mid] <= chunk) lo = mid; else hi = mid;
-    }
-    return lo;
-}
-
 // ------------------------------------------------------------------------------------------ object-split binning
 // FindObjectSplit's hot loop (BVH.cpp:474-482) for all big nodes of a level, all three axes in one pass.
 __global__ void __launch_bounds__(kBigBlock)
-bin_big(const Task* __restrict__ tasks, const LevelInfo* __restrict__ info, const uint32_t* __restrict__ chunkBase,
+bin_big(const Task* __restrict__ tasks, const LevelInfo* __restrict__ info, const ChunkInfo* __restrict__ chunkInfo,
         const float4* __restrict__ rlo, const float4* __restrict__ rhi, int* __restrict__ gbins, uint32_t nb) {
-    extern __shared__ int sb[];   // [3][nb][8]
-    __shared__ uint32_t sTask;
-    const uint32_t nChunks = info->nChunks, nTasks = info->nTasks;
+    extern __shared__ int sb[];   // [3][nb][kSmemBin]
+    const uint32_t nChunks = info->nChunks;
     // every CTA takes a contiguous run of chunks and keeps accumulating in shared memory while the run stays inside one
     // node, so the shared bins are merged into the node's global bins once per (CTA, node) instead of once per chunk
     const uint32_t perCta = (nChunks + gridDim.x - 1) / gridDim.x;
     const uint32_t c0 = blockIdx.x * perCta, c1 = min(nChunks, c0 + perCta);
     uint32_t cur = 0xffffffffu;
+    AxisBins ab[3];
     auto flush = [&](uint32_t t) {
         __syncthreads();
         int* g = gbins + size_t(t) * 3 * nb * kBinWords;
         for (uint32_t e = threadIdx.x; e < 3 * nb; e += kBigBlock) {
-            const int* rec = sb + e * kBinWords;
+            const int* rec = sb + e * kSmemBin;
             if (rec[6] > 0) {
                 int* d = g + e * kBinWords;
 #pragma unroll
@@ -268,40 +299,44 @@ bin_big(const Task* __restrict__ tasks, const LevelInfo* __restrict__ info, cons
         __syncthreads();
     };
     for (uint32_t c = c0; c < c1; c++) {
-        if (threadIdx.x == 0) sTask = find_task(chunkBase, nTasks, c);
-        __syncthreads();
-        const uint32_t t = sTask;
-        if (t != cur) {
-            if (cur != 0xffffffffu) flush(cur);
-            for (uint32_t e = threadIdx.x; e < 3 * nb; e += kBigBlock) bin_init(sb + e * kBinWords);
-            cur = t;
-            __syncthreads();
-        }
-        const Task& tk = tasks[t];
-        const uint32_t off = (c - chunkBase[t]) * kChunk;
-        const uint32_t end = tk.start + tk.count;
-        AxisBins ab[3];
-#pragma unroll
-        for (int a = 0; a < 3; a++) ab[a] = axis_bins(tk.lo[a], tk.hi[a], nb);
+        const ChunkInfo ci = chunkInfo[c];
+        // all of the thread's refs are requested before anything else happens to them
+        float4 l[kChunk / kBigBlock], h[kChunk / kBigBlock];
 #pragma unroll
         for (uint32_t r = 0; r < kChunk / kBigBlock; r++) {
-            const uint32_t p = tk.start + off + r * kBigBlock + threadIdx.x;
-            if (p < end) {
-                const float4 l = rlo[p], h = rhi[p];
-                const int ol[3] = {ord_from_float(l.x), ord_from_float(l.y), ord_from_float(l.z)};
-                const int oh[3] = {ord_from_float(h.x), ord_from_float(h.y), ord_from_float(h.z)};
+            const uint32_t i = r * kBigBlock + threadIdx.x;
+            if (i < ci.nValid) { l[r] = rlo[ci.refStart + i]; h[r] = rhi[ci.refStart + i]; }
+        }
+        if (ci.task != cur) {
+            if (cur != 0xffffffffu) flush(cur);
+            for (uint32_t e = threadIdx.x; e < 3 * nb; e += kBigBlock) bin_init(sb + e * kSmemBin);
+            cur = ci.task;
+            const Task& tk = tasks[cur];
+#pragma unroll
+            for (int a = 0; a < 3; a++) ab[a] = axis_bins(tk.lo[a], tk.hi[a], nb);
+            __syncthreads();
+        }
+#pragma unroll
+        for (uint32_t r = 0; r < kChunk / kBigBlock; r++) {
+            if (r * kBigBlock + threadIdx.x < ci.nValid) {
+                const int ol[3] = {ord_from_float(l[r].x), ord_from_float(l[r].y), ord_from_float(l[r].z)};
+                const int oh[3] = {ord_from_float(h[r].x), ord_from_float(h[r].y), ord_from_float(h[r].z)};
 #pragma unroll
                 for (int a = 0; a < 3; a++) {
                     if (!ab[a].active) continue;
-                    const uint32_t b = bin_of(bin_centre(comp(l, a), comp(h, a)), ab[a].start, ab[a].inv, nb);
-                    int* rec = sb + (a * nb + b) * kBinWords;
+                    const uint32_t b = bin_of(bin_centre(comp(l[r], a), comp(h[r], a)), ab[a].start, ab[a].inv, nb);
+                    int* rec = sb + (a * nb + b) * kSmemBin;
+                    // min/max only move one way, so a plain read that already covers the value makes the atomic
+                    // unnecessary; after the first few refs of a bin almost every atomic is skipped
 #pragma unroll
-                    for (int k = 0; k < 3; k++) { atomicMin(rec + k, ol[k]); atomicMax(rec + 3 + k, oh[k]); }
+                    for (int k = 0; k < 3; k++) {
+                        if (ol[k] < rec[k]) atomicMin(rec + k, ol[k]);
+                        if (oh[k] > rec[3 + k]) atomicMax(rec + 3 + k, oh[k]);
+                    }
                     atomicAdd(rec + 6, 1);
                 }
             }
         }
-        __syncthreads();   // sTask is rewritten at the top of the next iteration
     }
     if (cur != 0xffffffffu) flush(cur);
 }
@@ -444,18 +479,16 @@ __global__ void select_root_object(Task* __restrict__ tasks, LevelInfo* __restri
     }
 }
 
-// SplitReference — BVH.cpp:760-798. tri = 9 floats; cur = box of the reference being split.
-__device__ inline void split_reference(const float* __restrict__ tri, const Box3& cur, Box3& L, Box3& R, float plane, int axis) {
+// SplitReference — BVH.cpp:760-798. v = the triangle's vertices; cur = box of the reference being split.
+template <int AXIS>
+__device__ __forceinline__ void split_reference_t(const float (&v)[3][3], const Box3& cur, Box3& L, Box3& R, float plane) {
     L = empty_box();
     R = empty_box();
-    float v[3][3];
-#pragma unroll
-    for (int k = 0; k < 9; k++) v[k / 3][k % 3] = tri[k];
 #pragma unroll
     for (int e = 0; e < 3; e++) {
         const float* a = v[e];
         const float* b = v[(e + 1) % 3];
-        const float av = a[axis], bv = b[axis];
+        const float av = a[AXIS], bv = b[AXIS];
         if ((av < plane && bv > plane) || (av > plane && bv < plane)) {
             const float off = gl_clamp(__fdiv_rn(__fsub_rn(plane, av), __fsub_rn(bv, av)), 0.0f, 1.0f);
 #pragma unroll
@@ -474,8 +507,8 @@ __device__ inline void split_reference(const float* __restrict__ tri, const Box3
             for (int k = 0; k < 3; k++) { R.hi[k] = gl_max(a[k], R.hi[k]); R.lo[k] = gl_min(a[k], R.lo[k]); }
         }
     }
-    L.hi[axis] = plane;
-    R.lo[axis] = plane;
+    L.hi[AXIS] = plane;
+    R.lo[AXIS] = plane;
 #pragma unroll
     for (int k = 0; k < 3; k++) {   // Intersect(currentRef.aabb)
         L.lo[k] = gl_max(L.lo[k], cur.lo[k]); L.hi[k] = gl_min(L.hi[k], cur.hi[k]);
@@ -483,17 +516,56 @@ __device__ inline void split_reference(const float* __restrict__ tri, const Box3
     }
 }
 
-__device__ __forceinline__ void bin_grow_shared(int* rec, const Box3& b) {
+__device__ inline void split_reference(const float* __restrict__ tri, const Box3& cur, Box3& L, Box3& R, float plane, int axis) {
+    float v[3][3];
 #pragma unroll
-    for (int k = 0; k < 3; k++) { atomicMin(rec + k, ord_from_float(b.lo[k])); atomicMax(rec + 3 + k, ord_from_float(b.hi[k])); }
+    for (int k = 0; k < 9; k++) v[k / 3][k % 3] = tri[k];
+    if (axis == 0) split_reference_t<0>(v, cur, L, R, plane);
+    else if (axis == 1) split_reference_t<1>(v, cur, L, R, plane);
+    else split_reference_t<2>(v, cur, L, R, plane);
 }
 
-// FindSpatialSplit's binning (BVH.cpp:589-619) over the root's refs; one ref per thread, bins in shared memory.
-__global__ void __launch_bounds__(kBigBlock)
-spatial_bin_root(const Task* __restrict__ tasks, const float4* __restrict__ rlo, const float4* __restrict__ rhi,
-                 const float* __restrict__ tris, int* __restrict__ gbins, uint32_t nb) {
-    extern __shared__ int sb[];   // [3][nb][8]
-    for (uint32_t e = threadIdx.x; e < 3 * nb; e += kBigBlock) bin_init(sb + e * kBinWords);
+__device__ __forceinline__ void bin_grow_shared(int* rec, const Box3& b) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int l = ord_from_float(b.lo[k]), h = ord_from_float(b.hi[k]);
+        if (l < rec[k]) atomicMin(rec + k, l);          // monotone values: a covering plain read makes the atomic unnecessary
+        if (h > rec[3 + k]) atomicMax(rec + 3 + k, h);
+    }
+}
+
+// One axis of FindSpatialSplit's binning for one ref (BVH.cpp:589-619): the ref's box is chopped at every bin boundary
+// it straddles, each piece grows its bin, and the first / last bin count an entry / an exit.
+template <int A>
+__device__ __forceinline__ void spatial_bin_axis(int* base, const AxisBins& ab, uint32_t nb, const Box3& box, const float (&v)[3][3]) {
+    if (!ab.active) return;
+    const uint32_t b0 = bin_of(box.lo[A], ab.start, ab.inv, nb);
+    const uint32_t b1 = bin_of(box.hi[A], ab.start, ab.inv, nb);
+    if (b0 == b1) {
+        bin_grow_shared(base + b0 * kSmemBin, box);
+    } else {
+        Box3 rest = box;
+        for (uint32_t j = b0; j < b1; j++) {
+            Box3 cl, cr;
+            const float plane = __fadd_rn(ab.start, __fmul_rn(__uint2float_rn(j + 1u), ab.width));
+            split_reference_t<A>(v, rest, cl, cr, plane);
+            bin_grow_shared(base + j * kSmemBin, cl);
+            rest = cr;
+        }
+        bin_grow_shared(base + b1 * kSmemBin, rest);
+    }
+    atomicAdd(base + b0 * kSmemBin + 6, 1);
+    atomicAdd(base + b1 * kSmemBin + 7, 1);
+}
+
+// FindSpatialSplit's binning over the root's refs; one ref per thread, bins in shared memory. Falls through when the
+// object split's children do not overlap enough for a spatial split to be considered (BVH.cpp:282-283).
+__global__ void __launch_bounds__(kBigBlock, 3)
+spatial_bin_root(const Task* __restrict__ tasks, const LevelInfo* __restrict__ info, const float4* __restrict__ rlo,
+                 const float4* __restrict__ rhi, const float* __restrict__ tris, int* __restrict__ gbins, uint32_t nb) {
+    extern __shared__ int sb[];   // [3][nb][kSmemBin]
+    if (!info->rootNeedSpatial) return;
+    for (uint32_t e = threadIdx.x; e < 3 * nb; e += kBigBlock) bin_init(sb + e * kSmemBin);
     __syncthreads();
     const Task& tk = tasks[0];
     AxisBins ab[3];
@@ -504,35 +576,17 @@ spatial_bin_root(const Task* __restrict__ tasks, const float4* __restrict__ rlo,
         Box3 box;
         box.lo[0] = l.x; box.lo[1] = l.y; box.lo[2] = l.z;
         box.hi[0] = h.x; box.hi[1] = h.y; box.hi[2] = h.z;
-        const uint32_t src = __float_as_uint(l.w);
-#pragma unroll 1
-        for (int a = 0; a < 3; a++) {
-            if (!ab[a].active) continue;
-            const uint32_t b0 = bin_of(box.lo[a], ab[a].start, ab[a].inv, nb);
-            const uint32_t b1 = bin_of(box.hi[a], ab[a].start, ab[a].inv, nb);
-            int* base = sb + a * nb * kBinWords;
-            if (b0 == b1) {
-                bin_grow_shared(base + b0 * kBinWords, box);
-                atomicAdd(base + b0 * kBinWords + 6, 1);
-                atomicAdd(base + b0 * kBinWords + 7, 1);
-                continue;
-            }
-            Box3 rest = box;
-            for (uint32_t j = b0; j < b1; j++) {
-                Box3 cl, cr;
-                const float plane = __fadd_rn(ab[a].start, __fmul_rn(__uint2float_rn(j + 1u), ab[a].width));
-                split_reference(tris + 9 * size_t(src), rest, cl, cr, plane, a);
-                bin_grow_shared(base + j * kBinWords, cl);
-                rest = cr;
-            }
-            bin_grow_shared(base + b1 * kBinWords, rest);
-            atomicAdd(base + b0 * kBinWords + 6, 1);
-            atomicAdd(base + b1 * kBinWords + 7, 1);
-        }
+        const float* tri = tris + 9 * size_t(__float_as_uint(l.w));
+        float v[3][3];
+#pragma unroll
+        for (int k = 0; k < 9; k++) v[k / 3][k % 3] = tri[k];
+        spatial_bin_axis<0>(sb, ab[0], nb, box, v);
+        spatial_bin_axis<1>(sb + nb * kSmemBin, ab[1], nb, box, v);
+        spatial_bin_axis<2>(sb + 2 * nb * kSmemBin, ab[2], nb, box, v);
     }
     __syncthreads();
     for (uint32_t e = threadIdx.x; e < 3 * nb; e += kBigBlock) {
-        const int* rec = sb + e * kBinWords;
+        const int* rec = sb + e * kSmemBin;
         int* d = gbins + e * kBinWords;
         // a bin's box can be grown without its counters changing (chopped interior pieces), so test the box too
         if (rec[6] | rec[7] | (rec[0] != kOrdEmptyLo) | (rec[3] != kOrdEmptyHi)) {
@@ -547,8 +601,9 @@ spatial_bin_root(const Task* __restrict__ tasks, const float4* __restrict__ rlo,
 // Build #1, second half (BVH.cpp:276-301): choose between median, spatial and object split for the BLAS root.
 __global__ void select_root_final(Task* __restrict__ tasks, LevelInfo* __restrict__ info, const int* __restrict__ objBins,
                                   const int* __restrict__ spaBins, int* __restrict__ gsfx, int* __restrict__ medAcc,
-                                  RootSplit* __restrict__ root, Lists L, uint32_t nb, int trySpatial) {
+                                  RootSplit* __restrict__ root, Lists L, uint32_t nb) {
     const uint32_t lane = threadIdx.x & 31u;
+    const bool trySpatial = info->rootNeedSpatial != 0u;
     Task tk = tasks[0];
     BestSplit spa = best_none();
     if (trySpatial) {
@@ -609,19 +664,16 @@ __global__ void select_root_final(Task* __restrict__ tasks, LevelInfo* __restric
 // --------------------------------------------------------------------------------------------- median split
 // First loop of PerformMedianSplit (BVH.cpp:813-823) for big nodes flagged kMedian: side counts and side boxes.
 __global__ void __launch_bounds__(kBigBlock)
-median_reduce_big(const Task* __restrict__ tasks, const LevelInfo* __restrict__ info, const uint32_t* __restrict__ chunkBase,
+median_reduce_big(const Task* __restrict__ tasks, const LevelInfo* __restrict__ info, const ChunkInfo* __restrict__ chunkInfo,
                   const float4* __restrict__ rlo, const float4* __restrict__ rhi, int* __restrict__ medAcc) {
-    __shared__ uint32_t sTask;
     if (info->nMedian == 0) return;
-    const uint32_t nChunks = info->nChunks, nTasks = info->nTasks;
+    const uint32_t nChunks = info->nChunks;
     for (uint32_t c = blockIdx.x; c < nChunks; c += gridDim.x) {
-        __syncthreads();
-        if (threadIdx.x == 0) sTask = find_task(chunkBase, nTasks, c);
-        __syncthreads();
-        const uint32_t t = sTask;
+        const ChunkInfo ci = chunkInfo[c];
+        const uint32_t t = ci.task;
         const Task& tk = tasks[t];
         if (tk.kind != kMedian) continue;
-        const uint32_t off = (c - chunkBase[t]) * kChunk;
+        const uint32_t off = ci.off;
         const uint32_t end = tk.start + tk.count;
         OBox L = obox_empty(), R = obox_empty();
         uint32_t nL = 0;
@@ -731,35 +783,34 @@ __device__ __forceinline__ bool goes_left(const Task& tk, const AxisBins& ab, ui
     return median_centre(comp(l, tk.axis), comp(h, tk.axis)) < tk.cutoff;
 }
 
+// The partition kernels give every warp a contiguous 128-ref slice of the chunk (4 coalesced rounds of 32 refs).
+constexpr uint32_t kWarpSlice = kChunk / (kBigBlock / 32);
+static_assert(kWarpSlice == 128, "partition kernels assume 4 rounds of 32 refs per warp");
+
 __global__ void __launch_bounds__(kBigBlock)
-partition_count(const Task* __restrict__ tasks, const LevelInfo* __restrict__ info, const uint32_t* __restrict__ chunkBase,
+partition_count(const Task* __restrict__ tasks, const LevelInfo* __restrict__ info, const ChunkInfo* __restrict__ chunkInfo,
                 const float4* __restrict__ rlo, const float4* __restrict__ rhi, uint32_t* __restrict__ chunkFirst, uint32_t nb) {
-    __shared__ uint32_t sTask;
-    __shared__ uint32_t sCount;
-    const uint32_t nChunks = info->nChunks, nTasks = info->nTasks;
+    const uint32_t nChunks = info->nChunks;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     for (uint32_t c = blockIdx.x; c < nChunks; c += gridDim.x) {
-        __syncthreads();
-        if (threadIdx.x == 0) { sTask = find_task(chunkBase, nTasks, c); sCount = 0; }
-        __syncthreads();
-        const uint32_t t = sTask;
-        const Task& tk = tasks[t];
+        const ChunkInfo ci = chunkInfo[c];
+        float4 l[4], h[4];
+#pragma unroll
+        for (uint32_t r = 0; r < 4; r++) {
+            const uint32_t i = warp * kWarpSlice + r * 32u + lane;
+            if (i < ci.nValid) { l[r] = rlo[ci.refStart + i]; h[r] = rhi[ci.refStart + i]; }
+        }
+        const Task& tk = tasks[ci.task];
         if (tk.kind != kObject && tk.kind != kMedian) continue;
         const AxisBins ab = axis_bins(tk.lo[tk.axis], tk.hi[tk.axis], nb);
-        const uint32_t off = (c - chunkBase[t]) * kChunk;
-        const uint32_t end = tk.start + tk.count;
         uint32_t mine = 0;
 #pragma unroll
-        for (uint32_t r = 0; r < kChunk / kBigBlock; r++) {
-            const uint32_t p = tk.start + off + r * kBigBlock + threadIdx.x;
-            if (p < end) {
-                const bool first = goes_left(tk, ab, nb, rlo[p], rhi[p]) != (tk.leftIsSecond != 0u);
-                mine += first ? 1u : 0u;
-            }
+        for (uint32_t r = 0; r < 4; r++) {
+            const uint32_t i = warp * kWarpSlice + r * 32u + lane;
+            if (i < ci.nValid) mine += (goes_left(tk, ab, nb, l[r], h[r]) != (tk.leftIsSecond != 0u)) ? 1u : 0u;
         }
         mine = __reduce_add_sync(kFullMask, mine);
-        if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&sCount, mine);
-        __syncthreads();
-        if (threadIdx.x == 0) chunkFirst[c] = sCount;
+        if (lane == 0 && mine) atomicAdd(&chunkFirst[c], mine);   // zeroed by prepare_level
     }
 }
 
@@ -788,60 +839,61 @@ __global__ void partition_scan(const Task* __restrict__ tasks, const LevelInfo* 
 }
 
 __global__ void __launch_bounds__(kBigBlock)
-partition_scatter(const Task* __restrict__ tasks, const LevelInfo* __restrict__ info, const uint32_t* __restrict__ chunkBase,
+partition_scatter(const Task* __restrict__ tasks, const LevelInfo* __restrict__ info, const ChunkInfo* __restrict__ chunkInfo,
                   const uint32_t* __restrict__ chunkFirst, const float4* __restrict__ rlo, const float4* __restrict__ rhi,
                   float4* __restrict__ wlo, float4* __restrict__ whi, uint32_t* __restrict__ order, uint8_t* __restrict__ eon,
                   uint32_t nb) {
-    __shared__ uint32_t sTask;
-    __shared__ uint32_t sWarpFirst[kBigBlock / 32], sWarpSecond[kBigBlock / 32];
-    const uint32_t nChunks = info->nChunks, nTasks = info->nTasks;
+    __shared__ uint32_t sWarpFirst[2][kBigBlock / 32];   // double-buffered by iteration: one barrier per chunk
+    const uint32_t nChunks = info->nChunks;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t it = 0;
     for (uint32_t c = blockIdx.x; c < nChunks; c += gridDim.x) {
-        __syncthreads();
-        if (threadIdx.x == 0) sTask = find_task(chunkBase, nTasks, c);
-        __syncthreads();
-        const uint32_t t = sTask;
-        const Task& tk = tasks[t];
-        if (tk.kind != kObject && tk.kind != kMedian) continue;
-        const AxisBins ab = axis_bins(tk.lo[tk.axis], tk.hi[tk.axis], nb);
-        const uint32_t off = (c - chunkBase[t]) * kChunk;
-        const uint32_t end = tk.start + tk.count;
-        const uint32_t nFirst = tk.nFirst, nSecond = tk.count - tk.nFirst;
-        uint32_t baseFirst = chunkFirst[c];     // refs of this task before this chunk that go first
-        uint32_t baseSecond = off - baseFirst;  // ... and second
-        for (uint32_t r = 0; r < kChunk / kBigBlock; r++) {
-            const uint32_t p = tk.start + off + r * kBigBlock + threadIdx.x;
-            const bool valid = p < end;
-            float4 l = make_float4(0, 0, 0, 0), h = l;
-            bool first = false;
-            if (valid) {
-                l = rlo[p];
-                h = rhi[p];
-                first = goes_left(tk, ab, nb, l, h) != (tk.leftIsSecond != 0u);
-            }
-            const unsigned bf = __ballot_sync(kFullMask, valid && first);
-            const unsigned bs = __ballot_sync(kFullMask, valid && !first);
-            if (lane == 0) { sWarpFirst[warp] = __popc(bf); sWarpSecond[warp] = __popc(bs); }
-            __syncthreads();
-            uint32_t wf = 0, ws = 0, tf = 0, ts = 0;
+        const ChunkInfo ci = chunkInfo[c];
+        float4 l[4], h[4];
 #pragma unroll
-            for (int w = 0; w < kBigBlock / 32; w++) {
-                const uint32_t a = sWarpFirst[w], b = sWarpSecond[w];
-                if (uint32_t(w) < warp) { wf += a; ws += b; }
-                tf += a; ts += b;
-            }
-            if (valid) {
-                const unsigned lt = (1u << lane) - 1u;
-                const uint32_t dst = tk.start + (first ? baseFirst + wf + __popc(bf & lt)
-                                                       : nFirst + baseSecond + ws + __popc(bs & lt));
-                wlo[dst] = l;
-                whi[dst] = h;
-                if ((first ? nFirst : nSecond) == 1u) { order[dst] = __float_as_uint(l.w); eon[dst] = 1; }
-            }
-            baseFirst += tf;
-            baseSecond += ts;
-            __syncthreads();
+        for (uint32_t r = 0; r < 4; r++) {
+            const uint32_t i = warp * kWarpSlice + r * 32u + lane;
+            if (i < ci.nValid) { l[r] = rlo[ci.refStart + i]; h[r] = rhi[ci.refStart + i]; }
         }
+        const uint32_t baseFirst = chunkFirst[c];   // refs of this task before this chunk that go first
+        const Task& tk = tasks[ci.task];
+        if (tk.kind != kObject && tk.kind != kMedian) continue;   // uniform for the CTA
+        const AxisBins ab = axis_bins(tk.lo[tk.axis], tk.hi[tk.axis], nb);
+        const uint32_t nFirst = tk.nFirst, nSecond = tk.count - tk.nFirst;
+        unsigned bf[4], bv[4];
+        uint32_t myFirst = 0;
+#pragma unroll
+        for (uint32_t r = 0; r < 4; r++) {
+            const uint32_t i = warp * kWarpSlice + r * 32u + lane;
+            const bool valid = i < ci.nValid;
+            const bool first = valid && (goes_left(tk, ab, nb, l[r], h[r]) != (tk.leftIsSecond != 0u));
+            bf[r] = __ballot_sync(kFullMask, first);
+            bv[r] = __ballot_sync(kFullMask, valid);
+            myFirst += __popc(bf[r]);
+        }
+        if (lane == 0) sWarpFirst[it][warp] = myFirst;
+        __syncthreads();
+        uint32_t wf = 0;   // firsts in the slices of the warps before this one
+#pragma unroll
+        for (int w = 0; w < kBigBlock / 32; w++) wf += uint32_t(w) < warp ? sWarpFirst[it][w] : 0u;
+        // position inside the task of this warp's first ref = ci.off + warp * kWarpSlice; seconds before = that - firsts before
+        uint32_t doneFirst = baseFirst + wf;
+        uint32_t doneSecond = ci.off + min(warp * kWarpSlice, ci.nValid) - doneFirst;
+        const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+        for (uint32_t r = 0; r < 4; r++) {
+            const bool valid = (bv[r] >> lane) & 1u, first = (bf[r] >> lane) & 1u;
+            const unsigned bs = bv[r] & ~bf[r];
+            if (valid) {
+                const uint32_t dst = tk.start + (first ? doneFirst + __popc(bf[r] & lt) : nFirst + doneSecond + __popc(bs & lt));
+                wlo[dst] = l[r];
+                whi[dst] = h[r];
+                if ((first ? nFirst : nSecond) == 1u) { order[dst] = __float_as_uint(l[r].w); eon[dst] = 1; }
+            }
+            doneFirst += __popc(bf[r]);
+            doneSecond += __popc(bs);
+        }
+        it ^= 1u;   // only iterations that passed the barrier alternate the buffer
     }
 }
 
@@ -1555,7 +1607,7 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
     auto cleanup = [&]() {
         for (int k = 0; k < 2; k++) { dev_free(ctx, B.lo[k]); dev_free(ctx, B.hi[k]); dev_free(ctx, B.tasks[k]); }
         dev_free(ctx, B.small); dev_free(ctx, B.info); dev_free(ctx, B.root); dev_free(ctx, B.bins); dev_free(ctx, B.sfx);
-        dev_free(ctx, B.spaBins); dev_free(ctx, B.medAcc); dev_free(ctx, B.chunkBase); dev_free(ctx, B.chunkFirst);
+        dev_free(ctx, B.spaBins); dev_free(ctx, B.medAcc); dev_free(ctx, B.chunkBase); dev_free(ctx, B.chunkFirst); dev_free(ctx, B.chunkInfo);
         dev_free(ctx, B.rootBox); dev_free(ctx, tmpLlo); dev_free(ctx, tmpLhi); dev_free(ctx, tmpRlo); dev_free(ctx, tmpRhi);
         dev_free(ctx, strad); dev_free(ctx, spaCounts);
     };
@@ -1577,6 +1629,7 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
     ATLAS_CUDA_C(ctx, dev_alloc(ctx, &B.medAcc, size_t(maxTasks) * 16));
     ATLAS_CUDA_C(ctx, dev_alloc(ctx, &B.chunkBase, maxTasks));
     ATLAS_CUDA_C(ctx, dev_alloc(ctx, &B.chunkFirst, maxChunks));
+    ATLAS_CUDA_C(ctx, dev_alloc(ctx, &B.chunkInfo, maxChunks));
     ATLAS_CUDA_C(ctx, dev_alloc(ctx, &B.rootBox, 8));
     ATLAS_CUDA_C(ctx, cudaMemsetAsync(B.info, 0, sizeof(LevelInfo), st));
     ATLAS_CUDA_C(ctx, cudaMemsetAsync(B.root, 0, sizeof(RootSplit), st));
@@ -1622,37 +1675,35 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
         const uint32_t chunksBound = std::min<uint32_t>(totalRefs / kChunk + tasksBound + 1u, maxChunks);
         const uint32_t gridChunks = std::max(1u, std::min(chunksBound, persistent));
         const uint32_t warpGrid = (tasksBound * 32u + 127u) / 128u;
-        const size_t binSmem = size_t(3) * nb * kBinWords * sizeof(int);
+        const size_t binSmem = size_t(3) * nb * kSmemBin * sizeof(int);
         Task* tasks = B.tasks[cur];
         Lists L{B.tasks[cur ^ 1u], B.small, B.info, B.nodes, B.budget, cur ^ 1u, maxTasks, maxSmall};
         const float4 *rlo = B.lo[cur], *rhi = B.hi[cur];
         float4 *wlo = B.lo[cur ^ 1u], *whi = B.hi[cur ^ 1u];
 
-        prepare_level<<<1, 1024, 0, st>>>(tasks, B.info, B.chunkBase, depth > 0 ? 1 : 0);
+        prepare_level<<<1, 1024, 0, st>>>(tasks, B.info, B.chunkBase, B.chunkInfo, B.chunkFirst, depth > 0 ? 1 : 0);
         ATLAS_LAUNCHED(ctx);
         init_bins<<<std::max(1u, std::min<uint32_t>(persistent, (tasksBound * 3u * nb + 255u) / 256u)), 256, 0, st>>>(B.bins, B.info, 3u * nb);
         ATLAS_LAUNCHED(ctx);
         const uint32_t gridBin = std::max(1u, std::min(chunksBound, uint32_t(ctx->smCount) * 2u));
-        bin_big<<<gridBin, kBigBlock, binSmem, st>>>(tasks, B.info, B.chunkBase, rlo, rhi, B.bins, nb);
+        bin_big<<<gridBin, kBigBlock, binSmem, st>>>(tasks, B.info, B.chunkInfo, rlo, rhi, B.bins, nb);
         ATLAS_LAUNCHED(ctx);
 
         bool spatialPath = false;
         if (depth == 0 && !tlas) {
             select_root_object<<<1, 32, 0, st>>>(tasks, B.info, B.bins, B.sfx, B.root, nb);
             ATLAS_LAUNCHED(ctx);
-            ATLAS_TRY(read_back(ctx, B.info, &info));
-            const int trySpatial = info.rootNeedSpatial ? 1 : 0;
-            if (trySpatial) {
-                const int initGrid = 3;
-                init_bins<<<initGrid, 256, 0, st>>>(B.spaBins, B.info, 3u * nb);   // nTasks == 1
-                ATLAS_LAUNCHED(ctx);
-                spatial_bin_root<<<gridBin, kBigBlock, binSmem, st>>>(tasks, rlo, rhi, B.tris, B.spaBins, nb);
-                ATLAS_LAUNCHED(ctx);
-            }
-            select_root_final<<<1, 32, 0, st>>>(tasks, B.info, B.bins, B.spaBins, B.sfx, B.medAcc, B.root, L, nb, trySpatial);
+            // the spatial binning is enqueued unconditionally and falls through on the device when the object split's
+            // children do not overlap enough (no host round trip for that decision)
+            init_bins<<<3, 256, 0, st>>>(B.spaBins, B.info, 3u * nb);   // nTasks == 1
+            ATLAS_LAUNCHED(ctx);
+            spatial_bin_root<<<std::max(1u, std::min(chunksBound, uint32_t(ctx->smCount) * 3u)), kBigBlock, binSmem, st>>>(
+                tasks, B.info, rlo, rhi, B.tris, B.spaBins, nb);
+            ATLAS_LAUNCHED(ctx);
+            select_root_final<<<1, 32, 0, st>>>(tasks, B.info, B.bins, B.spaBins, B.sfx, B.medAcc, B.root, L, nb);
             ATLAS_LAUNCHED(ctx);
             ATLAS_TRY(read_back(ctx, B.info, &info));
-            out->stats[0] = trySpatial;
+            out->stats[0] = info.rootNeedSpatial ? 1 : 0;
             spatialPath = info.rootKind == uint32_t(kSpatial);
         } else {
             select_big<<<warpGrid, 128, 0, st>>>(tasks, B.info, B.bins, B.sfx, B.medAcc, L, nb);
@@ -1681,16 +1732,16 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
             spatial_place<<<gridChunks, 256, 0, st>>>(tasks, B.root, tmpLlo, tmpLhi, tmpRlo, tmpRhi, wlo, whi, B.order, B.eon);
             ATLAS_LAUNCHED(ctx);
         } else {
-            median_reduce_big<<<gridChunks, kBigBlock, 0, st>>>(tasks, B.info, B.chunkBase, rlo, rhi, B.medAcc);
+            median_reduce_big<<<gridChunks, kBigBlock, 0, st>>>(tasks, B.info, B.chunkInfo, rlo, rhi, B.medAcc);
             ATLAS_LAUNCHED(ctx);
             median_finalize_big<<<warpGrid, 128, 0, st>>>(tasks, B.info, B.medAcc, B.lo[cur], B.hi[cur], wlo, whi, B.order, B.eon, L,
                                                           (!tlas && depth == 0) ? 1 : 0);
             ATLAS_LAUNCHED(ctx);
-            partition_count<<<gridChunks, kBigBlock, 0, st>>>(tasks, B.info, B.chunkBase, rlo, rhi, B.chunkFirst, nb);
+            partition_count<<<gridChunks, kBigBlock, 0, st>>>(tasks, B.info, B.chunkInfo, rlo, rhi, B.chunkFirst, nb);
             ATLAS_LAUNCHED(ctx);
             partition_scan<<<warpGrid, 128, 0, st>>>(tasks, B.info, B.chunkBase, B.chunkFirst);
             ATLAS_LAUNCHED(ctx);
-            partition_scatter<<<gridChunks, kBigBlock, 0, st>>>(tasks, B.info, B.chunkBase, B.chunkFirst, rlo, rhi, wlo, whi, B.order,
+            partition_scatter<<<gridChunks, kBigBlock, 0, st>>>(tasks, B.info, B.chunkInfo, B.chunkFirst, rlo, rhi, wlo, whi, B.order,
                                                                 B.eon, nb);
             ATLAS_LAUNCHED(ctx);
         }
