@@ -162,6 +162,7 @@ int atlas_rt_context_create(int device, void* stream, atlas_rt_context** out_ctx
     if (const char* e = getenv("ATLAS_RT_TRACE_RAYS_PER_WARP")) ctx->traceRaysPerWarp = std::max(1, atoi(e));
     if (const char* e = getenv("ATLAS_RT_TRACE_LONGEST_FIRST")) ctx->traceLongestFirst = atoi(e);
     if (const char* e = getenv("ATLAS_RT_TRACE_BLOCKS_PER_SM")) ctx->traceBlocksPerSM = std::max(1, std::min(9, atoi(e)));
+    if (const char* e = getenv("ATLAS_RT_BIN_CTAS_PER_SM")) ctx->binCtasPerSM = std::max(1, std::min(8, atoi(e)));
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t keep = ~0ull;

@@ -94,7 +94,6 @@ struct BuildBuffers {
     LevelInfo* info;
     RootSplit* root;
     int* bins;          // [task][axis][bin][8]
-    int* sfx;           // [task][bin][6]
     int* spaBins;       // [axis][256][8] root spatial bins
     int* medAcc;        // [task][16]
     uint32_t* chunkBase;    // [task]
@@ -290,8 +289,12 @@ bin_big(const Task* __restrict__ tasks, const LevelInfo* __restrict__ info, cons
             const int* rec = sb + e * kSmemBin;
             if (rec[6] > 0) {
                 int* d = g + e * kBinWords;
+                // same monotone-value shortcut as in shared memory, reading past L1 (this level's values only)
 #pragma unroll
-                for (int k = 0; k < 3; k++) { atomicMin(d + k, rec[k]); atomicMax(d + 3 + k, rec[3 + k]); }
+                for (int k = 0; k < 3; k++) {
+                    if (rec[k] < __ldcg(d + k)) atomicMin(d + k, rec[k]);
+                    if (rec[3 + k] > __ldcg(d + 3 + k)) atomicMax(d + 3 + k, rec[3 + k]);
+                }
                 atomicAdd(d + 6, rec[6]);
                 atomicAdd(d + 7, rec[6]);   // exit == enter == primitiveCount for the object split
             }
@@ -411,21 +414,46 @@ __device__ __forceinline__ void start_median(Task& t, int* acc, LevelInfo* info)
 }
 
 // ------------------------------------------------------------------------------------------- split selection
-// Build #2 decision (BVH.cpp:351-370) for every big node of the level: one warp per node.
-__global__ void select_big(Task* __restrict__ tasks, LevelInfo* __restrict__ info, const int* __restrict__ gbins,
-                           int* __restrict__ gsfx, int* __restrict__ medAcc, Lists L, uint32_t nb) {
-    const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+constexpr int kSelectBlock = 128;
+__host__ __device__ constexpr size_t select_smem(uint32_t nb) { return size_t(3) * nb * (kSmemBin + 6) * sizeof(int); }
+
+// Best object / spatial split of one node from its global bins, by a CTA of kSelectBlock threads: the bins are staged
+// in shared memory (stride kSmemBin; they stay there for warp_split_boxes), warps 0..2 sweep one axis each, and the
+// results are combined in axis order with a strict <, i.e. the lowest axis wins ties like the loop of BVH.cpp:463-523.
+__device__ inline BestSplit cta_best_split(const int* __restrict__ gbins, uint32_t nb, const Task& tk, int* sbins, int* ssfx,
+                                           BestSplit* sBest) {
+    for (uint32_t i = threadIdx.x; i < 3u * nb * kBinWords; i += kSelectBlock) sbins[(i >> 3) * kSmemBin + (i & 7u)] = gbins[i];
+    __syncthreads();
+    const uint32_t warp = threadIdx.x >> 5;
+    if (warp < 3u) {
+        BestSplit b = best_none();
+        const AxisBins ab = axis_bins(tk.lo[warp], tk.hi[warp], nb);
+        if (ab.active) warp_sweep_axis(sbins + warp * nb * kSmemBin, nb, ssfx + warp * nb * 6, tk.count, int(warp), b, kSmemBin);
+        if ((threadIdx.x & 31u) == 0u) sBest[warp] = b;
+    }
+    __syncthreads();
+    BestSplit best = best_none();
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const BestSplit b = sBest[a];
+        if (b.axis >= 0 && b.cost < best.cost) best = b;
+    }
+    return best;
+}
+
+// Build #2 decision (BVH.cpp:351-370) for every big node of the level: one CTA per node.
+__global__ void __launch_bounds__(kSelectBlock)
+select_big(Task* __restrict__ tasks, LevelInfo* __restrict__ info, const int* __restrict__ gbins, int* __restrict__ medAcc, Lists L,
+           uint32_t nb) {
+    extern __shared__ int ss[];   // bins [3][nb][kSmemBin], suffix boxes [3][nb][6]
+    __shared__ BestSplit sBest[3];
+    const uint32_t t = blockIdx.x;
     if (t >= info->nTasks) return;
     const uint32_t lane = threadIdx.x & 31u;
     Task tk = tasks[t];
-    const int* bins = gbins + size_t(t) * 3 * nb * kBinWords;
-    int* sfx = gsfx + size_t(t) * nb * 6;
-    BestSplit best = best_none();
-    for (int a = 0; a < 3; a++) {
-        const AxisBins ab = axis_bins(tk.lo[a], tk.hi[a], nb);
-        if (!ab.active) continue;
-        warp_sweep_axis(bins + size_t(a) * nb * kBinWords, nb, sfx, tk.count, a, best);
-    }
+    int* sbins = ss;
+    const BestSplit best = cta_best_split(gbins + size_t(t) * 3 * nb * kBinWords, nb, tk, sbins, ss + 3 * nb * kSmemBin, sBest);
+    if (threadIdx.x >= 32u) return;
     const float nodeCost = __fmul_rn(__uint2float_rn(tk.count), surface_area(tk.lo, tk.hi));   // BVH.cpp:238
     if (best.axis < 0 || best.cost >= nodeCost) {
         if (lane == 0) {
@@ -436,7 +464,7 @@ __global__ void select_big(Task* __restrict__ tasks, LevelInfo* __restrict__ inf
     }
     OBox l, r;
     uint32_t nLeft, nExit;
-    warp_split_boxes(bins + size_t(best.axis) * nb * kBinWords, nb, best.bin, l, r, nLeft, nExit);
+    warp_split_boxes(sbins + size_t(best.axis) * nb * kSmemBin, nb, best.bin, l, r, nLeft, nExit, kSmemBin);
     if (lane == 0) {
         tk.kind = kObject;
         tk.axis = best.axis;
@@ -447,21 +475,21 @@ __global__ void select_big(Task* __restrict__ tasks, LevelInfo* __restrict__ inf
 }
 
 // Build #1, first half (BVH.cpp:258-268): object split of the BLAS root and the "try a spatial split?" test.
-__global__ void select_root_object(Task* __restrict__ tasks, LevelInfo* __restrict__ info, const int* __restrict__ gbins,
-                                   int* __restrict__ gsfx, RootSplit* __restrict__ root, uint32_t nb) {
+__global__ void __launch_bounds__(kSelectBlock)
+select_root_object(Task* __restrict__ tasks, LevelInfo* __restrict__ info, const int* __restrict__ gbins, RootSplit* __restrict__ root,
+                   uint32_t nb) {
+    extern __shared__ int ss[];
+    __shared__ BestSplit sBest[3];
     const uint32_t lane = threadIdx.x & 31u;
     Task tk = tasks[0];
-    BestSplit best = best_none();
-    for (int a = 0; a < 3; a++) {
-        const AxisBins ab = axis_bins(tk.lo[a], tk.hi[a], nb);
-        if (!ab.active) continue;
-        warp_sweep_axis(gbins + size_t(a) * nb * kBinWords, nb, gsfx, tk.count, a, best);
-    }
+    int* sbins = ss;
+    const BestSplit best = cta_best_split(gbins, nb, tk, sbins, ss + 3 * nb * kSmemBin, sBest);
+    if (threadIdx.x >= 32u) return;
     Box3 l = empty_box(), r = empty_box();
     if (best.axis >= 0) {
         OBox ol, orr;
         uint32_t nLeft, nExit;
-        warp_split_boxes(gbins + size_t(best.axis) * nb * kBinWords, nb, best.bin, ol, orr, nLeft, nExit);
+        warp_split_boxes(sbins + size_t(best.axis) * nb * kSmemBin, nb, best.bin, ol, orr, nLeft, nExit, kSmemBin);
         l = obox_to_box(ol);
         r = obox_to_box(orr);
     }
@@ -599,20 +627,18 @@ spatial_bin_root(const Task* __restrict__ tasks, const LevelInfo* __restrict__ i
 }
 
 // Build #1, second half (BVH.cpp:276-301): choose between median, spatial and object split for the BLAS root.
-__global__ void select_root_final(Task* __restrict__ tasks, LevelInfo* __restrict__ info, const int* __restrict__ objBins,
-                                  const int* __restrict__ spaBins, int* __restrict__ gsfx, int* __restrict__ medAcc,
-                                  RootSplit* __restrict__ root, Lists L, uint32_t nb) {
+__global__ void __launch_bounds__(kSelectBlock)
+select_root_final(Task* __restrict__ tasks, LevelInfo* __restrict__ info, const int* __restrict__ objBins,
+                  const int* __restrict__ spaBins, int* __restrict__ medAcc, RootSplit* __restrict__ root, Lists L, uint32_t nb) {
+    extern __shared__ int ss[];
+    __shared__ BestSplit sBest[3];
     const uint32_t lane = threadIdx.x & 31u;
     const bool trySpatial = info->rootNeedSpatial != 0u;
     Task tk = tasks[0];
+    int* sbins = ss;   // the spatial bins when a spatial split is tried
     BestSplit spa = best_none();
-    if (trySpatial) {
-        for (int a = 0; a < 3; a++) {
-            const AxisBins ab = axis_bins(tk.lo[a], tk.hi[a], nb);
-            if (!ab.active) continue;
-            warp_sweep_axis(spaBins + size_t(a) * nb * kBinWords, nb, gsfx, tk.count, a, spa);
-        }
-    }
+    if (trySpatial) spa = cta_best_split(spaBins, nb, tk, sbins, ss + 3 * nb * kSmemBin, sBest);
+    if (threadIdx.x >= 32u) return;
     const float objCost = root->objCost;
     const int objAxis = root->objAxis;
     const float nodeCost = __fmul_rn(__uint2float_rn(tk.count), surface_area(tk.lo, tk.hi));   // BVH.cpp:230
@@ -627,7 +653,7 @@ __global__ void select_root_final(Task* __restrict__ tasks, LevelInfo* __restric
     if (spa.cost < objCost) {
         OBox l, r;
         uint32_t nEnter, nExit;
-        warp_split_boxes(spaBins + size_t(spa.axis) * nb * kBinWords, nb, spa.bin, l, r, nEnter, nExit);
+        warp_split_boxes(sbins + size_t(spa.axis) * nb * kSmemBin, nb, spa.bin, l, r, nEnter, nExit, kSmemBin);
         if (lane == 0) {
             const AxisBins ab = axis_bins(tk.lo[spa.axis], tk.hi[spa.axis], nb);
             tk.kind = kSpatial;
@@ -1606,7 +1632,7 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
     uint32_t* spaCounts = nullptr;
     auto cleanup = [&]() {
         for (int k = 0; k < 2; k++) { dev_free(ctx, B.lo[k]); dev_free(ctx, B.hi[k]); dev_free(ctx, B.tasks[k]); }
-        dev_free(ctx, B.small); dev_free(ctx, B.info); dev_free(ctx, B.root); dev_free(ctx, B.bins); dev_free(ctx, B.sfx);
+        dev_free(ctx, B.small); dev_free(ctx, B.info); dev_free(ctx, B.root); dev_free(ctx, B.bins);
         dev_free(ctx, B.spaBins); dev_free(ctx, B.medAcc); dev_free(ctx, B.chunkBase); dev_free(ctx, B.chunkFirst); dev_free(ctx, B.chunkInfo);
         dev_free(ctx, B.rootBox); dev_free(ctx, tmpLlo); dev_free(ctx, tmpLhi); dev_free(ctx, tmpRlo); dev_free(ctx, tmpRhi);
         dev_free(ctx, strad); dev_free(ctx, spaCounts);
@@ -1624,7 +1650,6 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
     ATLAS_CUDA_C(ctx, dev_alloc(ctx, &B.info, 1));
     ATLAS_CUDA_C(ctx, dev_alloc(ctx, &B.root, 1));
     ATLAS_CUDA_C(ctx, dev_alloc(ctx, &B.bins, binRecords * 3 * kBinWords));
-    ATLAS_CUDA_C(ctx, dev_alloc(ctx, &B.sfx, binRecords * 6));
     ATLAS_CUDA_C(ctx, dev_alloc(ctx, &B.spaBins, size_t(3) * 256 * kBinWords));
     ATLAS_CUDA_C(ctx, dev_alloc(ctx, &B.medAcc, size_t(maxTasks) * 16));
     ATLAS_CUDA_C(ctx, dev_alloc(ctx, &B.chunkBase, maxTasks));
@@ -1685,13 +1710,13 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
         ATLAS_LAUNCHED(ctx);
         init_bins<<<std::max(1u, std::min<uint32_t>(persistent, (tasksBound * 3u * nb + 255u) / 256u)), 256, 0, st>>>(B.bins, B.info, 3u * nb);
         ATLAS_LAUNCHED(ctx);
-        const uint32_t gridBin = std::max(1u, std::min(chunksBound, uint32_t(ctx->smCount) * 2u));
+        const uint32_t gridBin = std::max(1u, std::min(chunksBound, uint32_t(ctx->smCount) * uint32_t(ctx->binCtasPerSM)));
         bin_big<<<gridBin, kBigBlock, binSmem, st>>>(tasks, B.info, B.chunkInfo, rlo, rhi, B.bins, nb);
         ATLAS_LAUNCHED(ctx);
 
         bool spatialPath = false;
         if (depth == 0 && !tlas) {
-            select_root_object<<<1, 32, 0, st>>>(tasks, B.info, B.bins, B.sfx, B.root, nb);
+            select_root_object<<<1, kSelectBlock, select_smem(nb), st>>>(tasks, B.info, B.bins, B.root, nb);
             ATLAS_LAUNCHED(ctx);
             // the spatial binning is enqueued unconditionally and falls through on the device when the object split's
             // children do not overlap enough (no host round trip for that decision)
@@ -1700,13 +1725,13 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
             spatial_bin_root<<<std::max(1u, std::min(chunksBound, uint32_t(ctx->smCount) * 3u)), kBigBlock, binSmem, st>>>(
                 tasks, B.info, rlo, rhi, B.tris, B.spaBins, nb);
             ATLAS_LAUNCHED(ctx);
-            select_root_final<<<1, 32, 0, st>>>(tasks, B.info, B.bins, B.spaBins, B.sfx, B.medAcc, B.root, L, nb);
+            select_root_final<<<1, kSelectBlock, select_smem(nb), st>>>(tasks, B.info, B.bins, B.spaBins, B.medAcc, B.root, L, nb);
             ATLAS_LAUNCHED(ctx);
             ATLAS_TRY(read_back(ctx, B.info, &info));
             out->stats[0] = info.rootNeedSpatial ? 1 : 0;
             spatialPath = info.rootKind == uint32_t(kSpatial);
         } else {
-            select_big<<<warpGrid, 128, 0, st>>>(tasks, B.info, B.bins, B.sfx, B.medAcc, L, nb);
+            select_big<<<tasksBound, kSelectBlock, select_smem(nb), st>>>(tasks, B.info, B.bins, B.medAcc, L, nb);
             ATLAS_LAUNCHED(ctx);
         }
 

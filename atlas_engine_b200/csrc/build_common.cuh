@@ -173,7 +173,7 @@ struct LaneGroup {
 // axis improved `best`.
 template <int G, bool STORE_PREFIX, typename BinPtr>
 __device__ inline bool group_sweep_axis(const LaneGroup<G>& g, BinPtr bins, uint32_t nb, int* sfx, uint32_t total, int axis,
-                                        BestSplit& best) {
+                                        BestSplit& best, int stride = kBinWords) {
     const uint32_t lane = g.lane;
     const uint32_t chunks = (nb + G - 1u) / G;
     // ---- backward pass: sfx[k] = union of bins[k..nb-1]
@@ -183,7 +183,7 @@ __device__ inline bool group_sweep_axis(const LaneGroup<G>& g, BinPtr bins, uint
         OBox b = obox_empty();
         if (k < nb) {
 #pragma unroll
-            for (int w = 0; w < 3; w++) { b.lo[w] = bins[k * kBinWords + w]; b.hi[w] = bins[k * kBinWords + 3 + w]; }
+            for (int w = 0; w < 3; w++) { b.lo[w] = bins[k * stride + w]; b.hi[w] = bins[k * stride + 3 + w]; }
         }
 #pragma unroll
         for (int off = 1; off < G; off <<= 1) {
@@ -212,9 +212,9 @@ __device__ inline bool group_sweep_axis(const LaneGroup<G>& g, BinPtr bins, uint
         uint32_t en = 0, ex = 0;
         if (k < nb) {
 #pragma unroll
-            for (int w = 0; w < 3; w++) { b.lo[w] = bins[k * kBinWords + w]; b.hi[w] = bins[k * kBinWords + 3 + w]; }
-            en = uint32_t(bins[k * kBinWords + 6]);
-            ex = uint32_t(bins[k * kBinWords + 7]);
+            for (int w = 0; w < 3; w++) { b.lo[w] = bins[k * stride + w]; b.hi[w] = bins[k * stride + 3 + w]; }
+            en = uint32_t(bins[k * stride + 6]);
+            ex = uint32_t(bins[k * stride + 7]);
         }
 #pragma unroll
         for (int off = 1; off < G; off <<= 1) {
@@ -228,7 +228,7 @@ __device__ inline bool group_sweep_axis(const LaneGroup<G>& g, BinPtr bins, uint
         en += ecarry;
         ex += xcarry;
         if (STORE_PREFIX && k < nb) {
-            int* rec = const_cast<int*>(bins) + k * kBinWords;
+            int* rec = const_cast<int*>(bins) + k * stride;
 #pragma unroll
             for (int w = 0; w < 3; w++) { rec[w] = b.lo[w]; rec[3 + w] = b.hi[w]; }
             rec[6] = int(en);
@@ -367,14 +367,15 @@ __device__ __forceinline__ bool group_sweep_single(const LaneGroup<G>& g, const 
     return true;
 }
 
-__device__ inline void warp_sweep_axis(const int* bins, uint32_t nb, int* sfx, uint32_t total, int axis, BestSplit& best) {
+__device__ inline void warp_sweep_axis(const int* bins, uint32_t nb, int* sfx, uint32_t total, int axis, BestSplit& best,
+                                       int stride = kBinWords) {
     const LaneGroup<32> g;
-    group_sweep_axis<32, false>(g, bins, nb, sfx, total, axis, best);
+    group_sweep_axis<32, false>(g, bins, nb, sfx, total, axis, best, stride);
 }
 
 // leftAABB / rightAABB / primitivesLeft of the chosen split, recomputed from the bins of the winning axis.
 __device__ inline void warp_split_boxes(const int* bins, uint32_t nb, uint32_t j, OBox& left, OBox& right, uint32_t& nLeft,
-                                        uint32_t& nExitLeft) {
+                                        uint32_t& nExitLeft, int stride = kBinWords) {
     const uint32_t lane = threadIdx.x & 31u;
     left = obox_empty();
     right = obox_empty();
@@ -382,11 +383,11 @@ __device__ inline void warp_split_boxes(const int* bins, uint32_t nb, uint32_t j
     for (uint32_t k = lane; k < nb; k += 32u) {
         OBox b;
 #pragma unroll
-        for (int w = 0; w < 3; w++) { b.lo[w] = bins[k * kBinWords + w]; b.hi[w] = bins[k * kBinWords + 3 + w]; }
+        for (int w = 0; w < 3; w++) { b.lo[w] = bins[k * stride + w]; b.hi[w] = bins[k * stride + 3 + w]; }
         if (k < j) {
             obox_grow(left, b);
-            en += uint32_t(bins[k * kBinWords + 6]);
-            ex += uint32_t(bins[k * kBinWords + 7]);
+            en += uint32_t(bins[k * stride + 6]);
+            ex += uint32_t(bins[k * stride + 7]);
         } else {
             obox_grow(right, b);
         }

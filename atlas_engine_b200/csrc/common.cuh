@@ -86,6 +86,7 @@ struct atlas_rt_context {
     int traceLeafThreshold = 8;     // lanes waiting at a leaf before the warp runs a leaf round
     int traceRefillThreshold = 16;  // idle lanes before the warp fetches new rays (swept with the longest-first order: 16-20 is best)
     int traceBlocksPerSM = 9;
+    int binCtasPerSM = 2;        // CTAs per SM of the builder's binning kernel (each merges its shared bins into global ones)
     int traceLongestFirst = 1;      // fetch rays longest-estimated-path first (hides the drain of the longest rays)
     int traceLongestFirstMin = 65536;
     int traceRaysPerWarp = 96;      // small batches use fewer persistent warps so each warp still sees this many rays
