@@ -553,41 +553,14 @@ __device__ inline void split_reference(const float* __restrict__ tri, const Box3
     else split_reference_t<2>(v, cur, L, R, plane);
 }
 
-__device__ __forceinline__ void bin_grow_shared(int* rec, const Box3& b) {
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        const int l = ord_from_float(b.lo[k]), h = ord_from_float(b.hi[k]);
-        if (l < rec[k]) atomicMin(rec + k, l);          // monotone values: a covering plain read makes the atomic unnecessary
-        if (h > rec[3 + k]) atomicMax(rec + 3 + k, h);
-    }
-}
-
-// One axis of FindSpatialSplit's binning for one ref (BVH.cpp:589-619): the ref's box is chopped at every bin boundary
-// it straddles, each piece grows its bin, and the first / last bin count an entry / an exit.
-template <int A>
-__device__ __forceinline__ void spatial_bin_axis(int* base, const AxisBins& ab, uint32_t nb, const Box3& box, const float (&v)[3][3]) {
-    if (!ab.active) return;
-    const uint32_t b0 = bin_of(box.lo[A], ab.start, ab.inv, nb);
-    const uint32_t b1 = bin_of(box.hi[A], ab.start, ab.inv, nb);
-    if (b0 == b1) {
-        bin_grow_shared(base + b0 * kSmemBin, box);
-    } else {
-        Box3 rest = box;
-        for (uint32_t j = b0; j < b1; j++) {
-            Box3 cl, cr;
-            const float plane = __fadd_rn(ab.start, __fmul_rn(__uint2float_rn(j + 1u), ab.width));
-            split_reference_t<A>(v, rest, cl, cr, plane);
-            bin_grow_shared(base + j * kSmemBin, cl);
-            rest = cr;
-        }
-        bin_grow_shared(base + b1 * kSmemBin, rest);
-    }
-    atomicAdd(base + b0 * kSmemBin + 6, 1);
-    atomicAdd(base + b1 * kSmemBin + 7, 1);
-}
-
-// FindSpatialSplit's binning over the root's refs; one ref per thread, bins in shared memory. Falls through when the
-// object split's children do not overlap enough for a spatial split to be considered (BVH.cpp:282-283).
+// FindSpatialSplit's binning over the root's refs (BVH.cpp:589-619): on every axis a ref's box is chopped at each bin
+// boundary it straddles (SplitReference chain), each piece grows its bin, the first / last bin count an entry / an exit.
+// Bins in shared memory. Chains differ in length from 1 to many pieces, so a lane does not own a ref for a fixed number
+// of steps: every lane walks its own sequence of (ref, axis) chains and all lanes of a warp emit ONE piece per step,
+// starting their next chain as soon as the current one ends. The chain's axis is kept in component 0 by rotating the
+// triangle and the box (x,y,z -> y,z,x) each time the axis advances — SplitReference treats the other two components
+// alike, so the arithmetic is the reference's, bit for bit — and results are rotated back when they grow a bin.
+// Falls through when the object split's children do not overlap enough for a spatial split to be tried (BVH.cpp:282).
 __global__ void __launch_bounds__(kBigBlock, 3)
 spatial_bin_root(const Task* __restrict__ tasks, const LevelInfo* __restrict__ info, const float4* __restrict__ rlo,
                  const float4* __restrict__ rhi, const float* __restrict__ tris, int* __restrict__ gbins, uint32_t nb) {
@@ -596,21 +569,80 @@ spatial_bin_root(const Task* __restrict__ tasks, const LevelInfo* __restrict__ i
     for (uint32_t e = threadIdx.x; e < 3 * nb; e += kBigBlock) bin_init(sb + e * kSmemBin);
     __syncthreads();
     const Task& tk = tasks[0];
+    const uint32_t count = tk.count;
     AxisBins ab[3];
 #pragma unroll
     for (int a = 0; a < 3; a++) ab[a] = axis_bins(tk.lo[a], tk.hi[a], nb);
-    for (uint32_t p = blockIdx.x * kBigBlock + threadIdx.x; p < tk.count; p += gridDim.x * kBigBlock) {
-        const float4 l = rlo[p], h = rhi[p];
-        Box3 box;
-        box.lo[0] = l.x; box.lo[1] = l.y; box.lo[2] = l.z;
-        box.hi[0] = h.x; box.hi[1] = h.y; box.hi[2] = h.z;
-        const float* tri = tris + 9 * size_t(__float_as_uint(l.w));
-        float v[3][3];
+    const uint32_t stride = gridDim.x * kBigBlock;
+    uint32_t p = blockIdx.x * kBigBlock + threadIdx.x;
+    float v[3][3];        // triangle, rotated so that the chain's axis is component 0
+    Box3 rest;            // what is left of the ref's box on this chain (rotated)
+    Box3 whole;           // the ref's box (rotated)
+    int axis = 2;         // axis of the current chain
+    bool haveRef = false;
+    bool alive = p < count;
+    uint32_t j = 1, b1 = 0;   // next piece's bin and the chain's last bin; j > b1: chain finished
+    float cStart = 0.0f, cWidth = 0.0f;
+    int* base = sb;
+    while (true) {
+        // ---- lanes whose chain is finished move to their next one
+        if (alive && j > b1) {
+            while (true) {
+                if (!haveRef) {
+                    if (p >= count) { alive = false; break; }
+                    const float4 l = rlo[p], h = rhi[p];
+                    const float* tri = tris + 9 * size_t(__float_as_uint(l.w));
 #pragma unroll
-        for (int k = 0; k < 9; k++) v[k / 3][k % 3] = tri[k];
-        spatial_bin_axis<0>(sb, ab[0], nb, box, v);
-        spatial_bin_axis<1>(sb + nb * kSmemBin, ab[1], nb, box, v);
-        spatial_bin_axis<2>(sb + 2 * nb * kSmemBin, ab[2], nb, box, v);
+                    for (int k = 0; k < 9; k++) v[k / 3][k % 3] = tri[k];
+                    whole.lo[0] = l.x; whole.lo[1] = l.y; whole.lo[2] = l.z;
+                    whole.hi[0] = h.x; whole.hi[1] = h.y; whole.hi[2] = h.z;
+                    haveRef = true;
+                    axis = 0;
+                } else {
+                    axis++;
+                    if (axis == 3) { haveRef = false; p += stride; continue; }
+                    // x,y,z -> y,z,x
+#pragma unroll
+                    for (int e = 0; e < 3; e++) { const float t0 = v[e][0]; v[e][0] = v[e][1]; v[e][1] = v[e][2]; v[e][2] = t0; }
+                    { const float t0 = whole.lo[0]; whole.lo[0] = whole.lo[1]; whole.lo[1] = whole.lo[2]; whole.lo[2] = t0; }
+                    { const float t0 = whole.hi[0]; whole.hi[0] = whole.hi[1]; whole.hi[1] = whole.hi[2]; whole.hi[2] = t0; }
+                }
+                const bool active = axis == 0 ? ab[0].active : (axis == 1 ? ab[1].active : ab[2].active);
+                if (!active) continue;
+                cStart = axis == 0 ? ab[0].start : (axis == 1 ? ab[1].start : ab[2].start);
+                cWidth = axis == 0 ? ab[0].width : (axis == 1 ? ab[1].width : ab[2].width);
+                const float inv = axis == 0 ? ab[0].inv : (axis == 1 ? ab[1].inv : ab[2].inv);
+                j = bin_of(whole.lo[0], cStart, inv, nb);
+                b1 = bin_of(whole.hi[0], cStart, inv, nb);
+                base = sb + axis * nb * kSmemBin;
+                rest = whole;
+                atomicAdd(base + j * kSmemBin + 6, 1);
+                break;
+            }
+        }
+        if (!__any_sync(kFullMask, alive)) break;
+        // ---- every live lane emits one piece of its chain
+        if (alive) {
+            Box3 piece = rest;
+            if (j < b1) {
+                Box3 cr;
+                const float plane = __fadd_rn(cStart, __fmul_rn(__uint2float_rn(j + 1u), cWidth));
+                split_reference_t<0>(v, rest, piece, cr, plane);
+                rest = cr;
+            }
+            int* rec = base + j * kSmemBin;
+            // rotated component k is the original component (k + axis) % 3
+            const int c0 = axis, c1 = axis == 2 ? 0 : axis + 1, c2 = axis == 0 ? 2 : axis - 1;
+            const int cc[3] = {c0, c1, c2};
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const int lo = ord_from_float(piece.lo[k]), hi = ord_from_float(piece.hi[k]);
+                if (lo < rec[cc[k]]) atomicMin(rec + cc[k], lo);   // monotone values: a covering plain read makes the atomic unnecessary
+                if (hi > rec[3 + cc[k]]) atomicMax(rec + 3 + cc[k], hi);
+            }
+            if (j == b1) atomicAdd(rec + 7, 1);
+            j++;
+        }
     }
     __syncthreads();
     for (uint32_t e = threadIdx.x; e < 3 * nb; e += kBigBlock) {
@@ -840,36 +872,21 @@ partition_count(const Task* __restrict__ tasks, const LevelInfo* __restrict__ in
     }
 }
 
-// exclusive scan of chunkFirst inside every task (one warp per task)
-__global__ void partition_scan(const Task* __restrict__ tasks, const LevelInfo* __restrict__ info,
-                               const uint32_t* __restrict__ chunkBase, uint32_t* __restrict__ chunkFirst) {
-    const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (t >= info->nTasks) return;
-    const uint32_t lane = threadIdx.x & 31u;
-    const Task& tk = tasks[t];
-    if (tk.kind != kObject && tk.kind != kMedian) return;
-    const uint32_t base = chunkBase[t], n = (tk.count + kChunk - 1) / kChunk;
-    uint32_t carry = 0;
-    for (uint32_t b = 0; b < n; b += 32u) {
-        const uint32_t i = b + lane;
-        const uint32_t v = i < n ? chunkFirst[base + i] : 0u;
-        uint32_t s = v;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const uint32_t o = __shfl_up_sync(kFullMask, s, off);
-            if (lane >= uint32_t(off)) s += o;
-        }
-        if (i < n) chunkFirst[base + i] = carry + s - v;
-        carry += __shfl_sync(kFullMask, s, 31);
-    }
-}
-
+// Stable partition of every big node into its children's final segments. A chunk's base = the firsts of the chunks of
+// the same node before it, summed here from the per-chunk counts (at most a few KB, L2 resident) — no separate scan.
+// Also resets the global bins of the NEXT level's nodes, which nothing reads at this point.
 __global__ void __launch_bounds__(kBigBlock)
 partition_scatter(const Task* __restrict__ tasks, const LevelInfo* __restrict__ info, const ChunkInfo* __restrict__ chunkInfo,
                   const uint32_t* __restrict__ chunkFirst, const float4* __restrict__ rlo, const float4* __restrict__ rhi,
                   float4* __restrict__ wlo, float4* __restrict__ whi, uint32_t* __restrict__ order, uint8_t* __restrict__ eon,
-                  uint32_t nb) {
+                  uint32_t nb, int* __restrict__ nextBins, uint32_t nextBinsPerTask3, uint32_t nextTaskCap) {
     __shared__ uint32_t sWarpFirst[2][kBigBlock / 32];   // double-buffered by iteration: one barrier per chunk
+    __shared__ uint32_t sWarpBase[2][kBigBlock / 32];
+    {
+        const uint64_t total = uint64_t(min(info->nNext, nextTaskCap)) * nextBinsPerTask3;   // (the cap only matters for a build that is failing)
+        for (uint64_t i = blockIdx.x * uint64_t(kBigBlock) + threadIdx.x; i < total; i += uint64_t(gridDim.x) * kBigBlock)
+            bin_init(nextBins + i * kBinWords);
+    }
     const uint32_t nChunks = info->nChunks;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint32_t it = 0;
@@ -881,9 +898,13 @@ partition_scatter(const Task* __restrict__ tasks, const LevelInfo* __restrict__ 
             const uint32_t i = warp * kWarpSlice + r * 32u + lane;
             if (i < ci.nValid) { l[r] = rlo[ci.refStart + i]; h[r] = rhi[ci.refStart + i]; }
         }
-        const uint32_t baseFirst = chunkFirst[c];   // refs of this task before this chunk that go first
         const Task& tk = tasks[ci.task];
         if (tk.kind != kObject && tk.kind != kMedian) continue;   // uniform for the CTA
+        // firsts of this node's chunks before this one
+        const uint32_t before = ci.off / kChunk;
+        uint32_t myBase = 0;
+        for (uint32_t i = threadIdx.x; i < before; i += kBigBlock) myBase += chunkFirst[c - before + i];
+        myBase = __reduce_add_sync(kFullMask, myBase);
         const AxisBins ab = axis_bins(tk.lo[tk.axis], tk.hi[tk.axis], nb);
         const uint32_t nFirst = tk.nFirst, nSecond = tk.count - tk.nFirst;
         unsigned bf[4], bv[4];
@@ -897,11 +918,14 @@ partition_scatter(const Task* __restrict__ tasks, const LevelInfo* __restrict__ 
             bv[r] = __ballot_sync(kFullMask, valid);
             myFirst += __popc(bf[r]);
         }
-        if (lane == 0) sWarpFirst[it][warp] = myFirst;
+        if (lane == 0) { sWarpFirst[it][warp] = myFirst; sWarpBase[it][warp] = myBase; }
         __syncthreads();
-        uint32_t wf = 0;   // firsts in the slices of the warps before this one
+        uint32_t wf = 0, baseFirst = 0;   // firsts in the slices of the warps before this one; firsts in the chunks before this one
 #pragma unroll
-        for (int w = 0; w < kBigBlock / 32; w++) wf += uint32_t(w) < warp ? sWarpFirst[it][w] : 0u;
+        for (int w = 0; w < kBigBlock / 32; w++) {
+            wf += uint32_t(w) < warp ? sWarpFirst[it][w] : 0u;
+            baseFirst += sWarpBase[it][w];
+        }
         // position inside the task of this warp's first ref = ci.off + warp * kWarpSlice; seconds before = that - firsts before
         uint32_t doneFirst = baseFirst + wf;
         uint32_t doneSecond = ci.off + min(warp * kWarpSlice, ci.nValid) - doneFirst;
@@ -1349,6 +1373,15 @@ __device__ inline void build_group_node(const SubNode nd, const SmallTask& task,
     AxisBins ab[3];
 #pragma unroll
     for (int a = 0; a < 3; a++) ab[a] = axis_bins(blo[a], bhi[a], nb);
+    // a node with at most one ref per lane (the common case) keeps it in registers for the three axes and the partition
+    const bool oneEach = n <= uint32_t(G);
+    float4 l0 = make_float4(0, 0, 0, 0), h0 = l0;
+    OBox o0 = obox_empty();
+    if (oneEach && lane < n) {
+        l0 = cLo[s + lane];
+        h0 = cHi[s + lane];
+        o0 = obox_of_ref(l0, h0);
+    }
     // ---- FindObjectSplit, one axis at a time
     BestSplit best = best_none();
     OBox objL = obox_empty(), objR = obox_empty();
@@ -1358,13 +1391,23 @@ __device__ inline void build_group_node(const SubNode nd, const SmallTask& task,
         if (!ab[a].active) continue;
         for (uint32_t e = lane; e < nb; e += G) sub_bin_init(bins + e * kSubBinWords);
         g.sync();
-        for (uint32_t i = lane; i < n; i += G) {
-            const float4 l = cLo[s + i], h = cHi[s + i];
-            const uint32_t b = bin_of(bin_centre(comp(l, a), comp(h, a)), ab[a].start, ab[a].inv, nb);
-            int* rec = bins + b * kSubBinWords;
-            atomicMin(rec + 0, ord_from_float(l.x)); atomicMin(rec + 1, ord_from_float(l.y)); atomicMin(rec + 2, ord_from_float(l.z));
-            atomicMax(rec + 3, ord_from_float(h.x)); atomicMax(rec + 4, ord_from_float(h.y)); atomicMax(rec + 5, ord_from_float(h.z));
-            atomicAdd(rec + 6, 1);
+        if (oneEach) {
+            if (lane < n) {
+                const uint32_t b = bin_of(bin_centre(comp(l0, a), comp(h0, a)), ab[a].start, ab[a].inv, nb);
+                int* rec = bins + b * kSubBinWords;
+                atomicMin(rec + 0, o0.lo[0]); atomicMin(rec + 1, o0.lo[1]); atomicMin(rec + 2, o0.lo[2]);
+                atomicMax(rec + 3, o0.hi[0]); atomicMax(rec + 4, o0.hi[1]); atomicMax(rec + 5, o0.hi[2]);
+                atomicAdd(rec + 6, 1);
+            }
+        } else {
+            for (uint32_t i = lane; i < n; i += G) {
+                const float4 l = cLo[s + i], h = cHi[s + i];
+                const uint32_t b = bin_of(bin_centre(comp(l, a), comp(h, a)), ab[a].start, ab[a].inv, nb);
+                int* rec = bins + b * kSubBinWords;
+                atomicMin(rec + 0, ord_from_float(l.x)); atomicMin(rec + 1, ord_from_float(l.y)); atomicMin(rec + 2, ord_from_float(l.z));
+                atomicMax(rec + 3, ord_from_float(h.x)); atomicMax(rec + 4, ord_from_float(h.y)); atomicMax(rec + 5, ord_from_float(h.z));
+                atomicAdd(rec + 6, 1);
+            }
         }
         g.sync();
         if constexpr (G == 32) {
@@ -1447,8 +1490,9 @@ __device__ inline void build_group_node(const SubNode nd, const SmallTask& task,
         float4 l = make_float4(0, 0, 0, 0), h = l;
         bool first = false;
         if (valid) {
-            l = cLo[s + i];
-            h = cHi[s + i];
+            // (mode 2 has re-sorted the refs in shared memory, so the registers are stale there)
+            l = (oneEach && mode != 2) ? l0 : cLo[s + i];
+            h = (oneEach && mode != 2) ? h0 : cHi[s + i];
             bool isLeft;
             if (mode == 0) isLeft = bin_of(bin_centre(comp(l, axis), comp(h, axis)), ab[axis].start, ab[axis].inv, nb) < splitBin;
             else if (mode == 1) isLeft = median_centre(comp(l, axis), comp(h, axis)) < cutoff;
@@ -1674,6 +1718,7 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
     LevelInfo info;
     memset(&info, 0, sizeof(info));
     bool rootLeaf = false;
+    bool binsReady = false;
     uint32_t totalRefs = n;
     // The level loop is enqueued WITHOUT waiting for the device: grids are sized from upper bounds, the kernels read the
     // real task / chunk counts from device memory and fall through when a level is empty. After each level the 128-byte
@@ -1708,8 +1753,11 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
 
         prepare_level<<<1, 1024, 0, st>>>(tasks, B.info, B.chunkBase, B.chunkInfo, B.chunkFirst, depth > 0 ? 1 : 0);
         ATLAS_LAUNCHED(ctx);
-        init_bins<<<std::max(1u, std::min<uint32_t>(persistent, (tasksBound * 3u * nb + 255u) / 256u)), 256, 0, st>>>(B.bins, B.info, 3u * nb);
-        ATLAS_LAUNCHED(ctx);
+        if (!binsReady) {   // otherwise the previous level's partition_scatter has reset this level's bins
+            init_bins<<<std::max(1u, std::min<uint32_t>(persistent, (tasksBound * 3u * nb + 255u) / 256u)), 256, 0, st>>>(B.bins, B.info, 3u * nb);
+            ATLAS_LAUNCHED(ctx);
+        }
+        binsReady = false;
         const uint32_t gridBin = std::max(1u, std::min(chunksBound, uint32_t(ctx->smCount) * uint32_t(ctx->binCtasPerSM)));
         bin_big<<<gridBin, kBigBlock, binSmem, st>>>(tasks, B.info, B.chunkInfo, rlo, rhi, B.bins, nb);
         ATLAS_LAUNCHED(ctx);
@@ -1764,10 +1812,10 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
             ATLAS_LAUNCHED(ctx);
             partition_count<<<gridChunks, kBigBlock, 0, st>>>(tasks, B.info, B.chunkInfo, rlo, rhi, B.chunkFirst, nb);
             ATLAS_LAUNCHED(ctx);
-            partition_scan<<<warpGrid, 128, 0, st>>>(tasks, B.info, B.chunkBase, B.chunkFirst);
-            ATLAS_LAUNCHED(ctx);
             partition_scatter<<<gridChunks, kBigBlock, 0, st>>>(tasks, B.info, B.chunkInfo, B.chunkFirst, rlo, rhi, wlo, whi, B.order,
-                                                                B.eon, nb);
+                                                                B.eon, nb, B.bins, 3u * bins_at_depth(B.budget, depth + 1u),
+                                                                std::min<uint32_t>(depth < 30u ? (2u << depth) : maxTasks, maxTasks));
+            binsReady = true;
             ATLAS_LAUNCHED(ctx);
         }
         ATLAS_CUDA_C(ctx, cudaMemcpyAsync(&slots[depth % 32u], B.info, sizeof(LevelInfo), cudaMemcpyDeviceToHost, st));

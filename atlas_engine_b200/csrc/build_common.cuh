@@ -346,11 +346,22 @@ __device__ __forceinline__ bool group_sweep_single(const LaneGroup<G>& g, const 
             if (cost < kFltMax) { myCost = cost; myBin = j; }   // NaN / inf never beat the initial best (BVH.cpp:519)
         }
     }
+    if constexpr (G == 32) {
+        // costs are sums of non-negative products, so their ordered-int images compare like the floats; one REDUX finds
+        // the minimum and the lowest lane holding it is the lowest bin
+        const int key = ord_from_float(myCost);
+        const int m = __reduce_min_sync(kFullMask, key);
+        const unsigned who = __ballot_sync(kFullMask, key == m && myBin != 0xffffffffu);
+        if (who == 0u) return false;
+        myCost = float_from_ord(m);
+        myBin = uint32_t(__ffs(int(who)));   // lane + 1
+    } else {
 #pragma unroll
-    for (int off = G / 2; off > 0; off >>= 1) {
-        const float oc = g.bxor(myCost, off);
-        const uint32_t ob = g.bxor(myBin, off);
-        if (oc < myCost || (oc == myCost && ob < myBin)) { myCost = oc; myBin = ob; }   // lanes without a candidate hold (FLT_MAX, ~0)
+        for (int off = G / 2; off > 0; off >>= 1) {
+            const float oc = g.bxor(myCost, off);
+            const uint32_t ob = g.bxor(myBin, off);
+            if (oc < myCost || (oc == myCost && ob < myBin)) { myCost = oc; myBin = ob; }   // lanes without a candidate hold (FLT_MAX, ~0)
+        }
     }
     if (myBin == 0xffffffffu || !(myCost < best.cost)) return false;
     best.cost = myCost;
