@@ -166,10 +166,10 @@ trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restr
     const float4* tris = nullptr;
     uint32_t cTlas = 0, cInst = 0, cBlas = 0, cTri = 0, cMaxSp = 1;
 
+    const bool inPlace = in == out;   // origin, ID and direction are already where they belong
     auto finish = [&]() {   // PackRay, common.hsh:61-73 (+ barycentrics in the two lanes GLSL leaves unwritten)
-        const float4 r0 = in[3 * size_t(ray)], r1 = in[3 * size_t(ray) + 1];
-        out[3 * size_t(ray)] = r0;
-        out[3 * size_t(ray) + 1] = make_float4(r1.x, r1.y, r1.z, (ANY && OPACITY) ? transparency : baryU);
+        // origin, ID and direction were passed through when the ray was fetched; only the hit fields are written here
+        reinterpret_cast<float*>(out + 3 * size_t(ray) + 1)[3] = (ANY && OPACITY) ? transparency : baryU;
         out[3 * size_t(ray) + 2] = make_float4(hitT, __int_as_float(hitID), __int_as_float(hitInst), baryV);
         alive = false;
     };
@@ -211,6 +211,7 @@ trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restr
                 if (idx < count && idx >= base) {
                     ray = perm ? perm[idx] : idx;   // longest-first fetch order; results still go to the ray's own slot
                     const float4 r0 = in[3 * size_t(ray)], r1 = in[3 * size_t(ray) + 1], r2 = in[3 * size_t(ray) + 2];
+                    if (!inPlace) { out[3 * size_t(ray)] = r0; out[3 * size_t(ray) + 1] = r1; }
                     const int id = __float_as_int(r0.w);
                     hitID = -1;
                     hitInst = __float_as_int(r2.z);
