@@ -177,6 +177,7 @@ int atlas_rt_context_create(int device, void* stream, atlas_rt_context** out_ctx
         if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { cudaFreeHost(ctx->pinned); cudaFree(ctx->dCounters); delete ctx; return ATLAS_RT_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&ctx->copyIn, cudaStreamNonBlocking) != cudaSuccess) ctx->copyIn = nullptr;
     if (cudaStreamCreateWithFlags(&ctx->copyOut, cudaStreamNonBlocking) != cudaSuccess) ctx->copyOut = nullptr;
+    if (cudaStreamCreateWithFlags(&ctx->compute2, cudaStreamNonBlocking) != cudaSuccess) ctx->compute2 = nullptr;
     for (auto& ev : ctx->pipeEvents)
         if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { ev = nullptr; ctx->copyIn = nullptr; }
     *out_ctx = ctx;
@@ -191,6 +192,7 @@ void atlas_rt_context_destroy(atlas_rt_context* ctx) {
     for (auto& ev : ctx->levelEvents) if (ev) cudaEventDestroy(ev);
     if (ctx->copyIn) cudaStreamDestroy(ctx->copyIn);
     if (ctx->copyOut) cudaStreamDestroy(ctx->copyOut);
+    if (ctx->compute2) cudaStreamDestroy(ctx->compute2);
     cudaFree(ctx->dCounters);
     cudaFreeHost(ctx->pinned);
     if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
@@ -533,23 +535,30 @@ static int trace_common(atlas_rt_context* ctx, const atlas_rt_scene* scene, cons
     if (!devIn && !devOut && count >= kPipeMin && ctx->copyIn && ctx->copyOut) {
         // Host buffers on both sides: split the batch and overlap H2D of chunk i+1, the trace of chunk i and D2H of
         // chunk i-1 on the two copy engines (pays off with pinned host memory; pageable memory still works).
-        uint32_t chunks = count >= 16 * kPipeMin ? 4u : 2u;   // every launch pays the latency of its longest ray: keep chunks large
+        // every launch pays the latency of its longest ray, so chunks stay large: about a third of a million rays each (swept)
+        uint32_t chunks = uint32_t(std::max<uint64_t>(2, std::min<uint64_t>(8, (count + 175000) / 350000)));
         if (const char* e = getenv("ATLAS_RT_PIPE_CHUNKS")) chunks = uint32_t(std::max(1, std::min(8, atoi(e))));
         cudaEvent_t* ev = ctx->pipeEvents;   // [0] staging ready, [1+c] chunk c uploaded, [9+c] chunk c traced, [19] all downloaded
-        cudaError_t e = cudaEventRecord(ev[0], ctx->stream);
+        // Chunks alternate between the context stream and a second compute stream (each with its own ray-queue head), so
+        // the thin tail of one chunk's persistent kernel overlaps the start of the next chunk's.
+        cudaError_t e = cudaMemsetAsync(ctx->dCounters, 0, 6 * sizeof(unsigned long long), ctx->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ev[0], ctx->stream);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copyIn, ev[0], 0);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copyOut, ev[0], 0);
+        if (e == cudaSuccess && ctx->compute2) e = cudaStreamWaitEvent(ctx->compute2, ev[0], 0);
         for (uint32_t c = 0; c < chunks && e == cudaSuccess && rc == ATLAS_RT_OK; c++) {
             const uint64_t b = (count * c / chunks) & ~uint64_t(31), end = c + 1 == chunks ? count : ((count * (c + 1) / chunks) & ~uint64_t(31));
             const char* hIn = static_cast<const char*>(rays_in) + 48 * b;
             char* hOut = static_cast<char*>(rays_out) + 48 * b;
+            const int slot = (ctx->compute2 && (c & 1u)) ? 1 : 0;
+            cudaStream_t cs = slot ? ctx->compute2 : ctx->stream;
             e = cudaMemcpyAsync(dIn + 3 * b, hIn, 48 * (end - b), cudaMemcpyHostToDevice, ctx->copyIn);
             if (e == cudaSuccess) e = cudaEventRecord(ev[1 + c], ctx->copyIn);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev[1 + c], 0);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, ev[1 + c], 0);
             if (e != cudaSuccess) break;
-            rc = launch_trace(ctx, scene, dIn + 3 * b, dIn + 3 * b, end - b, cull_mask, t_min, t_max, any, perRay, counters, c == 0, opacity);
+            rc = launch_trace(ctx, scene, dIn + 3 * b, dIn + 3 * b, end - b, cull_mask, t_min, t_max, any, perRay, counters, false, opacity, cs, slot);
             if (rc != ATLAS_RT_OK) break;
-            e = cudaEventRecord(ev[9 + c], ctx->stream);
+            e = cudaEventRecord(ev[9 + c], cs);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copyOut, ev[9 + c], 0);
             if (e == cudaSuccess) e = cudaMemcpyAsync(hOut, dIn + 3 * b, 48 * (end - b), cudaMemcpyDeviceToHost, ctx->copyOut);
         }

@@ -79,6 +79,7 @@ struct atlas_rt_context {
     size_t pinnedBytes = 0;
     // copy engines used to overlap H2D / trace / D2H when a trace call is given host buffers (api.cu)
     cudaStream_t copyIn = nullptr, copyOut = nullptr;
+    cudaStream_t compute2 = nullptr;   // second compute stream: alternate chunks of a pipelined host-buffer trace overlap their tails
     cudaEvent_t pipeEvents[20] = {};
     cudaEvent_t levelEvents[32] = {};          // builder: one per in-flight level read-back (build.cu)
     void* levelSlots = nullptr;                // pinned, 32 x 128 B level read-back slots
@@ -149,6 +150,15 @@ inline cudaError_t dev_alloc(atlas_rt_context* ctx, T** p, size_t count) {
 inline void dev_free(atlas_rt_context* ctx, const void* p) {
     if (p) cudaFreeAsync(const_cast<void*>(p), ctx->stream);
 }
+template <typename T>
+inline cudaError_t dev_alloc_on(cudaStream_t st, T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    return cudaMallocAsync(reinterpret_cast<void**>(p), count * sizeof(T), st);
+}
+inline void dev_free_on(cudaStream_t st, const void* p) {
+    if (p) cudaFreeAsync(const_cast<void*>(p), st);
+}
 
 // Copy count*bytes from src (host or device according to `device`) into device memory on the context stream.
 cudaError_t copy_in(atlas_rt_context* ctx, void* dst, const void* src, size_t bytes, bool srcDevice);
@@ -163,6 +173,6 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
 int scene_fast_flag(atlas_rt_context* ctx, atlas_rt_scene* scene, const uint32_t* dNodeCounts);
 int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float4* dIn, float4* dOut, uint64_t count,
                  uint32_t cullMask, float tMin, float tMax, bool any, bool perRayTMax, bool counters, bool resetCounters = true,
-                 bool opacity = false);
+                 bool opacity = false, cudaStream_t st = nullptr /* context stream */, int queueSlot = 0);
 
 }   // namespace atlas

@@ -526,7 +526,9 @@ int scene_fast_flag(atlas_rt_context* ctx, atlas_rt_scene* scene, const uint32_t
 }
 
 int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float4* dIn, float4* dOut, uint64_t count,
-                 uint32_t cullMask, float tMin, float tMax, bool any, bool perRayTMax, bool counters, bool resetCounters, bool opacity) {
+                 uint32_t cullMask, float tMin, float tMax, bool any, bool perRayTMax, bool counters, bool resetCounters, bool opacity,
+                 cudaStream_t st, int queueSlot) {
+    if (!st) st = ctx->stream;
     if (count == 0) return ATLAS_RT_OK;
     if (count > 0x7fffffffull) return fail(ctx, ATLAS_RT_ERR_UNSUPPORTED, "more than 2^31-1 rays in one batch");
     SceneDev sc{scene->tlas->nodes, scene->instances, scene->blasNodes, scene->bvhTris, scene->triangles};
@@ -536,29 +538,30 @@ int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float
     const uint32_t grid = std::min<uint32_t>(std::min<uint32_t>((n + kTraceBlock - 1) / kTraceBlock, wantBlocks), uint32_t(ctx->smCount) * uint32_t(ctx->traceBlocksPerSM));
     const int lt = ctx->traceLeafThreshold, rt = ctx->traceRefillThreshold;
     // words 0-5: visit counters + overflow flag (kept across the chunks of one pipelined call), word 6: the ray queue head
-    if (resetCounters) ATLAS_CUDA(ctx, cudaMemsetAsync(ctx->dCounters, 0, 7 * sizeof(unsigned long long), ctx->stream));
-    else ATLAS_CUDA(ctx, cudaMemsetAsync(ctx->dCounters + 6, 0, sizeof(unsigned long long), ctx->stream));
-    unsigned int* rayCounter = reinterpret_cast<unsigned int*>(ctx->dCounters + 6);
+    // (word 7: a second queue head, for a launch that overlaps the previous one on another stream)
+    if (resetCounters) ATLAS_CUDA(ctx, cudaMemsetAsync(ctx->dCounters, 0, 6 * sizeof(unsigned long long), st));
+    ATLAS_CUDA(ctx, cudaMemsetAsync(ctx->dCounters + 6 + queueSlot, 0, sizeof(unsigned long long), st));
+    unsigned int* rayCounter = reinterpret_cast<unsigned int*>(ctx->dCounters + 6 + queueSlot);
     // ---- longest-first fetch order for batches large enough to have a tail worth hiding
     uint32_t* perm = nullptr;
     uint8_t* bucketOf = nullptr;
     unsigned int* hist = nullptr;
     if (ctx->traceLongestFirst && n >= uint32_t(ctx->traceLongestFirstMin) && scene->tlas->nodeCount > 0) {
-        ATLAS_CUDA(ctx, dev_alloc(ctx, &perm, n));
-        ATLAS_CUDA(ctx, dev_alloc(ctx, &bucketOf, n));
-        ATLAS_CUDA(ctx, dev_alloc(ctx, &hist, kCostBuckets + 2));
-        ATLAS_CUDA(ctx, cudaMemsetAsync(hist, 0, (kCostBuckets + 2) * sizeof(unsigned int), ctx->stream));
+        ATLAS_CUDA(ctx, dev_alloc_on(st, &perm, n));
+        ATLAS_CUDA(ctx, dev_alloc_on(st, &bucketOf, n));
+        ATLAS_CUDA(ctx, dev_alloc_on(st, &hist, kCostBuckets + 2));
+        ATLAS_CUDA(ctx, cudaMemsetAsync(hist, 0, (kCostBuckets + 2) * sizeof(unsigned int), st));
         const uint32_t sortGrid = (n + kSortBlock * kSortPerThread - 1) / (kSortBlock * kSortPerThread);
-        ray_cost_histogram<<<sortGrid, kSortBlock, 0, ctx->stream>>>(dIn, n, scene->tlas->nodes, bucketOf, hist);
+        ray_cost_histogram<<<sortGrid, kSortBlock, 0, st>>>(dIn, n, scene->tlas->nodes, bucketOf, hist);
         ATLAS_LAUNCH_CHECK(ctx);
-        ray_cost_offsets<<<1, 32, 0, ctx->stream>>>(hist, n);
+        ray_cost_offsets<<<1, 32, 0, st>>>(hist, n);
         ATLAS_LAUNCH_CHECK(ctx);
-        ray_cost_scatter<<<sortGrid, kSortBlock, 0, ctx->stream>>>(bucketOf, n, hist, perm);
+        ray_cost_scatter<<<sortGrid, kSortBlock, 0, st>>>(bucketOf, n, hist, perm);
         ATLAS_LAUNCH_CHECK(ctx);
     }
     const int pr = perRayTMax ? 1 : 0, sf = scene->fastDivision;
 #define ATLAS_TRACE_LAUNCH(A, C, O) \
-    trace_kernel<A, C, O><<<grid, kTraceBlock, 0, ctx->stream>>>(sc, dIn, dOut, perm, hist ? hist + kCostBuckets + 1 : nullptr, n, cullMask, tMin, tMax, pr, sf, lt, rt, rayCounter, ctx->dCounters)
+    trace_kernel<A, C, O><<<grid, kTraceBlock, 0, st>>>(sc, dIn, dOut, perm, hist ? hist + kCostBuckets + 1 : nullptr, n, cullMask, tMin, tMax, pr, sf, lt, rt, rayCounter, ctx->dCounters)
     if (opacity) {
         if (any) { if (counters) ATLAS_TRACE_LAUNCH(true, true, true); else ATLAS_TRACE_LAUNCH(true, false, true); }
         else { if (counters) ATLAS_TRACE_LAUNCH(false, true, true); else ATLAS_TRACE_LAUNCH(false, false, true); }
@@ -567,9 +570,9 @@ int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float
         else { if (counters) ATLAS_TRACE_LAUNCH(false, true, false); else ATLAS_TRACE_LAUNCH(false, false, false); }
     }
 #undef ATLAS_TRACE_LAUNCH
-    dev_free(ctx, perm);
-    dev_free(ctx, bucketOf);
-    dev_free(ctx, hist);
+    dev_free_on(st, perm);
+    dev_free_on(st, bucketOf);
+    dev_free_on(st, hist);
     ATLAS_LAUNCH_CHECK(ctx);
     return ATLAS_RT_OK;
 }

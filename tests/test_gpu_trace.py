@@ -126,6 +126,17 @@ def test_full_size_c2_properties(ctx, oracle):
     out = ctx.trace(scene, rays)
     ref, _ = oracle.trace(osc, rays[:100000], nthreads=8)
     assert np.array_equal(out[:100000].view(np.uint32), ref.view(np.uint32))
+    # the host-buffer call is pipelined in chunks over two compute streams: check the last chunk against the oracle too,
+    # and the whole batch against the device-pointer call (in place and into a separate buffer)
+    tail, _ = oracle.trace(osc, rays[-50000:], nthreads=8)
+    assert np.array_equal(out[-50000:].view(np.uint32), tail.view(np.uint32))
+    import torch
+    d_rays = torch.from_numpy(rays).cuda()
+    d_out = torch.empty_like(d_rays)
+    ctx.trace(scene, d_rays, len(rays), out=d_out)
+    assert np.array_equal(d_out.cpu().numpy().view(np.uint32), out.view(np.uint32))
+    ctx.trace(scene, d_rays, len(rays))
+    assert np.array_equal(d_rays.cpu().numpy().view(np.uint32), out.view(np.uint32))
     hit = out[:, 9].view(np.int32) >= 0
     t = out[:, 8]
     assert 0.1 < hit.mean() < 0.9 and np.all(t[~hit] == np.float32(1e12))
