@@ -238,12 +238,15 @@ class BVH:
         self.ctx.check(self.ctx.L.atlas_rt_bvh_counts(self.h, C.byref(n), C.byref(m)))
         return int(n.value), int(m.value)
 
-    def download(self):
-        """(nodes (n,14) uint32 in the 56 B BVHNode layout, order (m,) uint32, end_of_node (m,) uint8)."""
+    def download(self, nodes=None, order=None, flags=None):
+        """(nodes (n,14) uint32 in the 56 B BVHNode layout, order (m,) uint32, end_of_node (m,) uint8). Preallocated
+        (e.g. pinned) arrays at least that large may be passed in; the returned arrays are views of their first rows."""
         n, m = self.counts()
-        nodes = np.zeros((n, 14), dtype=np.uint32)
-        order = np.zeros(m, dtype=np.uint32)
-        flags = np.zeros(m, dtype=np.uint8)
+        nodes = np.zeros((n, 14), dtype=np.uint32) if nodes is None else nodes[:n]
+        order = np.zeros(m, dtype=np.uint32) if order is None else order[:m]
+        flags = np.zeros(m, dtype=np.uint8) if flags is None else flags[:m]
+        assert nodes.shape == (n, 14) and nodes.dtype == np.uint32 and nodes.flags.c_contiguous
+        assert order.shape == (m,) and order.dtype == np.uint32 and flags.shape == (m,) and flags.dtype == np.uint8
         self.ctx.check(self.ctx.L.atlas_rt_bvh_download(self.h, _addr(nodes), _addr(order), _addr(flags), 0))
         return nodes, order, flags
 

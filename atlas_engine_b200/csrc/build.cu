@@ -62,7 +62,7 @@ struct SmallTask {   // root of a shared-memory subtree (48 B)
 
 struct LevelInfo {   // device-resident, read back once per level
     uint32_t nTasks, nChunks, nNext, nSmall, nMedian, rootNeedSpatial, rootKind, rootLeaf;
-    uint32_t totalRefs, negZero, nStraddle, nL0, nR0, levels, overflow, pad2;
+    uint32_t totalRefs, negZero, nStraddle, nL0, nR0, levels, overflow, subTicket;
     unsigned long long stats[8];   // [2] duplicates [3] median splits [4] sort fallbacks [5] largest sort fallback
 };
 
@@ -1522,10 +1522,12 @@ constexpr size_t kSubtreeSmem = size_t(4) * kSubtreeMax * sizeof(float4) + size_
                                 size_t(kSubWarps) * 2 * kSubtreeBins * kSubBinWords * sizeof(int) + size_t(2) * kSubNodes * sizeof(uint16_t);
 static_assert(2 * (kSubtreeSmem + 1024 + 128) <= 228 * 1024, "two subtree CTAs must fit one SM");
 
+// Persistent: the grid is sized for the machine (two CTAs per SM) and every CTA draws subtrees from a ticket counter until
+// none are left, so the launch does not need the subtree count on the host (no round trip after the level loop).
 __global__ void __launch_bounds__(kSubBlock)
-build_subtrees(const SmallTask* __restrict__ small, uint32_t nSmall, float4* const lo0, float4* const hi0, float4* const lo1,
+build_subtrees(const SmallTask* __restrict__ small, float4* const lo0, float4* const hi0, float4* const lo1,
                float4* const hi1, float4* nodes, uint32_t* __restrict__ order, uint8_t* __restrict__ eon,
-               LevelInfo* __restrict__ info, uint32_t budget) {
+               LevelInfo* __restrict__ info, uint32_t budget, uint32_t maxSmall) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     float4* sLo = reinterpret_cast<float4*>(smemRaw);                      // [2][kSubtreeMax]
     float4* sHi = sLo + 2 * kSubtreeMax;                                   // [2][kSubtreeMax]
@@ -1537,9 +1539,15 @@ build_subtrees(const SmallTask* __restrict__ small, uint32_t nSmall, float4* con
     __shared__ uint32_t sCls[3];               // nodes of the level by size class: <= kTinyMax, half warp, warp
     __shared__ unsigned long long sStats[3];   // median splits, sort fallbacks, largest fallback
 
+    __shared__ uint32_t sTicket;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    if (blockIdx.x >= nSmall) return;
-    const SmallTask task = small[blockIdx.x];
+    const uint32_t nSmall = min(info->nSmall, maxSmall);
+  while (true) {
+    __syncthreads();   // the previous subtree is finished with shared memory
+    if (tid == 0) sTicket = atomicAdd(&info->subTicket, 1u);
+    __syncthreads();
+    if (sTicket >= nSmall) break;
+    const SmallTask task = small[sTicket];
     const float4* gLo = task.buf ? lo1 : lo0;
     const float4* gHi = task.buf ? hi1 : hi0;
     for (uint32_t i = tid; i < task.count; i += kSubBlock) {
@@ -1603,6 +1611,7 @@ build_subtrees(const SmallTask* __restrict__ small, uint32_t nSmall, float4* con
         if (sStats[1]) atomicAdd(&info->stats[4], sStats[1]);
         if (sStats[2]) atomicMax(&info->stats[5], sStats[2]);
     }
+  }
 }
 
 template <typename T>
@@ -1829,6 +1838,13 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
         }
         cur ^= 1u;
     }
+    // the subtrees are enqueued straight behind the last level (the kernel reads their number on the device); the one
+    // read-back that follows waits for the whole build
+    if (!rootLeaf) {
+        build_subtrees<<<uint32_t(ctx->smCount) * 2u, kSubBlock, kSubtreeSmem, st>>>(B.small, B.lo[0], B.hi[0], B.lo[1], B.hi[1], B.nodes, B.order,
+                                                                                    B.eon, B.info, B.budget, maxSmall);
+        ATLAS_LAUNCHED(ctx);
+    }
     ATLAS_TRY(read_back(ctx, B.info, &info));
     if (info.overflow) { cleanup(); return fail(ctx, ATLAS_RT_ERR_UNSUPPORTED, "task list overflow"); }
     totalRefs = info.totalRefs;
@@ -1840,12 +1856,6 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
         out->nodeCount = 0;
         out->refCount = n;
     } else {
-        if (info.nSmall) {
-            build_subtrees<<<info.nSmall, kSubBlock, kSubtreeSmem, st>>>(B.small, info.nSmall, B.lo[0], B.hi[0], B.lo[1], B.hi[1], B.nodes,
-                                                                         B.order, B.eon, B.info, B.budget);
-            ATLAS_LAUNCHED(ctx);
-            ATLAS_TRY(read_back(ctx, B.info, &info));
-        }
         out->refCount = totalRefs;
         out->nodeCount = totalRefs - 1u;
     }

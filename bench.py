@@ -284,7 +284,8 @@ def main():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        total_ms = sum(a.elapsed_time(b) for a, b in evs)
+        timed.samples = [a.elapsed_time(b) for a, b in evs]
+        total_ms = sum(timed.samples)
         if world > 1:
             t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -311,7 +312,11 @@ def main():
             b.free()
         built.clear()
         built.append(build_once())
-    build_ms = timed(build_step, args.steps, args.warmup)
+    # (the sampler's shutdown leaves the GPU idle for ~0.3 s and the first builds after it run at ramping clocks with
+    # cold host caches: 9 / 3.5 / 2.5 ms before settling at 2.27 ms, so this loop gets a longer warm-up than W)
+    build_ms = timed(build_step, args.steps, max(args.warmup, 10))
+    print("build samples (ms):", " ".join(f"{x:.2f}" for x in timed.samples), file=sys.stderr)
+    build_samples = sorted(timed.samples)
     for b in built:
         b.free()
     clocks = clk.summary()
@@ -350,11 +355,14 @@ def main():
     hb = torch.from_numpy(boxes).pin_memory()
     ht = torch.from_numpy(tris).pin_memory()
     reps = max(3, args.steps // 4)
+    hn = torch.empty((2 * N_TRIS, 14), dtype=torch.int32).pin_memory().numpy().view(np.uint32)   # room for spatial-split duplicates
+    ho = torch.empty(2 * N_TRIS, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+    hf = torch.empty(2 * N_TRIS, dtype=torch.uint8).pin_memory().numpy()
     ctx.build_blas(hb.numpy(), ht.numpy()).free()
     t0 = time.perf_counter()
     for _ in range(reps):
         b = ctx.build_blas(hb.numpy(), ht.numpy())
-        nodes, order, eon = b.download()
+        nodes, order, eon = b.download(hn, ho, hf)
         b.free()
     build_e2e_ms = (time.perf_counter() - t0) * 1e3 / reps
 
@@ -391,7 +399,8 @@ def main():
         "roofline": {"kernel": "trace_kernel<closest>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": pk_src,
                      "algorithmic_bytes_per_launch": bytes_per_launch, "visits": ct},
-        "build": {"metric": "bvh_build", "value": N_TRIS / build_ms / 1e3, "unit": "Mtris/s", "ms_per_build": build_ms, "n_gpus": 1,
+        "build": {"metric": "bvh_build", "value": N_TRIS / build_ms / 1e3, "unit": "Mtris/s", "ms_per_build": build_ms, "ms_per_build_median": statistics.median(build_samples),
+                  "ms_per_build_min_max": [build_samples[0], build_samples[-1]], "n_gpus": 1,
                   "e2e": {"value": N_TRIS / build_e2e_ms / 1e3, "unit": "Mtris/s", "ms": build_e2e_ms,
                           "h2d_bytes": 60 * N_TRIS, "d2h_bytes": 56 * nodes_n + 5 * refs_n},
                   "nodes": nodes_n, "refs": refs_n, "stats": build_stats},
