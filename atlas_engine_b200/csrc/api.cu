@@ -163,6 +163,7 @@ int atlas_rt_context_create(int device, void* stream, atlas_rt_context** out_ctx
     if (const char* e = getenv("ATLAS_RT_TRACE_LONGEST_FIRST")) ctx->traceLongestFirst = atoi(e);
     if (const char* e = getenv("ATLAS_RT_TRACE_BLOCKS_PER_SM")) ctx->traceBlocksPerSM = std::max(1, std::min(9, atoi(e)));
     if (const char* e = getenv("ATLAS_RT_BIN_CTAS_PER_SM")) ctx->binCtasPerSM = std::max(1, std::min(8, atoi(e)));
+    if (const char* e = getenv("ATLAS_RT_CHAIN_LAUNCH")) ctx->chainLaunch = atoi(e);
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t keep = ~0ull;
@@ -173,8 +174,6 @@ int atlas_rt_context_create(int device, void* stream, atlas_rt_context** out_ctx
     ctx->pinnedBytes = 8192;
     if (cudaMallocHost(&ctx->pinned, ctx->pinnedBytes) != cudaSuccess) { cudaFree(ctx->dCounters); delete ctx; return ATLAS_RT_ERR_OOM; }
     ctx->levelSlots = static_cast<char*>(ctx->pinned) + 4096;
-    for (auto& ev : ctx->levelEvents)
-        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { cudaFreeHost(ctx->pinned); cudaFree(ctx->dCounters); delete ctx; return ATLAS_RT_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&ctx->copyIn, cudaStreamNonBlocking) != cudaSuccess) ctx->copyIn = nullptr;
     if (cudaStreamCreateWithFlags(&ctx->copyOut, cudaStreamNonBlocking) != cudaSuccess) ctx->copyOut = nullptr;
     if (cudaStreamCreateWithFlags(&ctx->compute2, cudaStreamNonBlocking) != cudaSuccess) ctx->compute2 = nullptr;
@@ -189,7 +188,6 @@ void atlas_rt_context_destroy(atlas_rt_context* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto& ev : ctx->pipeEvents) if (ev) cudaEventDestroy(ev);
-    for (auto& ev : ctx->levelEvents) if (ev) cudaEventDestroy(ev);
     if (ctx->copyIn) cudaStreamDestroy(ctx->copyIn);
     if (ctx->copyOut) cudaStreamDestroy(ctx->copyOut);
     if (ctx->compute2) cudaStreamDestroy(ctx->compute2);

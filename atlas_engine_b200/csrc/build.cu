@@ -44,6 +44,31 @@ constexpr int kBigBlock = 256;
 constexpr int kSubBlock = 256;
 constexpr int kSubWarps = kSubBlock / 32;
 
+// The kernels of the level loop form a chain of programmatic dependent launches: each one lets its successor be
+// scheduled right away and then waits until everything before it has completed (griddepcontrol.wait returns once the
+// prerequisite grids have finished and their memory is visible), so launch latency overlaps the predecessor's work.
+// Every kernel of the chain executes chain_begin() first, on every path, because a kernel that skipped the wait could
+// finish before ITS predecessor and release the kernel after it too early. Launched normally, both are no-ops.
+__device__ __forceinline__ void chain_begin() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <typename... P, typename... A>
+cudaError_t launch_chain(bool pdl, void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = pdl ? 1u : 0u;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<A>(args)...);
+}
+
 enum TaskKind : int32_t { kObject = 0, kMedian = 1, kDone = 2, kSpatial = 3, kPending = 4 };
 
 struct Task {   // one big node of the current level (64 B)
@@ -194,7 +219,9 @@ __device__ __forceinline__ void fill_chunk(ChunkInfo* __restrict__ chunkInfo, ui
 }
 
 __global__ void prepare_level(Task* __restrict__ tasks, LevelInfo* __restrict__ info, uint32_t* __restrict__ chunkBase,
-                              ChunkInfo* __restrict__ chunkInfo, uint32_t* __restrict__ chunkFirst, int advance) {
+                              ChunkInfo* __restrict__ chunkInfo, uint32_t* __restrict__ chunkFirst, int advance,
+                              volatile uint32_t* hostFlag) {
+    chain_begin();
     // single CTA: the level's task count (the previous level's nNext when `advance`), then an exclusive scan of
     // ceil(count / kChunk) over the level's tasks, and the chunk table
     __shared__ uint32_t carry;
@@ -204,6 +231,9 @@ __global__ void prepare_level(Task* __restrict__ tasks, LevelInfo* __restrict__ 
     if (threadIdx.x == 0) {
         if (advance) info->nTasks = min(info->nNext, 0x7fffffffu);
         sN = info->nTasks;
+        // tell the host (pinned memory) that this level has started and how many nodes it has: 1 = none, the tree is done
+        *hostFlag = sN + 1u;
+        __threadfence_system();
         if (sN) info->levels++;
         carry = 0;
         sBigN = 0;
@@ -264,6 +294,7 @@ __global__ void prepare_level(Task* __restrict__ tasks, LevelInfo* __restrict__ 
 }
 
 __global__ void init_bins(int* __restrict__ bins, const LevelInfo* __restrict__ info, uint32_t binsPerTask3) {
+    chain_begin();
     const uint64_t total = uint64_t(info->nTasks) * binsPerTask3;
     for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < total; i += uint64_t(gridDim.x) * blockDim.x)
         bin_init(bins + i * kBinWords);
@@ -274,6 +305,7 @@ __global__ void init_bins(int* __restrict__ bins, const LevelInfo* __restrict__ 
 __global__ void __launch_bounds__(kBigBlock)
 bin_big(const Task* __restrict__ tasks, const LevelInfo* __restrict__ info, const ChunkInfo* __restrict__ chunkInfo,
         const float4* __restrict__ rlo, const float4* __restrict__ rhi, int* __restrict__ gbins, uint32_t nb) {
+    chain_begin();
     extern __shared__ int sb[];   // [3][nb][kSmemBin]
     const uint32_t nChunks = info->nChunks;
     // every CTA takes a contiguous run of chunks and keeps accumulating in shared memory while the run stays inside one
@@ -445,6 +477,7 @@ __device__ inline BestSplit cta_best_split(const int* __restrict__ gbins, uint32
 __global__ void __launch_bounds__(kSelectBlock)
 select_big(Task* __restrict__ tasks, LevelInfo* __restrict__ info, const int* __restrict__ gbins, int* __restrict__ medAcc, Lists L,
            uint32_t nb) {
+    chain_begin();
     extern __shared__ int ss[];   // bins [3][nb][kSmemBin], suffix boxes [3][nb][6]
     __shared__ BestSplit sBest[3];
     const uint32_t t = blockIdx.x;
@@ -724,6 +757,7 @@ select_root_final(Task* __restrict__ tasks, LevelInfo* __restrict__ info, const 
 __global__ void __launch_bounds__(kBigBlock)
 median_reduce_big(const Task* __restrict__ tasks, const LevelInfo* __restrict__ info, const ChunkInfo* __restrict__ chunkInfo,
                   const float4* __restrict__ rlo, const float4* __restrict__ rhi, int* __restrict__ medAcc) {
+    chain_begin();
     if (info->nMedian == 0) return;
     const uint32_t nChunks = info->nChunks;
     for (uint32_t c = blockIdx.x; c < nChunks; c += gridDim.x) {
@@ -771,6 +805,7 @@ __global__ void median_finalize_big(Task* __restrict__ tasks, LevelInfo* __restr
                                     float4* __restrict__ curLo, float4* __restrict__ curHi, float4* __restrict__ nxtLo,
                                     float4* __restrict__ nxtHi, uint32_t* __restrict__ order, uint8_t* __restrict__ eon,
                                     Lists L, int blasRoot) {
+    chain_begin();
     if (info->nMedian == 0) return;
     const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (t >= info->nTasks) return;
@@ -848,6 +883,7 @@ static_assert(kWarpSlice == 128, "partition kernels assume 4 rounds of 32 refs p
 __global__ void __launch_bounds__(kBigBlock)
 partition_count(const Task* __restrict__ tasks, const LevelInfo* __restrict__ info, const ChunkInfo* __restrict__ chunkInfo,
                 const float4* __restrict__ rlo, const float4* __restrict__ rhi, uint32_t* __restrict__ chunkFirst, uint32_t nb) {
+    chain_begin();
     const uint32_t nChunks = info->nChunks;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     for (uint32_t c = blockIdx.x; c < nChunks; c += gridDim.x) {
@@ -880,6 +916,7 @@ partition_scatter(const Task* __restrict__ tasks, const LevelInfo* __restrict__ 
                   const uint32_t* __restrict__ chunkFirst, const float4* __restrict__ rlo, const float4* __restrict__ rhi,
                   float4* __restrict__ wlo, float4* __restrict__ whi, uint32_t* __restrict__ order, uint8_t* __restrict__ eon,
                   uint32_t nb, int* __restrict__ nextBins, uint32_t nextBinsPerTask3, uint32_t nextTaskCap) {
+    chain_begin();
     __shared__ uint32_t sWarpFirst[2][kBigBlock / 32];   // double-buffered by iteration: one barrier per chunk
     __shared__ uint32_t sWarpBase[2][kBigBlock / 32];
     {
@@ -1528,6 +1565,7 @@ __global__ void __launch_bounds__(kSubBlock)
 build_subtrees(const SmallTask* __restrict__ small, float4* const lo0, float4* const hi0, float4* const lo1,
                float4* const hi1, float4* nodes, uint32_t* __restrict__ order, uint8_t* __restrict__ eon,
                LevelInfo* __restrict__ info, uint32_t budget, uint32_t maxSmall) {
+    chain_begin();
     extern __shared__ __align__(16) unsigned char smemRaw[];
     float4* sLo = reinterpret_cast<float4*>(smemRaw);                      // [2][kSubtreeMax]
     float4* sHi = sLo + 2 * kSubtreeMax;                                   // [2][kSubtreeMax]
@@ -1735,19 +1773,33 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
     // complete) to learn that the tree is finished, so host latency never stalls the GPU. Only the BLAS root, whose
     // outcome decides which kernels run and what must be allocated, is read back synchronously.
     constexpr uint32_t kLookahead = 3;
-    LevelInfo* slots = static_cast<LevelInfo*>(ctx->levelSlots);
+    constexpr uint32_t kFlagRing = 64;
+    volatile uint32_t* flags = static_cast<volatile uint32_t*>(ctx->levelSlots);   // [kFlagRing], pinned: level d's node count + 1
+    for (uint32_t k = 0; k < kFlagRing; k++) flags[k] = 0u;
+    const bool pdl = ctx->chainLaunch != 0;
+    auto wait_flag = [&](uint32_t level) -> int {   // spin until prepare_level(level) has run; watch for a dead stream
+        for (uint64_t spins = 0; flags[level % kFlagRing] == 0u; spins++) {
+            if ((spins & 0xfffu) == 0xfffu) {
+                const cudaError_t q = cudaStreamQuery(st);
+                if (q != cudaSuccess && q != cudaErrorNotReady) return fail(ctx, ATLAS_RT_ERR_CUDA, "level loop", q);
+                if (q == cudaSuccess && flags[level % kFlagRing] == 0u) return fail(ctx, ATLAS_RT_ERR_CUDA, "level flag never written");
+            }
+        }
+        return ATLAS_RT_OK;
+    };
 
     for (uint32_t depth = 0; depth < 100000u; depth++) {
         if (depth > 0) {
-            bool finished = false;
-            const uint32_t oldest = depth > kLookahead ? depth - kLookahead - 1u : 0u;
-            for (uint32_t k = oldest; k < depth && !finished; k++) {
-                if (k == oldest && depth > kLookahead) ATLAS_CUDA_C(ctx, cudaEventSynchronize(ctx->levelEvents[k % 32u]));
-                else if (cudaEventQuery(ctx->levelEvents[k % 32u]) != cudaSuccess) break;
-                if (slots[k % 32u].nNext == 0u) finished = true;
+            // the host runs at most kLookahead levels ahead of the device and stops at the first level found empty
+            if (depth > kLookahead) {
+                const int rc = wait_flag(depth - kLookahead);
+                if (rc != ATLAS_RT_OK) { cleanup(); return rc; }
             }
-            (void)cudaGetLastError();   // cudaEventQuery's cudaErrorNotReady is not an error
+            bool finished = false;
+            for (uint32_t k = depth > kLookahead + 1u ? depth - kLookahead - 1u : 1u; k < depth && !finished; k++)
+                if (flags[k % kFlagRing] == 1u) finished = true;
             if (finished) break;
+            flags[depth % kFlagRing] = 0u;   // (level depth - kFlagRing was consumed long ago)
         }
         const uint32_t nb = bins_at_depth(B.budget, depth);
         const uint32_t tasksBound = depth == 0 ? 1u : std::min<uint32_t>(depth < 31u ? (1u << depth) : maxTasks, maxTasks);
@@ -1760,16 +1812,18 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
         const float4 *rlo = B.lo[cur], *rhi = B.hi[cur];
         float4 *wlo = B.lo[cur ^ 1u], *whi = B.hi[cur ^ 1u];
 
-        prepare_level<<<1, 1024, 0, st>>>(tasks, B.info, B.chunkBase, B.chunkInfo, B.chunkFirst, depth > 0 ? 1 : 0);
-        ATLAS_LAUNCHED(ctx);
+        ATLAS_CUDA_C(ctx, launch_chain(pdl, prepare_level, 1, 1024, 0, st, tasks, B.info, B.chunkBase, B.chunkInfo, B.chunkFirst, depth > 0 ? 1 : 0,
+                                       flags + depth % kFlagRing));
+        ctx->launches++;
         if (!binsReady) {   // otherwise the previous level's partition_scatter has reset this level's bins
-            init_bins<<<std::max(1u, std::min<uint32_t>(persistent, (tasksBound * 3u * nb + 255u) / 256u)), 256, 0, st>>>(B.bins, B.info, 3u * nb);
-            ATLAS_LAUNCHED(ctx);
+            ATLAS_CUDA_C(ctx, launch_chain(pdl, init_bins, std::max(1u, std::min<uint32_t>(persistent, (tasksBound * 3u * nb + 255u) / 256u)), 256, 0, st,
+                                           B.bins, B.info, 3u * nb));
+            ctx->launches++;
         }
         binsReady = false;
         const uint32_t gridBin = std::max(1u, std::min(chunksBound, uint32_t(ctx->smCount) * uint32_t(ctx->binCtasPerSM)));
-        bin_big<<<gridBin, kBigBlock, binSmem, st>>>(tasks, B.info, B.chunkInfo, rlo, rhi, B.bins, nb);
-        ATLAS_LAUNCHED(ctx);
+        ATLAS_CUDA_C(ctx, launch_chain(pdl, bin_big, gridBin, kBigBlock, binSmem, st, tasks, B.info, B.chunkInfo, rlo, rhi, B.bins, nb));
+        ctx->launches++;
 
         bool spatialPath = false;
         if (depth == 0 && !tlas) {
@@ -1788,8 +1842,8 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
             out->stats[0] = info.rootNeedSpatial ? 1 : 0;
             spatialPath = info.rootKind == uint32_t(kSpatial);
         } else {
-            select_big<<<tasksBound, kSelectBlock, select_smem(nb), st>>>(tasks, B.info, B.bins, B.medAcc, L, nb);
-            ATLAS_LAUNCHED(ctx);
+            ATLAS_CUDA_C(ctx, launch_chain(pdl, select_big, tasksBound, kSelectBlock, select_smem(nb), st, tasks, B.info, B.bins, B.medAcc, L, nb));
+            ctx->launches++;
         }
 
         if (spatialPath) {
@@ -1814,25 +1868,22 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
             spatial_place<<<gridChunks, 256, 0, st>>>(tasks, B.root, tmpLlo, tmpLhi, tmpRlo, tmpRhi, wlo, whi, B.order, B.eon);
             ATLAS_LAUNCHED(ctx);
         } else {
-            median_reduce_big<<<gridChunks, kBigBlock, 0, st>>>(tasks, B.info, B.chunkInfo, rlo, rhi, B.medAcc);
-            ATLAS_LAUNCHED(ctx);
-            median_finalize_big<<<warpGrid, 128, 0, st>>>(tasks, B.info, B.medAcc, B.lo[cur], B.hi[cur], wlo, whi, B.order, B.eon, L,
-                                                          (!tlas && depth == 0) ? 1 : 0);
-            ATLAS_LAUNCHED(ctx);
-            partition_count<<<gridChunks, kBigBlock, 0, st>>>(tasks, B.info, B.chunkInfo, rlo, rhi, B.chunkFirst, nb);
-            ATLAS_LAUNCHED(ctx);
-            partition_scatter<<<gridChunks, kBigBlock, 0, st>>>(tasks, B.info, B.chunkInfo, B.chunkFirst, rlo, rhi, wlo, whi, B.order,
-                                                                B.eon, nb, B.bins, 3u * bins_at_depth(B.budget, depth + 1u),
-                                                                std::min<uint32_t>(depth < 30u ? (2u << depth) : maxTasks, maxTasks));
+            ATLAS_CUDA_C(ctx, launch_chain(pdl, median_reduce_big, gridChunks, kBigBlock, 0, st, tasks, B.info, B.chunkInfo, rlo, rhi, B.medAcc));
+            ctx->launches++;
+            ATLAS_CUDA_C(ctx, launch_chain(pdl, median_finalize_big, warpGrid, 128, 0, st, tasks, B.info, B.medAcc, B.lo[cur], B.hi[cur], wlo, whi,
+                                           B.order, B.eon, L, (!tlas && depth == 0) ? 1 : 0));
+            ctx->launches++;
+            ATLAS_CUDA_C(ctx, launch_chain(pdl, partition_count, gridChunks, kBigBlock, 0, st, tasks, B.info, B.chunkInfo, rlo, rhi, B.chunkFirst, nb));
+            ctx->launches++;
+            ATLAS_CUDA_C(ctx, launch_chain(pdl, partition_scatter, gridChunks, kBigBlock, 0, st, tasks, B.info, B.chunkInfo, B.chunkFirst, rlo, rhi, wlo,
+                                           whi, B.order, B.eon, nb, B.bins, 3u * bins_at_depth(B.budget, depth + 1u),
+                                           std::min<uint32_t>(depth < 30u ? (2u << depth) : maxTasks, maxTasks)));
             binsReady = true;
-            ATLAS_LAUNCHED(ctx);
+            ctx->launches++;
         }
-        ATLAS_CUDA_C(ctx, cudaMemcpyAsync(&slots[depth % 32u], B.info, sizeof(LevelInfo), cudaMemcpyDeviceToHost, st));
-        ATLAS_CUDA_C(ctx, cudaEventRecord(ctx->levelEvents[depth % 32u], st));
-        if (depth == 0 && !tlas) {
-            // the root's outcome (spatial duplicates, a root that stayed a leaf) sizes everything that follows
-            ATLAS_CUDA_C(ctx, cudaEventSynchronize(ctx->levelEvents[0]));
-            info = slots[0];
+        if (depth == 0 && !tlas && info.rootKind != uint32_t(kObject)) {
+            // a spatial root adds duplicates and a median root may have stayed a leaf: both size what follows
+            ATLAS_TRY(read_back(ctx, B.info, &info));
             totalRefs = info.totalRefs;
             if (info.rootLeaf) { rootLeaf = true; break; }
         }
@@ -1841,9 +1892,9 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
     // the subtrees are enqueued straight behind the last level (the kernel reads their number on the device); the one
     // read-back that follows waits for the whole build
     if (!rootLeaf) {
-        build_subtrees<<<uint32_t(ctx->smCount) * 2u, kSubBlock, kSubtreeSmem, st>>>(B.small, B.lo[0], B.hi[0], B.lo[1], B.hi[1], B.nodes, B.order,
-                                                                                    B.eon, B.info, B.budget, maxSmall);
-        ATLAS_LAUNCHED(ctx);
+        ATLAS_CUDA_C(ctx, launch_chain(pdl, build_subtrees, uint32_t(ctx->smCount) * 2u, kSubBlock, kSubtreeSmem, st, B.small, B.lo[0], B.hi[0], B.lo[1],
+                                       B.hi[1], B.nodes, B.order, B.eon, B.info, B.budget, maxSmall));
+        ctx->launches++;
     }
     ATLAS_TRY(read_back(ctx, B.info, &info));
     if (info.overflow) { cleanup(); return fail(ctx, ATLAS_RT_ERR_UNSUPPORTED, "task list overflow"); }

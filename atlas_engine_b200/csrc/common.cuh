@@ -81,12 +81,12 @@ struct atlas_rt_context {
     cudaStream_t copyIn = nullptr, copyOut = nullptr;
     cudaStream_t compute2 = nullptr;   // second compute stream: alternate chunks of a pipelined host-buffer trace overlap their tails
     cudaEvent_t pipeEvents[20] = {};
-    cudaEvent_t levelEvents[32] = {};          // builder: one per in-flight level read-back (build.cu)
-    void* levelSlots = nullptr;                // pinned, 32 x 128 B level read-back slots
+    void* levelSlots = nullptr;                // pinned: per-level flags the builder's kernels write for the host (build.cu)
     // scheduling knobs of the persistent traversal kernel (trace.cu); ATLAS_RT_TRACE_* environment variables override
     int traceLeafThreshold = 8;     // lanes waiting at a leaf before the warp runs a leaf round
     int traceRefillThreshold = 16;  // idle lanes before the warp fetches new rays (swept with the longest-first order: 16-20 is best)
     int traceBlocksPerSM = 9;
+    int chainLaunch = 1;         // builder level loop as a chain of programmatic dependent launches
     int binCtasPerSM = 2;        // CTAs per SM of the builder's binning kernel (each merges its shared bins into global ones)
     int traceLongestFirst = 1;      // fetch rays longest-estimated-path first (hides the drain of the longest rays)
     int traceLongestFirstMin = 65536;
