@@ -26,3 +26,7 @@ sh = rays.copy()
 sh[:, 8] = 10.0
 occ = ctx.trace(sc, sh, any_hit=True, flags=capi.PER_RAY_TMAX)
 print("hits", int((out[:, 9].view(np.int32) >= 0).sum()), "occluded", int((occ[:, 9].view(np.int32) >= 0).sum()), ctx.trace_counters())
+# the pipelined host-buffer path (two compute streams, >= 262144 rays) and an in-place device batch
+big = W.random_rays(300000, ib[:, :3].min(0), ib[:, 3:].max(0), seed=7)
+res = ctx.trace(sc, big)
+print("pipelined hits", int((res[:, 9].view(np.int32) >= 0).sum()))
