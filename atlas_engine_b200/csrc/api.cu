@@ -530,9 +530,10 @@ static int trace_common(atlas_rt_context* ctx, const atlas_rt_scene* scene, cons
     }
     int rc = ATLAS_RT_OK;
     const uint64_t kPipeMin = 262144;
-    if (!devIn && !devOut && count >= kPipeMin && ctx->copyIn && ctx->copyOut) {
-        // Host buffers on both sides: split the batch and overlap H2D of chunk i+1, the trace of chunk i and D2H of
-        // chunk i-1 on the two copy engines (pays off with pinned host memory; pageable memory still works).
+    if (!devIn && count >= kPipeMin && ctx->copyIn && ctx->copyOut) {
+        // Host input: split the batch and overlap H2D of chunk i+1, the trace of chunk i and (host output) D2H of
+        // chunk i-1 on the two copy engines (pays off with pinned host memory; pageable memory still works). With
+        // ATLAS_RT_DEVICE_OUTPUT the hits stay on the device, e.g. for an NCCL gather.
         // every launch pays the latency of its longest ray, so chunks stay large: about a third of a million rays each (swept)
         uint32_t chunks = uint32_t(std::max<uint64_t>(2, std::min<uint64_t>(8, (count + 175000) / 350000)));
         if (const char* e = getenv("ATLAS_RT_PIPE_CHUNKS")) chunks = uint32_t(std::max(1, std::min(8, atoi(e))));
@@ -554,11 +555,12 @@ static int trace_common(atlas_rt_context* ctx, const atlas_rt_scene* scene, cons
             if (e == cudaSuccess) e = cudaEventRecord(ev[1 + c], ctx->copyIn);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, ev[1 + c], 0);
             if (e != cudaSuccess) break;
-            rc = launch_trace(ctx, scene, dIn + 3 * b, dIn + 3 * b, end - b, cull_mask, t_min, t_max, any, perRay, counters, false, opacity, cs, slot);
+            float4* dst = devOut ? out + 3 * b : dIn + 3 * b;   // host output: in place on the staging buffer
+            rc = launch_trace(ctx, scene, dIn + 3 * b, dst, end - b, cull_mask, t_min, t_max, any, perRay, counters, false, opacity, cs, slot);
             if (rc != ATLAS_RT_OK) break;
             e = cudaEventRecord(ev[9 + c], cs);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copyOut, ev[9 + c], 0);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(hOut, dIn + 3 * b, 48 * (end - b), cudaMemcpyDeviceToHost, ctx->copyOut);
+            if (e == cudaSuccess && !devOut) e = cudaMemcpyAsync(hOut, dIn + 3 * b, 48 * (end - b), cudaMemcpyDeviceToHost, ctx->copyOut);
         }
         if (e == cudaSuccess) e = cudaEventRecord(ev[19], ctx->copyOut);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev[19], 0);   // the context stream now orders after the downloads

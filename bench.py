@@ -323,16 +323,17 @@ def main():
 
     # ---- end to end with HOST ray buffers (pinned): H2D + trace + (gather) + D2H inside the timed region.
     # N == 1: one atlas_rt_trace_closest call with host pointers (the library stages, pipelines and copies). N > 1: the
-    # same copies issued from torch around the device-pointer call so the all-gather can run on the device-resident
-    # hits; every rank then reads back its own 16 B/ray share of the gathered hit records.
+    # same call with host rays in and ATLAS_RT_DEVICE_OUTPUT, so the all-gather runs on the device-resident hits; every
+    # rank then reads back its own 16 B/ray share of the gathered hit records.
     h_hits = torch.empty((N_RAYS, 4), dtype=torch.float32).pin_memory() if world > 1 else None
 
     def e2e_step():
         if world == 1:
             ctx.check(ctx.L.atlas_rt_trace_closest(ctx.h, scene.h, h_rays.data_ptr(), N_RAYS, capi.MASK_ALL, 0.0, capi.INF, h_out.data_ptr(), 0))
         else:
-            d_rays.copy_(h_rays, non_blocking=True)
-            ctx.trace(scene, d_rays, N_RAYS, out=d_out, flags=capi.ASYNC)
+            # host rays in, hits left on the device for the gather: the library overlaps the upload with the trace
+            ctx.check(ctx.L.atlas_rt_trace_closest(ctx.h, scene.h, h_rays.data_ptr(), N_RAYS, capi.MASK_ALL, 0.0, capi.INF, d_out.data_ptr(),
+                                                   capi.DEVICE_OUTPUT | capi.ASYNC))
             sharding.gather_hits(d_out, gathered)
             h_hits.copy_(gathered[rank * N_RAYS:(rank + 1) * N_RAYS], non_blocking=True)   # this rank's share of the gathered hits
             stream.synchronize()

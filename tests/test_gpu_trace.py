@@ -137,6 +137,10 @@ def test_full_size_c2_properties(ctx, oracle):
     assert np.array_equal(d_out.cpu().numpy().view(np.uint32), out.view(np.uint32))
     ctx.trace(scene, d_rays, len(rays))
     assert np.array_equal(d_rays.cpu().numpy().view(np.uint32), out.view(np.uint32))
+    # host rays in, hits left on the device (the multi-GPU bench's call): same pipeline without the download
+    ctx.check(ctx.L.atlas_rt_trace_closest(ctx.h, scene.h, rays.ctypes.data, len(rays), capi.MASK_ALL, 0.0, capi.INF, d_out.data_ptr(),
+                                           capi.DEVICE_OUTPUT))
+    assert np.array_equal(d_out.cpu().numpy().view(np.uint32), out.view(np.uint32))
     hit = out[:, 9].view(np.int32) >= 0
     t = out[:, 8]
     assert 0.1 < hit.mean() < 0.9 and np.all(t[~hit] == np.float32(1e12))
