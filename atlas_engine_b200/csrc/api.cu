@@ -534,9 +534,12 @@ static int trace_common(atlas_rt_context* ctx, const atlas_rt_scene* scene, cons
         // Host input: split the batch and overlap H2D of chunk i+1, the trace of chunk i and (host output) D2H of
         // chunk i-1 on the two copy engines (pays off with pinned host memory; pageable memory still works). With
         // ATLAS_RT_DEVICE_OUTPUT the hits stay on the device, e.g. for an NCCL gather.
-        // every launch pays the latency of its longest ray, so chunks stay large: about a third of a million rays each (swept)
-        uint32_t chunks = uint32_t(std::max<uint64_t>(2, std::min<uint64_t>(8, (count + 175000) / 350000)));
-        if (const char* e = getenv("ATLAS_RT_PIPE_CHUNKS")) chunks = uint32_t(std::max(1, std::min(8, atoi(e))));
+        // every launch pays the latency of its longest ray, so chunks stay large: about a third of a million rays each
+        // (swept), with half-size first and last chunks so that the first trace starts early and the last download is short
+        const uint32_t whole = uint32_t(std::max<uint64_t>(2, std::min<uint64_t>(7, (count + 175000) / 350000)));
+        uint32_t chunks = whole + 1u;
+        bool equalSplit = false;
+        if (const char* e = getenv("ATLAS_RT_PIPE_CHUNKS")) { chunks = uint32_t(std::max(1, std::min(8, atoi(e)))); equalSplit = true; }
         cudaEvent_t* ev = ctx->pipeEvents;   // [0] staging ready, [1+c] chunk c uploaded, [9+c] chunk c traced, [19] all downloaded
         // Chunks alternate between the context stream and a second compute stream (each with its own ray-queue head), so
         // the thin tail of one chunk's persistent kernel overlaps the start of the next chunk's.
@@ -545,8 +548,22 @@ static int trace_common(atlas_rt_context* ctx, const atlas_rt_scene* scene, cons
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copyIn, ev[0], 0);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copyOut, ev[0], 0);
         if (e == cudaSuccess && ctx->compute2) e = cudaStreamWaitEvent(ctx->compute2, ev[0], 0);
+        // chunk boundaries as fractions of the batch; ATLAS_RT_PIPE_SPLIT="0.15,0.5,0.85" overrides the equal split
+        double cut[9];
+        for (uint32_t c = 0; c <= chunks; c++) cut[c] = equalSplit ? double(c) / chunks : (c == 0 ? 0.0 : (c == chunks ? 1.0 : (c - 0.5) / whole));
+        if (const char* sp = getenv("ATLAS_RT_PIPE_SPLIT")) {
+            uint32_t k = 1;
+            for (const char* q = sp; *q && k < 8; k++) {
+                cut[k] = atof(q);
+                const char* comma = strchr(q, ',');
+                if (!comma) { k++; break; }
+                q = comma + 1;
+            }
+            chunks = k;
+            cut[chunks] = 1.0;
+        }
         for (uint32_t c = 0; c < chunks && e == cudaSuccess && rc == ATLAS_RT_OK; c++) {
-            const uint64_t b = (count * c / chunks) & ~uint64_t(31), end = c + 1 == chunks ? count : ((count * (c + 1) / chunks) & ~uint64_t(31));
+            const uint64_t b = uint64_t(count * cut[c]) & ~uint64_t(31), end = c + 1 == chunks ? count : (uint64_t(count * cut[c + 1]) & ~uint64_t(31));
             const char* hIn = static_cast<const char*>(rays_in) + 48 * b;
             char* hOut = static_cast<char*>(rays_out) + 48 * b;
             const int slot = (ctx->compute2 && (c & 1u)) ? 1 : 0;
