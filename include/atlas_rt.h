@@ -168,7 +168,10 @@ void atlas_rt_scene_free(atlas_rt_scene* scene);
 /* Closest hit for a batch of PackedRay (48 B). Replaces the traceClosest.csh dispatch issued by
  * RayTracingHelper::DispatchHitClosest (src/engine/renderer/helper/RayTracingHelper.cpp:346-364) = HitClosest,
  * data/shader/raytracer/bvh.hsh:191-273: rays with ID < 0 are passed through with hitID = -1, t = 0; otherwise
- * t = tMax and hitID = -1 on a miss. rays_out may alias rays_in. */
+ * t = tMax and hitID = -1 on a miss. rays_out may alias rays_in (an in-place batch only writes the hit fields).
+ * ATLAS_RT_DEVICE_INPUT / ATLAS_RT_DEVICE_OUTPUT are independent: with host rays (pinned memory pays off) batches of
+ * 262144 rays or more are uploaded, traced and, for host output, downloaded in overlapping chunks; host rays with
+ * device output leave the hits on the device, e.g. for an NCCL gather. */
 int atlas_rt_trace_closest(atlas_rt_context* ctx, const atlas_rt_scene* scene, const void* rays_in, uint64_t count,
                            uint32_t cull_mask, float t_min, float t_max, void* rays_out, uint32_t flags);
 
