@@ -169,14 +169,16 @@ int atlas_rt_context_create(int device, void* stream, atlas_rt_context** out_ctx
         uint64_t keep = ~0ull;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
-    if (cudaMalloc(&ctx->dCounters, 8 * sizeof(unsigned long long)) != cudaSuccess) { delete ctx; return ATLAS_RT_ERR_OOM; }
-    cudaMemset(ctx->dCounters, 0, 8 * sizeof(unsigned long long));
+    if (cudaMalloc(&ctx->dCounters, 16 * sizeof(unsigned long long)) != cudaSuccess) { delete ctx; return ATLAS_RT_ERR_OOM; }
+    cudaMemset(ctx->dCounters, 0, 16 * sizeof(unsigned long long));
     ctx->pinnedBytes = 8192;
     if (cudaMallocHost(&ctx->pinned, ctx->pinnedBytes) != cudaSuccess) { cudaFree(ctx->dCounters); delete ctx; return ATLAS_RT_ERR_OOM; }
     ctx->levelSlots = static_cast<char*>(ctx->pinned) + 4096;
     if (cudaStreamCreateWithFlags(&ctx->copyIn, cudaStreamNonBlocking) != cudaSuccess) ctx->copyIn = nullptr;
     if (cudaStreamCreateWithFlags(&ctx->copyOut, cudaStreamNonBlocking) != cudaSuccess) ctx->copyOut = nullptr;
-    if (cudaStreamCreateWithFlags(&ctx->compute2, cudaStreamNonBlocking) != cudaSuccess) ctx->compute2 = nullptr;
+    for (auto& cs : ctx->computeExtra)
+        if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) cs = nullptr;
+    if (const char* e = getenv("ATLAS_RT_PIPE_STREAMS")) ctx->pipeStreams = std::max(1, std::min(8, atoi(e)));
     for (auto& ev : ctx->pipeEvents)
         if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { ev = nullptr; ctx->copyIn = nullptr; }
     *out_ctx = ctx;
@@ -190,7 +192,7 @@ void atlas_rt_context_destroy(atlas_rt_context* ctx) {
     for (auto& ev : ctx->pipeEvents) if (ev) cudaEventDestroy(ev);
     if (ctx->copyIn) cudaStreamDestroy(ctx->copyIn);
     if (ctx->copyOut) cudaStreamDestroy(ctx->copyOut);
-    if (ctx->compute2) cudaStreamDestroy(ctx->compute2);
+    for (auto& cs : ctx->computeExtra) if (cs) cudaStreamDestroy(cs);
     cudaFree(ctx->dCounters);
     cudaFreeHost(ctx->pinned);
     if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
@@ -534,26 +536,27 @@ static int trace_common(atlas_rt_context* ctx, const atlas_rt_scene* scene, cons
         // Host input: split the batch and overlap H2D of chunk i+1, the trace of chunk i and (host output) D2H of
         // chunk i-1 on the two copy engines (pays off with pinned host memory; pageable memory still works). With
         // ATLAS_RT_DEVICE_OUTPUT the hits stay on the device, e.g. for an NCCL gather.
-        // every launch pays the latency of its longest ray, so chunks stay large: about a third of a million rays each
-        // (swept), with half-size first and last chunks so that the first trace starts early and the last download is short
-        const uint32_t whole = uint32_t(std::max<uint64_t>(2, std::min<uint64_t>(7, (count + 175000) / 350000)));
-        uint32_t chunks = whole + 1u;
-        bool equalSplit = false;
-        if (const char* e = getenv("ATLAS_RT_PIPE_CHUNKS")) { chunks = uint32_t(std::max(1, std::min(8, atoi(e)))); equalSplit = true; }
-        cudaEvent_t* ev = ctx->pipeEvents;   // [0] staging ready, [1+c] chunk c uploaded, [9+c] chunk c traced, [19] all downloaded
+        // Chunks of about 125 k rays, spread over up to 8 compute streams: a launch that small occupies a fraction of the
+        // GPU for the latency of its longest ray, and several of them run side by side while later chunks are still
+        // arriving and earlier ones are going back (swept on C2: 8 chunks x 8 streams 1.89 ms, 4 x 2 2.04 ms, 1 x 1 2.75 ms)
+        uint32_t chunks = uint32_t(std::max<uint64_t>(2, std::min<uint64_t>(16, (count + 62500) / 125000)));
+        if (const char* e = getenv("ATLAS_RT_PIPE_CHUNKS")) chunks = uint32_t(std::max(1, std::min(16, atoi(e))));
+        cudaEvent_t* ev = ctx->pipeEvents;   // [0] staging ready, [1+c] chunk c uploaded, [17+c] chunk c traced, [33] all downloaded
         // Chunks alternate between the context stream and a second compute stream (each with its own ray-queue head), so
         // the thin tail of one chunk's persistent kernel overlaps the start of the next chunk's.
         cudaError_t e = cudaMemsetAsync(ctx->dCounters, 0, 6 * sizeof(unsigned long long), ctx->stream);
         if (e == cudaSuccess) e = cudaEventRecord(ev[0], ctx->stream);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copyIn, ev[0], 0);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copyOut, ev[0], 0);
-        if (e == cudaSuccess && ctx->compute2) e = cudaStreamWaitEvent(ctx->compute2, ev[0], 0);
+        uint32_t nStreams = 1;   // usable compute streams: the context stream + the extra ones that exist
+        while (nStreams < uint32_t(ctx->pipeStreams) && ctx->computeExtra[nStreams - 1]) nStreams++;
+        for (uint32_t k = 1; k < nStreams && e == cudaSuccess; k++) e = cudaStreamWaitEvent(ctx->computeExtra[k - 1], ev[0], 0);
         // chunk boundaries as fractions of the batch; ATLAS_RT_PIPE_SPLIT="0.15,0.5,0.85" overrides the equal split
-        double cut[9];
-        for (uint32_t c = 0; c <= chunks; c++) cut[c] = equalSplit ? double(c) / chunks : (c == 0 ? 0.0 : (c == chunks ? 1.0 : (c - 0.5) / whole));
+        double cut[17];
+        for (uint32_t c = 0; c <= chunks; c++) cut[c] = double(c) / chunks;
         if (const char* sp = getenv("ATLAS_RT_PIPE_SPLIT")) {
             uint32_t k = 1;
-            for (const char* q = sp; *q && k < 8; k++) {
+            for (const char* q = sp; *q && k < 16; k++) {
                 cut[k] = atof(q);
                 const char* comma = strchr(q, ',');
                 if (!comma) { k++; break; }
@@ -566,8 +569,8 @@ static int trace_common(atlas_rt_context* ctx, const atlas_rt_scene* scene, cons
             const uint64_t b = uint64_t(count * cut[c]) & ~uint64_t(31), end = c + 1 == chunks ? count : (uint64_t(count * cut[c + 1]) & ~uint64_t(31));
             const char* hIn = static_cast<const char*>(rays_in) + 48 * b;
             char* hOut = static_cast<char*>(rays_out) + 48 * b;
-            const int slot = (ctx->compute2 && (c & 1u)) ? 1 : 0;
-            cudaStream_t cs = slot ? ctx->compute2 : ctx->stream;
+            const int slot = int(c % nStreams);
+            cudaStream_t cs = slot ? ctx->computeExtra[slot - 1] : ctx->stream;
             e = cudaMemcpyAsync(dIn + 3 * b, hIn, 48 * (end - b), cudaMemcpyHostToDevice, ctx->copyIn);
             if (e == cudaSuccess) e = cudaEventRecord(ev[1 + c], ctx->copyIn);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, ev[1 + c], 0);
@@ -575,12 +578,12 @@ static int trace_common(atlas_rt_context* ctx, const atlas_rt_scene* scene, cons
             float4* dst = devOut ? out + 3 * b : dIn + 3 * b;   // host output: in place on the staging buffer
             rc = launch_trace(ctx, scene, dIn + 3 * b, dst, end - b, cull_mask, t_min, t_max, any, perRay, counters, false, opacity, cs, slot);
             if (rc != ATLAS_RT_OK) break;
-            e = cudaEventRecord(ev[9 + c], cs);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copyOut, ev[9 + c], 0);
+            e = cudaEventRecord(ev[17 + c], cs);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copyOut, ev[17 + c], 0);
             if (e == cudaSuccess && !devOut) e = cudaMemcpyAsync(hOut, dIn + 3 * b, 48 * (end - b), cudaMemcpyDeviceToHost, ctx->copyOut);
         }
-        if (e == cudaSuccess) e = cudaEventRecord(ev[19], ctx->copyOut);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev[19], 0);   // the context stream now orders after the downloads
+        if (e == cudaSuccess) e = cudaEventRecord(ev[33], ctx->copyOut);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev[33], 0);   // the context stream now orders after the downloads
         if (e != cudaSuccess && rc == ATLAS_RT_OK) rc = fail(ctx, ATLAS_RT_ERR_CUDA, "pipelined trace", e);
     } else {
         if (!devIn) {

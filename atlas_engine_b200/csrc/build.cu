@@ -85,7 +85,7 @@ struct SmallTask {   // root of a shared-memory subtree (48 B)
     uint32_t start, count, flatIdx, depth, buf, pad;
 };
 
-struct LevelInfo {   // device-resident, read back once per level
+struct LevelInfo {   // device-resident state of the build; read back after the root decision and at the end
     uint32_t nTasks, nChunks, nNext, nSmall, nMedian, rootNeedSpatial, rootKind, rootLeaf;
     uint32_t totalRefs, negZero, nStraddle, nL0, nR0, levels, overflow, subTicket;
     unsigned long long stats[8];   // [2] duplicates [3] median splits [4] sort fallbacks [5] largest sort fallback

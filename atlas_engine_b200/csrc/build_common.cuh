@@ -168,10 +168,8 @@ struct LaneGroup {
 // Candidate j in [1, nb): left = bins[0..j-1], right = bins[j..nb-1], nLeft = sum enter[0..j-1],
 // nRight = total - sum exit[0..j-1]; skipped when either is 0; cost = SA(left)*float(nLeft) + SA(right)*float(nRight);
 // strictly smaller cost wins, i.e. the lowest (axis, j) among equal costs.
-// With STORE_PREFIX the forward pass overwrites bins[k] with the prefix union / prefix enter count of bins[0..k], so that
-// the caller can read the winning split's boxes as bins[j-1] and sfx[j] without another pass. Returns true when this
-// axis improved `best`.
-template <int G, bool STORE_PREFIX, typename BinPtr>
+// Returns true when this axis improved `best`. `stride` = ints between two bin records.
+template <int G, typename BinPtr>
 __device__ inline bool group_sweep_axis(const LaneGroup<G>& g, BinPtr bins, uint32_t nb, int* sfx, uint32_t total, int axis,
                                         BestSplit& best, int stride = kBinWords) {
     const uint32_t lane = g.lane;
@@ -227,12 +225,6 @@ __device__ inline bool group_sweep_axis(const LaneGroup<G>& g, BinPtr bins, uint
         obox_grow(b, pcarry);
         en += ecarry;
         ex += xcarry;
-        if (STORE_PREFIX && k < nb) {
-            int* rec = const_cast<int*>(bins) + k * stride;
-#pragma unroll
-            for (int w = 0; w < 3; w++) { rec[w] = b.lo[w]; rec[3 + w] = b.hi[w]; }
-            rec[6] = int(en);
-        }
         const uint32_t j = k + 1u;   // split after bin k
         if (j < nb) {
             const uint32_t nLeft = en, nRight = total - ex;
@@ -381,7 +373,7 @@ __device__ __forceinline__ bool group_sweep_single(const LaneGroup<G>& g, const 
 __device__ inline void warp_sweep_axis(const int* bins, uint32_t nb, int* sfx, uint32_t total, int axis, BestSplit& best,
                                        int stride = kBinWords) {
     const LaneGroup<32> g;
-    group_sweep_axis<32, false>(g, bins, nb, sfx, total, axis, best, stride);
+    group_sweep_axis<32>(g, bins, nb, sfx, total, axis, best, stride);
 }
 
 // leftAABB / rightAABB / primitivesLeft of the chosen split, recomputed from the bins of the winning axis.

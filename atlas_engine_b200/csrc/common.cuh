@@ -74,13 +74,14 @@ struct atlas_rt_context {
     int smCount = 148;
     uint64_t launches = 0;
     std::string error;
-    unsigned long long* dCounters = nullptr;   // 8 x u64 traversal counters / flags
+    unsigned long long* dCounters = nullptr;   // 16 x u64: [0..5] traversal counters / overflow flag, [8..15] ray-queue heads (one per compute stream)
     void* pinned = nullptr;                    // small pinned staging area for read-backs
     size_t pinnedBytes = 0;
     // copy engines used to overlap H2D / trace / D2H when a trace call is given host buffers (api.cu)
     cudaStream_t copyIn = nullptr, copyOut = nullptr;
-    cudaStream_t compute2 = nullptr;   // second compute stream: alternate chunks of a pipelined host-buffer trace overlap their tails
-    cudaEvent_t pipeEvents[20] = {};
+    cudaStream_t computeExtra[7] = {};   // extra compute streams: the chunks of a pipelined host-buffer trace run side by side
+    int pipeStreams = 8;                 // compute streams such a call uses (the context stream + computeExtra)
+    cudaEvent_t pipeEvents[34] = {};   // pipelined host-buffer trace: [0] staging ready, [1+c] chunk c uploaded, [17+c] chunk c traced, [33] all done
     void* levelSlots = nullptr;                // pinned: per-level flags the builder's kernels write for the host (build.cu)
     // scheduling knobs of the persistent traversal kernel (trace.cu); ATLAS_RT_TRACE_* environment variables override
     int traceLeafThreshold = 8;     // lanes waiting at a leaf before the warp runs a leaf round

@@ -538,10 +538,10 @@ int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float
     const uint32_t grid = std::min<uint32_t>(std::min<uint32_t>((n + kTraceBlock - 1) / kTraceBlock, wantBlocks), uint32_t(ctx->smCount) * uint32_t(ctx->traceBlocksPerSM));
     const int lt = ctx->traceLeafThreshold, rt = ctx->traceRefillThreshold;
     // words 0-5: visit counters + overflow flag (kept across the chunks of one pipelined call), word 6: the ray queue head
-    // (word 7: a second queue head, for a launch that overlaps the previous one on another stream)
+    // (words 8-15: ray-queue heads, one per compute stream, for launches that run side by side)
     if (resetCounters) ATLAS_CUDA(ctx, cudaMemsetAsync(ctx->dCounters, 0, 6 * sizeof(unsigned long long), st));
-    ATLAS_CUDA(ctx, cudaMemsetAsync(ctx->dCounters + 6 + queueSlot, 0, sizeof(unsigned long long), st));
-    unsigned int* rayCounter = reinterpret_cast<unsigned int*>(ctx->dCounters + 6 + queueSlot);
+    ATLAS_CUDA(ctx, cudaMemsetAsync(ctx->dCounters + 8 + queueSlot, 0, sizeof(unsigned long long), st));
+    unsigned int* rayCounter = reinterpret_cast<unsigned int*>(ctx->dCounters + 8 + queueSlot);
     // ---- longest-first fetch order for batches large enough to have a tail worth hiding
     uint32_t* perm = nullptr;
     uint8_t* bucketOf = nullptr;

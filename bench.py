@@ -294,7 +294,7 @@ def main():
 
     # clocks / throttle reasons are sampled with nvidia-smi while the headline (trace) region is timed; the build loop
     # runs after the sampler has stopped, because concurrent nvidia-smi queries stall the driver for milliseconds and
-    # the build's three root read-backs then wait on them (seen as 7-9 ms instead of 3.2 ms per build on a cold box)
+    # the build's read-backs then wait on them (seen as 7-9 ms instead of 3.2 ms per build on a cold box)
     with ClockSampler(local_rank) as clk:
         launches0 = ctx.launches()
         trace_ms = timed(trace_step, args.steps, args.warmup) if world == 1 else timed_pipelined(args.steps, args.warmup)
