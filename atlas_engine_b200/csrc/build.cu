@@ -1246,12 +1246,22 @@ __device__ __forceinline__ SubNode make_subnode(uint32_t start, uint32_t count, 
     return n;
 }
 
-constexpr uint32_t kTinyMax = 4;   // nodes with at most this many refs are handled by ONE lane (32 nodes per warp)
+constexpr uint32_t kTinyMax = 4;    // nodes with at most this many refs are handled by ONE lane (32 nodes per warp)
+constexpr uint32_t kSmallMax = 8;   // ... and so are nodes with up to this many, in packs of their own (longer unrolled code)
 
-// One lane builds one node with 2..kTinyMax refs. Same decisions as the warp path, evaluated without bins: with n refs
-// at most n-1 bin boundaries separate them, and every other candidate j of BVH.cpp:496-522 repeats the partition (and
-// hence the cost) of the nearest boundary below it, so scanning only the boundaries in ascending j and keeping strictly
-// smaller costs selects the same (axis, j). Boxes are reduced on the ordered-int image like everywhere else.
+// A ref held by one lane: the box as plain floats plus the primitive index.
+struct LaneRef {
+    float lo[3], hi[3];
+    uint32_t idx;
+};
+
+// One lane builds one node with 2..MAXN refs. Same decisions as the warp path, evaluated without bins: with n refs at
+// most n-1 bin boundaries separate them, and every other candidate j of BVH.cpp:496-522 repeats the partition (and hence
+// the cost) of the nearest boundary below it, so scanning only the boundaries in ascending j and keeping strictly
+// smaller costs selects the same (axis, j). Boxes are grown with float min/max here: no atomics are involved, and on
+// inputs without -0.0 (the documented exception, flagged by the builder) fminf/fmaxf and the ordered-int reductions of
+// the other paths give the same bits.
+template <uint32_t MAXN>
 __device__ inline void build_tiny_node(const SubNode nd, const SmallTask& task, uint32_t depth, uint32_t budget,
                                        const float4* __restrict__ cLo, const float4* __restrict__ cHi, float4* __restrict__ nLo,
                                        float4* __restrict__ nHi, float4* nodes, uint32_t* __restrict__ order, uint8_t* __restrict__ eon,
@@ -1262,15 +1272,24 @@ __device__ inline void build_tiny_node(const SubNode nd, const SmallTask& task, 
     float blo[3], bhi[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) { blo[k] = nd.lo[k]; bhi[k] = nd.hi[k]; }
-    float4 rl[kTinyMax], rh[kTinyMax];
-    OBox rb[kTinyMax];
+    LaneRef r[MAXN];
 #pragma unroll
-    for (uint32_t i = 0; i < kTinyMax; i++) {
-        if (i < n) { rl[i] = cLo[s + i]; rh[i] = cHi[s + i]; }
-        else { rl[i] = make_float4(kFltMax, kFltMax, kFltMax, 0.0f); rh[i] = make_float4(-kFltMax, -kFltMax, -kFltMax, 0.0f); }
-        rb[i].lo[0] = ord_from_float(rl[i].x); rb[i].lo[1] = ord_from_float(rl[i].y); rb[i].lo[2] = ord_from_float(rl[i].z);
-        rb[i].hi[0] = ord_from_float(rh[i].x); rb[i].hi[1] = ord_from_float(rh[i].y); rb[i].hi[2] = ord_from_float(rh[i].z);
+    for (uint32_t i = 0; i < MAXN; i++) {
+        if (i < n) {
+            const float4 l = cLo[s + i], h = cHi[s + i];
+            r[i].lo[0] = l.x; r[i].lo[1] = l.y; r[i].lo[2] = l.z;
+            r[i].hi[0] = h.x; r[i].hi[1] = h.y; r[i].hi[2] = h.z;
+            r[i].idx = __float_as_uint(l.w);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 3; k++) { r[i].lo[k] = kFltMax; r[i].hi[k] = -kFltMax; }
+            r[i].idx = 0;
+        }
     }
+    auto grow = [](Box3& b, const LaneRef& x) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { b.lo[k] = fminf(b.lo[k], x.lo[k]); b.hi[k] = fmaxf(b.hi[k], x.hi[k]); }
+    };
     // ---- FindObjectSplit over the bin boundaries that actually separate refs
     float bestCost = kFltMax;
     int bestAxis = -1;
@@ -1279,35 +1298,42 @@ __device__ inline void build_tiny_node(const SubNode nd, const SmallTask& task, 
     for (int a = 0; a < 3; a++) {
         const AxisBins ab = axis_bins(blo[a], bhi[a], nb);
         if (!ab.active) continue;
-        uint32_t b[kTinyMax];
+        uint32_t b[MAXN];
 #pragma unroll
-        for (uint32_t i = 0; i < kTinyMax; i++) b[i] = i < n ? bin_of(bin_centre(comp(rl[i], a), comp(rh[i], a)), ab.start, ab.inv, nb) : 0xffffffffu;
+        for (uint32_t i = 0; i < MAXN; i++) {
+            const float lo = a == 0 ? r[i].lo[0] : (a == 1 ? r[i].lo[1] : r[i].lo[2]);
+            const float hi = a == 0 ? r[i].hi[0] : (a == 1 ? r[i].hi[1] : r[i].hi[2]);
+            b[i] = i < n ? bin_of(bin_centre(lo, hi), ab.start, ab.inv, nb) : 0xffffffffu;
+        }
         uint32_t prevJ = 0;
 #pragma unroll 1
         for (uint32_t c = 0; c + 1 < n; c++) {
             uint32_t j = 0xffffffffu;
 #pragma unroll
-            for (uint32_t i = 0; i < kTinyMax; i++) if (i < n && b[i] + 1u > prevJ && b[i] + 1u < j) j = b[i] + 1u;
+            for (uint32_t i = 0; i < MAXN; i++) if (i < n && b[i] + 1u > prevJ && b[i] + 1u < j) j = b[i] + 1u;
             if (j == 0xffffffffu) break;
             prevJ = j;
-            OBox L = obox_empty(), R = obox_empty();
+            Box3 L = empty_box(), R = empty_box();
             uint32_t nL = 0, nR = 0;
 #pragma unroll
-            for (uint32_t i = 0; i < kTinyMax; i++) {
-                if (i < n) { if (b[i] < j) { obox_grow(L, rb[i]); nL++; } else { obox_grow(R, rb[i]); nR++; } }
+            for (uint32_t i = 0; i < MAXN; i++) {
+                if (i < n) { if (b[i] < j) { grow(L, r[i]); nL++; } else { grow(R, r[i]); nR++; } }
             }
             if (nL == 0u || nR == 0u) continue;
-            const float cost = __fadd_rn(__fmul_rn(obox_area(L), __uint2float_rn(nL)), __fmul_rn(obox_area(R), __uint2float_rn(nR)));
+            const float cost = __fadd_rn(__fmul_rn(surface_area(L), __uint2float_rn(nL)), __fmul_rn(surface_area(R), __uint2float_rn(nR)));
             if (cost < bestCost) { bestCost = cost; bestAxis = a; bestJ = j; }
         }
     }
     const float nodeCost = __fmul_rn(__uint2float_rn(n), surface_area(blo, bhi));
-    bool isLeft[kTinyMax];
+    bool isLeft[MAXN];
     if (!(bestAxis < 0 || bestCost >= nodeCost)) {
         const AxisBins ab = axis_bins(blo[bestAxis], bhi[bestAxis], nb);
 #pragma unroll
-        for (uint32_t i = 0; i < kTinyMax; i++)
-            isLeft[i] = i < n && bin_of(bin_centre(comp(rl[i], bestAxis), comp(rh[i], bestAxis)), ab.start, ab.inv, nb) < bestJ;
+        for (uint32_t i = 0; i < MAXN; i++) {
+            const float lo = bestAxis == 0 ? r[i].lo[0] : (bestAxis == 1 ? r[i].lo[1] : r[i].lo[2]);
+            const float hi = bestAxis == 0 ? r[i].hi[0] : (bestAxis == 1 ? r[i].hi[1] : r[i].hi[2]);
+            isLeft[i] = i < n && bin_of(bin_centre(lo, hi), ab.start, ab.inv, nb) < bestJ;
+        }
     } else {
         // ---- PerformMedianSplit
         int axis;
@@ -1315,43 +1341,41 @@ __device__ inline void build_tiny_node(const SubNode nd, const SmallTask& task, 
         median_plane(blo, bhi, axis, cutoff);
         atomicAdd(&sStats[0], 1ull);
         uint32_t nL = 0;
+        float key[MAXN];   // extent on the axis, the sort key of the fallback
 #pragma unroll
-        for (uint32_t i = 0; i < kTinyMax; i++) {
-            isLeft[i] = i < n && median_centre(comp(rl[i], axis), comp(rh[i], axis)) < cutoff;
+        for (uint32_t i = 0; i < MAXN; i++) {
+            const float lo = axis == 0 ? r[i].lo[0] : (axis == 1 ? r[i].lo[1] : r[i].lo[2]);
+            const float hi = axis == 0 ? r[i].hi[0] : (axis == 1 ? r[i].hi[1] : r[i].hi[2]);
+            isLeft[i] = i < n && median_centre(lo, hi) < cutoff;
             nL += isLeft[i] ? 1u : 0u;
+            key[i] = i < n ? __fsub_rn(hi, lo) : 0.0f;
         }
         if (nL == 0u || nL == n) {
             // std::sort on <= 16 elements is a plain insertion sort, i.e. THE stable order by key (extent on the axis)
             atomicAdd(&sStats[1], 1ull);
             atomicMax(&sStats[2], (unsigned long long)n);
-            float key[kTinyMax];
 #pragma unroll
-            for (uint32_t i = 0; i < kTinyMax; i++) key[i] = i < n ? __fsub_rn(comp(rh[i], axis), comp(rl[i], axis)) : 0.0f;
-#pragma unroll
-            for (uint32_t i = 1; i < kTinyMax; i++) {
+            for (uint32_t i = 1; i < MAXN; i++) {
 #pragma unroll
                 for (uint32_t k = i; k > 0; k--) {
                     if (i < n && key[k] < key[k - 1]) {
                         const float tk = key[k]; key[k] = key[k - 1]; key[k - 1] = tk;
-                        const float4 tl = rl[k]; rl[k] = rl[k - 1]; rl[k - 1] = tl;
-                        const float4 th = rh[k]; rh[k] = rh[k - 1]; rh[k - 1] = th;
-                        const OBox tb = rb[k]; rb[k] = rb[k - 1]; rb[k - 1] = tb;
+                        const LaneRef tr = r[k]; r[k] = r[k - 1]; r[k - 1] = tr;
                     }
                 }
             }
             const uint32_t half = n / 2u;
 #pragma unroll
-            for (uint32_t i = 0; i < kTinyMax; i++) isLeft[i] = i < half;
+            for (uint32_t i = 0; i < MAXN; i++) isLeft[i] = i < half;
         }
     }
-    OBox L = obox_empty(), R = obox_empty();
+    Box3 lb = empty_box(), rbx = empty_box();
     uint32_t nLeft = 0;
 #pragma unroll
-    for (uint32_t i = 0; i < kTinyMax; i++) {
-        if (i < n) { if (isLeft[i]) { obox_grow(L, rb[i]); nLeft++; } else obox_grow(R, rb[i]); }
+    for (uint32_t i = 0; i < MAXN; i++) {
+        if (i < n) { if (isLeft[i]) { grow(lb, r[i]); nLeft++; } else grow(rbx, r[i]); }
     }
     // ---- Flatten bookkeeping + stable placement
-    const Box3 lb = obox_to_box(L), rbx = obox_to_box(R);
     const bool swapped = surface_area(lb) < surface_area(rbx);
     const uint32_t nFirst = swapped ? n - nLeft : nLeft, nSecond = n - nFirst;
     const uint32_t slot = task.start + s;
@@ -1368,16 +1392,16 @@ __device__ inline void build_tiny_node(const SubNode nd, const SmallTask& task, 
     if (nSecond > 1u) nextList[atomicAdd(sNext, 1u)] = make_subnode(s + nFirst, nSecond, nd.rel + nFirst, g);
     uint32_t doneFirst = 0, doneSecond = 0;
 #pragma unroll
-    for (uint32_t i = 0; i < kTinyMax; i++) {
+    for (uint32_t i = 0; i < MAXN; i++) {
         if (i < n) {
             const bool first = isLeft[i] != swapped;
             const uint32_t dst = first ? doneFirst++ : nFirst + doneSecond++;
             if ((first ? nFirst : nSecond) == 1u) {
-                order[slot + dst] = __float_as_uint(rl[i].w);
+                order[slot + dst] = r[i].idx;
                 eon[slot + dst] = 1;
             } else {
-                nLo[s + dst] = rl[i];
-                nHi[s + dst] = rh[i];
+                nLo[s + dst] = make_float4(r[i].lo[0], r[i].lo[1], r[i].lo[2], __uint_as_float(r[i].idx));
+                nHi[s + dst] = make_float4(r[i].hi[0], r[i].hi[1], r[i].hi[2], 0.0f);
             }
         }
     }
@@ -1561,7 +1585,7 @@ static_assert(2 * (kSubtreeSmem + 1024 + 128) <= 228 * 1024, "two subtree CTAs m
 
 // Persistent: the grid is sized for the machine (two CTAs per SM) and every CTA draws subtrees from a ticket counter until
 // none are left, so the launch does not need the subtree count on the host (no round trip after the level loop).
-__global__ void __launch_bounds__(kSubBlock)
+__global__ void __launch_bounds__(kSubBlock, 2)
 build_subtrees(const SmallTask* __restrict__ small, float4* const lo0, float4* const hi0, float4* const lo1,
                float4* const hi1, float4* nodes, uint32_t* __restrict__ order, uint8_t* __restrict__ eon,
                LevelInfo* __restrict__ info, uint32_t budget, uint32_t maxSmall) {
@@ -1574,7 +1598,7 @@ build_subtrees(const SmallTask* __restrict__ small, float4* const lo0, float4* c
     uint16_t* clsA = reinterpret_cast<uint16_t*>(wBins + kSubWarps * 2 * kSubtreeBins * kSubBinWords);   // tiny nodes from the front, warp nodes from the back
     uint16_t* clsB = clsA + kSubNodes;                                     // half-warp nodes
     __shared__ uint32_t sNext;
-    __shared__ uint32_t sCls[3];               // nodes of the level by size class: <= kTinyMax, half warp, warp
+    __shared__ uint32_t sCls[4];               // nodes of the level by size class: <= kTinyMax, half warp, warp, <= kSmallMax
     __shared__ unsigned long long sStats[3];   // median splits, sort fallbacks, largest fallback
 
     __shared__ uint32_t sTicket;
@@ -1609,7 +1633,7 @@ build_subtrees(const SmallTask* __restrict__ small, float4* const lo0, float4* c
         const uint32_t depth = task.depth + level;
         const bool halfOk = bins_at_depth(budget, depth) <= 16u;   // a half warp sweeps one bin per lane
         if (tid == 0) sNext = 0;
-        if (tid < 3) sCls[tid] = 0;
+        if (tid < 4) sCls[tid] = 0;
         __syncthreads();
         const SubNode* curList = lists + (level & 1u) * kSubNodes;
         SubNode* nextList = lists + ((level + 1u) & 1u) * kSubNodes;
@@ -1622,22 +1646,28 @@ build_subtrees(const SmallTask* __restrict__ small, float4* const lo0, float4* c
         for (uint32_t ni = tid; ni < nCur; ni += kSubBlock) {
             const uint32_t c = curList[ni].count;
             if (c <= kTinyMax) clsA[atomicAdd(&sCls[0], 1u)] = uint16_t(ni);
+            else if (c <= kSmallMax) clsB[kSubNodes - 1u - atomicAdd(&sCls[3], 1u)] = uint16_t(ni);
             else if (c <= 16u && halfOk) clsB[atomicAdd(&sCls[1], 1u)] = uint16_t(ni);
             else clsA[kSubNodes - 1u - atomicAdd(&sCls[2], 1u)] = uint16_t(ni);
         }
         __syncthreads();
-        const uint32_t nTiny = sCls[0], nHalf = sCls[1], nWarp = sCls[2];
-        // tiny nodes: one lane each
-        for (uint32_t k = tid; k < nTiny; k += kSubBlock)
-            build_tiny_node(curList[clsA[k]], task, depth, budget, cLo, cHi, nLo, nHi, nodes, order, eon, nextList, &sNext, sStats);
-        // 5..16 refs: one half warp each
-        for (uint32_t k = warp * 2u + half; k < nHalf; k += kSubWarps * 2u)
-            build_group_node<16>(curList[clsB[k]], task, depth, budget, cLo, cHi, nLo, nHi, nodes, order, eon, nextList, &sNext, sStats, binsH);
-        __syncwarp();
-        // larger nodes: one warp each
+        const uint32_t nTiny = sCls[0], nHalf = sCls[1], nWarp = sCls[2], nSmallN = sCls[3];
+        // larger nodes first (they are the long poles of the level): one warp each
         for (uint32_t k = warp; k < nWarp; k += kSubWarps)
             build_group_node<32>(curList[clsA[kSubNodes - 1u - k]], task, depth, budget, cLo, cHi, nLo, nHi, nodes, order, eon, nextList, &sNext,
                                  sStats, binsW);
+        // 9..16 refs: one half warp each
+        for (uint32_t k = warp * 2u + half; k < nHalf; k += kSubWarps * 2u)
+            build_group_node<16>(curList[clsB[k]], task, depth, budget, cLo, cHi, nLo, nHi, nodes, order, eon, nextList, &sNext, sStats, binsH);
+        __syncwarp();
+        // 5..8 refs and 2..4 refs: one lane each, in packs of 32 handed out from the last warp backwards so that they
+        // land on the warps the classes above loaded least
+        for (uint32_t k = (kSubBlock - 1u - tid); k < nSmallN; k += kSubBlock)
+            build_tiny_node<kSmallMax>(curList[clsB[kSubNodes - 1u - k]], task, depth, budget, cLo, cHi, nLo, nHi, nodes, order, eon, nextList,
+                                       &sNext, sStats);
+        __syncwarp();
+        for (uint32_t k = (kSubBlock - 1u - tid); k < nTiny; k += kSubBlock)
+            build_tiny_node<kTinyMax>(curList[clsA[k]], task, depth, budget, cLo, cHi, nLo, nHi, nodes, order, eon, nextList, &sNext, sStats);
         __syncthreads();
         nCur = sNext;
         cur ^= 1u;
