@@ -1578,6 +1578,153 @@ __device__ inline void build_group_node(const SubNode nd, const SmallTask& task,
     }
 }
 
+constexpr uint32_t kCtaNodeMin = 256;   // nodes with more refs than this are built by the whole CTA (the top one or two levels)
+
+struct CtaSplit {   // one axis' sweep result, handed from the sweeping warp to the CTA
+    float cost;
+    uint32_t bin, nLeft;
+    int box[12];   // ord: left lo, left hi, right lo, right hi
+};
+
+// The whole CTA builds one node: the refs are binned on all three axes in one pass by all threads, warps 0..2 sweep one
+// axis each, and the partition gives every warp a contiguous slice. Same decisions as build_group_node; the median
+// fallback (rare) is handed to warp 0's group path. Contains barriers: every thread of the CTA must call it.
+__device__ inline void build_cta_node(const SubNode nd, const SmallTask& task, uint32_t depth, uint32_t budget, float4* cLo, float4* cHi,
+                                      float4* __restrict__ nLo, float4* __restrict__ nHi, float4* nodes, uint32_t* __restrict__ order,
+                                      uint8_t* __restrict__ eon, SubNode* nextList, uint32_t* sNext, unsigned long long* sStats,
+                                      int* bins3 /*[3][32][kSubBinWords]*/, CtaSplit* sSplit /*[3]*/, uint32_t* sWarpFirst /*[kSubWarps]*/) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t n = nd.count, s = nd.start;
+    const uint32_t nb = bins_at_depth(budget, depth);
+    const uint32_t flatIdx = task.flatIdx + nd.rel;
+    float blo[3], bhi[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { blo[k] = nd.lo[k]; bhi[k] = nd.hi[k]; }
+    AxisBins ab[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) ab[a] = axis_bins(blo[a], bhi[a], nb);
+    for (uint32_t e = tid; e < 3u * kSubtreeBins; e += kSubBlock) sub_bin_init(bins3 + e * kSubBinWords);
+    __syncthreads();
+    // ---- binning, all three axes in one pass
+    for (uint32_t i = tid; i < n; i += kSubBlock) {
+        const float4 l = cLo[s + i], h = cHi[s + i];
+        const OBox o = obox_of_ref(l, h);
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            if (!ab[a].active) continue;
+            const uint32_t b = bin_of(bin_centre(comp(l, a), comp(h, a)), ab[a].start, ab[a].inv, nb);
+            int* rec = bins3 + (a * kSubtreeBins + b) * kSubBinWords;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                if (o.lo[k] < rec[k]) atomicMin(rec + k, o.lo[k]);   // monotone: a covering plain read makes the atomic unnecessary
+                if (o.hi[k] > rec[3 + k]) atomicMax(rec + 3 + k, o.hi[k]);
+            }
+            atomicAdd(rec + 6, 1);
+        }
+    }
+    __syncthreads();
+    // ---- one warp per axis sweeps its bins
+    if (warp < 3u) {
+        const LaneGroup<32> g;
+        BestSplit b = best_none();
+        OBox L = obox_empty(), R = obox_empty();
+        uint32_t nl = 0;
+        if (ab[warp].active) {
+            if (nb <= 16u) group_sweep_single<32, true>(g, bins3 + warp * kSubtreeBins * kSubBinWords, nb, n, int(warp), b, L, R, nl);
+            else group_sweep_single<32, false>(g, bins3 + warp * kSubtreeBins * kSubBinWords, nb, n, int(warp), b, L, R, nl);
+        }
+        if (lane == 0) {
+            CtaSplit& o = sSplit[warp];
+            o.cost = b.axis >= 0 ? b.cost : kFltMax;
+            o.bin = b.bin;
+            o.nLeft = nl;
+#pragma unroll
+            for (int k = 0; k < 3; k++) { o.box[k] = L.lo[k]; o.box[3 + k] = L.hi[k]; o.box[6 + k] = R.lo[k]; o.box[9 + k] = R.hi[k]; }
+        }
+    }
+    __syncthreads();
+    // ---- the lowest axis wins ties (the reference's axis loop keeps strictly smaller costs)
+    int axis = -1;
+    float cost = kFltMax;
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+        if (sSplit[a].cost < cost) { cost = sSplit[a].cost; axis = a; }
+    const float nodeCost = __fmul_rn(__uint2float_rn(n), surface_area(blo, bhi));
+    if (axis < 0 || cost >= nodeCost) {
+        // PerformMedianSplit: rare up here; warp 0 runs the group path on the node (it bins again on its own)
+        if (warp == 0u) build_group_node<32>(nd, task, depth, budget, cLo, cHi, nLo, nHi, nodes, order, eon, nextList, sNext, sStats, bins3);
+        __syncthreads();
+        return;
+    }
+    const uint32_t splitBin = sSplit[axis].bin, nLeft = sSplit[axis].nLeft;
+    OBox L, R;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { L.lo[k] = sSplit[axis].box[k]; L.hi[k] = sSplit[axis].box[3 + k]; R.lo[k] = sSplit[axis].box[6 + k]; R.hi[k] = sSplit[axis].box[9 + k]; }
+    const Box3 lb = obox_to_box(L), rb = obox_to_box(R);
+    const bool swapped = surface_area(lb) < surface_area(rb);
+    const uint32_t nFirst = swapped ? n - nLeft : nLeft, nSecond = n - nFirst;
+    const uint32_t slot = task.start + s;
+    if (tid == 0) {
+        const Box3& f = swapped ? rb : lb;
+        const Box3& h2 = swapped ? lb : rb;
+        const int32_t ptr1 = nFirst > 1u ? int32_t(flatIdx + 1u) : ~int32_t(slot);
+        const int32_t ptr2 = nSecond > 1u ? int32_t(flatIdx + nFirst) : ~int32_t(slot + nFirst);
+        float4* N = nodes + 4 * size_t(flatIdx);
+        N[0] = make_float4(f.lo[0], f.lo[1], f.lo[2], f.hi[0]);
+        N[1] = make_float4(f.hi[1], f.hi[2], h2.lo[0], h2.lo[1]);
+        N[2] = make_float4(h2.lo[2], h2.hi[0], h2.hi[1], h2.hi[2]);
+        N[3] = make_float4(__int_as_float(ptr1), __int_as_float(ptr2), 0.0f, 0.0f);
+        if (nFirst > 1u) nextList[atomicAdd(sNext, 1u)] = make_subnode(s, nFirst, nd.rel + 1u, f);
+        if (nSecond > 1u) nextList[atomicAdd(sNext, 1u)] = make_subnode(s + nFirst, nSecond, nd.rel + nFirst, h2);
+    }
+    // ---- stable partition: warp w owns refs [w * per, (w + 1) * per)
+    const uint32_t per = ((n + kSubBlock - 1u) / kSubBlock) * 32u;
+    const uint32_t begin = min(warp * per, n), end = min(begin + per, n);
+    uint32_t myFirst = 0;
+    for (uint32_t b = begin; b < end; b += 32u) {
+        const uint32_t i = b + lane;
+        bool first = false;
+        if (i < end) {
+            const float4 l = cLo[s + i], h = cHi[s + i];
+            first = (bin_of(bin_centre(comp(l, axis), comp(h, axis)), ab[axis].start, ab[axis].inv, nb) < splitBin) != swapped;
+        }
+        myFirst += __popc(__ballot_sync(kFullMask, first));
+    }
+    if (lane == 0) sWarpFirst[warp] = myFirst;
+    __syncthreads();
+    uint32_t doneFirst = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < uint32_t(kSubWarps); w++) doneFirst += w < warp ? sWarpFirst[w] : 0u;
+    uint32_t doneSecond = begin - doneFirst;
+    for (uint32_t b = begin; b < end; b += 32u) {
+        const uint32_t i = b + lane;
+        const bool valid = i < end;
+        float4 l = make_float4(0, 0, 0, 0), h = l;
+        bool first = false;
+        if (valid) {
+            l = cLo[s + i];
+            h = cHi[s + i];
+            first = (bin_of(bin_centre(comp(l, axis), comp(h, axis)), ab[axis].start, ab[axis].inv, nb) < splitBin) != swapped;
+        }
+        const unsigned bf = __ballot_sync(kFullMask, valid && first);
+        const unsigned bs = __ballot_sync(kFullMask, valid && !first);
+        if (valid) {
+            const unsigned lt = (1u << lane) - 1u;
+            const uint32_t dst = first ? doneFirst + __popc(bf & lt) : nFirst + doneSecond + __popc(bs & lt);
+            if ((first ? nFirst : nSecond) == 1u) {
+                order[slot + dst] = __float_as_uint(l.w);
+                eon[slot + dst] = 1;
+            } else {
+                nLo[s + dst] = l;
+                nHi[s + dst] = h;
+            }
+        }
+        doneFirst += __popc(bf);
+        doneSecond += __popc(bs);
+    }
+    __syncthreads();   // the scratch areas are free again
+}
+
 constexpr uint32_t kSubNodes = kSubtreeMax / 2;   // most nodes one level of a subtree can hold (each has >= 2 refs)
 constexpr size_t kSubtreeSmem = size_t(4) * kSubtreeMax * sizeof(float4) + size_t(2) * kSubNodes * sizeof(SubNode) +
                                 size_t(kSubWarps) * 2 * kSubtreeBins * kSubBinWords * sizeof(int) + size_t(2) * kSubNodes * sizeof(uint16_t);
@@ -1598,7 +1745,10 @@ build_subtrees(const SmallTask* __restrict__ small, float4* const lo0, float4* c
     uint16_t* clsA = reinterpret_cast<uint16_t*>(wBins + kSubWarps * 2 * kSubtreeBins * kSubBinWords);   // tiny nodes from the front, warp nodes from the back
     uint16_t* clsB = clsA + kSubNodes;                                     // half-warp nodes
     __shared__ uint32_t sNext;
-    __shared__ uint32_t sCls[4];               // nodes of the level by size class: <= kTinyMax, half warp, warp, <= kSmallMax
+    __shared__ uint32_t sCls[5];               // nodes of the level by size class: <= kTinyMax, half warp, warp, <= kSmallMax, whole CTA
+    __shared__ uint16_t sCtaIdx[kSubtreeMax / kCtaNodeMin];
+    __shared__ CtaSplit sSplit[3];
+    __shared__ uint32_t sWarpFirst[kSubWarps];
     __shared__ unsigned long long sStats[3];   // median splits, sort fallbacks, largest fallback
 
     __shared__ uint32_t sTicket;
@@ -1633,7 +1783,7 @@ build_subtrees(const SmallTask* __restrict__ small, float4* const lo0, float4* c
         const uint32_t depth = task.depth + level;
         const bool halfOk = bins_at_depth(budget, depth) <= 16u;   // a half warp sweeps one bin per lane
         if (tid == 0) sNext = 0;
-        if (tid < 4) sCls[tid] = 0;
+        if (tid < 5) sCls[tid] = 0;
         __syncthreads();
         const SubNode* curList = lists + (level & 1u) * kSubNodes;
         SubNode* nextList = lists + ((level + 1u) & 1u) * kSubNodes;
@@ -1645,13 +1795,18 @@ build_subtrees(const SmallTask* __restrict__ small, float4* const lo0, float4* c
         // sort the level's nodes into size classes so that lanes / half warps / warps each get a dense run of work
         for (uint32_t ni = tid; ni < nCur; ni += kSubBlock) {
             const uint32_t c = curList[ni].count;
-            if (c <= kTinyMax) clsA[atomicAdd(&sCls[0], 1u)] = uint16_t(ni);
+            if (c > kCtaNodeMin) sCtaIdx[atomicAdd(&sCls[4], 1u)] = uint16_t(ni);   // fewer than kSubtreeMax / kCtaNodeMin of them
+            else if (c <= kTinyMax) clsA[atomicAdd(&sCls[0], 1u)] = uint16_t(ni);
             else if (c <= kSmallMax) clsB[kSubNodes - 1u - atomicAdd(&sCls[3], 1u)] = uint16_t(ni);
             else if (c <= 16u && halfOk) clsB[atomicAdd(&sCls[1], 1u)] = uint16_t(ni);
             else clsA[kSubNodes - 1u - atomicAdd(&sCls[2], 1u)] = uint16_t(ni);
         }
         __syncthreads();
-        const uint32_t nTiny = sCls[0], nHalf = sCls[1], nWarp = sCls[2], nSmallN = sCls[3];
+        const uint32_t nTiny = sCls[0], nHalf = sCls[1], nWarp = sCls[2], nSmallN = sCls[3], nCta = sCls[4];
+        // the biggest nodes (top of the subtree) by the whole CTA, one after the other
+        for (uint32_t k = 0; k < nCta; k++)
+            build_cta_node(curList[sCtaIdx[k]], task, depth, budget, cLo, cHi, nLo, nHi, nodes, order, eon, nextList, &sNext, sStats, wBins,
+                           sSplit, sWarpFirst);
         // larger nodes first (they are the long poles of the level): one warp each
         for (uint32_t k = warp; k < nWarp; k += kSubWarps)
             build_group_node<32>(curList[clsA[kSubNodes - 1u - k]], task, depth, budget, cLo, cHi, nLo, nHi, nodes, order, eon, nextList, &sNext,
