@@ -327,8 +327,7 @@ bin_big(const Task* __restrict__ tasks, const LevelInfo* __restrict__ info, cons
                     if (rec[k] < __ldcg(d + k)) atomicMin(d + k, rec[k]);
                     if (rec[3 + k] > __ldcg(d + 3 + k)) atomicMax(d + 3 + k, rec[3 + k]);
                 }
-                atomicAdd(d + 6, rec[6]);
-                atomicAdd(d + 7, rec[6]);   // exit == enter == primitiveCount for the object split
+                atomicAdd(d + 6, rec[6]);   // exit == enter == primitiveCount for the object split: the selection kernels mirror it
             }
         }
         __syncthreads();
@@ -453,8 +452,10 @@ __host__ __device__ constexpr size_t select_smem(uint32_t nb) { return size_t(3)
 // in shared memory (stride kSmemBin; they stay there for warp_split_boxes), warps 0..2 sweep one axis each, and the
 // results are combined in axis order with a strict <, i.e. the lowest axis wins ties like the loop of BVH.cpp:463-523.
 __device__ inline BestSplit cta_best_split(const int* __restrict__ gbins, uint32_t nb, const Task& tk, int* sbins, int* ssfx,
-                                           BestSplit* sBest) {
-    for (uint32_t i = threadIdx.x; i < 3u * nb * kBinWords; i += kSelectBlock) sbins[(i >> 3) * kSmemBin + (i & 7u)] = gbins[i];
+                                           BestSplit* sBest, bool objectBins) {
+    // (object bins carry one count: exit == enter, word 7 is not maintained in global memory)
+    for (uint32_t i = threadIdx.x; i < 3u * nb * kBinWords; i += kSelectBlock)
+        sbins[(i >> 3) * kSmemBin + (i & 7u)] = gbins[(objectBins && (i & 7u) == 7u) ? i - 1u : i];
     __syncthreads();
     const uint32_t warp = threadIdx.x >> 5;
     if (warp < 3u) {
@@ -485,7 +486,7 @@ select_big(Task* __restrict__ tasks, LevelInfo* __restrict__ info, const int* __
     const uint32_t lane = threadIdx.x & 31u;
     Task tk = tasks[t];
     int* sbins = ss;
-    const BestSplit best = cta_best_split(gbins + size_t(t) * 3 * nb * kBinWords, nb, tk, sbins, ss + 3 * nb * kSmemBin, sBest);
+    const BestSplit best = cta_best_split(gbins + size_t(t) * 3 * nb * kBinWords, nb, tk, sbins, ss + 3 * nb * kSmemBin, sBest, true);
     if (threadIdx.x >= 32u) return;
     const float nodeCost = __fmul_rn(__uint2float_rn(tk.count), surface_area(tk.lo, tk.hi));   // BVH.cpp:238
     if (best.axis < 0 || best.cost >= nodeCost) {
@@ -516,7 +517,7 @@ select_root_object(Task* __restrict__ tasks, LevelInfo* __restrict__ info, const
     const uint32_t lane = threadIdx.x & 31u;
     Task tk = tasks[0];
     int* sbins = ss;
-    const BestSplit best = cta_best_split(gbins, nb, tk, sbins, ss + 3 * nb * kSmemBin, sBest);
+    const BestSplit best = cta_best_split(gbins, nb, tk, sbins, ss + 3 * nb * kSmemBin, sBest, true);
     if (threadIdx.x >= 32u) return;
     Box3 l = empty_box(), r = empty_box();
     if (best.axis >= 0) {
@@ -588,12 +589,13 @@ __device__ inline void split_reference(const float* __restrict__ tri, const Box3
 
 // FindSpatialSplit's binning over the root's refs (BVH.cpp:589-619): on every axis a ref's box is chopped at each bin
 // boundary it straddles (SplitReference chain), each piece grows its bin, the first / last bin count an entry / an exit.
-// Bins in shared memory. Chains differ in length from 1 to many pieces, so a lane does not own a ref for a fixed number
-// of steps: every lane walks its own sequence of (ref, axis) chains and all lanes of a warp emit ONE piece per step,
-// starting their next chain as soon as the current one ends. The chain's axis is kept in component 0 by rotating the
-// triangle and the box (x,y,z -> y,z,x) each time the axis advances — SplitReference treats the other two components
-// alike, so the arithmetic is the reference's, bit for bit — and results are rotated back when they grow a bin.
+// Bins in shared memory. One thread per (ref, axis) chain — three neighbouring lanes share a ref, so its loads are
+// broadcast — and the chain's axis is moved to component 0 by rotating triangle and box (x,y,z -> y,z,x once or twice).
+// SplitReference treats the two other components alike, so the arithmetic is the reference's bit for bit, every lane
+// runs the same code whatever its axis, and results are rotated back when they grow a bin.
 // Falls through when the object split's children do not overlap enough for a spatial split to be tried (BVH.cpp:282).
+constexpr uint32_t kChainsPerBlock = (kBigBlock / 3) * 3;   // 255: the last thread of a block idles
+
 __global__ void __launch_bounds__(kBigBlock, 3)
 spatial_bin_root(const Task* __restrict__ tasks, const LevelInfo* __restrict__ info, const float4* __restrict__ rlo,
                  const float4* __restrict__ rhi, const float* __restrict__ tris, int* __restrict__ gbins, uint32_t nb) {
@@ -602,79 +604,57 @@ spatial_bin_root(const Task* __restrict__ tasks, const LevelInfo* __restrict__ i
     for (uint32_t e = threadIdx.x; e < 3 * nb; e += kBigBlock) bin_init(sb + e * kSmemBin);
     __syncthreads();
     const Task& tk = tasks[0];
-    const uint32_t count = tk.count;
-    AxisBins ab[3];
+    const uint64_t chains = uint64_t(tk.count) * 3u;
+    const int axis = int(threadIdx.x % 3u);
+    const AxisBins ab = axis_bins(axis == 0 ? tk.lo[0] : (axis == 1 ? tk.lo[1] : tk.lo[2]),
+                                  axis == 0 ? tk.hi[0] : (axis == 1 ? tk.hi[1] : tk.hi[2]), nb);
+    int* base = sb + axis * nb * kSmemBin;
+    // rotated component k is the original component (k + axis) % 3
+    const int c0 = axis, c1 = axis == 2 ? 0 : axis + 1, c2 = axis == 0 ? 2 : axis - 1;
+    if (threadIdx.x < kChainsPerBlock && ab.active) {
+        for (uint64_t c = uint64_t(blockIdx.x) * kChainsPerBlock + threadIdx.x; c < chains; c += uint64_t(gridDim.x) * kChainsPerBlock) {
+            const uint32_t p = uint32_t(c / 3u);
+            const float4 l = rlo[p], h = rhi[p];
+            const float* tri = tris + 9 * size_t(__float_as_uint(l.w));
+            float t[9];
 #pragma unroll
-    for (int a = 0; a < 3; a++) ab[a] = axis_bins(tk.lo[a], tk.hi[a], nb);
-    const uint32_t stride = gridDim.x * kBigBlock;
-    uint32_t p = blockIdx.x * kBigBlock + threadIdx.x;
-    float v[3][3];        // triangle, rotated so that the chain's axis is component 0
-    Box3 rest;            // what is left of the ref's box on this chain (rotated)
-    Box3 whole;           // the ref's box (rotated)
-    int axis = 2;         // axis of the current chain
-    bool haveRef = false;
-    bool alive = p < count;
-    uint32_t j = 1, b1 = 0;   // next piece's bin and the chain's last bin; j > b1: chain finished
-    float cStart = 0.0f, cWidth = 0.0f;
-    int* base = sb;
-    while (true) {
-        // ---- lanes whose chain is finished move to their next one
-        if (alive && j > b1) {
-            while (true) {
-                if (!haveRef) {
-                    if (p >= count) { alive = false; break; }
-                    const float4 l = rlo[p], h = rhi[p];
-                    const float* tri = tris + 9 * size_t(__float_as_uint(l.w));
+            for (int k = 0; k < 9; k++) t[k] = tri[k];
+            float v[3][3];
+            Box3 rest;
 #pragma unroll
-                    for (int k = 0; k < 9; k++) v[k / 3][k % 3] = tri[k];
-                    whole.lo[0] = l.x; whole.lo[1] = l.y; whole.lo[2] = l.z;
-                    whole.hi[0] = h.x; whole.hi[1] = h.y; whole.hi[2] = h.z;
-                    haveRef = true;
-                    axis = 0;
-                } else {
-                    axis++;
-                    if (axis == 3) { haveRef = false; p += stride; continue; }
-                    // x,y,z -> y,z,x
-#pragma unroll
-                    for (int e = 0; e < 3; e++) { const float t0 = v[e][0]; v[e][0] = v[e][1]; v[e][1] = v[e][2]; v[e][2] = t0; }
-                    { const float t0 = whole.lo[0]; whole.lo[0] = whole.lo[1]; whole.lo[1] = whole.lo[2]; whole.lo[2] = t0; }
-                    { const float t0 = whole.hi[0]; whole.hi[0] = whole.hi[1]; whole.hi[1] = whole.hi[2]; whole.hi[2] = t0; }
+            for (int e = 0; e < 3; e++) {
+                v[e][0] = axis == 0 ? t[3 * e] : (axis == 1 ? t[3 * e + 1] : t[3 * e + 2]);
+                v[e][1] = axis == 0 ? t[3 * e + 1] : (axis == 1 ? t[3 * e + 2] : t[3 * e]);
+                v[e][2] = axis == 0 ? t[3 * e + 2] : (axis == 1 ? t[3 * e] : t[3 * e + 1]);
+            }
+            rest.lo[0] = axis == 0 ? l.x : (axis == 1 ? l.y : l.z);
+            rest.lo[1] = axis == 0 ? l.y : (axis == 1 ? l.z : l.x);
+            rest.lo[2] = axis == 0 ? l.z : (axis == 1 ? l.x : l.y);
+            rest.hi[0] = axis == 0 ? h.x : (axis == 1 ? h.y : h.z);
+            rest.hi[1] = axis == 0 ? h.y : (axis == 1 ? h.z : h.x);
+            rest.hi[2] = axis == 0 ? h.z : (axis == 1 ? h.x : h.y);
+            const uint32_t b0 = bin_of(rest.lo[0], ab.start, ab.inv, nb);
+            const uint32_t b1 = bin_of(rest.hi[0], ab.start, ab.inv, nb);
+            atomicAdd(base + b0 * kSmemBin + 6, 1);
+            for (uint32_t j = b0;; j++) {
+                Box3 piece = rest;
+                if (j < b1) {
+                    Box3 cr;
+                    const float plane = __fadd_rn(ab.start, __fmul_rn(__uint2float_rn(j + 1u), ab.width));
+                    split_reference_t<0>(v, rest, piece, cr, plane);
+                    rest = cr;
                 }
-                const bool active = axis == 0 ? ab[0].active : (axis == 1 ? ab[1].active : ab[2].active);
-                if (!active) continue;
-                cStart = axis == 0 ? ab[0].start : (axis == 1 ? ab[1].start : ab[2].start);
-                cWidth = axis == 0 ? ab[0].width : (axis == 1 ? ab[1].width : ab[2].width);
-                const float inv = axis == 0 ? ab[0].inv : (axis == 1 ? ab[1].inv : ab[2].inv);
-                j = bin_of(whole.lo[0], cStart, inv, nb);
-                b1 = bin_of(whole.hi[0], cStart, inv, nb);
-                base = sb + axis * nb * kSmemBin;
-                rest = whole;
-                atomicAdd(base + j * kSmemBin + 6, 1);
-                break;
-            }
-        }
-        if (!__any_sync(kFullMask, alive)) break;
-        // ---- every live lane emits one piece of its chain
-        if (alive) {
-            Box3 piece = rest;
-            if (j < b1) {
-                Box3 cr;
-                const float plane = __fadd_rn(cStart, __fmul_rn(__uint2float_rn(j + 1u), cWidth));
-                split_reference_t<0>(v, rest, piece, cr, plane);
-                rest = cr;
-            }
-            int* rec = base + j * kSmemBin;
-            // rotated component k is the original component (k + axis) % 3
-            const int c0 = axis, c1 = axis == 2 ? 0 : axis + 1, c2 = axis == 0 ? 2 : axis - 1;
-            const int cc[3] = {c0, c1, c2};
+                int* rec = base + j * kSmemBin;
+                const int cc[3] = {c0, c1, c2};
 #pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const int lo = ord_from_float(piece.lo[k]), hi = ord_from_float(piece.hi[k]);
-                if (lo < rec[cc[k]]) atomicMin(rec + cc[k], lo);   // monotone values: a covering plain read makes the atomic unnecessary
-                if (hi > rec[3 + cc[k]]) atomicMax(rec + 3 + cc[k], hi);
+                for (int k = 0; k < 3; k++) {
+                    const int lo = ord_from_float(piece.lo[k]), hi = ord_from_float(piece.hi[k]);
+                    if (lo < rec[cc[k]]) atomicMin(rec + cc[k], lo);   // monotone values: a covering plain read makes the atomic unnecessary
+                    if (hi > rec[3 + cc[k]]) atomicMax(rec + 3 + cc[k], hi);
+                }
+                if (j >= b1) break;
             }
-            if (j == b1) atomicAdd(rec + 7, 1);
-            j++;
+            atomicAdd(base + b1 * kSmemBin + 7, 1);
         }
     }
     __syncthreads();
@@ -702,7 +682,7 @@ select_root_final(Task* __restrict__ tasks, LevelInfo* __restrict__ info, const 
     Task tk = tasks[0];
     int* sbins = ss;   // the spatial bins when a spatial split is tried
     BestSplit spa = best_none();
-    if (trySpatial) spa = cta_best_split(spaBins, nb, tk, sbins, ss + 3 * nb * kSmemBin, sBest);
+    if (trySpatial) spa = cta_best_split(spaBins, nb, tk, sbins, ss + 3 * nb * kSmemBin, sBest, false);
     if (threadIdx.x >= 32u) return;
     const float objCost = root->objCost;
     const int objAxis = root->objAxis;
