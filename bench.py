@@ -12,6 +12,7 @@ own loop of the same K steps. N > 1 is weak scaling: the BVH is replicated (ever
 own 1M rays, and one NCCL all-gather of the 16-byte hit records per step is inside the timed region.
 """
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -26,6 +27,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_TRIS = 1_000_000
+SETTLE_S = 0.4        # seconds of untimed load before a timed region (single-GPU loops)
+SETTLE_STEPS = 300    # ... and the step count that replaces it where all ranks must agree
 N_RAYS = 1_000_000
 WORKLOAD = "C2: synthetic 1M-triangle random soup (seed 1234): BLAS build + 1M random-direction closest-hit rays (seed 5678)"
 
@@ -249,7 +252,9 @@ def main():
                 ev.record(side)
             done[k % 2] = ev
         done = [None, None]
-        for k in range(warmup):
+        # warm-up: W steps at least, and (same count on every rank, the steps contain a collective) enough of them to keep
+        # the GPU under load for a few hundred ms: the first ~100 ms after an idle spell run at ramping clocks
+        for k in range(max(warmup, SETTLE_STEPS)):
             run(k, done)
         stream.wait_stream(side)
         torch.cuda.synchronize()
@@ -267,15 +272,31 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()) / steps
 
+    # the cyclic garbage collector stays off while timing: a full collection in the middle of a build (whose host code
+    # waits for the device twice) shows up as device time
+    gc.collect()
+    gc.disable()
+
     def timed(fn, steps, warmup):
-        for _ in range(warmup):
+        # warm-up: W steps at least, continued until the GPU has been under load for SETTLE_S: after an idle spell (scene
+        # set-up on the host, the clock sampler's teardown) the first ~100 ms run at ramping clocks with stalls of
+        # milliseconds (seen: single 1.8 ms builds taking 9, 33 and 120 ms among the first four timed ones)
+        t_settle = time.perf_counter() + SETTLE_S
+        n = 0
+        while n < warmup or time.perf_counter() < t_settle:
             flush.zero_()
             fn()
+            torch.cuda.synchronize()
+            n += 1
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in evs:             # torch creates the CUDA event at its first record(): do that outside the timed region
+            a.record(stream)
+            b.record(stream)
+        torch.cuda.synchronize()
         for a, b in evs:
             flush.zero_()            # L2 flush between timed iterations (outside the event bracket)
             a.record(stream)
@@ -292,9 +313,23 @@ def main():
             total_ms = float(t.item())
         return total_ms / steps
 
-    # clocks / throttle reasons are sampled with nvidia-smi while the headline (trace) region is timed; the build loop
-    # runs after the sampler has stopped, because concurrent nvidia-smi queries stall the driver for milliseconds and
-    # the build's read-backs then wait on them (seen as 7-9 ms instead of 3.2 ms per build on a cold box)
+    # The build loop is timed FIRST, with no nvidia-smi process anywhere near it: the sampler's start-up, its queries and
+    # above all its teardown stall the driver for milliseconds (a build's read-backs then wait on it: single builds of
+    # 9 ms and once 120 ms were seen right after the sampler stopped, against a steady 1.8-2.3 ms).
+    built = []
+
+    def build_step():
+        for b in built:
+            b.free()
+        built.clear()
+        built.append(build_once())
+    build_ms = timed(build_step, args.steps, args.warmup)
+    print("build samples (ms):", " ".join(f"{x:.2f}" for x in timed.samples), file=sys.stderr)
+    build_samples = sorted(timed.samples)
+    for b in built:
+        b.free()
+
+    # clocks / throttle reasons are sampled with nvidia-smi while the headline (trace) region is timed
     with ClockSampler(local_rank) as clk:
         launches0 = ctx.launches()
         trace_ms = timed(trace_step, args.steps, args.warmup) if world == 1 else timed_pipelined(args.steps, args.warmup)
@@ -304,21 +339,6 @@ def main():
             for _ in range(max(0, extra)):
                 trace_step()
             torch.cuda.synchronize()
-
-    built = []
-
-    def build_step():
-        for b in built:
-            b.free()
-        built.clear()
-        built.append(build_once())
-    # (the sampler's shutdown leaves the GPU idle for ~0.3 s and the first builds after it run at ramping clocks with
-    # cold host caches: 9 / 3.5 / 2.5 ms before settling at 2.27 ms, so this loop gets a longer warm-up than W)
-    build_ms = timed(build_step, args.steps, max(args.warmup, 10))
-    print("build samples (ms):", " ".join(f"{x:.2f}" for x in timed.samples), file=sys.stderr)
-    build_samples = sorted(timed.samples)
-    for b in built:
-        b.free()
     clocks = clk.summary()
 
     # ---- end to end with HOST ray buffers (pinned): H2D + trace + (gather) + D2H inside the timed region.
@@ -339,6 +359,15 @@ def main():
             stream.synchronize()
     for _ in range(args.warmup):
         e2e_step()
+    torch.cuda.synchronize()
+    # untimed settling as in timed(): the sampler's teardown has left the GPU idle for a few hundred ms
+    if world == 1:
+        t_settle = time.perf_counter() + SETTLE_S
+        while time.perf_counter() < t_settle:
+            e2e_step()
+    else:
+        for _ in range(SETTLE_STEPS // 2):   # same count on every rank: the step contains a collective
+            e2e_step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
