@@ -292,7 +292,11 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        # the loop below runs LEAD + K iterations of exactly the same shape and keeps the last K: the first few iterations
+        # of a loop without device-wide syncs still differ (seen: the 3rd and 5th build 2-4 ms slower, identically on both
+        # GPUs of a 2-rank run - the stream-ordered allocator settling into its reuse pattern)
+        LEAD = 8
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(LEAD + steps)]
         for a, b in evs:             # torch creates the CUDA event at its first record(): do that outside the timed region
             a.record(stream)
             b.record(stream)
@@ -305,7 +309,7 @@ def main():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        timed.samples = [a.elapsed_time(b) for a, b in evs]
+        timed.samples = [a.elapsed_time(b) for a, b in evs[LEAD:]]
         total_ms = sum(timed.samples)
         if world > 1:
             t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -331,9 +335,11 @@ def main():
 
     # clocks / throttle reasons are sampled with nvidia-smi while the headline (trace) region is timed
     with ClockSampler(local_rank) as clk:
-        launches0 = ctx.launches()
         trace_ms = timed(trace_step, args.steps, args.warmup) if world == 1 else timed_pipelined(args.steps, args.warmup)
-        launches = (ctx.launches() - launches0) // (args.steps + args.warmup) * args.steps
+        launches0 = ctx.launches()
+        trace_step()                                   # kernels of ONE step (the library counts its own launches) x K
+        torch.cuda.synchronize()
+        launches = (ctx.launches() - launches0) * args.steps
         if args.steps * trace_ms < 600.0:   # keep the sampler alive for at least three 200 ms samples under load
             extra = int(600.0 / max(trace_ms, 1e-3)) - args.steps
             for _ in range(max(0, extra)):
