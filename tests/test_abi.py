@@ -63,3 +63,22 @@ def test_layout_sizes():
     text = open(os.path.join(ROOT, "atlas_engine_b200", "csrc", "layouts.h")).read()
     for name, size in (("HostAABB", 24), ("HostBVHNode", 56), ("GPUBVHNode", 64), ("GPUBVHTriangle", 48), ("GPUBVHInstance", 64), ("PackedRay", 48)):
         assert f"sizeof({name}) == {size}" in text
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under atlas_engine_b200/ (Python, C++ or CUDA) may import, include,
+    load or execute it, and the Python binding must have no CPU fallback (it raises when the library is missing)."""
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "atlas_engine_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                continue
+            text = open(os.path.join(dirpath, f), errors="replace").read()
+            if re.search(r"import\s+oracle|from\s+oracle|oracle/|pyoracle|libatlas_oracle|libatlas_ref", text):
+                offenders.append(os.path.relpath(os.path.join(dirpath, f), root))
+    assert offenders == []
+    src = open(os.path.join(root, "capi.py")).read()
+    assert "raise" in src and "libatlas_rt.so" in src
