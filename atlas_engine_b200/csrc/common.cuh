@@ -85,7 +85,7 @@ struct atlas_rt_context {
     void* levelSlots = nullptr;                // pinned: per-level flags the builder's kernels write for the host (build.cu)
     // scheduling knobs of the persistent traversal kernel (trace.cu); ATLAS_RT_TRACE_* environment variables override
     int traceLeafThreshold = 8;     // lanes waiting at a leaf before the warp runs a leaf round
-    int traceRefillThreshold = 16;  // idle lanes before the warp fetches new rays (swept with the longest-first order: 16-20 is best)
+    int traceRefillThreshold = 10;  // idle lanes before the warp fetches new rays (swept again with the final kernel: 8-12 is best, 16 costs 1.5-3 %)
     int traceBlocksPerSM = 9;
     int chainLaunch = 1;         // builder level loop as a chain of programmatic dependent launches
     int binCtasPerSM = 2;        // CTAs per SM of the builder's binning kernel (each merges its shared bins into global ones)

@@ -14,18 +14,18 @@ dev = torch.device("cuda", 0)
 stream = torch.cuda.Stream(device=dev); torch.cuda.set_stream(stream)
 d_rays = torch.from_numpy(rays).to(dev); d_out = torch.empty_like(d_rays)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-grid = [(8, 16, 9, 1), (8, 16, 9, 1), (8, 16, 8, 1)]
+grid = [(8, 12, 9, 1), (8, 10, 9, 1), (8, 8, 9, 1), (8, 14, 9, 1), (6, 12, 9, 1), (6, 10, 9, 1), (7, 12, 9, 1), (5, 12, 9, 1), (8, 12, 9, 1), (8, 16, 9, 1)]
 for (l, r, b, p) in grid:
     os.environ["ATLAS_RT_TRACE_LEAF_THRESHOLD"] = str(l); os.environ["ATLAS_RT_TRACE_REFILL_THRESHOLD"] = str(r); os.environ["ATLAS_RT_TRACE_BLOCKS_PER_SM"] = str(b); os.environ["ATLAS_RT_TRACE_LONGEST_FIRST"] = str(p)
     ctx = capi.Context(0, stream.cuda_stream)
     blas = ctx.build_blas(boxes, tris); tlas = ctx.build_tlas(root); mesh = ctx.pack_mesh(blas, tris)
     scene = ctx.create_scene([mesh], W.identity_instance(), tlas)
     ts = []
-    for i in range(8):
+    for i in range(14):
         flush.zero_()
         a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream); ctx.trace(scene, d_rays, N, out=d_out, flags=capi.ASYNC); e.record(stream)
         torch.cuda.synchronize(); ts.append(a.elapsed_time(e))
-    print(f"leaf={l:2d} refill={r:2d} blocks={b} longest_first={p} ms={np.median(ts[2:]):.3f}", flush=True)
+    print(f"leaf={l:2d} refill={r:2d} blocks={b} longest_first={p} ms={np.median(ts[4:]):.4f}", flush=True)
     for o in (scene, mesh, tlas, blas): o.free()
     ctx.close()
