@@ -161,6 +161,32 @@ inline void dev_free_on(cudaStream_t st, const void* p) {
     if (p) cudaFreeAsync(const_cast<void*>(p), st);
 }
 
+// Kernels that follow each other on a stream (the builder's level loop, the ray sort + trace) form a chain of
+// programmatic dependent launches: each one lets its successor be
+// scheduled right away and then waits until everything before it has completed (griddepcontrol.wait returns once the
+// prerequisite grids have finished and their memory is visible), so launch latency overlaps the predecessor's work.
+// Every kernel of the chain executes chain_begin() first, on every path, because a kernel that skipped the wait could
+// finish before ITS predecessor and release the kernel after it too early. Launched normally, both are no-ops.
+__device__ __forceinline__ void chain_begin() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <typename... P, typename... A>
+cudaError_t launch_chain(bool pdl, void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = pdl ? 1u : 0u;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<A>(args)...);
+}
+
 // Copy count*bytes from src (host or device according to `device`) into device memory on the context stream.
 cudaError_t copy_in(atlas_rt_context* ctx, void* dst, const void* src, size_t bytes, bool srcDevice);
 cudaError_t copy_out(atlas_rt_context* ctx, void* dst, const void* src, size_t bytes, bool dstDevice);

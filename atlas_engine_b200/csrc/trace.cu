@@ -149,6 +149,7 @@ trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restr
              uint32_t count, uint32_t cullMask, float tMin, float tMaxArg,
              int perRayTMax, int sceneFast, int kLeafThreshold, int kRefillThreshold, unsigned int* __restrict__ rayCounter,
              unsigned long long* __restrict__ counters) {
+    chain_begin();
     __shared__ int stack[kStack][kTraceBlock];
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     const unsigned ltMask = (1u << lane) - 1u;
@@ -411,6 +412,7 @@ __device__ __forceinline__ void scene_box(const float4* __restrict__ tlasNodes, 
 __global__ void __launch_bounds__(kSortBlock)
 ray_cost_histogram(const float4* __restrict__ rays, uint32_t count, const float4* __restrict__ tlasNodes, uint8_t* __restrict__ bucketOf,
                    unsigned int* __restrict__ hist) {
+    chain_begin();
     __shared__ unsigned int sh[kCostBuckets + 1];   // [kCostBuckets] = pairs of neighbouring rays that are coherent
     if (threadIdx.x <= kCostBuckets) sh[threadIdx.x] = 0;
     __syncthreads();
@@ -448,6 +450,7 @@ ray_cost_histogram(const float4* __restrict__ rays, uint32_t count, const float4
 }
 
 __global__ void ray_cost_offsets(unsigned int* __restrict__ hist, uint32_t count) {   // exclusive prefix over 64 buckets, in place (one warp)
+    chain_begin();
     const unsigned lane = threadIdx.x;
     // hist[kCostBuckets + 1] = 1 when the batch should be reordered: coherent batches (most neighbours are near copies)
     // keep their own order, which is worth more than starting the long rays first
@@ -466,6 +469,7 @@ __global__ void ray_cost_offsets(unsigned int* __restrict__ hist, uint32_t count
 
 __global__ void __launch_bounds__(kSortBlock)
 ray_cost_scatter(const uint8_t* __restrict__ bucketOf, uint32_t count, unsigned int* __restrict__ offsets, uint32_t* __restrict__ perm) {
+    chain_begin();
     __shared__ unsigned int cnt[kCostBuckets], base[kCostBuckets];
     if (offsets[kCostBuckets + 1] == 0u) return;   // coherent batch: the trace kernel ignores the permutation
     if (threadIdx.x < kCostBuckets) cnt[threadIdx.x] = 0;
@@ -552,16 +556,18 @@ int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float
         ATLAS_CUDA(ctx, dev_alloc_on(st, &hist, kCostBuckets + 2));
         ATLAS_CUDA(ctx, cudaMemsetAsync(hist, 0, (kCostBuckets + 2) * sizeof(unsigned int), st));
         const uint32_t sortGrid = (n + kSortBlock * kSortPerThread - 1) / (kSortBlock * kSortPerThread);
-        ray_cost_histogram<<<sortGrid, kSortBlock, 0, st>>>(dIn, n, scene->tlas->nodes, bucketOf, hist);
-        ATLAS_LAUNCH_CHECK(ctx);
-        ray_cost_offsets<<<1, 32, 0, st>>>(hist, n);
-        ATLAS_LAUNCH_CHECK(ctx);
-        ray_cost_scatter<<<sortGrid, kSortBlock, 0, st>>>(bucketOf, n, hist, perm);
-        ATLAS_LAUNCH_CHECK(ctx);
+        const bool pdl = ctx->chainLaunch != 0;
+        ATLAS_CUDA(ctx, launch_chain(pdl, ray_cost_histogram, sortGrid, kSortBlock, 0, st, dIn, n, scene->tlas->nodes, bucketOf, hist));
+        ctx->launches++;
+        ATLAS_CUDA(ctx, launch_chain(pdl, ray_cost_offsets, 1, 32, 0, st, hist, n));
+        ctx->launches++;
+        ATLAS_CUDA(ctx, launch_chain(pdl, ray_cost_scatter, sortGrid, kSortBlock, 0, st, bucketOf, n, hist, perm));
+        ctx->launches++;
     }
     const int pr = perRayTMax ? 1 : 0, sf = scene->fastDivision;
+    cudaError_t launchErr = cudaSuccess;
 #define ATLAS_TRACE_LAUNCH(A, C, O) \
-    trace_kernel<A, C, O><<<grid, kTraceBlock, 0, st>>>(sc, dIn, dOut, perm, hist ? hist + kCostBuckets + 1 : nullptr, n, cullMask, tMin, tMax, pr, sf, lt, rt, rayCounter, ctx->dCounters)
+    launchErr = launch_chain(ctx->chainLaunch != 0, trace_kernel<A, C, O>, grid, kTraceBlock, 0, st, sc, dIn, dOut, perm, hist ? hist + kCostBuckets + 1 : nullptr, n, cullMask, tMin, tMax, pr, sf, lt, rt, rayCounter, ctx->dCounters)
     if (opacity) {
         if (any) { if (counters) ATLAS_TRACE_LAUNCH(true, true, true); else ATLAS_TRACE_LAUNCH(true, false, true); }
         else { if (counters) ATLAS_TRACE_LAUNCH(false, true, true); else ATLAS_TRACE_LAUNCH(false, false, true); }
@@ -573,7 +579,8 @@ int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float
     dev_free_on(st, perm);
     dev_free_on(st, bucketOf);
     dev_free_on(st, hist);
-    ATLAS_LAUNCH_CHECK(ctx);
+    ctx->launches++;
+    if (launchErr != cudaSuccess) return fail(ctx, ATLAS_RT_ERR_CUDA, "trace launch", launchErr);
     return ATLAS_RT_OK;
 }
 
