@@ -111,6 +111,7 @@ __device__ __forceinline__ float comp(const float4& v, int axis) { return axis =
 __global__ void __launch_bounds__(256)
 init_refs(const float* __restrict__ aabbs, uint32_t n, float4* __restrict__ lo, float4* __restrict__ hi,
           int* __restrict__ rootBox, LevelInfo* __restrict__ info) {
+    chain_begin();
     // refs[i] = {idx = i, aabb = aabbs[i]} and the root box (BVH.cpp:21-31); grid-stride so that only one set of
     // atomics per CTA reaches the six root-box words.
     __shared__ int sBox[6];
@@ -152,6 +153,7 @@ init_refs(const float* __restrict__ aabbs, uint32_t n, float4* __restrict__ lo, 
 
 __global__ void make_root(const int* __restrict__ rootBox, uint32_t n, Task* __restrict__ tasks, LevelInfo* __restrict__ info,
                           RootSplit* __restrict__ root) {
+    chain_begin();
     Task t;
     for (int k = 0; k < 3; k++) { t.lo[k] = float_from_ord(rootBox[k]); t.hi[k] = float_from_ord(rootBox[3 + k]); }
     t.start = 0; t.count = n; t.flatIdx = 0; t.depth = 0;
@@ -487,6 +489,7 @@ select_big(Task* __restrict__ tasks, LevelInfo* __restrict__ info, const int* __
 __global__ void __launch_bounds__(kSelectBlock)
 select_root_object(Task* __restrict__ tasks, LevelInfo* __restrict__ info, const int* __restrict__ gbins, RootSplit* __restrict__ root,
                    uint32_t nb) {
+    chain_begin();
     extern __shared__ int ss[];
     __shared__ BestSplit sBest[3];
     const uint32_t lane = threadIdx.x & 31u;
@@ -574,6 +577,7 @@ constexpr uint32_t kChainsPerBlock = (kBigBlock / 3) * 3;   // 255: the last thr
 __global__ void __launch_bounds__(kBigBlock, 3)
 spatial_bin_root(const Task* __restrict__ tasks, const LevelInfo* __restrict__ info, const float4* __restrict__ rlo,
                  const float4* __restrict__ rhi, const float* __restrict__ tris, int* __restrict__ gbins, uint32_t nb) {
+    chain_begin();
     extern __shared__ int sb[];   // [3][nb][kSmemBin]
     if (!info->rootNeedSpatial) return;
     for (uint32_t e = threadIdx.x; e < 3 * nb; e += kBigBlock) bin_init(sb + e * kSmemBin);
@@ -650,6 +654,7 @@ spatial_bin_root(const Task* __restrict__ tasks, const LevelInfo* __restrict__ i
 __global__ void __launch_bounds__(kSelectBlock)
 select_root_final(Task* __restrict__ tasks, LevelInfo* __restrict__ info, const int* __restrict__ objBins,
                   const int* __restrict__ spaBins, int* __restrict__ medAcc, RootSplit* __restrict__ root, Lists L, uint32_t nb) {
+    chain_begin();
     extern __shared__ int ss[];
     __shared__ BestSplit sBest[3];
     const uint32_t lane = threadIdx.x & 31u;
@@ -1895,10 +1900,12 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
         memcpy(ctx->pinned, initBox, sizeof(initBox));
         ATLAS_CUDA_C(ctx, cudaMemcpyAsync(B.rootBox, ctx->pinned, sizeof(initBox), cudaMemcpyHostToDevice, st));
     }
-    init_refs<<<std::max(1u, std::min<uint32_t>((n + 255) / 256, uint32_t(ctx->smCount) * 8u)), 256, 0, st>>>(dAabbs, n, B.lo[0], B.hi[0], B.rootBox, B.info);
-    ATLAS_LAUNCHED(ctx);
-    make_root<<<1, 1, 0, st>>>(B.rootBox, n, B.tasks[0], B.info, B.root);
-    ATLAS_LAUNCHED(ctx);
+    const bool pdl = ctx->chainLaunch != 0;
+    ATLAS_CUDA_C(ctx, launch_chain(pdl, init_refs, std::max(1u, std::min<uint32_t>((n + 255) / 256, uint32_t(ctx->smCount) * 8u)), 256, 0, st, dAabbs, n,
+                                   B.lo[0], B.hi[0], B.rootBox, B.info));
+    ctx->launches++;
+    ATLAS_CUDA_C(ctx, launch_chain(pdl, make_root, 1, 1, 0, st, B.rootBox, n, B.tasks[0], B.info, B.root));
+    ctx->launches++;
 
     const uint32_t persistent = uint32_t(ctx->smCount) * 4u;
     uint32_t cur = 0;
@@ -1916,7 +1923,6 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
     constexpr uint32_t kFlagRing = 64;
     volatile uint32_t* flags = static_cast<volatile uint32_t*>(ctx->levelSlots);   // [kFlagRing], pinned: level d's node count + 1
     for (uint32_t k = 0; k < kFlagRing; k++) flags[k] = 0u;
-    const bool pdl = ctx->chainLaunch != 0;
     auto wait_flag = [&](uint32_t level) -> int {   // spin until prepare_level(level) has run; watch for a dead stream
         for (uint64_t spins = 0; flags[level % kFlagRing] == 0u; spins++) {
             if ((spins & 0xfffu) == 0xfffu) {
@@ -1967,17 +1973,18 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
 
         bool spatialPath = false;
         if (depth == 0 && !tlas) {
-            select_root_object<<<1, kSelectBlock, select_smem(nb), st>>>(tasks, B.info, B.bins, B.root, nb);
-            ATLAS_LAUNCHED(ctx);
+            ATLAS_CUDA_C(ctx, launch_chain(pdl, select_root_object, 1, kSelectBlock, select_smem(nb), st, tasks, B.info, B.bins, B.root, nb));
+            ctx->launches++;
             // the spatial binning is enqueued unconditionally and falls through on the device when the object split's
             // children do not overlap enough (no host round trip for that decision)
-            init_bins<<<3, 256, 0, st>>>(B.spaBins, B.info, 3u * nb);   // nTasks == 1
-            ATLAS_LAUNCHED(ctx);
-            spatial_bin_root<<<std::max(1u, std::min(chunksBound, uint32_t(ctx->smCount) * 3u)), kBigBlock, binSmem, st>>>(
-                tasks, B.info, rlo, rhi, B.tris, B.spaBins, nb);
-            ATLAS_LAUNCHED(ctx);
-            select_root_final<<<1, kSelectBlock, select_smem(nb), st>>>(tasks, B.info, B.bins, B.spaBins, B.medAcc, B.root, L, nb);
-            ATLAS_LAUNCHED(ctx);
+            ATLAS_CUDA_C(ctx, launch_chain(pdl, init_bins, 3, 256, 0, st, B.spaBins, B.info, 3u * nb));   // nTasks == 1
+            ctx->launches++;
+            ATLAS_CUDA_C(ctx, launch_chain(pdl, spatial_bin_root, std::max(1u, std::min(chunksBound, uint32_t(ctx->smCount) * 3u)), kBigBlock, binSmem, st,
+                                           tasks, B.info, rlo, rhi, B.tris, B.spaBins, nb));
+            ctx->launches++;
+            ATLAS_CUDA_C(ctx, launch_chain(pdl, select_root_final, 1, kSelectBlock, select_smem(nb), st, tasks, B.info, B.bins, B.spaBins, B.medAcc, B.root,
+                                           L, nb));
+            ctx->launches++;
             ATLAS_TRY(read_back(ctx, B.info, &info));
             out->stats[0] = info.rootNeedSpatial ? 1 : 0;
             spatialPath = info.rootKind == uint32_t(kSpatial);
