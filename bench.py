@@ -175,7 +175,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="for runs under ncu: no settling warm-up, no lead iterations, no sampler keep-alive loop (numbers are not bench values)")
     args = ap.parse_args()
+    global SETTLE_S, SETTLE_STEPS
+    if args.profile:
+        SETTLE_S, SETTLE_STEPS = 0.0, 0
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -295,7 +300,7 @@ def main():
         # the loop below runs LEAD + K iterations of exactly the same shape and keeps the last K: the first few iterations
         # of a loop without device-wide syncs still differ (seen: the 3rd and 5th build 2-4 ms slower, identically on both
         # GPUs of a 2-rank run - the stream-ordered allocator settling into its reuse pattern)
-        LEAD = 8
+        LEAD = 0 if args.profile else 8
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(LEAD + steps)]
         for a, b in evs:             # torch creates the CUDA event at its first record(): do that outside the timed region
             a.record(stream)
@@ -340,7 +345,7 @@ def main():
         trace_step()                                   # kernels of ONE step (the library counts its own launches) x K
         torch.cuda.synchronize()
         launches = (ctx.launches() - launches0) * args.steps
-        if args.steps * trace_ms < 600.0:   # keep the sampler alive for at least three 200 ms samples under load
+        if args.steps * trace_ms < 600.0 and not args.profile:   # keep the sampler alive for at least three 200 ms samples under load
             extra = int(600.0 / max(trace_ms, 1e-3)) - args.steps
             for _ in range(max(0, extra)):
                 trace_step()
