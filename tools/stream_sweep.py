@@ -18,7 +18,7 @@ for streams in (8,):
     ctx = capi.Context(0, stream.cuda_stream)
     blas = ctx.build_blas(boxes, tris); tlas = ctx.build_tlas(root); mesh = ctx.pack_mesh(blas, tris)
     scene = ctx.create_scene([mesh], W.identity_instance(), tlas)
-    for chunks in (6, 7, 8, 9):
+    for chunks in (6, 8, 10, 12):
         if chunks == "default": os.environ.pop("ATLAS_RT_PIPE_CHUNKS", None)
         else: os.environ["ATLAS_RT_PIPE_CHUNKS"] = str(chunks)
         ts = []
