@@ -1403,12 +1403,39 @@ __device__ inline void build_group_node(const SubNode nd, const SmallTask& task,
         h0 = cHi[s + lane];
         o0 = obox_of_ref(l0, h0);
     }
-    // ---- FindObjectSplit, one axis at a time
+    // ---- FindObjectSplit
     BestSplit best = best_none();
     OBox objL = obox_empty(), objR = obox_empty();
     uint32_t objLeft = 0;
+    bool swept = false;
+    if constexpr (G == 32) {
+        if (nb <= 16u) {
+            // a whole warp and at most 16 bins: the three axes are binned in one pass over the refs and swept together
+            swept = true;
+            const uint32_t active = (ab[0].active ? 1u : 0u) | (ab[1].active ? 2u : 0u) | (ab[2].active ? 4u : 0u);
+            for (uint32_t e = lane; e < 48u; e += 32u) sub_bin_init(bins + e * kSubBinWords);
+            g.sync();
+            for (uint32_t i = lane; i < n; i += 32u) {
+                float4 l = l0, h = h0;
+                OBox o = o0;
+                if (!oneEach) { l = cLo[s + i]; h = cHi[s + i]; o = obox_of_ref(l, h); }
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    if (!ab[a].active) continue;
+                    const uint32_t b = bin_of(bin_centre(comp(l, a), comp(h, a)), ab[a].start, ab[a].inv, nb);
+                    int* rec = bins + (a * 16 + b) * kSubBinWords;
+                    atomicMin(rec + 0, o.lo[0]); atomicMin(rec + 1, o.lo[1]); atomicMin(rec + 2, o.lo[2]);
+                    atomicMax(rec + 3, o.hi[0]); atomicMax(rec + 4, o.hi[1]); atomicMax(rec + 5, o.hi[2]);
+                    atomicAdd(rec + 6, 1);
+                }
+            }
+            g.sync();
+            warp_sweep3_rev(bins, nb, n, active, best, objL, objR, objLeft);
+            g.sync();
+        }
+    }
 #pragma unroll 1
-    for (int a = 0; a < 3; a++) {
+    for (int a = 0; a < 3 && !swept; a++) {
         if (!ab[a].active) continue;
         for (uint32_t e = lane; e < nb; e += G) sub_bin_init(bins + e * kSubBinWords);
         g.sync();

@@ -370,6 +370,83 @@ __device__ __forceinline__ bool group_sweep_single(const LaneGroup<G>& g, const 
     return true;
 }
 
+// The three axes of a node swept together by one warp, nb <= 16 bins per axis: the reversed layout of
+// group_sweep_single<32, true> for each axis, with the scan steps of the three axes issued side by side so that their
+// shuffle and min/max latencies overlap. `bins3` = [3][16] records of kSubBinWords ints; `active` = bit a set when axis
+// a takes part (BVH.cpp:466). Same candidates, costs and tie rule (lowest axis, then lowest bin) as three calls in a row.
+__device__ __forceinline__ void warp_sweep3_rev(const int* bins3, uint32_t nb, uint32_t total, uint32_t active, BestSplit& best,
+                                                OBox& outL, OBox& outR, uint32_t& outLeft) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t m = lane & 15u;
+    const uint32_t k = lane < 16u ? m : nb - 1u - m;
+    OBox pre[3];
+    uint32_t en[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        pre[a] = obox_empty();
+        en[a] = 0;
+        if (m < nb && ((active >> a) & 1u)) {
+            const int* rec = bins3 + (a * 16 + k) * kSubBinWords;
+#pragma unroll
+            for (int w = 0; w < 3; w++) { pre[a].lo[w] = rec[w]; pre[a].hi[w] = rec[3 + w]; }
+            en[a] = uint32_t(rec[6]);
+        }
+    }
+#pragma unroll
+    for (int off = 1; off < 16; off <<= 1) {
+        OBox o[3];
+        uint32_t oe[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+#pragma unroll
+            for (int w = 0; w < 3; w++) { o[a].lo[w] = __shfl_up_sync(kFullMask, pre[a].lo[w], off, 16); o[a].hi[w] = __shfl_up_sync(kFullMask, pre[a].hi[w], off, 16); }
+            oe[a] = __shfl_up_sync(kFullMask, en[a], off, 16);
+        }
+        if (m >= uint32_t(off)) {
+#pragma unroll
+            for (int a = 0; a < 3; a++) { obox_grow(pre[a], o[a]); en[a] += oe[a]; }
+        }
+    }
+    // suffix over bins [j, nb) of an axis sits in lane 16 + (nb - 1 - j)
+    const int src = 16 + int((nb - 2u - lane) & 15u);
+    const uint32_t j = lane + 1u;
+    const bool cand = lane < 16u && j < nb;
+    int key[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        OBox right;
+#pragma unroll
+        for (int w = 0; w < 3; w++) { right.lo[w] = __shfl_sync(kFullMask, pre[a].lo[w], src); right.hi[w] = __shfl_sync(kFullMask, pre[a].hi[w], src); }
+        float cost = kFltMax;
+        const uint32_t nLeft = en[a], nRight = total - en[a];
+        if (cand && nLeft != 0u && nRight != 0u) {
+            const float c = __fadd_rn(__fmul_rn(obox_area(pre[a]), __uint2float_rn(nLeft)), __fmul_rn(obox_area(right), __uint2float_rn(nRight)));
+            if (c < kFltMax) cost = c;   // NaN / inf never beat the initial best (BVH.cpp:519)
+        }
+        key[a] = ord_from_float(cost);   // costs are sums of non-negative products: ordered-int images compare like the floats
+    }
+    const int kEmpty = ord_from_float(kFltMax);
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const int mn = __reduce_min_sync(kFullMask, key[a]);
+        if (mn == kEmpty) continue;   // warp-uniform
+        const float c = float_from_ord(mn);
+        if (!(c < best.cost)) continue;
+        const unsigned who = __ballot_sync(kFullMask, key[a] == mn);
+        const uint32_t bin = uint32_t(__ffs(int(who)));   // lowest lane holding the minimum = lowest bin; j = lane + 1
+        best.cost = c;
+        best.axis = a;
+        best.bin = bin;
+        const int lsrc = int(bin) - 1, rsrc = 16 + int(nb - 1u - bin);
+#pragma unroll
+        for (int w = 0; w < 3; w++) {
+            outL.lo[w] = __shfl_sync(kFullMask, pre[a].lo[w], lsrc); outL.hi[w] = __shfl_sync(kFullMask, pre[a].hi[w], lsrc);
+            outR.lo[w] = __shfl_sync(kFullMask, pre[a].lo[w], rsrc); outR.hi[w] = __shfl_sync(kFullMask, pre[a].hi[w], rsrc);
+        }
+        outLeft = __shfl_sync(kFullMask, en[a], lsrc);
+    }
+}
+
 __device__ inline void warp_sweep_axis(const int* bins, uint32_t nb, int* sfx, uint32_t total, int axis, BestSplit& best,
                                        int stride = kBinWords) {
     const LaneGroup<32> g;
