@@ -285,3 +285,17 @@ def pack_shading_triangles(tris, order, end_of_node, material_idx=None, opacity=
     out[:, 18] = np.where(np.asarray(end_of_node) != 0, np.float32(1.0), np.float32(-1.0)).astype(np.float32).view(np.uint32)
     out[:, 20:23], out[:, 23] = p[:, 8:11], op.view(np.uint32)
     return out.view(np.float32)
+
+
+def geometric_clusters(clusters=150, per_cluster=1500, ratio=1.5, seed=77):
+    """Clusters of small triangles at x = ratio^k: every binned split peels only the farthest cluster(s) off, so the tree
+    is a long chain of big nodes — dozens of builder levels instead of ~log2(n)."""
+    rng = np.random.default_rng(seed)
+    out = np.empty((clusters * per_cluster, 3, 3), dtype=np.float32)
+    for k in range(clusters):
+        x = np.float32(ratio) ** np.float32(k)
+        c = rng.random((per_cluster, 1, 3), dtype=np.float32) * np.float32(0.05) * x
+        c[:, :, 0] += x
+        off = (rng.random((per_cluster, 3, 3), dtype=np.float32) - np.float32(0.5)) * np.float32(0.002) * x
+        out[k * per_cluster:(k + 1) * per_cluster] = c + off
+    return out.reshape(-1, 9)

@@ -170,3 +170,17 @@ def test_device_pointers_and_device_download(ctx):
     ctx.check(ctx.L.atlas_rt_bvh_download(b.h, d_nodes.data_ptr(), d_order.data_ptr(), None, capi.DEVICE_OUTPUT))
     assert np.array_equal(d_nodes.cpu().numpy().view(np.uint32), nodes) and np.array_equal(d_order.cpu().numpy().view(np.uint32), order)
     assert p_nodes.value and p_order.value and p_eon.value
+
+
+def test_deep_chain_of_big_nodes(ctx, oracle):
+    """Clusters at geometrically growing distance: every split peels the farthest cluster(s) off, so the builder runs
+    ~50 levels of big nodes (against ~11 for a soup of the same size) with one or two nodes each — the asynchronous level
+    loop, its host flags and the chunk tables at their least favourable."""
+    tris = W.geometric_clusters()
+    boxes = W.tri_boxes(tris)
+    b = ctx.build_blas(boxes, tris)
+    o = oracle.build_blas(boxes, tris)
+    n, od, e = b.download()
+    assert CS.same_tree(n, od, e, o)
+    assert b.stats()["levels"] >= 40
+    b.free()
