@@ -27,6 +27,7 @@ SIGNATURES = {
     "atlas_rt_last_error": (C.c_char_p, [_vp]),
     "atlas_rt_kernel_launches": (_u64, [_vp]),
     "atlas_rt_build_blas": (_i32, [_vp, _vp, _vp, _u64, _u32, C.POINTER(_vp)]),
+    "atlas_rt_build_blas_batch": (_i32, [_vp, _u32, _vp, _vp, _vp, _u32, _vp]),
     "atlas_rt_build_tlas": (_i32, [_vp, _vp, _u64, _u32, C.POINTER(_vp)]),
     "atlas_rt_bvh_upload": (_i32, [_vp, _vp, _u64, _vp, _vp, _u64, C.POINTER(_vp)]),
     "atlas_rt_bvh_import": (_i32, [_vp, _vp, _u64, _vp, _vp, _u64, _u32, C.POINTER(_vp)]),
@@ -41,6 +42,13 @@ SIGNATURES = {
     "atlas_rt_mesh_counts": (_i32, [_vp, C.POINTER(_u64), C.POINTER(_u64)]),
     "atlas_rt_mesh_download": (_i32, [_vp, _vp, _vp, _u32]),
     "atlas_rt_mesh_free": (None, [_vp]),
+    "atlas_rt_pack_shading_words": (_i32, [_vp, _vp, _vp, _vp, _vp, _u64, _vp, _u32]),
+    "atlas_rt_aemesh_open": (_i32, [C.c_char_p, C.POINTER(_vp)]),
+    "atlas_rt_aemesh_counts": (_i32, [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u32)]),
+    "atlas_rt_aemesh_material_path": (C.c_char_p, [_vp, _u32]),
+    "atlas_rt_aemesh_triangles": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "atlas_rt_aemesh_raw": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "atlas_rt_aemesh_close": (None, [_vp]),
     "atlas_rt_scene_create": (_i32, [_vp, _vp, _u32, _vp, _u64, _vp, _u32, C.POINTER(_vp)]),
     "atlas_rt_scene_download": (_i32, [_vp, _vp, _vp, _u32]),
     "atlas_rt_scene_free": (None, [_vp]),
@@ -143,6 +151,22 @@ class Context:
         self.check(self.L.atlas_rt_build_blas(self.h, _addr(aabbs), _addr(tris), count, flags | (DEVICE_INPUT if dev else 0), C.byref(h)))
         return BVH(self, h)
 
+    def build_blas_batch(self, aabbs_list, tris_list, counts=None, flags=0):
+        """atlas_rt_build_blas_batch: lists of (n_i, 6) / (n_i, 9) host arrays, or of CUDA tensors / device pointers with
+        `counts` given. Returns one BVH per mesh."""
+        m = len(aabbs_list)
+        dev = m > 0 and _is_device(aabbs_list[0])
+        if not dev:
+            aabbs_list = [np.ascontiguousarray(a, dtype=np.float32) for a in aabbs_list]
+            tris_list = [np.ascontiguousarray(t, dtype=np.float32) for t in tris_list]
+            counts = [a.shape[0] for a in aabbs_list]
+        pa = (_vp * m)(*[_addr(a) for a in aabbs_list])
+        pt = (_vp * m)(*[_addr(t) for t in tris_list])
+        pc = (_u64 * m)(*[int(c) for c in counts])
+        out = (_vp * m)()
+        self.check(self.L.atlas_rt_build_blas_batch(self.h, m, pa, pt, pc, flags | (DEVICE_INPUT if dev else 0), out))
+        return [BVH(self, _vp(out[k])) for k in range(m)]
+
     def build_tlas(self, aabbs, count=None, flags=0):
         dev = _is_device(aabbs)
         if not dev:
@@ -180,6 +204,15 @@ class Context:
         self.check(self.L.atlas_rt_pack_mesh(self.h, blas.h, _addr(tris), count, _addr(material_idx), _addr(opacity),
                                              flags | (DEVICE_INPUT if dev else 0), C.byref(h)))
         return Mesh(self, h, blas)
+
+    def pack_shading_words(self, tris, normals9=None, uvs6=None, colors12=None):
+        """(n, 11) uint32 packed shading words (MeshData.cpp:176-228) computed on the device."""
+        tris = np.ascontiguousarray(tris, dtype=np.float32).reshape(-1, 9)
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float32) for a in (normals9, uvs6, colors12)]
+        out = np.zeros((tris.shape[0], 11), dtype=np.uint32)
+        self.check(self.L.atlas_rt_pack_shading_words(self.h, _addr(tris), _addr(arrs[0]), _addr(arrs[1]), _addr(arrs[2]), tris.shape[0],
+                                                      _addr(out), 0))
+        return out
 
     def create_scene(self, meshes, instances, tlas, flags=0):
         instances = np.ascontiguousarray(instances).view(np.uint32).reshape(-1, 16)
@@ -323,6 +356,36 @@ class Scene:
         if self.h:
             self.ctx.L.atlas_rt_scene_free(self.h)
             self.h = None
+
+
+def load_aemesh(path):
+    """.aemesh -> dict(tris (n,9), boxes (n,6), material_idx (n,), normals (n,9), uvs (n,6), colors (n,12), materials [paths])
+    exactly as the first loop of MeshData::BuildBVH expands the file (atlas_rt_aemesh_*; host-only code in the library)."""
+    L = lib()
+    h = _vp()
+    rc = L.atlas_rt_aemesh_open(os.fsencode(path), C.byref(h))
+    if rc != 0:
+        raise AtlasError(f"atlas_rt_aemesh_open({path}) -> {STATUS.get(rc, rc)}")
+    try:
+        nv, ni, nt, ns = _u64(), _u64(), _u64(), _u32()
+        L.atlas_rt_aemesh_counts(h, C.byref(nv), C.byref(ni), C.byref(nt), C.byref(ns))
+        n = int(nt.value)
+        out = dict(tris=np.zeros((n, 9), np.float32), boxes=np.zeros((n, 6), np.float32), material_idx=np.zeros(n, np.int32),
+                   normals=np.zeros((n, 9), np.float32), uvs=np.zeros((n, 6), np.float32), colors=np.zeros((n, 12), np.float32))
+        rc = L.atlas_rt_aemesh_triangles(h, _addr(out["tris"]), _addr(out["boxes"]), _addr(out["material_idx"]), _addr(out["normals"]),
+                                         _addr(out["uvs"]), _addr(out["colors"]))
+        if rc != 0:
+            raise AtlasError(STATUS.get(rc, rc))
+        out["vertex_count"], out["index_count"], out["sub_meshes"] = int(nv.value), int(ni.value), int(ns.value)
+        out["materials"] = []
+        for k in range(64):
+            p = L.atlas_rt_aemesh_material_path(h, k)
+            if not p:
+                break
+            out["materials"].append(p.decode())
+        return out
+    finally:
+        L.atlas_rt_aemesh_close(h)
 
 
 def shard_range(count, rank, world, align=64):

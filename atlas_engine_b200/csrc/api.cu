@@ -1,5 +1,8 @@
 // api.cu — C ABI glue (include/atlas_rt.h): contexts, object lifetime, host<->device staging, pack and scene kernels.
 #include <algorithm>
+#include <atomic>
+#include <numeric>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -19,6 +22,23 @@ int fail(atlas_rt_context* ctx, int status, const char* what, cudaError_t e) {
         }
     }
     return status;
+}
+
+void ctx_retain(atlas_rt_context* ctx) { ctx->refs.fetch_add(1, std::memory_order_relaxed); }
+
+void ctx_release(atlas_rt_context* ctx) {
+    if (ctx->refs.fetch_sub(1, std::memory_order_acq_rel) != 1) return;
+    for (auto& w : ctx->workers) if (w) { atlas_rt_context_destroy(w); w = nullptr; }
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& ev : ctx->pipeEvents) if (ev) cudaEventDestroy(ev);
+    if (ctx->copyIn) cudaStreamDestroy(ctx->copyIn);
+    if (ctx->copyOut) cudaStreamDestroy(ctx->copyOut);
+    for (auto& cs : ctx->computeExtra) if (cs) cudaStreamDestroy(cs);
+    cudaFree(ctx->dCounters);
+    cudaFreeHost(ctx->pinned);
+    if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
 }
 
 cudaError_t copy_in(atlas_rt_context* ctx, void* dst, const void* src, size_t bytes, bool srcDevice) {
@@ -164,6 +184,7 @@ int atlas_rt_context_create(int device, void* stream, atlas_rt_context** out_ctx
     if (const char* e = getenv("ATLAS_RT_TRACE_BLOCKS_PER_SM")) ctx->traceBlocksPerSM = std::max(1, std::min(9, atoi(e)));
     if (const char* e = getenv("ATLAS_RT_BIN_CTAS_PER_SM")) ctx->binCtasPerSM = std::max(1, std::min(8, atoi(e)));
     if (const char* e = getenv("ATLAS_RT_CHAIN_LAUNCH")) ctx->chainLaunch = atoi(e);
+    if (const char* e = getenv("ATLAS_RT_BATCH_WORKERS")) ctx->batchWorkers = std::max(1, std::min(8, atoi(e)));
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t keep = ~0ull;
@@ -181,6 +202,7 @@ int atlas_rt_context_create(int device, void* stream, atlas_rt_context** out_ctx
     if (const char* e = getenv("ATLAS_RT_PIPE_STREAMS")) ctx->pipeStreams = std::max(1, std::min(8, atoi(e)));
     for (auto& ev : ctx->pipeEvents)
         if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { ev = nullptr; ctx->copyIn = nullptr; }
+    if (build_init_device(ctx) != ATLAS_RT_OK) { ctx_release(ctx); return ATLAS_RT_ERR_CUDA; }
     *out_ctx = ctx;
     return ATLAS_RT_OK;
 }
@@ -189,14 +211,7 @@ void atlas_rt_context_destroy(atlas_rt_context* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (auto& ev : ctx->pipeEvents) if (ev) cudaEventDestroy(ev);
-    if (ctx->copyIn) cudaStreamDestroy(ctx->copyIn);
-    if (ctx->copyOut) cudaStreamDestroy(ctx->copyOut);
-    for (auto& cs : ctx->computeExtra) if (cs) cudaStreamDestroy(cs);
-    cudaFree(ctx->dCounters);
-    cudaFreeHost(ctx->pinned);
-    if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
-    delete ctx;
+    ctx_release(ctx);   // objects that are still alive keep the context (and its stream) until they are freed
 }
 
 int atlas_rt_context_synchronize(atlas_rt_context* ctx) {
@@ -209,6 +224,12 @@ const char* atlas_rt_last_error(const atlas_rt_context* ctx) { return ctx ? ctx-
 uint64_t atlas_rt_kernel_launches(const atlas_rt_context* ctx) { return ctx ? ctx->launches : 0; }
 
 // ---------------------------------------------------------------------------------------------------- build
+static atlas_rt_bvh* new_bvh(atlas_rt_context* ctx) {
+    auto* bvh = new (std::nothrow) atlas_rt_bvh;
+    if (bvh) { bvh->ctx = ctx; ctx_retain(ctx); }
+    return bvh;
+}
+
 static int build_common(atlas_rt_context* ctx, const float* aabbs, const float* tris, uint64_t count, uint32_t flags,
                         bool tlas, atlas_rt_bvh** out_bvh) {
     if (!ctx || !out_bvh || (count && !aabbs) || (!tlas && count && !tris)) return fail(ctx, ATLAS_RT_ERR_INVALID, "null argument");
@@ -217,25 +238,28 @@ static int build_common(atlas_rt_context* ctx, const float* aabbs, const float* 
     ATLAS_CUDA(ctx, cudaSetDevice(ctx->device));
     const bool dev = flags & ATLAS_RT_DEVICE_INPUT;
     float *dA = nullptr, *dT = nullptr;
+    atlas_rt_bvh* bvh = nullptr;
+    auto done = [&](int rc) {
+        dev_free(ctx, dA);
+        dev_free(ctx, dT);
+        if (rc != ATLAS_RT_OK) atlas_rt_bvh_free(bvh); else *out_bvh = bvh;
+        return rc;
+    };
+#define ATLAS_TRY_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return done(fail(ctx, ATLAS_RT_ERR_CUDA, #call, e__)); } while (0)
     if (!dev) {
-        ATLAS_CUDA(ctx, dev_alloc(ctx, &dA, count * 6));
-        ATLAS_CUDA(ctx, copy_in(ctx, dA, aabbs, count * 24, false));
+        ATLAS_TRY_CUDA(dev_alloc(ctx, &dA, count * 6));
+        ATLAS_TRY_CUDA(copy_in(ctx, dA, aabbs, count * 24, false));
         if (!tlas) {
-            ATLAS_CUDA(ctx, dev_alloc(ctx, &dT, count * 9));
-            ATLAS_CUDA(ctx, copy_in(ctx, dT, tris, count * 36, false));
+            ATLAS_TRY_CUDA(dev_alloc(ctx, &dT, count * 9));
+            ATLAS_TRY_CUDA(copy_in(ctx, dT, tris, count * 36, false));
         }
     }
-    auto* bvh = new (std::nothrow) atlas_rt_bvh;
-    if (!bvh) return fail(ctx, ATLAS_RT_ERR_OOM, "host allocation");
-    bvh->ctx = ctx;
+    bvh = new_bvh(ctx);
+    if (!bvh) return done(fail(ctx, ATLAS_RT_ERR_OOM, "host allocation"));
     int rc = build_bvh(ctx, dev ? aabbs : dA, tlas ? nullptr : (dev ? tris : dT), count, tlas, bvh);
     if (rc == ATLAS_RT_OK) rc = ensure_node_storage(ctx, bvh);
-    if (!dev) { dev_free(ctx, dA); dev_free(ctx, dT); }
-    if (rc != ATLAS_RT_OK) { atlas_rt_bvh_free(bvh); return rc; }
-    rc = sync_unless_async(ctx, flags);
-    if (rc != ATLAS_RT_OK) { atlas_rt_bvh_free(bvh); return rc; }
-    *out_bvh = bvh;
-    return ATLAS_RT_OK;
+    if (rc == ATLAS_RT_OK) rc = sync_unless_async(ctx, flags);
+    return done(rc);
 }
 
 int atlas_rt_build_blas(atlas_rt_context* ctx, const float* aabbs, const float* tris, uint64_t count, uint32_t flags,
@@ -247,34 +271,94 @@ int atlas_rt_build_tlas(atlas_rt_context* ctx, const float* aabbs, uint64_t coun
     return build_common(ctx, aabbs, nullptr, count, flags, true, out_bvh);
 }
 
+// Many BLASes at once. The reference builds a scene's meshes concurrently from job-system workers (src/tests/App.cpp:362-370,
+// MeshData::BuildBVH per mesh); one GPU build of a small mesh is a chain of short, latency-bound launches that leaves most
+// of the device idle, so the batch runs up to 8 builds side by side, each on its own worker context (stream, pinned level
+// flags) driven by its own host thread, largest mesh first. Results are the same objects atlas_rt_build_blas returns.
+int atlas_rt_build_blas_batch(atlas_rt_context* ctx, uint32_t mesh_count, const float* const* aabbs, const float* const* tris,
+                              const uint64_t* counts, uint32_t flags, atlas_rt_bvh** out_bvhs) {
+    if (!ctx || !out_bvhs || (mesh_count && (!aabbs || !tris || !counts))) return fail(ctx, ATLAS_RT_ERR_INVALID, "null argument");
+    for (uint32_t m = 0; m < mesh_count; m++) out_bvhs[m] = nullptr;
+    if (mesh_count == 0) return ATLAS_RT_OK;
+    ATLAS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t nWorkers = std::min<uint32_t>(uint32_t(ctx->batchWorkers), mesh_count);
+    for (uint32_t w = 0; w < nWorkers; w++) {
+        if (!ctx->workers[w]) {
+            const int rc = atlas_rt_context_create(ctx->device, nullptr, &ctx->workers[w]);
+            if (rc != ATLAS_RT_OK) return fail(ctx, rc, "worker context");
+        }
+    }
+    // inputs produced on the context's stream (device pointers) must be complete before the workers read them
+    cudaEvent_t ready = ctx->pipeEvents[0];
+    ATLAS_CUDA(ctx, cudaEventRecord(ready, ctx->stream));
+    std::vector<uint32_t> bySize(mesh_count);
+    std::iota(bySize.begin(), bySize.end(), 0u);
+    std::stable_sort(bySize.begin(), bySize.end(), [&](uint32_t a, uint32_t b) { return counts[a] > counts[b]; });
+    std::atomic<uint32_t> next{0};
+    std::vector<int> status(nWorkers, ATLAS_RT_OK);
+    auto work = [&](uint32_t w) {
+        atlas_rt_context* wc = ctx->workers[w];
+        if (cudaSetDevice(wc->device) != cudaSuccess || cudaStreamWaitEvent(wc->stream, ready, 0) != cudaSuccess) { status[w] = ATLAS_RT_ERR_CUDA; return; }
+        for (;;) {
+            const uint32_t k = next.fetch_add(1);
+            if (k >= mesh_count) break;
+            const uint32_t m = bySize[k];
+            const int rc = build_common(wc, aabbs[m], tris[m], counts[m], flags | ATLAS_RT_ASYNC, false, &out_bvhs[m]);
+            if (rc != ATLAS_RT_OK && status[w] == ATLAS_RT_OK) status[w] = rc;
+        }
+    };
+    std::vector<std::thread> pool;
+    for (uint32_t w = 1; w < nWorkers; w++) pool.emplace_back(work, w);
+    work(0);
+    for (auto& t : pool) t.join();
+    int rc = ATLAS_RT_OK;
+    for (uint32_t w = 0; w < nWorkers; w++) {
+        atlas_rt_context* wc = ctx->workers[w];
+        ctx->launches += wc->launches;
+        wc->launches = 0;
+        if (status[w] != ATLAS_RT_OK && rc == ATLAS_RT_OK) { rc = status[w]; ctx->error = "batch build: " + wc->error; }
+        // the context's stream continues after every worker's builds
+        cudaEvent_t ev = ctx->pipeEvents[1 + w];
+        if (cudaEventRecord(ev, wc->stream) != cudaSuccess || cudaStreamWaitEvent(ctx->stream, ev, 0) != cudaSuccess) { if (rc == ATLAS_RT_OK) rc = fail(ctx, ATLAS_RT_ERR_CUDA, "batch join"); }
+    }
+    if (rc == ATLAS_RT_OK) rc = sync_unless_async(ctx, flags);
+    if (rc != ATLAS_RT_OK) {
+        for (uint32_t m = 0; m < mesh_count; m++) { atlas_rt_bvh_free(out_bvhs[m]); out_bvhs[m] = nullptr; }
+    }
+    return rc;
+}
+
 int atlas_rt_bvh_import(atlas_rt_context* ctx, const void* nodes56, uint64_t node_count, const uint32_t* order,
                         const uint8_t* end_of_node, uint64_t ref_count, uint32_t flags, atlas_rt_bvh** out_bvh) {
     if (!ctx || !out_bvh || (node_count && !nodes56) || (ref_count && (!order || !end_of_node))) return fail(ctx, ATLAS_RT_ERR_INVALID, "null argument");
     *out_bvh = nullptr;
     ATLAS_CUDA(ctx, cudaSetDevice(ctx->device));
     const bool dev = flags & ATLAS_RT_DEVICE_INPUT;
-    auto* bvh = new (std::nothrow) atlas_rt_bvh;
+    atlas_rt_bvh* bvh = new_bvh(ctx);
     if (!bvh) return fail(ctx, ATLAS_RT_ERR_OOM, "host allocation");
-    bvh->ctx = ctx;
     bvh->nodeCount = node_count;
     bvh->refCount = ref_count;
     uint32_t* staging = nullptr;
-    ATLAS_CUDA(ctx, dev_alloc(ctx, &bvh->nodes, (node_count ? node_count : 1) * 4));
-    ATLAS_CUDA(ctx, dev_alloc(ctx, &bvh->order, ref_count));
-    ATLAS_CUDA(ctx, dev_alloc(ctx, &bvh->endOfNode, ref_count));
-    ATLAS_CUDA(ctx, dev_alloc(ctx, &staging, node_count * 14));
-    ATLAS_CUDA(ctx, copy_in(ctx, staging, nodes56, node_count * 56, dev));
-    ATLAS_CUDA(ctx, copy_in(ctx, bvh->order, order, ref_count * 4, dev));
-    ATLAS_CUDA(ctx, copy_in(ctx, bvh->endOfNode, end_of_node, ref_count, dev));
+    auto done = [&](int rc) {
+        dev_free(ctx, staging);
+        if (rc != ATLAS_RT_OK) atlas_rt_bvh_free(bvh); else *out_bvh = bvh;
+        return rc;
+    };
+    ATLAS_TRY_CUDA(dev_alloc(ctx, &bvh->nodes, (node_count ? node_count : 1) * 4));
+    ATLAS_TRY_CUDA(dev_alloc(ctx, &bvh->order, ref_count));
+    ATLAS_TRY_CUDA(dev_alloc(ctx, &bvh->endOfNode, ref_count));
+    ATLAS_TRY_CUDA(dev_alloc(ctx, &staging, node_count * 14));
+    ATLAS_TRY_CUDA(copy_in(ctx, staging, nodes56, node_count * 56, dev));
+    ATLAS_TRY_CUDA(copy_in(ctx, bvh->order, order, ref_count * 4, dev));
+    ATLAS_TRY_CUDA(copy_in(ctx, bvh->endOfNode, end_of_node, ref_count, dev));
     if (node_count) {
         nodes56_to_64<<<grid_for(node_count * 16), kBlock, 0, ctx->stream>>>(staging, reinterpret_cast<uint32_t*>(bvh->nodes), node_count);
-        ATLAS_LAUNCH_CHECK(ctx);
+        ctx->launches++;
+        ATLAS_TRY_CUDA(cudaGetLastError());
     }
-    dev_free(ctx, staging);
-    { int rcn = ensure_node_storage(ctx, bvh); if (rcn != ATLAS_RT_OK) { atlas_rt_bvh_free(bvh); return rcn; } }
-    ATLAS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    *out_bvh = bvh;
-    return ATLAS_RT_OK;
+    int rc = ensure_node_storage(ctx, bvh);
+    if (rc == ATLAS_RT_OK) ATLAS_TRY_CUDA(cudaStreamSynchronize(ctx->stream));
+    return done(rc);
 }
 
 int atlas_rt_bvh_upload(atlas_rt_context* ctx, const void* nodes56, uint64_t node_count, const uint32_t* order,
@@ -329,37 +413,58 @@ void atlas_rt_bvh_free(atlas_rt_bvh* bvh) {
     dev_free(ctx, bvh->order);
     dev_free(ctx, bvh->endOfNode);
     delete bvh;
+    ctx_release(ctx);
 }
 
 // ----------------------------------------------------------------------------------------------------- pack
+// Objects may be used from any context on the same device (device memory is shared; only stream order differs): a mesh
+// built on a worker thread's context can be packed into a scene on the main thread's. The object must be complete, i.e.
+// created without ATLAS_RT_ASYNC or its context synchronised since.
+static inline bool same_device(const atlas_rt_context* a, const atlas_rt_context* b) { return a && b && a->device == b->device; }
+
+// Host arrays staged on the device for one call; freed (stream-ordered) when the helper goes out of scope.
+struct Staged {
+    atlas_rt_context* ctx;
+    std::vector<void*> ptrs;
+    explicit Staged(atlas_rt_context* c) : ctx(c) {}
+    ~Staged() { for (void* p : ptrs) dev_free(ctx, p); }
+    // returns the device pointer for `src` (host unless dev), or nullptr with *err set
+    const void* in(const void* src, size_t bytes, bool dev, cudaError_t* err) {
+        if (!src || dev) return src;
+        void* d = nullptr;
+        *err = cudaMallocAsync(&d, bytes ? bytes : 1, ctx->stream);
+        if (*err != cudaSuccess) return nullptr;
+        ptrs.push_back(d);
+        *err = copy_in(ctx, d, src, bytes, false);
+        return *err == cudaSuccess ? d : nullptr;
+    }
+};
+
 int atlas_rt_pack_mesh(atlas_rt_context* ctx, const atlas_rt_bvh* blas, const float* tris, uint64_t count,
                        const int32_t* material_idx, const float* opacity, uint32_t flags, atlas_rt_mesh** out_mesh) {
-    if (!ctx || !blas || !out_mesh || (count && !tris) || blas->ctx != ctx) return fail(ctx, ATLAS_RT_ERR_INVALID, "bad argument");
+    if (!ctx || !blas || !out_mesh || (count && !tris) || !same_device(blas->ctx, ctx)) return fail(ctx, ATLAS_RT_ERR_INVALID, "bad argument");
     *out_mesh = nullptr;
     ATLAS_CUDA(ctx, cudaSetDevice(ctx->device));
     const bool dev = flags & ATLAS_RT_DEVICE_INPUT;
-    float* dT = nullptr;
-    int32_t* dM = nullptr;
-    float* dO = nullptr;
-    if (!dev) {
-        ATLAS_CUDA(ctx, dev_alloc(ctx, &dT, count * 9));
-        ATLAS_CUDA(ctx, copy_in(ctx, dT, tris, count * 36, false));
-        if (material_idx) { ATLAS_CUDA(ctx, dev_alloc(ctx, &dM, count)); ATLAS_CUDA(ctx, copy_in(ctx, dM, material_idx, count * 4, false)); }
-        if (opacity) { ATLAS_CUDA(ctx, dev_alloc(ctx, &dO, count)); ATLAS_CUDA(ctx, copy_in(ctx, dO, opacity, count * 4, false)); }
-    }
+    Staged st(ctx);
+    cudaError_t e = cudaSuccess;
+    const float* dT = static_cast<const float*>(st.in(tris, count * 36, dev, &e));
+    const int32_t* dM = e == cudaSuccess ? static_cast<const int32_t*>(st.in(material_idx, count * 4, dev, &e)) : nullptr;
+    const float* dO = e == cudaSuccess ? static_cast<const float*>(st.in(opacity, count * 4, dev, &e)) : nullptr;
+    if (e != cudaSuccess) return fail(ctx, ATLAS_RT_ERR_CUDA, "staging the triangles", e);
     auto* mesh = new (std::nothrow) atlas_rt_mesh;
     if (!mesh) return fail(ctx, ATLAS_RT_ERR_OOM, "host allocation");
     mesh->ctx = ctx;
+    ctx_retain(ctx);
     mesh->blas = blas;
     mesh->triCount = blas->refCount;
-    ATLAS_CUDA(ctx, dev_alloc(ctx, &mesh->tris, mesh->triCount * 3));
-    if (mesh->triCount) {
-        pack_bvh_triangles<<<grid_for(mesh->triCount), kBlock, 0, ctx->stream>>>(
-            dev ? tris : dT, blas->order, blas->endOfNode, dev ? material_idx : dM, dev ? opacity : dO, mesh->tris, mesh->triCount);
-        ATLAS_LAUNCH_CHECK(ctx);
+    e = dev_alloc(ctx, &mesh->tris, mesh->triCount * 3);
+    if (e == cudaSuccess && mesh->triCount) {
+        pack_bvh_triangles<<<grid_for(mesh->triCount), kBlock, 0, ctx->stream>>>(dT, blas->order, blas->endOfNode, dM, dO, mesh->tris, mesh->triCount);
+        ctx->launches++;
+        e = cudaGetLastError();
     }
-    if (!dev) { dev_free(ctx, dT); dev_free(ctx, dM); dev_free(ctx, dO); }
-    int rc = sync_unless_async(ctx, flags);
+    int rc = e == cudaSuccess ? sync_unless_async(ctx, flags) : fail(ctx, ATLAS_RT_ERR_CUDA, "pack_bvh_triangles", e);
     if (rc != ATLAS_RT_OK) { atlas_rt_mesh_free(mesh); return rc; }
     *out_mesh = mesh;
     return ATLAS_RT_OK;
@@ -367,28 +472,22 @@ int atlas_rt_pack_mesh(atlas_rt_context* ctx, const atlas_rt_bvh* blas, const fl
 
 int atlas_rt_mesh_pack_shading(atlas_rt_context* ctx, atlas_rt_mesh* mesh, const float* tris, uint64_t count,
                                const int32_t* material_idx, const float* opacity, const uint32_t* payload11, uint32_t flags) {
-    if (!ctx || !mesh || mesh->ctx != ctx || (count && !tris)) return fail(ctx, ATLAS_RT_ERR_INVALID, "bad argument");
+    if (!ctx || !mesh || !same_device(mesh->ctx, ctx) || (count && !tris)) return fail(ctx, ATLAS_RT_ERR_INVALID, "bad argument");
     ATLAS_CUDA(ctx, cudaSetDevice(ctx->device));
     const bool dev = flags & ATLAS_RT_DEVICE_INPUT;
-    float* dT = nullptr;
-    int32_t* dM = nullptr;
-    float* dO = nullptr;
-    uint32_t* dP = nullptr;
-    if (!dev) {
-        ATLAS_CUDA(ctx, dev_alloc(ctx, &dT, count * 9));
-        ATLAS_CUDA(ctx, copy_in(ctx, dT, tris, count * 36, false));
-        if (material_idx) { ATLAS_CUDA(ctx, dev_alloc(ctx, &dM, count)); ATLAS_CUDA(ctx, copy_in(ctx, dM, material_idx, count * 4, false)); }
-        if (opacity) { ATLAS_CUDA(ctx, dev_alloc(ctx, &dO, count)); ATLAS_CUDA(ctx, copy_in(ctx, dO, opacity, count * 4, false)); }
-        if (payload11) { ATLAS_CUDA(ctx, dev_alloc(ctx, &dP, count * 11)); ATLAS_CUDA(ctx, copy_in(ctx, dP, payload11, count * 44, false)); }
-    }
+    Staged st(ctx);
+    cudaError_t e = cudaSuccess;
+    const float* dT = static_cast<const float*>(st.in(tris, count * 36, dev, &e));
+    const int32_t* dM = e == cudaSuccess ? static_cast<const int32_t*>(st.in(material_idx, count * 4, dev, &e)) : nullptr;
+    const float* dO = e == cudaSuccess ? static_cast<const float*>(st.in(opacity, count * 4, dev, &e)) : nullptr;
+    const uint32_t* dP = e == cudaSuccess ? static_cast<const uint32_t*>(st.in(payload11, count * 44, dev, &e)) : nullptr;
+    if (e != cudaSuccess) return fail(ctx, ATLAS_RT_ERR_CUDA, "staging the triangles", e);
     if (!mesh->tris96) ATLAS_CUDA(ctx, dev_alloc(ctx, &mesh->tris96, mesh->triCount * 6));
     if (mesh->triCount) {
-        pack_shading_triangles<<<grid_for(mesh->triCount), kBlock, 0, ctx->stream>>>(
-            dev ? tris : dT, mesh->blas->order, mesh->blas->endOfNode, dev ? material_idx : dM, dev ? opacity : dO, dev ? payload11 : dP,
-            mesh->tris96, mesh->triCount);
+        pack_shading_triangles<<<grid_for(mesh->triCount), kBlock, 0, ctx->stream>>>(dT, mesh->blas->order, mesh->blas->endOfNode, dM, dO, dP,
+                                                                                      mesh->tris96, mesh->triCount);
         ATLAS_LAUNCH_CHECK(ctx);
     }
-    if (!dev) { dev_free(ctx, dT); dev_free(ctx, dM); dev_free(ctx, dO); dev_free(ctx, dP); }
     return sync_unless_async(ctx, flags);
 }
 
@@ -421,66 +520,64 @@ int atlas_rt_mesh_download(const atlas_rt_mesh* mesh, void* gpu_nodes64, void* g
 void atlas_rt_mesh_free(atlas_rt_mesh* mesh) {
     if (!mesh) return;
     cudaSetDevice(mesh->ctx->device);
-    dev_free(mesh->ctx, mesh->tris);
-    dev_free(mesh->ctx, mesh->tris96);
+    atlas_rt_context* ctx = mesh->ctx;
+    dev_free(ctx, mesh->tris);
+    dev_free(ctx, mesh->tris96);
     delete mesh;
+    ctx_release(ctx);
 }
 
 // ---------------------------------------------------------------------------------------------------- scene
 int atlas_rt_scene_create(atlas_rt_context* ctx, const atlas_rt_mesh* const* meshes, uint32_t mesh_count,
                           const void* instances64, uint64_t instance_count, const atlas_rt_bvh* tlas, uint32_t flags,
                           atlas_rt_scene** out_scene) {
-    if (!ctx || !meshes || !mesh_count || !instances64 || !tlas || !out_scene || tlas->ctx != ctx) return fail(ctx, ATLAS_RT_ERR_INVALID, "bad argument");
+    if (!ctx || !meshes || !mesh_count || !instances64 || !tlas || !out_scene || !same_device(tlas->ctx, ctx)) return fail(ctx, ATLAS_RT_ERR_INVALID, "bad argument");
     *out_scene = nullptr;
     ATLAS_CUDA(ctx, cudaSetDevice(ctx->device));
     const bool dev = flags & ATLAS_RT_DEVICE_INPUT;
-    auto* scene = new (std::nothrow) atlas_rt_scene;
-    if (!scene) return fail(ctx, ATLAS_RT_ERR_OOM, "host allocation");
-    scene->ctx = ctx;
-    scene->tlas = tlas;
-    scene->meshCount = mesh_count;
-    scene->instanceCount = tlas->refCount;
     std::vector<const float4*> nodePtrs(mesh_count), triPtrs(mesh_count), tri96Ptrs(mesh_count);
     std::vector<uint32_t> nodeCounts(mesh_count);
-    scene->allShading = true;
+    bool allShading = true;
     for (uint32_t m = 0; m < mesh_count; m++) {
-        if (!meshes[m] || meshes[m]->ctx != ctx) { delete scene; return fail(ctx, ATLAS_RT_ERR_INVALID, "mesh from another context"); }
+        if (!meshes[m] || !same_device(meshes[m]->ctx, ctx)) return fail(ctx, ATLAS_RT_ERR_INVALID, "mesh missing or from another device");
         nodePtrs[m] = meshes[m]->blas->nodes;
         triPtrs[m] = meshes[m]->tris;
         tri96Ptrs[m] = meshes[m]->tris96;
-        scene->allShading = scene->allShading && meshes[m]->tris96 != nullptr;
+        allShading = allShading && meshes[m]->tris96 != nullptr;
         nodeCounts[m] = uint32_t(meshes[m]->blas->nodeCount);
     }
-    float4* dSrc = nullptr;
-    uint32_t* dNodeCounts = nullptr;
-    ATLAS_CUDA(ctx, dev_alloc(ctx, &dNodeCounts, mesh_count));
-    ATLAS_CUDA(ctx, cudaMemcpyAsync(dNodeCounts, nodeCounts.data(), mesh_count * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-    ATLAS_CUDA(ctx, dev_alloc(ctx, &scene->blasNodes, mesh_count));
-    ATLAS_CUDA(ctx, dev_alloc(ctx, &scene->bvhTris, mesh_count));
-    ATLAS_CUDA(ctx, dev_alloc(ctx, &scene->triangles, mesh_count));
-    ATLAS_CUDA(ctx, dev_alloc(ctx, &scene->instances, scene->instanceCount * 4));
-    // pointer tables are tiny: plain synchronous copies from pageable memory are fine here
-    ATLAS_CUDA(ctx, cudaMemcpyAsync(scene->blasNodes, nodePtrs.data(), mesh_count * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
-    ATLAS_CUDA(ctx, cudaMemcpyAsync(scene->bvhTris, triPtrs.data(), mesh_count * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
-    ATLAS_CUDA(ctx, cudaMemcpyAsync(scene->triangles, tri96Ptrs.data(), mesh_count * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
-    ATLAS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the std::vectors die at scope exit
-    {
-        int rcf = scene_fast_flag(ctx, scene, dNodeCounts);
-        dev_free(ctx, dNodeCounts);
-        if (rcf != ATLAS_RT_OK) { atlas_rt_scene_free(scene); return rcf; }
+    auto* scene = new (std::nothrow) atlas_rt_scene;
+    if (!scene) return fail(ctx, ATLAS_RT_ERR_OOM, "host allocation");
+    scene->ctx = ctx;
+    ctx_retain(ctx);
+    scene->tlas = tlas;
+    scene->meshCount = mesh_count;
+    scene->instanceCount = tlas->refCount;
+    scene->allShading = allShading;
+    Staged st(ctx);
+    cudaError_t e = cudaSuccess;
+    const uint32_t* dNodeCounts = static_cast<const uint32_t*>(st.in(nodeCounts.data(), mesh_count * sizeof(uint32_t), false, &e));
+    if (e == cudaSuccess) e = dev_alloc(ctx, &scene->blasNodes, mesh_count);
+    if (e == cudaSuccess) e = dev_alloc(ctx, &scene->bvhTris, mesh_count);
+    if (e == cudaSuccess) e = dev_alloc(ctx, &scene->triangles, mesh_count);
+    if (e == cudaSuccess) e = dev_alloc(ctx, &scene->instances, scene->instanceCount * 4);
+    // pointer tables are tiny: plain copies from pageable memory are fine here
+    if (e == cudaSuccess) e = cudaMemcpyAsync(scene->blasNodes, nodePtrs.data(), mesh_count * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(scene->bvhTris, triPtrs.data(), mesh_count * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(scene->triangles, tri96Ptrs.data(), mesh_count * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // the std::vectors die at scope exit
+    int rc = e == cudaSuccess ? scene_fast_flag(ctx, scene, dNodeCounts) : fail(ctx, ATLAS_RT_ERR_CUDA, "scene tables", e);
+    if (rc == ATLAS_RT_OK) {
+        const float4* src = static_cast<const float4*>(st.in(instances64, instance_count * 64, dev, &e));
+        if (e != cudaSuccess) rc = fail(ctx, ATLAS_RT_ERR_CUDA, "staging the instances", e);
+        else if (scene->instanceCount) {
+            reorder_instances<<<grid_for(scene->instanceCount), kBlock, 0, ctx->stream>>>(src, tlas->order, tlas->endOfNode, scene->instances, scene->instanceCount);
+            ctx->launches++;
+            e = cudaGetLastError();
+            if (e != cudaSuccess) rc = fail(ctx, ATLAS_RT_ERR_CUDA, "reorder_instances", e);
+        }
     }
-    const float4* src = static_cast<const float4*>(instances64);
-    if (!dev) {
-        ATLAS_CUDA(ctx, dev_alloc(ctx, &dSrc, instance_count * 4));
-        ATLAS_CUDA(ctx, copy_in(ctx, dSrc, instances64, instance_count * 64, false));
-        src = dSrc;
-    }
-    if (scene->instanceCount) {
-        reorder_instances<<<grid_for(scene->instanceCount), kBlock, 0, ctx->stream>>>(src, tlas->order, tlas->endOfNode, scene->instances, scene->instanceCount);
-        ATLAS_LAUNCH_CHECK(ctx);
-    }
-    dev_free(ctx, dSrc);
-    int rc = sync_unless_async(ctx, flags);
+    if (rc == ATLAS_RT_OK) rc = sync_unless_async(ctx, flags);
     if (rc != ATLAS_RT_OK) { atlas_rt_scene_free(scene); return rc; }
     *out_scene = scene;
     return ATLAS_RT_OK;
@@ -499,17 +596,19 @@ int atlas_rt_scene_download(const atlas_rt_scene* scene, void* instances64, void
 void atlas_rt_scene_free(atlas_rt_scene* scene) {
     if (!scene) return;
     cudaSetDevice(scene->ctx->device);
-    dev_free(scene->ctx, scene->instances);
-    dev_free(scene->ctx, scene->blasNodes);
-    dev_free(scene->ctx, scene->bvhTris);
-    dev_free(scene->ctx, scene->triangles);
+    atlas_rt_context* ctx = scene->ctx;
+    dev_free(ctx, scene->instances);
+    dev_free(ctx, scene->blasNodes);
+    dev_free(ctx, scene->bvhTris);
+    dev_free(ctx, scene->triangles);
     delete scene;
+    ctx_release(ctx);
 }
 
 // ---------------------------------------------------------------------------------------------------- trace
 static int trace_common(atlas_rt_context* ctx, const atlas_rt_scene* scene, const void* rays_in, uint64_t count,
                         uint32_t cull_mask, float t_min, float t_max, void* rays_out, uint32_t flags, bool any) {
-    if (!ctx || !scene || scene->ctx != ctx || (count && (!rays_in || !rays_out))) return fail(ctx, ATLAS_RT_ERR_INVALID, "bad argument");
+    if (!ctx || !scene || !same_device(scene->ctx, ctx) || (count && (!rays_in || !rays_out))) return fail(ctx, ATLAS_RT_ERR_INVALID, "bad argument");
     ATLAS_CUDA(ctx, cudaSetDevice(ctx->device));
     const bool devIn = flags & ATLAS_RT_DEVICE_INPUT, devOut = flags & ATLAS_RT_DEVICE_OUTPUT;
     float4 *dIn = nullptr, *dOut = nullptr;
@@ -595,6 +694,11 @@ static int trace_common(atlas_rt_context* ctx, const atlas_rt_scene* scene, cons
             cudaError_t e = copy_out(ctx, rays_out, out, count * 48, false);
             if (e != cudaSuccess) rc = fail(ctx, ATLAS_RT_ERR_CUDA, "copy_out", e);
         }
+    }
+    if (rc != ATLAS_RT_OK) {   // the copy / extra compute streams may still be touching the staging buffer
+        if (ctx->copyIn) cudaStreamSynchronize(ctx->copyIn);
+        if (ctx->copyOut) cudaStreamSynchronize(ctx->copyOut);
+        for (auto& cs : ctx->computeExtra) if (cs) cudaStreamSynchronize(cs);
     }
     dev_free(ctx, dIn);
     dev_free(ctx, dOut);

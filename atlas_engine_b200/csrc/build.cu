@@ -1852,18 +1852,20 @@ int read_back(atlas_rt_context* ctx, const T* dev, T* host) {
         if (e__ != cudaSuccess) { cleanup(); return fail((ctx), ATLAS_RT_ERR_CUDA, "kernel launch", e__); } \
     } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE property of the function, so it is set for every context at
+// creation (after cudaSetDevice), not once per process: a second context on another GPU would otherwise launch
+// build_subtrees with > 48 KB of dynamic shared memory it never opted in to.
+int build_init_device(atlas_rt_context* ctx) {
+    ATLAS_CUDA(ctx, cudaFuncSetAttribute(build_subtrees, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSubtreeSmem)));
+    return ATLAS_RT_OK;
+}
+
 int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, uint64_t count64, bool tlas, atlas_rt_bvh* out) {
     const uint32_t n = uint32_t(count64);
     cudaStream_t st = ctx->stream;
     out->nodeCount = 0;
     out->refCount = 0;
     if (n == 0) return ATLAS_RT_OK;   // the reference dereferences a null child for an empty input; we return an empty BVH
-
-    static bool attrSet = false;
-    if (!attrSet) {
-        cudaFuncSetAttribute(build_subtrees, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSubtreeSmem));
-        attrSet = true;
-    }
 
     if (tlas && n == 1) {
         ATLAS_CUDA(ctx, dev_alloc(ctx, &out->nodes, 4));

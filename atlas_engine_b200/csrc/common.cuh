@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <string>
 
 #include "../../include/atlas_rt.h"
@@ -68,6 +69,10 @@ __device__ __forceinline__ float surface_area(const Box3& b) { return surface_ar
 
 // ------------------------------------------------------------------------------------------------ host objects
 struct atlas_rt_context {
+    // Objects (bvh / mesh / scene) outlive calls and may be freed from another thread after the creating thread has
+    // destroyed "its" context (engine meshes are built on job-system workers and assembled elsewhere), so the context is
+    // reference counted: atlas_rt_context_destroy drops the creator's reference, every live object holds one more.
+    std::atomic<int> refs{1};
     int device = 0;
     cudaStream_t stream = nullptr;
     bool ownStream = false;
@@ -92,6 +97,9 @@ struct atlas_rt_context {
     int traceLongestFirst = 1;      // fetch rays longest-estimated-path first (hides the drain of the longest rays)
     int traceLongestFirstMin = 65536;
     int traceRaysPerWarp = 96;      // small batches use fewer persistent warps so each warp still sees this many rays
+    // worker contexts (own stream + own pinned level flags each) that atlas_rt_build_blas_batch builds on side by side
+    atlas_rt_context* workers[8] = {};
+    int batchWorkers = 8;
 };
 
 struct atlas_rt_bvh {
@@ -127,6 +135,8 @@ struct atlas_rt_scene {
 namespace atlas {
 
 int fail(atlas_rt_context* ctx, int status, const char* what, cudaError_t e = cudaSuccess);
+void ctx_retain(atlas_rt_context* ctx);
+void ctx_release(atlas_rt_context* ctx);   // destroys the context when the last reference goes
 
 #define ATLAS_CUDA(ctx, call)                                                          \
     do {                                                                               \
@@ -194,6 +204,7 @@ cudaError_t copy_out(atlas_rt_context* ctx, void* dst, const void* src, size_t b
 int ensure_node_storage(atlas_rt_context* ctx, atlas_rt_bvh* bvh);
 
 // builder entry points (build.cu)
+int build_init_device(atlas_rt_context* ctx);   // per-device kernel attributes (opt-in shared memory); called by context_create
 int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, uint64_t count, bool tlas, atlas_rt_bvh* out);
 
 // traversal entry points (trace.cu)

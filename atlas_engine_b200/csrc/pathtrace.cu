@@ -262,7 +262,7 @@ int atlas_rt_generate_primary_rays(atlas_rt_context* ctx, const atlas_rt_camera*
 int atlas_rt_pathtrace_bounce(atlas_rt_context* ctx, const atlas_rt_scene* scene, const atlas_rt_bounce_params* params,
                               const void* rays_in, const void* payload_in, uint64_t count, void* rays_out,
                               void* payload_out, float* accum, uint64_t* out_count, uint32_t flags) {
-    if (!ctx || !scene || scene->ctx != ctx || !params || !rays_out || !payload_out || !accum || !out_count || (count && !rays_in))
+    if (!ctx || !scene || scene->ctx->device != ctx->device || !params || !rays_out || !payload_out || !accum || !out_count || (count && !rays_in))
         return fail(ctx, ATLAS_RT_ERR_INVALID, "bad argument");
     if ((flags & (ATLAS_RT_DEVICE_INPUT | ATLAS_RT_DEVICE_OUTPUT)) != (ATLAS_RT_DEVICE_INPUT | ATLAS_RT_DEVICE_OUTPUT))
         return fail(ctx, ATLAS_RT_ERR_UNSUPPORTED, "atlas_rt_pathtrace_bounce works on device-resident ray / payload / accumulation buffers");

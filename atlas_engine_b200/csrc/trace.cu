@@ -270,7 +270,12 @@ trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restr
                         nodes = sc.blasNodes[meshPtr];
                         tris = OPACITY ? sc.triangles[meshPtr] : sc.bvhTris[meshPtr];
                     } else {
-                        pop();   // the transformed ray is discarded: the TLAS branch restores the original anyway
+                        // Culled by the mask. HitClosest and the *Transparency variants restore the world-space ray at the
+                        // top of their next TLAS iteration (bvh.hsh:218-220, :302-304, :469-471), so o/d simply stay as they
+                        // are. Plain HitAny restores only after leaving a BLAS (:387-390): it walks on through the TLAS with
+                        // the ray CheckInstance has already transformed, and a later culled instance transforms it again.
+                        if (ANY && !OPACITY) set_ray(no, nd);
+                        pop();
                     }
                 } else {
                     // CheckLeafClosest (bvh.hsh:44-72) / CheckLeaf (:74-104); with OPACITY CheckLeafClosestTransparency

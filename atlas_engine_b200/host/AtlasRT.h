@@ -12,14 +12,21 @@
 // rest of the engine uses (layouts are identical); stand-alone it brings its own PODs.
 //
 // Threading: like the reference constructors, everything here is synchronous and may be called concurrently from
-// several job-system workers; each calling thread lazily gets its own atlas_rt_context (CUDA stream).
+// several job-system workers; each calling thread lazily gets its own atlas_rt_context (CUDA stream). Long-lived objects
+// (MeshBVH, World) may be built on one thread and used or released on another: the library accepts objects from any
+// context of the same device and keeps a context alive until the last object created on it has been freed, so a worker
+// thread may exit while its meshes live on (the engine builds meshes on job-system workers, MeshData::BuildBVH, and
+// assembles the scene elsewhere, RayTracingWorld::UpdateForSoftwareRayTracing).
 // Errors: the reference has no error channel on this path (size mismatch => silently empty BVH, BVH.cpp:18-19); the
 // same holds here, and a CUDA failure additionally leaves the object empty with the message in Atlas::RayTracing::LastError().
 #pragma once
 
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/atlas_rt.h"
@@ -146,6 +153,16 @@ public:
     };
 };
 
+class Ray {   // volume/Ray.h: what BVH::GetIntersection* read
+public:
+    Ray() = default;
+    Ray(vec3 origin, vec3 direction, float tMin = 0.0f, float tMax = 2048.0f) : origin(origin), direction(direction), tMin(tMin), tMax(tMax) {}
+    vec3 origin = vec3(0.0f);
+    vec3 direction = vec3(0.0f, 1.0f, 0.0f);
+    float tMin = 0.0f;
+    float tMax = 2048.0f;
+};
+
 class BVH {   // volume/BVH.h:114-138
 public:
     BVH() = default;
@@ -196,11 +213,43 @@ public:
                 refs[i].aabb = aabbs[order[i]];
                 this->aabbs[i] = aabbs[order[i]];
             }
+            FillNodeIdx();
         }
         atlas_rt_bvh_free(h);
     }
 
+    // BVH.cpp:103-174. The closest triangle hit by `ray` within (ray.tMin, ray.tMax): `closest` = data[slot],
+    // intersection = (t, u, v) with weights v0: 1-u-v, v1: u, v2: v; intersection.x = ray.tMax when nothing is hit.
+    // Runs as a one-ray batch through atlas_rt_trace_closest over a device copy of this tree that is created on first use
+    // from the public members (so a tree assigned by hand works too) — there is no CPU traversal in this library. The
+    // reference's return value is unreliable (it compares against a tMax it has shrunk itself); here it is "something
+    // was hit". `stack` is unused (the traversal stack lives in the kernel).
+    bool GetIntersection(std::vector<std::pair<int32_t, float>>& stack, Ray ray, BVHTriangle& closest, vec3& intersection) {
+        (void)stack;
+        intersection.x = ray.tMax;
+        PackedHit hit;
+        if (!TraceOne(ray, false, hit) || hit.id < 0 || size_t(hit.id) >= data.size()) return false;
+        closest = data[size_t(hit.id)];
+        intersection = vec3(hit.t, hit.u, hit.v);
+        return true;
+    }
+
+    // BVH.cpp:176-217: is anything hit before ray.tMax?
+    bool GetIntersectionAny(std::vector<std::pair<int32_t, float>>& stack, Ray ray) {
+        (void)stack;
+        PackedHit hit;
+        return TraceOne(ray, true, hit) && hit.id >= 0;
+    }
+
     std::vector<BVHNode>& GetTree() { return nodes; }
+
+    void Clear() {   // declared in volume/BVH.h:130
+        aabbs.clear(); aabbs.shrink_to_fit();
+        data.clear(); data.shrink_to_fit();
+        refs.clear(); refs.shrink_to_fit();
+        nodes.clear(); nodes.shrink_to_fit();
+        query.reset();
+    }
 
     std::vector<AABB> aabbs;
     std::vector<BVHTriangle> data;
@@ -208,6 +257,91 @@ public:
     std::vector<BVHNode> nodes;
 
 private:
+    struct PackedHit { float t = 0.0f, u = 0.0f, v = 0.0f; int32_t id = -1; };
+    // Device copy used by the CPU-query methods; shared between copies of the BVH object, released with the last one.
+    struct Query {
+        atlas_rt_bvh* blas = nullptr;
+        atlas_rt_mesh* mesh = nullptr;
+        atlas_rt_bvh* tlas = nullptr;
+        atlas_rt_scene* scene = nullptr;
+        ~Query() {
+            if (scene) atlas_rt_scene_free(scene);
+            if (tlas) atlas_rt_bvh_free(tlas);
+            if (mesh) atlas_rt_mesh_free(mesh);
+            if (blas) atlas_rt_bvh_free(blas);
+        }
+    };
+    std::shared_ptr<Query> query;
+
+    bool EnsureQuery(atlas_rt_context* ctx) {
+        if (query) return query->scene != nullptr;
+        if (data.empty()) return false;
+        query = std::make_shared<Query>();
+        std::vector<uint32_t> order(data.size());
+        std::vector<uint8_t> flags(data.size());
+        std::vector<float> tris(data.size() * 9);
+        float box[6] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+        for (size_t i = 0; i < data.size(); i++) {   // slot i of the device tree is data[i] itself
+            const BVHTriangle& t = data[i];
+            order[i] = uint32_t(i);
+            flags[i] = t.endOfNode ? 1 : 0;
+            const float v[9] = {t.v0.x, t.v0.y, t.v0.z, t.v1.x, t.v1.y, t.v1.z, t.v2.x, t.v2.y, t.v2.z};
+            std::memcpy(&tris[9 * i], v, sizeof(v));
+            for (int k = 0; k < 9; k++) { box[k % 3] = v[k] < box[k % 3] ? v[k] : box[k % 3]; box[3 + k % 3] = v[k] > box[3 + k % 3] ? v[k] : box[3 + k % 3]; }
+        }
+        GPUBVHInstance inst;
+        inst.inverseMatrix[0] = vec4(1, 0, 0, 0); inst.inverseMatrix[1] = vec4(0, 1, 0, 0); inst.inverseMatrix[2] = vec4(0, 0, 1, 0);
+        inst.mask = MaskAll | MaskShadow;
+        using RayTracing::detail::Check;
+        const bool ok = Check(atlas_rt_bvh_upload(ctx, nodes.data(), nodes.size(), order.data(), flags.data(), data.size(), &query->blas)) &&
+                        Check(atlas_rt_pack_mesh(ctx, query->blas, tris.data(), data.size(), nullptr, nullptr, 0, &query->mesh)) &&
+                        Check(atlas_rt_build_tlas(ctx, box, 1, 0, &query->tlas)) &&
+                        Check(atlas_rt_scene_create(ctx, &query->mesh, 1, &inst, 1, query->tlas, 0, &query->scene));
+        if (!ok) { query = std::make_shared<Query>(); return false; }
+        return true;
+    }
+
+    bool TraceOne(const Ray& ray, bool any, PackedHit& hit) {
+        atlas_rt_context* ctx = RayTracing::detail::Context();
+        if (!ctx || !EnsureQuery(ctx)) return false;
+        PackedRay in, out;
+        in.origin = vec4(ray.origin.x, ray.origin.y, ray.origin.z, 0.0f);   // ID 0 (>= 0: a live ray)
+        in.direction = vec4(ray.direction.x, ray.direction.y, ray.direction.z, 0.0f);
+        const int32_t none = -1;
+        std::memcpy(&in.hit.y, &none, 4);
+        const int rc = any ? atlas_rt_trace_any(ctx, query->scene, &in, 1, MaskAll, ray.tMin, ray.tMax, &out, 0)
+                           : atlas_rt_trace_closest(ctx, query->scene, &in, 1, MaskAll, ray.tMin, ray.tMax, &out, 0);
+        if (!RayTracing::detail::Check(rc)) return false;
+        hit.t = out.hit.x; hit.u = out.direction.w; hit.v = out.hit.w;
+        std::memcpy(&hit.id, &out.hit.y, 4);
+        return true;
+    }
+
+    // Ref::nodeIdx as Flatten leaves it (BVH.cpp:413): the index of the node pushed LAST before the leaf was reached in
+    // the pre-order walk — the parent for a left leaf, the last node of the left subtree for a right leaf.
+    void FillNodeIdx() {
+        if (nodes.empty() || refs.empty()) return;
+        if (refs.size() == 2 && nodes.size() == 1 && nodes[0].leftPtr == ~0 && nodes[0].rightPtr == ~0) return;   // count == 1 quirk: both stay 0
+        std::vector<int32_t> todo;   // pending right children, as pointers
+        uint32_t pushed = 0;
+        int32_t ptr = 0;
+        for (;;) {
+            if (ptr >= 0) {
+                pushed = uint32_t(ptr) + 1;   // pre-order: node ptr is the pushed-th node
+                todo.push_back(nodes[size_t(ptr)].rightPtr);
+                ptr = nodes[size_t(ptr)].leftPtr;
+                continue;
+            }
+            for (size_t slot = size_t(~ptr); slot < refs.size(); slot++) {
+                refs[slot].nodeIdx = pushed - 1;
+                if (refs[slot].endOfNode) break;
+            }
+            if (todo.empty()) break;
+            ptr = todo.back();
+            todo.pop_back();
+        }
+    }
+
     bool Fetch(atlas_rt_bvh* h, std::vector<uint32_t>& order, std::vector<uint8_t>& flags) {
         uint64_t n = 0, m = 0;
         atlas_rt_bvh_counts(h, &n, &m);
@@ -232,8 +366,22 @@ struct MeshBVH {
     std::vector<GPUBVHNode> gpuBvhNodes;
     atlas_rt_bvh* blas = nullptr;
     atlas_rt_mesh* mesh = nullptr;
-    atlas_rt_context* owner = nullptr;
+    MeshBVH() = default;
+    MeshBVH(const MeshBVH&) = delete;              // owns device memory: movable, not copyable
+    MeshBVH& operator=(const MeshBVH&) = delete;
+    MeshBVH(MeshBVH&& o) noexcept { *this = std::move(o); }
+    MeshBVH& operator=(MeshBVH&& o) noexcept {
+        if (this != &o) {
+            Release();
+            gpuTriangles = std::move(o.gpuTriangles); gpuBvhTriangles = std::move(o.gpuBvhTriangles); gpuBvhNodes = std::move(o.gpuBvhNodes);
+            blas = o.blas; mesh = o.mesh;
+            o.blas = nullptr; o.mesh = nullptr;
+        }
+        return *this;
+    }
+    ~MeshBVH() { Release(); }
     bool IsBVHBuilt() const { return gpuBvhTriangles.size() > 0; }   // MeshData.cpp:273-277
+    // May be called from any thread: the handles keep the context they were created on alive.
     void Release() {
         if (mesh) atlas_rt_mesh_free(mesh);
         if (blas) atlas_rt_bvh_free(blas);
@@ -259,7 +407,6 @@ inline bool BuildMeshBVH(const std::vector<vec3>& vertices, const std::vector<ui
         }
     }
     out.Release();
-    out.owner = ctx;
     if (!detail::Check(atlas_rt_build_blas(ctx, boxes.data(), tris.data(), n, 0, &out.blas))) return false;
     std::vector<int32_t> mats(n, materialIdx);
     std::vector<float> ops(n, opacity);
@@ -307,6 +454,10 @@ struct World {
     std::vector<GPUBVHNode> tlasNodes;
     atlas_rt_bvh* tlas = nullptr;
     atlas_rt_scene* scene = nullptr;
+    World() = default;
+    World(const World&) = delete;
+    World& operator=(const World&) = delete;
+    ~World() { Release(); }
     void Release() {
         if (scene) atlas_rt_scene_free(scene);
         if (tlas) atlas_rt_bvh_free(tlas);

@@ -49,7 +49,7 @@ typedef enum atlas_rt_status {
     ATLAS_RT_ERR_INVALID = -1,      /* null pointer, mismatched sizes, object from another context */
     ATLAS_RT_ERR_CUDA = -2,         /* a CUDA call failed or no device */
     ATLAS_RT_ERR_OOM = -3,          /* device or host allocation failed */
-    ATLAS_RT_ERR_UNSUPPORTED = -4,  /* input outside the documented contract (e.g. > 2^31-2 references) */
+    ATLAS_RT_ERR_UNSUPPORTED = -4,  /* input outside the documented contract (e.g. more than 2^30-1 primitives in one build) */
     ATLAS_RT_ERR_STACK = -5         /* a ray needed more than ATLAS_RT_STACK_SIZE stack entries (UB in the reference) */
 } atlas_rt_status;
 
@@ -93,6 +93,14 @@ int atlas_rt_version(void);
  * The result holds nodes, the flattened order (source index per slot, duplicates possible) and endOfNode flags. */
 int atlas_rt_build_blas(atlas_rt_context* ctx, const float* aabbs, const float* tris, uint64_t count, uint32_t flags,
                         atlas_rt_bvh** out_bvh);
+
+/* The BLASes of many meshes in one call: aabbs[m] / tris[m] / counts[m] as for atlas_rt_build_blas, out_bvhs[m] receives
+ * mesh m's tree. Replaces the engine building its meshes concurrently on job-system workers (src/tests/App.cpp:362-370,
+ * src/demo/App.cpp:1092 -> Mesh::MeshData::BuildBVH): up to 8 builds run side by side on the device, so a scene of many
+ * small meshes is not serialised behind per-build launch latency. Every tree is identical to the one atlas_rt_build_blas
+ * returns for that mesh. */
+int atlas_rt_build_blas_batch(atlas_rt_context* ctx, uint32_t mesh_count, const float* const* aabbs, const float* const* tris,
+                              const uint64_t* counts, uint32_t flags, atlas_rt_bvh** out_bvhs);
 
 /* TLAS build + flatten. Replaces Atlas::Volume::BVH::BVH(const std::vector<AABB>&, bool) — BVH.cpp:58-101 (64 bins,
  * object/median splits only, the count == 1 special node and its two-entry refs quirk). */
@@ -151,6 +159,39 @@ int atlas_rt_mesh_counts(const atlas_rt_mesh* mesh, uint64_t* node_count, uint64
 /* Copy out gpuBvhNodes (64 B each) and gpuBvhTriangles (48 B each); either may be NULL. */
 int atlas_rt_mesh_download(const atlas_rt_mesh* mesh, void* gpu_nodes64, void* gpu_bvh_triangles48, uint32_t flags);
 void atlas_rt_mesh_free(atlas_rt_mesh* mesh);
+
+/* The 11 packed shading words per SOURCE triangle that atlas_rt_mesh_pack_shading takes as `payload11`, computed on the
+ * device: pn0, pn1, pn2 (10-10-10-2 signed), puv0, puv1, puv2 (half2), pt, pbt (tangent frame from positions + uvs),
+ * pc0, pc1, pc2 (unorm4x8). Replaces the arithmetic of the second loop of MeshData::BuildBVH —
+ * src/engine/mesh/MeshData.cpp:176-228 with Common::Packing::PackSignedVector3x10_1x2 (src/engine/common/Packing.cpp:24-35),
+ * glm::packHalf2x16 and glm::packUnorm4x8 (glm 0.9.8), including x86's float->int conversion of the NaN tangents that
+ * degenerate texture coordinates produce. Inputs are per triangle, expanded as MeshData.cpp:102-133 does: tris count x 9,
+ * normals9 count x 9 (already normalised n0 n1 n2; NULL = zero), uvs6 count x 6 (NULL = zero), colors12 count x 12
+ * (NULL = one). payload11: count x 11 words. */
+int atlas_rt_pack_shading_words(atlas_rt_context* ctx, const float* tris, const float* normals9, const float* uvs6,
+                                const float* colors12, uint64_t count, uint32_t* payload11, uint32_t flags);
+
+/* ------------------------------------------------------------------------------------------ mesh ingestion ---- */
+/* Reader for the engine's .aemesh files (MessagePack-encoded JSON written by Loader::MeshLoader::SaveMesh —
+ * src/engine/loader/MeshLoader.cpp:7-37, src/engine/mesh/MeshSerializer.cpp:62-133, MeshSerializer.h:52-70) and the
+ * triangle expansion of the first loop of MeshData::BuildBVH (src/engine/mesh/MeshData.cpp:89-159), whose output feeds
+ * atlas_rt_build_blas / atlas_rt_pack_mesh / atlas_rt_pack_shading_words directly. Host-only; needs no context. */
+typedef struct atlas_rt_aemesh atlas_rt_aemesh;
+int atlas_rt_aemesh_open(const char* path, atlas_rt_aemesh** out_mesh);
+int atlas_rt_aemesh_counts(const atlas_rt_aemesh* mesh, uint64_t* vertex_count, uint64_t* index_count,
+                           uint64_t* triangle_count, uint32_t* sub_mesh_count);
+/* Path of material `index` as stored in the file ("materials/....aematerial"), or NULL. */
+const char* atlas_rt_aemesh_material_path(const atlas_rt_aemesh* mesh, uint32_t index);
+/* Per triangle k (all sub meshes, in order): tris9 = positions, aabbs6 = glm::min/max box, material_idx = the sub mesh's
+ * materialIdx, normals9 = normalize(vec4 normal).xyz per corner, uvs6 (zero without texCoords), colors12 (one without
+ * colours). Any pointer may be NULL. */
+int atlas_rt_aemesh_triangles(const atlas_rt_aemesh* mesh, float* tris9, float* aabbs6, int32_t* material_idx,
+                              float* normals9, float* uvs6, float* colors12);
+/* Borrowed pointers to the raw components (valid until close): indices u32, vertices 3 floats, normals 4 floats,
+ * texCoords 2 floats (NULL if absent). */
+int atlas_rt_aemesh_raw(const atlas_rt_aemesh* mesh, const uint32_t** indices, const float** vertices3,
+                        const float** normals4, const float** tex_coords2);
+void atlas_rt_aemesh_close(atlas_rt_aemesh* mesh);
 
 /* -------------------------------------------------------------------------------------------------- scene ---- */
 /* Assemble the two-level scene. Replaces RayTracingWorld::UpdateForSoftwareRayTracing — src/engine/raytracing/

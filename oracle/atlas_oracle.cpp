@@ -544,9 +544,13 @@ bool traverse(const SceneView& sc, RayState& ray, uint32_t cullMask, float tMin,
     while (sp != 0u && !(ANY && !OPACITY && hit) && !(ANY && OPACITY && !(ray.transparency > 0.0f))) {
         const bool inTlas = sp < tlasIndex;
         if (inTlas) {
-            // HitClosest restores unconditionally (bvh.hsh:218-220); HitAny only when leaving a BLAS (:387-390) —
-            // identical values either way.
-            for (int a = 0; a < 3; a++) { ray.o[a] = o0[a]; ray.d[a] = d0[a]; }
+            // HitClosest and both *Transparency variants restore unconditionally (bvh.hsh:218-220, :302-304, :469-471);
+            // plain HitAny only when it has just left a BLAS (:387-390). That difference is observable: CheckInstance
+            // transforms the ray BEFORE the mask test, so after an instance culled by the mask plain HitAny walks on
+            // through the TLAS with the instance-space ray (and a second culled instance transforms it again) until the
+            // next BLAS exit restores it. Reproduced as is — it is what the reference computes.
+            if (!ANY || OPACITY || tlasIndex != kTlasInvalid)
+                for (int a = 0; a < 3; a++) { ray.o[a] = o0[a]; ray.d[a] = d0[a]; }
             tlasIndex = kTlasInvalid;
         }
         if (inTlas && nodePtr < 0) {

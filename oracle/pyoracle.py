@@ -175,6 +175,7 @@ class Oracle:
         L.oracle_tree_free.argtypes = [_vp]
         L.oracle_trace.argtypes = [_vp, _vp, _vp, _vp, _vp, _u64, _u32, _f32, _f32, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, C.c_int]
         L.oracle_brute_force.argtypes = [_vp, _u32, _vp, _vp, _vp, _u64, _u32, _f32, _f32, _vp, _vp, _vp, C.c_int]
+        L.oracle_pack_shading_words.argtypes = [_vp, _vp, _vp, _vp, _u64, _vp]
 
     def _collect(self, h):
         n, m = self.lib.oracle_tree_node_count(h), self.lib.oracle_tree_ref_count(h)
@@ -206,6 +207,14 @@ class Oracle:
                               _ptr(rays), rays.shape[0], cull_mask, t_min, t_max, int(any_hit), int(per_ray_tmax),
                               _ptr(out), _ptr(ct), nthreads, scene._tri96_ptrs if opacity else None, int(opacity))
         return out, dict(zip(COUNTER_NAMES, (int(x) for x in ct)))
+
+    def pack_shading_words(self, tris, normals9=None, uvs6=None, colors12=None):
+        """(n, 11) uint32: the packed shading words of MeshData.cpp:176-228 per source triangle."""
+        tris = _f32c(tris).reshape(-1, 9)
+        arrs = [None if a is None else _f32c(a) for a in (normals9, uvs6, colors12)]
+        out = np.zeros((tris.shape[0], 11), dtype=np.uint32)
+        self.lib.oracle_pack_shading_words(_ptr(tris), *[None if a is None else _ptr(a) for a in arrs], tris.shape[0], _ptr(out))
+        return out
 
     def brute_force(self, scene, rays, cull_mask=1 << 7, t_min=0.0, t_max=1e12, nthreads=1):
         rays = _f32c(rays).reshape(-1, 12)

@@ -96,6 +96,12 @@ void ref_bvh_copy_order(void* h, uint32_t* order, uint8_t* flags) {
     }
 }
 
+// Ref::nodeIdx of a TLAS as Flatten left it (BVH.cpp:413).
+void ref_bvh_copy_node_idx(void* h, uint32_t* out) {
+    auto* r = static_cast<RefBVH*>(h);
+    for (size_t i = 0; i < r->bvh.refs.size(); i++) out[i] = r->bvh.refs[i].nodeIdx;
+}
+
 // aabbs member (unclipped source boxes in flattened order), 6 floats each.
 void ref_bvh_copy_aabbs(void* h, float* out) {
     auto* r = static_cast<RefBVH*>(h);

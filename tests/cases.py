@@ -1,4 +1,6 @@
 """Shared input batteries for the parity tests (same seeds on CPU and GPU)."""
+import os
+
 import numpy as np
 
 from atlas_engine_b200 import workloads as W
@@ -34,6 +36,30 @@ def build_cases(big=False):
         cases["heightfield1m"] = W.heightfield(707, 707)
         cases["atrium_big"] = W.atrium(128)
         cases["giants200k"] = W.soup_with_giants(200000, seed=5)
+    return cases
+
+
+def chromesphere_bin(path=None):
+    """data/chromesphere.bin of the reference (copied to tests/golden/meshes by make_golden.py): 3840 float3 positions at
+    byte 0 and 3840 u16 indices at byte 122880 (chromesphere.gltf bufferViews 0 / 3) -> 1280 triangles."""
+    path = path or os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "meshes", "chromesphere.bin")
+    raw = open(path, "rb").read()
+    pos = np.frombuffer(raw[:3840 * 12], dtype=np.float32).reshape(-1, 3)
+    idx = np.frombuffer(raw[122880:122880 + 3840 * 2], dtype=np.uint16).astype(np.int64)
+    return pos[idx].reshape(-1, 9).astype(np.float32)
+
+
+def aemesh_path(name):
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "meshes", name + ".aemesh")
+
+
+def real_mesh_cases():
+    """Real geometry from the reference's data directory: the glTF sphere's raw buffer and the three .aemesh files read
+    through the library's own reader (atlas_rt_aemesh_*)."""
+    from atlas_engine_b200 import capi
+    cases = {"chromesphere_bin": chromesphere_bin()}
+    for n in ("chromesphere", "capsule", "metallicwall"):
+        cases["aemesh_" + n] = capi.load_aemesh(aemesh_path(n))["tris"]
     return cases
 
 

@@ -4,6 +4,7 @@
 #include <dlfcn.h>
 
 #include <cstdio>
+#include <cmath>
 #include <cstdlib>
 #include <random>
 #include <thread>
@@ -19,6 +20,9 @@ typedef uint64_t (*ref_count_t)(void*);
 typedef void (*ref_copy_nodes_t)(void*, void*);
 typedef void (*ref_copy_order_t)(void*, uint32_t*, uint8_t*);
 typedef void (*ref_free_t)(void*);
+typedef void (*ref_copy_node_idx_t)(void*, uint32_t*);
+typedef void (*ref_intersect_closest_t)(void*, const float*, uint64_t, float*, int32_t*, int);
+typedef void (*ref_intersect_any_t)(void*, const float*, uint64_t, uint8_t*, int);
 typedef int (*ref_void_t)();
 
 static std::vector<Volume::BVHTriangle> soup(size_t n, unsigned seed, float extent) {
@@ -57,6 +61,9 @@ int main(int argc, char** argv) {
     auto ref_copy_order = (ref_copy_order_t)dlsym(lib, "ref_bvh_copy_order");
     auto ref_free = (ref_free_t)dlsym(lib, "ref_bvh_free");
     auto ref_shutdown = (ref_void_t)dlsym(lib, "ref_shutdown");
+    auto ref_copy_node_idx = (ref_copy_node_idx_t)dlsym(lib, "ref_bvh_copy_node_idx");
+    auto ref_intersect_closest = (ref_intersect_closest_t)dlsym(lib, "ref_bvh_intersect_closest");
+    auto ref_intersect_any = (ref_intersect_any_t)dlsym(lib, "ref_bvh_intersect_any");
     int failures = 0;
 
     // ---- BLAS through Volume::BVH(aabbs, data), several meshes concurrently
@@ -101,7 +108,7 @@ int main(int argc, char** argv) {
         failures += ok ? 0 : 1;
     }
     // ---- TLAS through Volume::BVH(aabbs)
-    for (size_t m : {size_t(1), size_t(2), size_t(300)}) {
+    for (size_t m : {size_t(1), size_t(2), size_t(3), size_t(300), size_t(5000)}) {
         std::vector<Volume::AABB> ib(boxes[3].begin(), boxes[3].begin() + m);
         Volume::BVH tl(ib);
         void* r = ref_build_tlas(reinterpret_cast<const float*>(ib.data()), m, 1);
@@ -113,6 +120,13 @@ int main(int argc, char** argv) {
         ref_free(r);
         bool ok = rn.size() == tl.nodes.size() && ro.size() == tl.refs.size() && memcmp(rn.data(), tl.nodes.data(), rn.size() * sizeof(Volume::BVHNode)) == 0;
         for (size_t i = 0; ok && i < ro.size(); i++) ok = tl.refs[i].idx == ro[i] && tl.refs[i].endOfNode == (rf[i] != 0);
+        if (ok && ref_copy_node_idx) {   // Ref::nodeIdx, BVH.cpp:413
+            std::vector<uint32_t> ni(ro.size());
+            void* r2 = ref_build_tlas(reinterpret_cast<const float*>(ib.data()), m, 1);
+            ref_copy_node_idx(r2, ni.data());
+            ref_free(r2);
+            for (size_t i = 0; ok && i < ni.size(); i++) ok = tl.refs[i].nodeIdx == ni[i];
+        }
         printf("TLAS %zu instances: nodes %zu refs %zu %s\n", m, tl.nodes.size(), tl.refs.size(), ok ? "== reference" : "MISMATCH");
         failures += ok ? 0 : 1;
     }
@@ -158,6 +172,102 @@ int main(int argc, char** argv) {
         failures += ok ? 0 : 1;
         world.Release();
         mesh.Release();
+    }
+    // ---- BVH::GetIntersection / GetIntersectionAny on the drop-in class (volume/BVH.h:124-127) against the reference's
+    if (ref_intersect_closest && ref_intersect_any) {
+        const int k = 1;   // the 20000-triangle soup
+        std::vector<float> flat(sizes[k] * 9);
+        for (size_t i = 0; i < sizes[k]; i++) {
+            const float v[9] = {tris[k][i].v0.x, tris[k][i].v0.y, tris[k][i].v0.z, tris[k][i].v1.x, tris[k][i].v1.y, tris[k][i].v1.z,
+                                tris[k][i].v2.x, tris[k][i].v2.y, tris[k][i].v2.z};
+            memcpy(&flat[9 * i], v, sizeof(v));
+        }
+        void* r = ref_build_blas(reinterpret_cast<const float*>(boxes[k].data()), flat.data(), sizes[k], 1);
+        std::mt19937 rng(4711);
+        std::uniform_real_distribution<float> u(0.0f, 1.0f);
+        const int nq = 400;
+        std::vector<float> q(8 * nq), tuv(3 * nq);
+        std::vector<int32_t> idx(nq);
+        std::vector<uint8_t> anyRef(nq);
+        for (int i = 0; i < nq; i++) {
+            float d[3] = {u(rng) - 0.5f, u(rng) - 0.5f, u(rng) - 0.5f};
+            const float l = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) + 1e-6f;
+            const float v[8] = {u(rng), u(rng), u(rng), d[0] / l, d[1] / l, d[2] / l, 0.0f, i % 3 ? 1.0e12f : 0.15f};
+            memcpy(&q[8 * i], v, sizeof(v));
+        }
+        ref_intersect_closest(r, q.data(), nq, tuv.data(), idx.data(), 1);
+        ref_intersect_any(r, q.data(), nq, anyRef.data(), 1);
+        ref_free(r);
+        std::vector<std::pair<int32_t, float>> stack(256);
+        bool ok = true;
+        int hits = 0;
+        Volume::BVH copy = built[k];   // copies share the lazily created device tree
+        for (int i = 0; ok && i < nq; i++) {
+            Volume::Ray ray(vec3(q[8 * i], q[8 * i + 1], q[8 * i + 2]), vec3(q[8 * i + 3], q[8 * i + 4], q[8 * i + 5]), q[8 * i + 6], q[8 * i + 7]);
+            Volume::BVHTriangle closest;
+            closest.idx = 0xffffffffu;
+            vec3 sol;
+            const bool hit = (i & 1 ? copy : built[k]).GetIntersection(stack, ray, closest, sol);
+            ok = hit == (idx[i] >= 0) && sol.x == tuv[3 * i] && (!hit || (int32_t(closest.idx) == idx[i] && sol.y == tuv[3 * i + 1] && sol.z == tuv[3 * i + 2]));
+            ok = ok && built[k].GetIntersectionAny(stack, ray) == (anyRef[i] != 0);
+            hits += hit ? 1 : 0;
+        }
+        ok = ok && hits > nq / 10;
+        printf("BVH::GetIntersection / GetIntersectionAny on %d rays (%d hits): %s\n", nq, hits, ok ? "== reference" : "MISMATCH");
+        failures += ok ? 0 : 1;
+    }
+    // ---- meshes built on job-system-like worker threads that EXIT, scene assembled and traced on this thread, meshes
+    // released afterwards (MeshData::BuildBVH on workers, RayTracingWorld::UpdateForSoftwareRayTracing elsewhere)
+    {
+        const int nm = 6;
+        std::vector<RayTracing::MeshBVH> meshes(nm);
+        std::vector<std::thread> pool;
+        std::vector<int> built_ok(nm, 0);
+        for (int k = 0; k < nm; k++) pool.emplace_back([&, k] {
+            std::vector<vec3> verts;
+            std::vector<uint32_t> idx;
+            const int g = 10 + 7 * k;
+            for (int z = 0; z <= g; z++) for (int x = 0; x <= g; x++) verts.push_back(vec3(float(x) * 10.0f / g, 0.5f * sinf(0.9f * x + k) * cosf(0.7f * z), float(z) * 10.0f / g));
+            for (int z = 0; z < g; z++) for (int x = 0; x < g; x++) {
+                const uint32_t a = z * (g + 1) + x, b = a + 1, c = a + g + 1, d = c + 1;
+                for (uint32_t v : {a, b, d, a, d, c}) idx.push_back(v);
+            }
+            RayTracing::MeshBVH local;
+            built_ok[k] = RayTracing::BuildMeshBVH(verts, idx, k, 1.0f, local, false) ? 1 : 0;
+            meshes[k] = std::move(local);
+        });
+        for (auto& w : pool) w.join();   // the workers' thread-local contexts are gone now; their meshes must live on
+        bool ok = true;
+        for (int k = 0; k < nm; k++) ok = ok && built_ok[k] && meshes[k].mesh;
+        std::vector<GPUBVHInstance> inst(nm);
+        std::vector<Volume::AABB> actor(nm);
+        std::vector<const RayTracing::MeshBVH*> ptrs(nm);
+        for (int k = 0; k < nm; k++) {
+            const float dx = 20.0f * k;
+            inst[k].inverseMatrix[0] = vec4(1, 0, 0, -dx); inst[k].inverseMatrix[1] = vec4(0, 1, 0, 0); inst[k].inverseMatrix[2] = vec4(0, 0, 1, 0);
+            inst[k].meshOffset = k; inst[k].mask = MaskAll | MaskShadow;
+            actor[k] = Volume::AABB(vec3(dx, -0.5f, 0.0f), vec3(dx + 10.0f, 0.5f, 10.0f));
+            ptrs[k] = &meshes[k];
+        }
+        RayTracing::World world;
+        ok = ok && RayTracing::UpdateForSoftwareRayTracing(inst, actor, ptrs, world);
+        std::vector<PackedRay> rays(nm), out;
+        for (int k = 0; k < nm; k++) {
+            rays[k].origin = vec4(20.0f * k + 5.1f, 30.0f, 4.9f, 0.0f);
+            memcpy(&rays[k].origin.w, &k, 4);
+            rays[k].direction = vec4(0.001f, -1.0f, 0.002f, 0.0f);
+        }
+        ok = ok && RayTracing::Tracer::HitClosest(world, rays, out);
+        for (int k = 0; ok && k < nm; k++) {
+            int hitID, hitInst;
+            memcpy(&hitID, &out[k].hit.y, 4);
+            memcpy(&hitInst, &out[k].hit.z, 4);
+            ok = hitID >= 0 && hitInst >= 0 && hitInst < nm && inst[hitInst].meshOffset == k && out[k].hit.x > 29.0f && out[k].hit.x < 31.0f;
+        }
+        std::thread releaser([&] { world.Release(); for (auto& m : meshes) m.Release(); });   // freed from yet another thread
+        releaser.join();
+        printf("meshes from exited worker threads + scene on the main thread: %s (%s)\n", ok ? "ok" : "MISMATCH", RayTracing::LastError().c_str());
+        failures += ok ? 0 : 1;
     }
     if (ref_shutdown) ref_shutdown();
     printf(failures ? "FAILED %d\n" : "ALL OK\n", failures);

@@ -34,6 +34,22 @@ for name, tris in CS.build_cases().items():
         small[name + "_nodes"], small[name + "_order"], small[name + "_flags"] = t.nodes, t.order, t.end_of_node
 for name, boxes in CS.tlas_cases().items():
     gold["tlas"][name] = digest(ref.build_tlas(boxes))
+
+# ---- real geometry shipped with the reference: copied here so they travel to the GPU box, digests made
+# by the reference builder. data/chromesphere.bin: 3840 float3 positions at byte 0, 3840 u16 indices at byte 122880
+# (data/chromesphere.gltf bufferViews 0 and 3); data/meshes/*.aemesh: the engine's own mesh files.
+import shutil
+from atlas_engine_b200 import capi
+REFDATA = "/root/reference/data"
+os.makedirs(os.path.join(HERE, "meshes"), exist_ok=True)
+shutil.copyfile(os.path.join(REFDATA, "chromesphere.bin"), os.path.join(HERE, "meshes", "chromesphere.bin"))
+for n in ("chromesphere", "capsule", "metallicwall"):
+    shutil.copyfile(os.path.join(REFDATA, "meshes", n + ".aemesh"), os.path.join(HERE, "meshes", n + ".aemesh"))
+gold["real"] = {}
+for name, tris in CS.real_mesh_cases().items():
+    t = ref.build_blas(W.tri_boxes(tris), tris, parallel=True)
+    gold["real"][name] = digest(t)
+    small["real_" + name + "_order"] = t.order
 with open(os.path.join(HERE, "build_hashes.json"), "w") as f:
     json.dump(gold, f, indent=1, sort_keys=True)
 np.savez_compressed(os.path.join(HERE, "build_small.npz"), **small)

@@ -184,3 +184,24 @@ def test_deep_chain_of_big_nodes(ctx, oracle):
     assert CS.same_tree(n, od, e, o)
     assert b.stats()["levels"] >= 40
     b.free()
+
+
+def test_plain_any_hit_after_culled_instances(ctx, oracle):
+    """Plain HitAny keeps the instance-space ray after an instance culled by the mask (bvh.hsh:387-390 restores only after
+    a BLAS exit); tests/test_oracle_anyhit_quirk.py pins the oracle against a literal transcription of the shader, here the
+    kernel must equal the oracle on the same kind of scene — for MASK_SHADOW shadow rays over instances without the bit."""
+    meshes = [W.uv_sphere(10, 6), W.heightfield(6, 6, spacing=0.5)]
+    mb = [np.concatenate([W.tri_boxes(t)[:, :3].min(0), W.tri_boxes(t)[:, 3:].max(0)]) for t in meshes]
+    ib, ir = W.random_instances(300, mb, seed=5, extent=(40.0, 8.0, 40.0), scale=(0.8, 2.5))
+    ir[::2, 15] = W.MASK_ALL
+    scene, osc = build_pair(ctx, oracle, meshes, ib, ir)
+    rays = W.random_rays(60000, ib[:, :3].min(0) - 1.0, ib[:, 3:].max(0) + 1.0, seed=12)
+    for mask in (W.MASK_SHADOW, W.MASK_ALL):
+        out = ctx.trace(scene, rays, any_hit=True, cull_mask=mask, t_max=80.0, flags=capi.COUNTERS)
+        gc = ctx.trace_counters()
+        ref, oc = oracle.trace(osc, rays, any_hit=True, cull_mask=mask, t_max=80.0, nthreads=8)
+        assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+        assert all(gc[k] == oc[k] for k in oc)
+    shadow, _ = oracle.trace(osc, rays, any_hit=True, cull_mask=W.MASK_SHADOW, t_max=80.0, nthreads=8)
+    closest = ctx.trace(scene, rays, cull_mask=W.MASK_SHADOW, t_max=80.0)      # HitClosest restores unconditionally
+    assert ((shadow[:, 9].view(np.int32) >= 0) != (closest[:, 9].view(np.int32) >= 0)).sum() > 0     # the quirk is exercised
