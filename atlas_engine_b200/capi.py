@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libatlas_rt.so")
 
 DEVICE_INPUT, DEVICE_OUTPUT, ASYNC, PER_RAY_TMAX, COUNTERS, OPACITY = 1, 2, 4, 8, 16, 32
+RAY_BINNING, ACCUM_TILE_ORDER, HITS_ONLY = 64, 128, 256
 MASK_ALL, MASK_SHADOW = 1 << 7, 1 << 6
 INF = 1e12
 STATUS = {0: "OK", -1: "ERR_INVALID", -2: "ERR_CUDA", -3: "ERR_OOM", -4: "ERR_UNSUPPORTED", -5: "ERR_STACK"}
@@ -56,7 +57,11 @@ SIGNATURES = {
     "atlas_rt_trace_any": (_i32, [_vp, _vp, _vp, _u64, _u32, _f32, _f32, _vp, _u32]),
     "atlas_rt_trace_counters": (_i32, [_vp, _vp]),
     "atlas_rt_generate_primary_rays": (_i32, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _u32]),
-    "atlas_rt_pathtrace_bounce": (_i32, [_vp, _vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, C.POINTER(_u64), _u32]),
+    "atlas_rt_sample_jitter": (None, [_i32, _vp]),
+    "atlas_rt_scene_set_materials": (_i32, [_vp, _vp, _vp, _u32, _vp, _u32]),
+    "atlas_rt_pathtrace_bounce": (_i32, [_vp, _vp, _vp, _f32, _u32, _vp, _vp, _u64, _vp, _vp, _vp, _u32, _u32, C.POINTER(_u64), _u32]),
+    "atlas_rt_pathtrace_bounces": (_i32, [_vp, _vp, _vp, _u32, _u32, _vp, _u32, _i32, _vp, _u64, _u64, _vp, C.POINTER(_u64), _u32]),
+    "atlas_rt_bin_rays": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _u32]),
     "atlas_rt_shard_range": (_i32, [_u64, _u32, _u32, _u32, C.POINTER(_u64), C.POINTER(_u64)]),
 }
 
@@ -88,10 +93,47 @@ class Camera(C.Structure):
     _fields_ = [("eye", _f32 * 3), ("origin", _f32 * 3), ("right", _f32 * 3), ("bottom", _f32 * 3)]
 
 
-class BounceParams(C.Structure):
-    """atlas_rt_bounce_params"""
-    _fields_ = [("light_dir", _f32 * 3), ("light_radiance", _f32 * 3), ("albedo", _f32 * 3), ("sky_radiance", _f32 * 3),
-                ("seed", _f32), ("bounce", _u32), ("max_bounces", _u32), ("samples", _u32)]
+class PtParams(C.Structure):
+    """atlas_rt_pt_params"""
+    _fields_ = [("light_dir", _f32 * 3), ("light_radiance", _f32 * 3), ("light_count", _i32), ("sky_radiance", _f32 * 3),
+                ("max_bounces", _u32), ("samples_per_frame", _u32)]
+
+
+def pt_params(light_dir, light_radiance, sky_radiance, max_bounces, samples_per_frame=1, light_count=1):
+    return PtParams((_f32 * 3)(*light_dir), (_f32 * 3)(*light_radiance), light_count, (_f32 * 3)(*sky_radiance), max_bounces, samples_per_frame)
+
+
+class Texture(C.Structure):
+    """atlas_rt_texture"""
+    _fields_ = [("width", _u32), ("height", _u32), ("texels", _vp)]
+
+
+# atlas_rt_material / RaytraceMaterial (data/shader/raytracer/structures.hsh:108-141): 23 words
+MATERIAL_DTYPE = np.dtype([("ID", np.int32), ("baseR", np.float32), ("baseG", np.float32), ("baseB", np.float32),
+                           ("emissR", np.float32), ("emissG", np.float32), ("emissB", np.float32), ("opacity", np.float32),
+                           ("roughness", np.float32), ("metalness", np.float32), ("ao", np.float32), ("reflectance", np.float32),
+                           ("normalScale", np.float32), ("invertUVs", np.int32), ("twoSided", np.int32), ("cullBackFaces", np.int32),
+                           ("useVertexColors", np.int32), ("baseColorTexture", np.int32), ("opacityTexture", np.int32),
+                           ("normalTexture", np.int32), ("roughnessTexture", np.int32), ("metalnessTexture", np.int32), ("aoTexture", np.int32)])
+
+
+def make_materials(n):
+    """n default materials: grey, opaque, rough dielectric, two-sided, no textures."""
+    m = np.zeros(n, dtype=MATERIAL_DTYPE)
+    m["ID"] = np.arange(n)
+    m["baseR"] = m["baseG"] = m["baseB"] = 0.8
+    m["opacity"] = m["roughness"] = m["ao"] = 1.0
+    m["reflectance"] = 0.5
+    m["twoSided"] = 1
+    for k in ("baseColorTexture", "opacityTexture", "normalTexture", "roughnessTexture", "metalnessTexture", "aoTexture"):
+        m[k] = -1
+    return m
+
+
+def sample_jitter(sample_count):
+    out = np.zeros(2, dtype=np.float32)
+    lib().atlas_rt_sample_jitter(sample_count, _addr(out))
+    return out
 
 
 def _addr(x):
@@ -231,7 +273,7 @@ class Context:
             self.check(fn(self.h, scene.h, _addr(rays), count, cull_mask, t_min, t_max, _addr(out), flags | DEVICE_INPUT | DEVICE_OUTPUT))
             return None
         rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 12)
-        res = np.empty_like(rays) if out is None else out
+        res = (np.empty((rays.shape[0], 4), np.float32) if flags & HITS_ONLY else np.empty_like(rays)) if out is None else out
         self.check(fn(self.h, scene.h, _addr(rays), rays.shape[0], cull_mask, t_min, t_max, _addr(res), flags))
         return res
 
@@ -247,13 +289,29 @@ class Context:
         self.check(self.L.atlas_rt_generate_primary_rays(self.h, C.byref(cam), width, height, samples, _addr(jit), _addr(out), DEVICE_OUTPUT))
         return out
 
-    def pathtrace_bounce(self, scene, params, rays_in, payload_in, count, rays_out, payload_out, accum):
-        """One diffuse bounce on device buffers; returns the number of surviving rays (compacted into rays_out)."""
+    def pathtrace_bounce(self, scene, params, seed, bounce, rays_in, payload_in, count, rays_out, payload_out, accum, width, height, flags=0):
+        """One bounce (traceClosest + rayHit.csh) on device buffers; returns the number of surviving rays (compacted into rays_out)."""
         n = _u64()
-        self.check(self.L.atlas_rt_pathtrace_bounce(self.h, scene.h, C.byref(params), _addr(rays_in), _addr(payload_in), count,
-                                                    _addr(rays_out), _addr(payload_out), _addr(accum), C.byref(n),
-                                                    DEVICE_INPUT | DEVICE_OUTPUT))
+        self.check(self.L.atlas_rt_pathtrace_bounce(self.h, scene.h, C.byref(params), seed, bounce, _addr(rays_in), _addr(payload_in), count,
+                                                    _addr(rays_out), _addr(payload_out), _addr(accum), width, height, C.byref(n),
+                                                    flags | DEVICE_INPUT | DEVICE_OUTPUT))
         return int(n.value)
+
+    def pathtrace_bounces(self, scene, camera, width, height, params, frames, first_sample_count, seeds, accum, slot_begin=0, slot_end=0,
+                          flags=0, count_rays=True):
+        """`frames` sample passes with the whole bounce loop on the device; returns the closest-hit rays traced (or None)."""
+        eye, origin, right, bottom = camera
+        cam = Camera((_f32 * 3)(*eye), (_f32 * 3)(*origin), (_f32 * 3)(*right), (_f32 * 3)(*bottom))
+        seeds = np.ascontiguousarray(seeds, dtype=np.float32)
+        assert seeds.size == frames * (params.max_bounces + 1)
+        n = _u64()
+        self.check(self.L.atlas_rt_pathtrace_bounces(self.h, scene.h, C.byref(cam), width, height, C.byref(params), frames, first_sample_count,
+                                                     _addr(seeds), slot_begin, slot_end, _addr(accum), C.byref(n) if count_rays else None, flags))
+        return int(n.value) if count_rays else None
+
+    def bin_rays(self, rays_in, payload_in, count, rays_out, payload_out, flags=0):
+        self.check(self.L.atlas_rt_bin_rays(self.h, _addr(rays_in), _addr(payload_in), count, _addr(rays_out), _addr(payload_out),
+                                            flags | DEVICE_INPUT | DEVICE_OUTPUT))
 
     def trace_counters(self):
         out = np.zeros(6, dtype=np.uint64)
@@ -344,6 +402,13 @@ class Mesh:
 class Scene:
     def __init__(self, ctx, h, meshes, tlas):
         self.ctx, self.h, self.meshes, self.tlas = ctx, h, list(meshes), tlas
+
+    def set_materials(self, materials, textures=()):
+        """materials: array of MATERIAL_DTYPE (or (k, 23) words); textures: list of (h, w) uint8 arrays (R8 opacity maps)."""
+        mats = np.ascontiguousarray(materials).view(np.uint32).reshape(-1, 23)
+        tex = [np.ascontiguousarray(t, dtype=np.uint8) for t in textures]
+        arr = (Texture * max(1, len(tex)))(*[Texture(t.shape[1], t.shape[0], t.ctypes.data) for t in tex])
+        self.ctx.check(self.ctx.L.atlas_rt_scene_set_materials(self.ctx.h, self.h, _addr(mats), mats.shape[0], arr if tex else None, len(tex)))
 
     def download(self):
         n, m = self.tlas.counts()

@@ -184,7 +184,7 @@ int atlas_rt_context_create(int device, void* stream, atlas_rt_context** out_ctx
     if (const char* e = getenv("ATLAS_RT_TRACE_BLOCKS_PER_SM")) ctx->traceBlocksPerSM = std::max(1, std::min(9, atoi(e)));
     if (const char* e = getenv("ATLAS_RT_BIN_CTAS_PER_SM")) ctx->binCtasPerSM = std::max(1, std::min(8, atoi(e)));
     if (const char* e = getenv("ATLAS_RT_CHAIN_LAUNCH")) ctx->chainLaunch = atoi(e);
-    if (const char* e = getenv("ATLAS_RT_BATCH_WORKERS")) ctx->batchWorkers = std::max(1, std::min(8, atoi(e)));
+    if (const char* e = getenv("ATLAS_RT_BATCH_WORKERS")) ctx->batchWorkers = std::max(1, std::min(16, atoi(e)));
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t keep = ~0ull;
@@ -583,6 +583,43 @@ int atlas_rt_scene_create(atlas_rt_context* ctx, const atlas_rt_mesh* const* mes
     return ATLAS_RT_OK;
 }
 
+int atlas_rt_scene_set_materials(atlas_rt_context* ctx, atlas_rt_scene* scene, const atlas_rt_material* materials, uint32_t material_count,
+                                 const atlas_rt_texture* textures, uint32_t texture_count) {
+    static_assert(sizeof(atlas_rt_material) == 92, "RaytraceMaterial is 23 words");
+    if (!ctx || !scene || !same_device(scene->ctx, ctx) || (material_count && !materials) || (texture_count && !textures)) return fail(ctx, ATLAS_RT_ERR_INVALID, "bad argument");
+    ATLAS_CUDA(ctx, cudaSetDevice(ctx->device));
+    ATLAS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // nothing may still be reading the old tables
+    dev_free(ctx, scene->materials); dev_free(ctx, scene->textures); dev_free(ctx, scene->texelStorage);
+    scene->materials = nullptr; scene->textures = nullptr; scene->texelStorage = nullptr;
+    scene->materialCount = scene->textureCount = 0;
+    size_t texelBytes = 0;
+    for (uint32_t t = 0; t < texture_count; t++) {
+        if (!textures[t].texels || !textures[t].width || !textures[t].height) return fail(ctx, ATLAS_RT_ERR_INVALID, "empty texture");
+        texelBytes += (size_t(textures[t].width) * textures[t].height + 15) & ~size_t(15);
+    }
+    if (material_count) {
+        ATLAS_CUDA(ctx, dev_alloc(ctx, &scene->materials, size_t(material_count) * 23));
+        ATLAS_CUDA(ctx, cudaMemcpyAsync(scene->materials, materials, size_t(material_count) * 92, cudaMemcpyHostToDevice, ctx->stream));
+        scene->materialCount = material_count;
+    }
+    std::vector<TextureDev> table(texture_count);
+    if (texture_count) {
+        ATLAS_CUDA(ctx, dev_alloc(ctx, &scene->texelStorage, texelBytes));
+        ATLAS_CUDA(ctx, dev_alloc(ctx, &scene->textures, texture_count));
+        size_t off = 0;
+        for (uint32_t t = 0; t < texture_count; t++) {
+            const size_t bytes = size_t(textures[t].width) * textures[t].height;
+            ATLAS_CUDA(ctx, cudaMemcpyAsync(scene->texelStorage + off, textures[t].texels, bytes, cudaMemcpyHostToDevice, ctx->stream));
+            table[t] = TextureDev{scene->texelStorage + off, textures[t].width, textures[t].height};
+            off += (bytes + 15) & ~size_t(15);
+        }
+        ATLAS_CUDA(ctx, cudaMemcpyAsync(scene->textures, table.data(), texture_count * sizeof(TextureDev), cudaMemcpyHostToDevice, ctx->stream));
+        scene->textureCount = texture_count;
+    }
+    ATLAS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // host arrays (caller's and `table`) are free to go
+    return ATLAS_RT_OK;
+}
+
 int atlas_rt_scene_download(const atlas_rt_scene* scene, void* instances64, void* tlas_nodes64, uint32_t flags) {
     if (!scene) return ATLAS_RT_ERR_INVALID;
     atlas_rt_context* ctx = scene->ctx;
@@ -601,6 +638,9 @@ void atlas_rt_scene_free(atlas_rt_scene* scene) {
     dev_free(ctx, scene->blasNodes);
     dev_free(ctx, scene->bvhTris);
     dev_free(ctx, scene->triangles);
+    dev_free(ctx, scene->materials);
+    dev_free(ctx, scene->textures);
+    dev_free(ctx, scene->texelStorage);
     delete scene;
     ctx_release(ctx);
 }
@@ -618,9 +658,16 @@ static int trace_common(atlas_rt_context* ctx, const atlas_rt_scene* scene, cons
         ATLAS_CUDA(ctx, dev_alloc(ctx, &dIn, count * 3));
         in = dIn;
     }
+    // ATLAS_RT_HITS_ONLY: the output is one 16-byte hit record per ray (never in place on the 48-byte rays)
+    const bool hitsOnly = (flags & ATLAS_RT_HITS_ONLY) != 0;
+    const size_t outStride = hitsOnly ? 1 : 3;   // float4s per ray in the output
     if (!devOut) {
-        if (dIn) out = dIn;   // in-place on the staging buffer
-        else { ATLAS_CUDA(ctx, dev_alloc(ctx, &dOut, count * 3)); out = dOut; }
+        if (dIn && !hitsOnly) out = dIn;   // in-place on the staging buffer
+        else {
+            const cudaError_t ea = dev_alloc(ctx, &dOut, count * outStride);
+            if (ea != cudaSuccess) { dev_free(ctx, dIn); return fail(ctx, ATLAS_RT_ERR_CUDA, "output staging", ea); }
+            out = dOut;
+        }
     }
     const bool perRay = (flags & ATLAS_RT_PER_RAY_TMAX) != 0, counters = (flags & ATLAS_RT_COUNTERS) != 0;
     const bool opacity = (flags & ATLAS_RT_OPACITY) != 0;
@@ -667,19 +714,19 @@ static int trace_common(atlas_rt_context* ctx, const atlas_rt_scene* scene, cons
         for (uint32_t c = 0; c < chunks && e == cudaSuccess && rc == ATLAS_RT_OK; c++) {
             const uint64_t b = uint64_t(count * cut[c]) & ~uint64_t(31), end = c + 1 == chunks ? count : (uint64_t(count * cut[c + 1]) & ~uint64_t(31));
             const char* hIn = static_cast<const char*>(rays_in) + 48 * b;
-            char* hOut = static_cast<char*>(rays_out) + 48 * b;
+            char* hOut = static_cast<char*>(rays_out) + 16 * outStride * b;
             const int slot = int(c % nStreams);
             cudaStream_t cs = slot ? ctx->computeExtra[slot - 1] : ctx->stream;
             e = cudaMemcpyAsync(dIn + 3 * b, hIn, 48 * (end - b), cudaMemcpyHostToDevice, ctx->copyIn);
             if (e == cudaSuccess) e = cudaEventRecord(ev[1 + c], ctx->copyIn);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, ev[1 + c], 0);
             if (e != cudaSuccess) break;
-            float4* dst = devOut ? out + 3 * b : dIn + 3 * b;   // host output: in place on the staging buffer
-            rc = launch_trace(ctx, scene, dIn + 3 * b, dst, end - b, cull_mask, t_min, t_max, any, perRay, counters, false, opacity, cs, slot);
+            float4* dst = out + outStride * b;   // host output of whole rays: in place on the staging buffer (out == dIn)
+            rc = launch_trace(ctx, scene, dIn + 3 * b, dst, end - b, cull_mask, t_min, t_max, any, perRay, counters, false, opacity, cs, slot, nullptr, hitsOnly);
             if (rc != ATLAS_RT_OK) break;
             e = cudaEventRecord(ev[17 + c], cs);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copyOut, ev[17 + c], 0);
-            if (e == cudaSuccess && !devOut) e = cudaMemcpyAsync(hOut, dIn + 3 * b, 48 * (end - b), cudaMemcpyDeviceToHost, ctx->copyOut);
+            if (e == cudaSuccess && !devOut) e = cudaMemcpyAsync(hOut, dst, 16 * outStride * (end - b), cudaMemcpyDeviceToHost, ctx->copyOut);
         }
         if (e == cudaSuccess) e = cudaEventRecord(ev[33], ctx->copyOut);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev[33], 0);   // the context stream now orders after the downloads
@@ -689,9 +736,9 @@ static int trace_common(atlas_rt_context* ctx, const atlas_rt_scene* scene, cons
             cudaError_t e = copy_in(ctx, dIn, rays_in, count * 48, false);
             if (e != cudaSuccess) rc = fail(ctx, ATLAS_RT_ERR_CUDA, "copy_in", e);
         }
-        if (rc == ATLAS_RT_OK) rc = launch_trace(ctx, scene, in, out, count, cull_mask, t_min, t_max, any, perRay, counters, true, opacity);
+        if (rc == ATLAS_RT_OK) rc = launch_trace(ctx, scene, in, out, count, cull_mask, t_min, t_max, any, perRay, counters, true, opacity, nullptr, 0, nullptr, hitsOnly);
         if (rc == ATLAS_RT_OK && !devOut) {
-            cudaError_t e = copy_out(ctx, rays_out, out, count * 48, false);
+            cudaError_t e = copy_out(ctx, rays_out, out, count * 16 * outStride, false);
             if (e != cudaSuccess) rc = fail(ctx, ATLAS_RT_ERR_CUDA, "copy_out", e);
         }
     }

@@ -7,6 +7,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 #include <atomic>
@@ -98,7 +99,7 @@ struct atlas_rt_context {
     int traceLongestFirstMin = 65536;
     int traceRaysPerWarp = 96;      // small batches use fewer persistent warps so each warp still sees this many rays
     // worker contexts (own stream + own pinned level flags each) that atlas_rt_build_blas_batch builds on side by side
-    atlas_rt_context* workers[8] = {};
+    atlas_rt_context* workers[16] = {};
     int batchWorkers = 8;
 };
 
@@ -119,6 +120,27 @@ struct atlas_rt_mesh {
     float4* tris96 = nullptr;     // GPUTriangle, 6 x float4 each (only after atlas_rt_mesh_pack_shading)
 };
 
+// R8 texture on the device (opacity maps): texels row-major, width * height bytes.
+struct TextureDev {
+    const uint8_t* texels;
+    uint32_t width, height;
+};
+
+// textureLod(sampler2D(...), uv, 0).r for an R8 texture: bilinear filter, repeat addressing, texel centres at (i + 0.5) / size.
+// Weights are kept in full fp32 (graphics hardware filters with 8 fractional bits; the difference is below 1/256 of a texel
+// step and documented in DESIGN.md).
+__device__ __forceinline__ float sample_r8(const TextureDev& t, float u, float v) {
+    const float x = __fsub_rn(__fmul_rn(u, float(t.width)), 0.5f), y = __fsub_rn(__fmul_rn(v, float(t.height)), 0.5f);
+    const float fx = floorf(x), fy = floorf(y);
+    const float wx = __fsub_rn(x, fx), wy = __fsub_rn(y, fy);
+    auto wrap = [](float f, uint32_t n) { long long i = (long long)f % (long long)n; if (i < 0) i += n; return uint32_t(i); };
+    const uint32_t x0 = wrap(fx, t.width), x1 = wrap(__fadd_rn(fx, 1.0f), t.width), y0 = wrap(fy, t.height), y1 = wrap(__fadd_rn(fy, 1.0f), t.height);
+    auto tx = [&](uint32_t xx, uint32_t yy) { return __fdiv_rn(float(t.texels[size_t(yy) * t.width + xx]), 255.0f); };
+    const float top = __fadd_rn(__fmul_rn(tx(x0, y0), __fsub_rn(1.0f, wx)), __fmul_rn(tx(x1, y0), wx));
+    const float bot = __fadd_rn(__fmul_rn(tx(x0, y1), __fsub_rn(1.0f, wx)), __fmul_rn(tx(x1, y1), wx));
+    return __fadd_rn(__fmul_rn(top, __fsub_rn(1.0f, wy)), __fmul_rn(bot, wy));
+}
+
 struct atlas_rt_scene {
     atlas_rt_context* ctx = nullptr;
     const atlas_rt_bvh* tlas = nullptr;
@@ -130,6 +152,12 @@ struct atlas_rt_scene {
     const float4** triangles = nullptr;      // device array [meshCount] of 96-byte triangle arrays (entries may be null)
     bool allShading = false;                 // every mesh has its 96-byte array: the opacity-aware variants may run
     int fastDivision = 0;                    // all scene coordinates below 2^60: slab tests may use div_by_rcp (trace.cu)
+    // material / texture tables (atlas_rt_scene_set_materials): textured opacity in traversal, shading in the path tracer
+    uint32_t* materials = nullptr;           // RaytraceMaterial, 23 words each
+    uint32_t materialCount = 0;
+    TextureDev* textures = nullptr;
+    uint32_t textureCount = 0;
+    uint8_t* texelStorage = nullptr;
 };
 
 namespace atlas {
@@ -211,6 +239,7 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
 int scene_fast_flag(atlas_rt_context* ctx, atlas_rt_scene* scene, const uint32_t* dNodeCounts);
 int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float4* dIn, float4* dOut, uint64_t count,
                  uint32_t cullMask, float tMin, float tMax, bool any, bool perRayTMax, bool counters, bool resetCounters = true,
-                 bool opacity = false, cudaStream_t st = nullptr /* context stream */, int queueSlot = 0);
+                 bool opacity = false, cudaStream_t st = nullptr /* context stream */, int queueSlot = 0,
+                 const uint32_t* dCount = nullptr /* batch size on the device (<= count) */, bool hitsOnly = false /* dOut = 16-byte hit records */);
 
 }   // namespace atlas

@@ -30,7 +30,30 @@ struct SceneDev {
     const float4* const* blasNodes;
     const float4* const* bvhTris;
     const float4* const* triangles;   // 96-byte GPUTriangle arrays (opacity-aware variants)
+    const uint32_t* materials;        // RaytraceMaterial records, 23 words each (null: textured opacity counts as 1)
+    const TextureDev* textures;       // R8 opacity textures
+    uint32_t materialCount, textureCount;
 };
+
+// GetOpacity, data/shader/raytracer/surface.hsh:147-160: texture coordinates interpolated from the triangle's half2 words
+// (d0.xyz), flipped for invertUVs, the material's opacity texture sampled bilinearly at mip 0, times the material opacity.
+__device__ __forceinline__ float get_opacity(const SceneDev& sc, const float4 d0, float s, float t, int materialOffset) {
+    if (!sc.materials) return 1.0f;
+    const uint32_t mi = uint32_t(__float_as_int(d0.w) + materialOffset);
+    if (mi >= sc.materialCount) return 1.0f;
+    const uint32_t* M = sc.materials + 23 * size_t(mi);
+    const float r = __fsub_rn(__fsub_rn(1.0f, s), t);
+    const uint32_t w0 = __float_as_uint(d0.x), w1 = __float_as_uint(d0.y), w2 = __float_as_uint(d0.z);
+    const float u0 = __half2float(__ushort_as_half(uint16_t(w0))), v0 = __half2float(__ushort_as_half(uint16_t(w0 >> 16)));
+    const float u1 = __half2float(__ushort_as_half(uint16_t(w1))), v1 = __half2float(__ushort_as_half(uint16_t(w1 >> 16)));
+    const float u2 = __half2float(__ushort_as_half(uint16_t(w2))), v2 = __half2float(__ushort_as_half(uint16_t(w2 >> 16)));
+    const float u = __fadd_rn(__fadd_rn(__fmul_rn(r, u0), __fmul_rn(s, u1)), __fmul_rn(t, u2));
+    float v = __fadd_rn(__fadd_rn(__fmul_rn(r, v0), __fmul_rn(s, v1)), __fmul_rn(t, v2));
+    if (int(M[13]) > 0) v = __fsub_rn(1.0f, v);                      // invertUVs
+    const int tex = int(M[18]);                                      // opacityTexture
+    const float texel = (tex < 0 || uint32_t(tex) >= sc.textureCount) ? 1.0f : sample_r8(sc.textures[tex], u, v);
+    return __fmul_rn(texel, __uint_as_float(M[7]));                  // * rayMat.opacity
+}
 
 // 256-bit read-only load (sm_100: LDG.E.256). A 64-byte node or instance record is two of these instead of four
 // 128-bit loads, which halves the L1TEX wavefronts per visit — the unit the traversal saturates (profiles/: l1tex
@@ -146,10 +169,11 @@ constexpr int kBlocksPerSM = 9;
 template <bool ANY, bool COUNT, bool OPACITY>
 __global__ void __launch_bounds__(kTraceBlock, kBlocksPerSM)
 trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restrict__ permIn, const unsigned int* __restrict__ usePerm,
-             uint32_t count, uint32_t cullMask, float tMin, float tMaxArg,
-             int perRayTMax, int sceneFast, int kLeafThreshold, int kRefillThreshold, unsigned int* __restrict__ rayCounter,
+             uint32_t count, const uint32_t* __restrict__ countPtr, uint32_t cullMask, float tMin, float tMaxArg,
+             int perRayTMax, int sceneFast, int hitsOnly, int kLeafThreshold, int kRefillThreshold, unsigned int* __restrict__ rayCounter,
              unsigned long long* __restrict__ counters) {
     chain_begin();
+    if (countPtr) count = min(count, *countPtr);   // batch size produced on the device (path-tracer bounces): no host round trip
     __shared__ int stack[kStack][kTraceBlock];
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     const unsigned ltMask = (1u << lane) - 1u;
@@ -159,7 +183,7 @@ trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restr
 
     bool alive = false, fast = false, moreRays = true, overflow = false;
     uint32_t ray = 0, sp = 0, tlasIndex = kTlasInvalid;
-    int nodePtr = 0, curInst = 0, hitID = -1, hitInst = 0;
+    int nodePtr = 0, curInst = 0, hitID = -1, hitInst = 0, matOffset = 0;
     float o[3] = {0, 0, 0}, d[3] = {1, 1, 1}, rc[3] = {1, 1, 1};
     float tMax = tMaxArg, hitT = 0.0f, baryU = 0.0f, baryV = 0.0f;
     float transparency = 1.0f;   // HitAnyTransparency's accumulator; reported in direction.w
@@ -167,11 +191,15 @@ trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restr
     const float4* tris = nullptr;
     uint32_t cTlas = 0, cInst = 0, cBlas = 0, cTri = 0, cMaxSp = 1;
 
-    const bool inPlace = in == out;   // origin, ID and direction are already where they belong
+    const bool inPlace = in == out || hitsOnly;   // origin, ID and direction are already where they belong (or not wanted)
     auto finish = [&]() {   // PackRay, common.hsh:61-73 (+ barycentrics in the two lanes GLSL leaves unwritten)
         // origin, ID and direction were passed through when the ray was fetched; only the hit fields are written here
-        reinterpret_cast<float*>(out + 3 * size_t(ray) + 1)[3] = (ANY && OPACITY) ? transparency : baryU;
-        out[3 * size_t(ray) + 2] = make_float4(hitT, __int_as_float(hitID), __int_as_float(hitInst), baryV);
+        if (hitsOnly) {   // compact 16-byte hit stream (the ray's `hit` vec4) for the multi-GPU gather
+            out[ray] = make_float4(hitT, __int_as_float(hitID), __int_as_float(hitInst), (ANY && OPACITY) ? transparency : baryV);
+        } else {
+            reinterpret_cast<float*>(out + 3 * size_t(ray) + 1)[3] = (ANY && OPACITY) ? transparency : baryU;
+            out[3 * size_t(ray) + 2] = make_float4(hitT, __int_as_float(hitID), __int_as_float(hitInst), baryV);
+        }
         alive = false;
     };
     auto set_ray = [&](const float oo[3], const float dd[3]) {
@@ -262,6 +290,7 @@ trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restr
                     nd[2] = __fadd_rn(dot3(d[0], d[1], d[2], c2.x, c2.y, c2.z), __fmul_rn(0.0f, c2.w));
                     curInst = inst;
                     const int meshPtr = __float_as_int(c3.x);
+                    if (OPACITY) matOffset = __float_as_int(c3.y);
                     const uint32_t mask = uint32_t(__float_as_int(c3.w));
                     nodePtr = 0;
                     if ((mask & cullMask) > 0u) {
@@ -285,15 +314,15 @@ trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restr
                     const float tmaxLeaf = ANY ? tMax : hitT;
                     float leafTransparency = transparency;
                     while (!end && !(ANY && !OPACITY && hit)) {
-                        float4 a, b, c;
+                        float4 a, b, c, d0 = make_float4(0, 0, 0, 0);
                         float triOpacity = 1.0f;
                         if (OPACITY) {
                             const float4* T = tris + 6 * size_t(triPtr);   // 96-byte records: three 256-bit loads
                             const Float8 tA = ldg256(T), tB = ldg256(T + 2), tC = ldg256(T + 4);
-                            a = tA.a; b = tA.b; c = tB.a;
+                            a = tA.a; b = tA.b; c = tB.a; d0 = tB.b;
                             const float4 d1 = tC.a, d2 = tC.b;
                             end = d1.z > 0.0f;
-                            triOpacity = d2.w < 0.0f ? 1.0f : d2.w;   // textured opacity is outside this path
+                            triOpacity = d2.w;   // < 0: textured, resolved with the hit's barycentrics below
                         } else {
                             const float4* T = tris + 3 * size_t(triPtr);
                             a = __ldg(T); b = __ldg(T + 1); c = __ldg(T + 2);
@@ -303,6 +332,9 @@ trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restr
                         float sol[3];
                         const bool inside = tri_test(o, d, a, b, c, sol);
                         if (inside && sol[0] > tMin && sol[0] < tmaxLeaf) {
+                            // tri.opacity < 0 ? GetOpacity(tri, sol.yz, materialOffset, 0) : tri.opacity (bvh.hsh:127, :163); the
+                            // closest-hit variant only evaluates it for a candidate that is nearer than the current hit
+                            if (OPACITY && triOpacity < 0.0f && (ANY || sol[0] < hitT)) triOpacity = get_opacity(sc, d0, sol[1], sol[2], matOffset);
                             if (OPACITY && ANY) {
                                 hitT = sol[0];
                                 hitID = triPtr;
@@ -415,9 +447,10 @@ __device__ __forceinline__ void scene_box(const float4* __restrict__ tlasNodes, 
 }
 
 __global__ void __launch_bounds__(kSortBlock)
-ray_cost_histogram(const float4* __restrict__ rays, uint32_t count, const float4* __restrict__ tlasNodes, uint8_t* __restrict__ bucketOf,
-                   unsigned int* __restrict__ hist) {
+ray_cost_histogram(const float4* __restrict__ rays, uint32_t count, const uint32_t* __restrict__ countPtr, const float4* __restrict__ tlasNodes,
+                   uint8_t* __restrict__ bucketOf, unsigned int* __restrict__ hist) {
     chain_begin();
+    if (countPtr) count = min(count, *countPtr);
     __shared__ unsigned int sh[kCostBuckets + 1];   // [kCostBuckets] = pairs of neighbouring rays that are coherent
     if (threadIdx.x <= kCostBuckets) sh[threadIdx.x] = 0;
     __syncthreads();
@@ -454,8 +487,9 @@ ray_cost_histogram(const float4* __restrict__ rays, uint32_t count, const float4
     if (threadIdx.x <= kCostBuckets && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
 }
 
-__global__ void ray_cost_offsets(unsigned int* __restrict__ hist, uint32_t count) {   // exclusive prefix over 64 buckets, in place (one warp)
+__global__ void ray_cost_offsets(unsigned int* __restrict__ hist, uint32_t count, const uint32_t* __restrict__ countPtr) {   // exclusive prefix over 64 buckets, in place (one warp)
     chain_begin();
+    if (countPtr) count = min(count, *countPtr);
     const unsigned lane = threadIdx.x;
     // hist[kCostBuckets + 1] = 1 when the batch should be reordered: coherent batches (most neighbours are near copies)
     // keep their own order, which is worth more than starting the long rays first
@@ -473,8 +507,10 @@ __global__ void ray_cost_offsets(unsigned int* __restrict__ hist, uint32_t count
 }
 
 __global__ void __launch_bounds__(kSortBlock)
-ray_cost_scatter(const uint8_t* __restrict__ bucketOf, uint32_t count, unsigned int* __restrict__ offsets, uint32_t* __restrict__ perm) {
+ray_cost_scatter(const uint8_t* __restrict__ bucketOf, uint32_t count, const uint32_t* __restrict__ countPtr, unsigned int* __restrict__ offsets,
+                 uint32_t* __restrict__ perm) {
     chain_begin();
+    if (countPtr) count = min(count, *countPtr);
     __shared__ unsigned int cnt[kCostBuckets], base[kCostBuckets];
     if (offsets[kCostBuckets + 1] == 0u) return;   // coherent batch: the trace kernel ignores the permutation
     if (threadIdx.x < kCostBuckets) cnt[threadIdx.x] = 0;
@@ -536,11 +572,12 @@ int scene_fast_flag(atlas_rt_context* ctx, atlas_rt_scene* scene, const uint32_t
 
 int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float4* dIn, float4* dOut, uint64_t count,
                  uint32_t cullMask, float tMin, float tMax, bool any, bool perRayTMax, bool counters, bool resetCounters, bool opacity,
-                 cudaStream_t st, int queueSlot) {
+                 cudaStream_t st, int queueSlot, const uint32_t* dCount, bool hitsOnly) {
     if (!st) st = ctx->stream;
     if (count == 0) return ATLAS_RT_OK;
     if (count > 0x7fffffffull) return fail(ctx, ATLAS_RT_ERR_UNSUPPORTED, "more than 2^31-1 rays in one batch");
-    SceneDev sc{scene->tlas->nodes, scene->instances, scene->blasNodes, scene->bvhTris, scene->triangles};
+    SceneDev sc{scene->tlas->nodes, scene->instances, scene->blasNodes, scene->bvhTris, scene->triangles,
+                scene->materials, scene->textures, scene->materialCount, scene->textureCount};
     const uint32_t n = uint32_t(count);
     // small batches get fewer persistent warps so that each still refills its lanes many times (>= traceRaysPerWarp rays per warp)
     const uint32_t wantBlocks = std::max<uint32_t>(uint32_t(ctx->smCount) * 2u, n / (uint32_t(ctx->traceRaysPerWarp) * (kTraceBlock / 32)));
@@ -562,17 +599,17 @@ int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float
         ATLAS_CUDA(ctx, cudaMemsetAsync(hist, 0, (kCostBuckets + 2) * sizeof(unsigned int), st));
         const uint32_t sortGrid = (n + kSortBlock * kSortPerThread - 1) / (kSortBlock * kSortPerThread);
         const bool pdl = ctx->chainLaunch != 0;
-        ATLAS_CUDA(ctx, launch_chain(pdl, ray_cost_histogram, sortGrid, kSortBlock, 0, st, dIn, n, scene->tlas->nodes, bucketOf, hist));
+        ATLAS_CUDA(ctx, launch_chain(pdl, ray_cost_histogram, sortGrid, kSortBlock, 0, st, dIn, n, dCount, scene->tlas->nodes, bucketOf, hist));
         ctx->launches++;
-        ATLAS_CUDA(ctx, launch_chain(pdl, ray_cost_offsets, 1, 32, 0, st, hist, n));
+        ATLAS_CUDA(ctx, launch_chain(pdl, ray_cost_offsets, 1, 32, 0, st, hist, n, dCount));
         ctx->launches++;
-        ATLAS_CUDA(ctx, launch_chain(pdl, ray_cost_scatter, sortGrid, kSortBlock, 0, st, bucketOf, n, hist, perm));
+        ATLAS_CUDA(ctx, launch_chain(pdl, ray_cost_scatter, sortGrid, kSortBlock, 0, st, bucketOf, n, dCount, hist, perm));
         ctx->launches++;
     }
-    const int pr = perRayTMax ? 1 : 0, sf = scene->fastDivision;
+    const int pr = perRayTMax ? 1 : 0, sf = scene->fastDivision, ho = hitsOnly ? 1 : 0;
     cudaError_t launchErr = cudaSuccess;
 #define ATLAS_TRACE_LAUNCH(A, C, O) \
-    launchErr = launch_chain(ctx->chainLaunch != 0, trace_kernel<A, C, O>, grid, kTraceBlock, 0, st, sc, dIn, dOut, perm, hist ? hist + kCostBuckets + 1 : nullptr, n, cullMask, tMin, tMax, pr, sf, lt, rt, rayCounter, ctx->dCounters)
+    launchErr = launch_chain(ctx->chainLaunch != 0, trace_kernel<A, C, O>, grid, kTraceBlock, 0, st, sc, dIn, dOut, perm, hist ? hist + kCostBuckets + 1 : nullptr, n, dCount, cullMask, tMin, tMax, pr, sf, ho, lt, rt, rayCounter, ctx->dCounters)
     if (opacity) {
         if (any) { if (counters) ATLAS_TRACE_LAUNCH(true, true, true); else ATLAS_TRACE_LAUNCH(true, false, true); }
         else { if (counters) ATLAS_TRACE_LAUNCH(false, true, true); else ATLAS_TRACE_LAUNCH(false, false, true); }

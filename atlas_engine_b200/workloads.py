@@ -299,3 +299,24 @@ def geometric_clusters(clusters=150, per_cluster=1500, ratio=1.5, seed=77):
         off = (rng.random((per_cluster, 3, 3), dtype=np.float32) - np.float32(0.5)) * np.float32(0.002) * x
         out[k * per_cluster:(k + 1) * per_cluster] = c + off
     return out.reshape(-1, 9)
+
+
+def smooth_normals(tris):
+    """Per-corner vertex normals (n, 9): area-weighted face normals averaged over corners that share a position, normalised —
+    what a modelling tool exports and MeshData keeps in `normals` (inputs to the packed shading words)."""
+    t = np.asarray(tris, dtype=np.float32).reshape(-1, 3, 3)
+    fn = np.cross(t[:, 1] - t[:, 0], t[:, 2] - t[:, 0]).astype(np.float64)
+    keys = np.ascontiguousarray(t.reshape(-1, 3)).view([("", np.float32)] * 3).reshape(-1)
+    _, inv = np.unique(keys, return_inverse=True)
+    acc = np.zeros((inv.max() + 1, 3))
+    np.add.at(acc, inv, np.repeat(fn, 3, axis=0))
+    nrm = acc[inv]
+    ln = np.linalg.norm(nrm, axis=1, keepdims=True)
+    nrm = np.where(ln > 1e-20, nrm / np.maximum(ln, 1e-20), np.array([0.0, 1.0, 0.0]))
+    return nrm.astype(np.float32).reshape(-1, 9)
+
+
+def planar_uvs(tris, scale=1.0):
+    """(n, 6) texture coordinates: xz of every corner times `scale`."""
+    t = np.asarray(tris, dtype=np.float32).reshape(-1, 3, 3)
+    return (t[:, :, [0, 2]] * np.float32(scale)).reshape(-1, 6).astype(np.float32)

@@ -60,6 +60,10 @@ typedef enum atlas_rt_status {
 #define ATLAS_RT_PER_RAY_TMAX  (1u << 3)   /* trace_any: take tMax from each ray's hit.x instead of the argument */
 #define ATLAS_RT_OPACITY       (1u << 5)   /* trace_*: the *Transparency variants over the 96-byte triangles (needs atlas_rt_mesh_pack_shading) */
 #define ATLAS_RT_COUNTERS      (1u << 4)   /* trace_*: also count visited nodes / triangles (slower; for parity + roofline) */
+#define ATLAS_RT_RAY_BINNING   (1u << 6)   /* pathtrace_bounces: order the rays of bounce >= 1 by the reference's 8x8 octahedral direction bins */
+#define ATLAS_RT_ACCUM_TILE_ORDER (1u << 7) /* pathtrace_*: index the accumulation buffer in rayGen's tile order instead of y * width + x */
+#define ATLAS_RT_HITS_ONLY     (1u << 8)   /* trace_*: rays_out receives count x 16-byte hit records (the ray's `hit` vec4: t, bits(hitID),
+                                              bits(hitInstanceID), v) instead of 48-byte rays — the compact stream the multi-GPU gather moves */
 
 /* Instance cull masks — InstanceCullMasks, src/engine/raytracing/RTStructures.h:9-12; common.hsh:14-15. */
 #define ATLAS_RT_MASK_ALL    (1u << 7)
@@ -225,8 +229,9 @@ int atlas_rt_trace_closest(atlas_rt_context* ctx, const atlas_rt_scene* scene, c
  *   any      HitAnyTransparency, bvh.hsh:443-524: walks on until the accumulated transparency reaches 0; the returned
  *            transparency is written to direction.w, and t / hitID / instanceID hold the LAST triangle intersected
  *            (exactly what the shader leaves in the ray), including the shader's `transparency *= leaf(transparency)` form.
- * Triangles with textured opacity (opacity < 0) would need the material and texture tables (GetOpacity,
- * surface.hsh:147-160), which are shading inputs outside this path: they count as opacity 1. */
+ * Triangles with textured opacity (opacity < 0) are resolved through GetOpacity (surface.hsh:147-160) once the scene has
+ * its material / texture tables (atlas_rt_scene_set_materials); without them they count as opacity 1.
+ * With ATLAS_RT_HITS_ONLY rays_out receives 16-byte hit records instead of rays (see the flag). */
 int atlas_rt_trace_any(atlas_rt_context* ctx, const atlas_rt_scene* scene, const void* rays_in, uint64_t count,
                        uint32_t cull_mask, float t_min, float t_max, void* rays_out, uint32_t flags);
 
@@ -245,37 +250,94 @@ typedef struct atlas_rt_camera {
 
 /* Primary rays. Replaces pathtracer/rayGen.csh:25-91 as dispatched by PathTracingRenderer::Render
  * (src/engine/renderer/PathTracingRenderer.cpp:146-155): width x height x samples rays, ID = (y*w+x)*samples + s,
- * stored in the shader's 8x8-tile order. jitter = per-sample sub-pixel offset in [0,1)^2 (2 floats per sample).
+ * stored in the shader's 8x8-tile order. jitter = per-sample sub-pixel offset in [0,1)^2 (2 floats per sample; NULL = 0.5;
+ * the shader's own value for a frame is atlas_rt_sample_jitter(sampleCount)).
  * rays_out: width*height*samples PackedRay, device memory if ATLAS_RT_DEVICE_OUTPUT. */
 int atlas_rt_generate_primary_rays(atlas_rt_context* ctx, const atlas_rt_camera* camera, uint32_t width,
                                    uint32_t height, uint32_t samples, const float* jitter, void* rays_out, uint32_t flags);
+/* rayGen.csh:33-34: jitter = (random(vec2(sampleCount, 0)), random(vec2(sampleCount, 1))) from the engine's hash RNG
+ * (data/shader/common/random.hsh:5-33). Pure integer arithmetic, computed on the host. */
+void atlas_rt_sample_jitter(int32_t sample_count, float jitter_xy[2]);
 
-typedef struct atlas_rt_bounce_params {
-    float light_dir[3];     /* direction TO the directional light (normalised) */
-    float light_radiance[3];
-    float albedo[3];        /* Lambertian base colour of every surface */
-    float sky_radiance[3];  /* constant environment */
-    float seed;             /* Uniforms.seed of this bounce */
-    uint32_t bounce;        /* Uniforms.bounceCount */
-    uint32_t max_bounces;   /* Uniforms.maxBounces */
-    uint32_t samples;       /* Uniforms.samplesPerFrame */
-} atlas_rt_bounce_params;
+/* RaytraceMaterial — data/shader/raytracer/structures.hsh:108-141 (23 words, std430 stride 92), as RayTracingWorld fills it. */
+typedef struct atlas_rt_material {
+    int32_t ID;
+    float baseR, baseG, baseB;
+    float emissR, emissG, emissB;
+    float opacity;
+    float roughness, metalness, ao;
+    float reflectance;
+    float normalScale;
+    int32_t invertUVs, twoSided, cullBackFaces, useVertexColors;
+    int32_t baseColorTexture, opacityTexture, normalTexture, roughnessTexture, metalnessTexture, aoTexture;
+} atlas_rt_material;
 
-/* One bounce of the diffuse path: closest-hit trace of `count` rays, then per ray: environment on a miss, one shadow
- * any-hit ray towards the light (origin = P + N*0.1, cull mask MaskShadow), cosine-weighted next direction from the
- * reference's hash RNG keyed by (ray.ID, seed), Russian roulette, and compaction of the surviving rays. Replaces one
- * iteration of the loop in PathTracingRenderer.cpp:177-192 = traceClosest.csh + the diffuse / shadow-ray parts of
- * pathtracer/rayHit.csh:160-337 for Lambertian, opaque, untextured, two-sided surfaces lit by one directional light
- * and a constant sky (materials, textures and light sampling are shading inputs outside this path's scope).
- * All buffers are DEVICE memory (flags must carry ATLAS_RT_DEVICE_INPUT | ATLAS_RT_DEVICE_OUTPUT):
+/* Single-channel 8-bit texture (an opacity map), row-major, width * height bytes, host memory. */
+typedef struct atlas_rt_texture {
+    uint32_t width, height;
+    const uint8_t* texels;
+} atlas_rt_texture;
+
+/* Material and texture tables of a scene (copied to the device). They are what `materials[]` and the bindless opacity
+ * textures are to the shaders: with them the opacity-aware traversal resolves triangles with textured opacity
+ * (opacity < 0) through GetOpacity — data/shader/raytracer/surface.hsh:147-160, bvh.hsh:127,163: texture coordinates
+ * interpolated from the triangle's half2 words, invertUVs, bilinear sample at mip 0 (repeat addressing; fp32 filter
+ * weights), times the material opacity — and the path tracer shades with them. A material's index is
+ * triangle.materialIndex + instance.materialOffset. Only opacityTexture is consulted; the other texture slots must be
+ * negative (material textures are shading inputs outside this path). Without this call textured opacity counts as 1 and the
+ * path tracer uses a grey default material. */
+int atlas_rt_scene_set_materials(atlas_rt_context* ctx, atlas_rt_scene* scene, const atlas_rt_material* materials,
+                                 uint32_t material_count, const atlas_rt_texture* textures, uint32_t texture_count);
+
+typedef struct atlas_rt_pt_params {
+    float light_dir[3];        /* direction TO the directional light: -light.N (normalised by the shader, direct.hsh:82) */
+    float light_radiance[3];   /* Light.radiance */
+    int32_t light_count;       /* PushConstants.lightCount: 0 or 1 */
+    float sky_radiance[3];     /* the environment map as a constant colour */
+    uint32_t max_bounces;      /* Uniforms.maxBounces */
+    uint32_t samples_per_frame;/* Uniforms.samplesPerFrame (1 outside the real-time mode) */
+} atlas_rt_pt_params;
+
+/* One iteration of the loop in PathTracingRenderer.cpp:177-192 on device buffers: traceClosest.csh with OPACITY_CHECK
+ * (HitClosestTransparency) in place over rays_in, then pathtracer/rayHit.csh:56-337 per ray — environment on a miss,
+ * emissive on the first bounce, direct light from one directional light with the shadow ray traced by
+ * HitAnyTransparency(INSTANCE_MASK_SHADOW) (only rays that are really cast are traced), the next direction from the
+ * diffuse / GGX-VNDF specular / refraction choice with the reference's hash RNG keyed by (ray.ID, seed) in the shader's
+ * draw order, Russian roulette, and either accumulation of the finished path or a compacted append of the surviving ray with
+ * its half-precision payload (PackRayPayload, raytracer/common.hsh:88-98).
+ * Surfaces are read from the 96-byte triangles (interpolated vertex normals, surface.hsh:64-138) and the scene's material
+ * table. All buffers are DEVICE memory (flags must carry ATLAS_RT_DEVICE_INPUT | ATLAS_RT_DEVICE_OUTPUT):
  *   rays_in      count PackedRay; updated IN PLACE with the closest hits (the shader's write to the other buffer half)
- *   payload_in   2 x float4 per ray (radiance.rgb, throughput.rgb); ignored when params->bounce == 0
+ *   payload_in   count x 16 B PackedRayPayload; ignored when bounce == 0
  *   rays_out / payload_out   capacity count; receive the surviving rays compacted to the front; must not alias the inputs
- *   accum        width*height x 4 floats (rgb sum, finished-path count), indexed by ray.ID / samples, updated atomically
+ *   accum        width*height x 4 floats (rgb sum, finished-path count) at pixel ray.ID / samples_per_frame, added atomically
  * out_count (host) receives the number of surviving rays; the call synchronises the stream to read it. */
-int atlas_rt_pathtrace_bounce(atlas_rt_context* ctx, const atlas_rt_scene* scene, const atlas_rt_bounce_params* params,
-                              const void* rays_in, const void* payload_in, uint64_t count, void* rays_out,
-                              void* payload_out, float* accum, uint64_t* out_count, uint32_t flags);
+int atlas_rt_pathtrace_bounce(atlas_rt_context* ctx, const atlas_rt_scene* scene, const atlas_rt_pt_params* params,
+                              float seed, uint32_t bounce, const void* rays_in, const void* payload_in, uint64_t count,
+                              void* rays_out, void* payload_out, float* accum, uint32_t width, uint32_t height,
+                              uint64_t* out_count, uint32_t flags);
+
+/* The whole of PathTracingRenderer::Render's ray work for `frames` sample passes (frame f uses sampleCount =
+ * first_sample_count + f for the jitter and seeds[f * (max_bounces + 1) + b] as Uniforms.seed of bounce b): ray
+ * generation, then max_bounces + 1 bounces, with the ray counts kept ON THE DEVICE — the kernels read them from device
+ * memory the way traceDispatch.csh + DispatchIndirect do (renderer/helper/RayTracingHelper.cpp:262-291,363), so the host
+ * enqueues everything without waiting once. [slot_begin, slot_end) selects a contiguous range of rayGen's storage slots
+ * (slot = tileOrderIndex * samples_per_frame + sample; slot_end == 0 means the whole frame): the unit of sharding an
+ * image across GPUs, 64 * samples_per_frame slots per 8x8 tile. accum: device, width*height x 4 floats, indexed by pixel or,
+ * with ATLAS_RT_ACCUM_TILE_ORDER, by tile-order index (then a slot range owns a contiguous slice). rays_traced (may be
+ * NULL) receives the number of closest-hit rays traced. ATLAS_RT_RAY_BINNING adds the reference's direction binning pass
+ * before every bounce after the first. */
+int atlas_rt_pathtrace_bounces(atlas_rt_context* ctx, const atlas_rt_scene* scene, const atlas_rt_camera* camera,
+                               uint32_t width, uint32_t height, const atlas_rt_pt_params* params, uint32_t frames,
+                               int32_t first_sample_count, const float* seeds, uint64_t slot_begin, uint64_t slot_end,
+                               float* accum, uint64_t* rays_traced, uint32_t flags);
+
+/* Ray binning between bounces — raytracer/tracing.hsh:18-29 (DetermineRayBin: 8x8 octahedral direction bins),
+ * binningOffset.csh, binning.csh; call site RayTracingHelper.cpp:304-344 (commented out in the reference). Rays (and their
+ * 16-byte payloads, if given) are moved to their bin's segment; inside a bin they keep their order (the shader's order
+ * inside a bin is arbitrary). Device buffers only; rays_out must not alias rays_in. */
+int atlas_rt_bin_rays(atlas_rt_context* ctx, const void* rays_in, const void* payload_in, uint64_t count, void* rays_out,
+                      void* payload_out, uint32_t flags);
 
 /* ---------------------------------------------------------------------------------------------- multi-GPU ---- */
 /* Contiguous share of `count` rays for `rank` of `world`, aligned to `align` rays (64 keeps rayGen's 8x8 tiles whole).

@@ -472,7 +472,16 @@ struct SceneView {
     const float* const* blasNodes;   // per mesh: 16 floats per node
     const float* const* bvhTris;     // per mesh: 12 floats per triangle (GPUBVHTriangle, RTStructures.h:23-27)
     const float* const* triangles;   // per mesh: 24 floats per triangle (GPUTriangle, RTStructures.h:14-21); only for the *Transparency variants
+    // material / texture tables for GetOpacity (textured opacity); null => textured triangles count as opacity 1
+    const uint32_t* materials = nullptr;     // RaytraceMaterial, 23 words each
+    uint32_t materialCount = 0;
+    const uint32_t* texDims = nullptr;       // width, height per texture
+    const uint8_t* const* texels = nullptr;  // R8
+    uint32_t textureCount = 0;
 };
+
+extern "C" float oracle_get_opacity(const float* tri, float s, float t, const uint32_t* material, const uint32_t* texDims,
+                                    const uint8_t* const* texels, uint32_t textureCount);   // atlas_oracle_shade.cpp
 
 struct Counters {
     uint64_t tlasNodes = 0, instances = 0, blasNodes = 0, triangles = 0, maxStack = 0, stackOverflows = 0;
@@ -533,7 +542,7 @@ bool traverse(const SceneView& sc, RayState& ray, uint32_t cullMask, float tMin,
     int32_t stack[kOracleStack];
     stack[0] = 0;
     uint32_t sp = 1;
-    int32_t nodePtr = 0, meshPtr = 0;
+    int32_t nodePtr = 0, meshPtr = 0, materialOffset = 0;
     const float o0[3] = {ray.o[0], ray.o[1], ray.o[2]}, d0[3] = {ray.d[0], ray.d[1], ray.d[2]};
     if (!ANY) ray.hitDistance = tMax;
     uint32_t tlasIndex = kTlasInvalid;
@@ -570,6 +579,7 @@ bool traverse(const SceneView& sc, RayState& ray, uint32_t cullMask, float tMin,
             std::memcpy(&meshOffset, I + 12, 4);
             std::memcpy(&mask, I + 15, 4);
             meshPtr = meshOffset;
+            std::memcpy(&materialOffset, I + 13, 4);
             nodePtr = 0;
             if ((uint32_t(mask) & cullMask) > 0u) tlasIndex = sp;
             else nodePtr = stack[--sp];
@@ -589,7 +599,16 @@ bool traverse(const SceneView& sc, RayState& ray, uint32_t cullMask, float tMin,
                 const bool in = tri_test(ray, T, T + 4, T + 8, sol);
                 if (in && sol[0] > tMin && sol[0] < tmaxLeaf) {
                     if (OPACITY) {
-                        const float triOpacity = T[23] < 0.0f ? 1.0f : T[23];   // d2.w
+                        // tri.opacity < 0.0 ? GetOpacity(tri, sol.yz, materialOffset, 0) : tri.opacity — bvh.hsh:127, :163
+                        float triOpacity = T[23];   // d2.w
+                        if (triOpacity < 0.0f) {
+                            int32_t matIndex;
+                            std::memcpy(&matIndex, T + 15, 4);
+                            const uint32_t mi = uint32_t(matIndex + materialOffset);
+                            triOpacity = (sc.materials && mi < sc.materialCount)
+                                             ? oracle_get_opacity(T, sol[1], sol[2], sc.materials + 23 * size_t(mi), sc.texDims, sc.texels, sc.textureCount)
+                                             : 1.0f;
+                        }
                         if (!ANY) {
                             if (sol[0] < ray.hitDistance && triOpacity > 0.0f) {
                                 ray.hitDistance = sol[0]; ray.hitID = triPtr; ray.hitInstanceID = ray.currentInstanceID;
@@ -742,8 +761,9 @@ void oracle_tree_free(void* h) { delete static_cast<OracleTree*>(h); }
 void oracle_trace(const float* tlasNodes, const float* instances, const float* const* blasNodes,
                   const float* const* bvhTris, const float* rays, uint64_t n, uint32_t cullMask, float tMin,
                   float tMax, int any, int perRayTMax, float* out, uint64_t* counters, int nthreads,
-                  const float* const* triangles96, int opacity) {
-    SceneView sc{tlasNodes, instances, blasNodes, bvhTris, triangles96};
+                  const float* const* triangles96, int opacity, const uint32_t* materials, uint32_t materialCount,
+                  const uint32_t* texDims, const uint8_t* const* texels, uint32_t textureCount) {
+    SceneView sc{tlasNodes, instances, blasNodes, bvhTris, triangles96, materials, materialCount, texDims, texels, textureCount};
     std::vector<Counters> perThread(size_t(std::max(nthreads, 1)));
     parallel_for(n, nthreads, [&](uint64_t b, uint64_t e, int tid) {
         Counters& ct = perThread[size_t(tid)];

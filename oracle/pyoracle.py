@@ -153,6 +153,21 @@ class Scene:
         self.tri_counts = np.array([t.shape[0] for t in self.bvh_tris], dtype=np.uint32)
         self.triangles96 = None if triangles96 is None else [_f32c(t).reshape(-1, 24) for t in triangles96]
         self._tri96_ptrs = None if triangles96 is None else (C.c_void_p * m)(*[t.ctypes.data for t in self.triangles96])
+        self.materials = None
+        self.textures = []
+
+    def set_materials(self, materials, textures=()):
+        """materials: (k, 23) uint32 RaytraceMaterial words; textures: list of (h, w) uint8 arrays (R8 opacity maps)."""
+        self.materials = np.ascontiguousarray(materials).view(np.uint32).reshape(-1, 23)
+        self.textures = [np.ascontiguousarray(t, dtype=np.uint8) for t in textures]
+        self._tex_dims = np.array([[t.shape[1], t.shape[0]] for t in self.textures], dtype=np.uint32).reshape(-1, 2)
+        self._tex_ptrs = (C.c_void_p * max(1, len(self.textures)))(*[t.ctypes.data for t in self.textures])
+
+    def material_args(self):
+        if self.materials is None:
+            return (None, 0, None, None, 0)
+        return (_ptr(self.materials), self.materials.shape[0], _ptr(self._tex_dims) if len(self.textures) else None,
+                self._tex_ptrs if len(self.textures) else None, len(self.textures))
 
 
 class Oracle:
@@ -173,7 +188,14 @@ class Oracle:
         L.oracle_tree_copy_order.argtypes = [_vp, _vp, _vp]
         L.oracle_tree_stats.argtypes = [_vp, _vp]
         L.oracle_tree_free.argtypes = [_vp]
-        L.oracle_trace.argtypes = [_vp, _vp, _vp, _vp, _vp, _u64, _u32, _f32, _f32, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, C.c_int]
+        L.oracle_trace.argtypes = [_vp, _vp, _vp, _vp, _vp, _u64, _u32, _f32, _f32, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, C.c_int,
+                                   _vp, _u32, _vp, _vp, _u32]
+        L.oracle_raygen.argtypes = [_vp, _vp, _vp, _vp, _u32, _u32, _u32, _i32, _vp]
+        L.oracle_pt_shadow_rays.argtypes = [_vp, _vp, _vp, _u32, _vp, _vp, _u32, _vp, _u64, _vp, _vp]
+        L.oracle_pt_shade.argtypes = [_vp, _vp, _vp, _u32, _vp, _vp, _u32, _vp, _vp, _vp, _u64, _vp, _f32, _u32, _vp, _vp, _vp, _vp, _vp]
+        L.oracle_ray_bins.argtypes = [_vp, _u64, _vp]
+        L.oracle_get_opacity.restype = _f32
+        L.oracle_get_opacity.argtypes = [_vp, _f32, _f32, _vp, _vp, _vp, _u32]
         L.oracle_brute_force.argtypes = [_vp, _u32, _vp, _vp, _vp, _u64, _u32, _f32, _f32, _vp, _vp, _vp, C.c_int]
         L.oracle_pack_shading_words.argtypes = [_vp, _vp, _vp, _vp, _u64, _vp]
 
@@ -205,8 +227,45 @@ class Oracle:
         ct = np.zeros(6, dtype=np.uint64)
         self.lib.oracle_trace(_ptr(scene.tlas_nodes), _ptr(scene.instances), scene._node_ptrs, scene._tri_ptrs,
                               _ptr(rays), rays.shape[0], cull_mask, t_min, t_max, int(any_hit), int(per_ray_tmax),
-                              _ptr(out), _ptr(ct), nthreads, scene._tri96_ptrs if opacity else None, int(opacity))
+                              _ptr(out), _ptr(ct), nthreads, scene._tri96_ptrs if opacity else None, int(opacity),
+                              *scene.material_args())
         return out, dict(zip(COUNTER_NAMES, (int(x) for x in ct)))
+
+    # ---------------------------------------------------------------------------------------------- path tracer
+    def raygen(self, eye, origin, right, bottom, width, height, samples=1, sample_count=0):
+        """pathtracer/rayGen.csh (non-REALTIME): (w*h*samples, 12) PackedRay in the shader's storage order."""
+        e, o, r, b = (_f32c(x) for x in (eye, origin, right, bottom))
+        out = np.zeros((width * height * samples, 12), dtype=np.float32)
+        self.lib.oracle_raygen(_ptr(e), _ptr(o), _ptr(r), _ptr(b), width, height, samples, sample_count, _ptr(out))
+        return out
+
+    def pt_shadow_rays(self, scene, rays, params):
+        rays = _f32c(rays).reshape(-1, 12)
+        out = np.zeros_like(rays)
+        self.lib.oracle_pt_shadow_rays(_ptr(scene.instances), scene._tri96_ptrs, *scene.material_args(), _ptr(rays), rays.shape[0],
+                                       C.byref(params), _ptr(out))
+        return out
+
+    def pt_shade(self, scene, rays, payload_in, visibility, params, seed, bounce):
+        """rayHit.csh on traced rays. Returns dict(alive (n,) bool, rays (n,12), payload (n,4) uint32, finished (n,3), rr (n,2))."""
+        rays = _f32c(rays).reshape(-1, 12)
+        n = rays.shape[0]
+        pay = np.zeros((n, 4), dtype=np.uint32) if payload_in is None else np.ascontiguousarray(payload_in).view(np.uint32).reshape(-1, 4)
+        vis = _f32c(visibility)
+        alive = np.zeros(n, dtype=np.uint8)
+        ro = np.zeros((n, 12), dtype=np.float32)
+        po = np.zeros((n, 4), dtype=np.uint32)
+        fin = np.zeros((n, 3), dtype=np.float32)
+        rr = np.zeros((n, 2), dtype=np.float32)
+        self.lib.oracle_pt_shade(_ptr(scene.instances), scene._tri96_ptrs, *scene.material_args(), _ptr(rays), _ptr(pay), _ptr(vis), n,
+                                 C.byref(params), seed, bounce, _ptr(alive), _ptr(ro), _ptr(po), _ptr(fin), _ptr(rr))
+        return dict(alive=alive.astype(bool), rays=ro, payload=po, finished=fin, rr=rr)
+
+    def ray_bins(self, rays):
+        rays = _f32c(rays).reshape(-1, 12)
+        out = np.zeros(rays.shape[0], dtype=np.uint32)
+        self.lib.oracle_ray_bins(_ptr(rays), rays.shape[0], _ptr(out))
+        return out
 
     def pack_shading_words(self, tris, normals9=None, uvs6=None, colors12=None):
         """(n, 11) uint32: the packed shading words of MeshData.cpp:176-228 per source triangle."""

@@ -209,7 +209,10 @@ int main(int argc, char** argv) {
             vec3 sol;
             const bool hit = (i & 1 ? copy : built[k]).GetIntersection(stack, ray, closest, sol);
             ok = hit == (idx[i] >= 0) && sol.x == tuv[3 * i] && (!hit || (int32_t(closest.idx) == idx[i] && sol.y == tuv[3 * i + 1] && sol.z == tuv[3 * i + 2]));
-            ok = ok && built[k].GetIntersectionAny(stack, ray) == (anyRef[i] != 0);
+            const bool anyHit = built[k].GetIntersectionAny(stack, ray);
+            ok = ok && anyHit == (anyRef[i] != 0);
+            if (!ok) printf("  ray %d: hit %d idx %d (ref %d) sol %.9g %.9g %.9g ref %.9g %.9g %.9g any %d (ref %d) tMax %g err '%s'\n", i, int(hit), int(closest.idx), idx[i],
+                            sol.x, sol.y, sol.z, tuv[3 * i], tuv[3 * i + 1], tuv[3 * i + 2], int(anyHit), int(anyRef[i]), q[8 * i + 7], RayTracing::LastError().c_str());
             hits += hit ? 1 : 0;
         }
         ok = ok && hits > nq / 10;

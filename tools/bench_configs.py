@@ -195,37 +195,28 @@ if "C4" in which or "C5" in which:
              blas_builds_total_ms_host_timed=blas_total_ms, tlas_build_ms=tlas_ms, closest=st, shadow_any=st2, blas_equal_oracle=okb,
              tlas_equals_oracle=bool(np.array_equal(n, otl.nodes) and np.array_equal(od, otl.order)), hits_equal_oracle_100k=okt)
     if "C5" in which:
+        # BASELINE configs[4]: 3840x2160 x 16 spp, 4 bounces, whole loop on the device (atlas_rt_pathtrace_bounces)
         w, h, spp, bounces = 3840, 2160, 16, 4
-        eye, origin, right, bottom = W.camera_frame((1000.0, 260.0, -300.0), (1000.0, 60.0, 1000.0), aspect=w / h)
-        n = w * h
-        d_a = torch.empty((n, 12), dtype=torch.float32, device=dev)
-        d_b = torch.empty_like(d_a)
-        p_a = torch.zeros((n, 8), dtype=torch.float32, device=dev)
-        p_b = torch.zeros_like(p_a)
-        accum = torch.zeros((n, 4), dtype=torch.float32, device=dev)
+        cam = W.camera_frame((1000.0, 260.0, -300.0), (1000.0, 60.0, 1000.0), aspect=w / h)
+        for m, t in zip(gm, meshes):
+            m.pack_shading(t, payload11=ctx.pack_shading_words(t, W.smooth_normals(t)))
+        scene5 = ctx.create_scene(gm, ir, tlas)
+        scene5.set_materials(capi.make_materials(1))
         ld = np.array([0.3, 0.9, -0.3]) / np.linalg.norm([0.3, 0.9, -0.3])
-        traced = 0
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        a.record(stream)
-        per_bounce = np.zeros(bounces + 1, dtype=np.int64)
-        for s in range(spp):   # one sample per pixel per pass, like the reference's samplesPerFrame loop
-            jit = np.array([[(s * 0.618034) % 1.0, (s * 0.754878) % 1.0]], dtype=np.float32)
-            ctx.generate_primary_rays(eye, origin, right, bottom, w, h, 1, jitter=jit, out=d_a)
-            count, ri, ro, pi, po = n, d_a, d_b, p_a, p_b
-            for bounce in range(bounces + 1):
-                bp = capi.BounceParams((capi._f32 * 3)(*ld), (capi._f32 * 3)(3.0, 3.0, 2.5), (capi._f32 * 3)(0.7, 0.6, 0.5), (capi._f32 * 3)(0.4, 0.5, 0.8),
-                                       float(s * 16 + bounce), bounce, bounces, 1)
-                per_bounce[bounce] += count
-                traced += count
-                count = ctx.pathtrace_bounce(scene, bp, ri, pi, count, ro, po, accum)
-                ri, ro, pi, po = ro, ri, po, pi
-                if count == 0:
-                    break
-        b.record(stream)
-        torch.cuda.synchronize()
-        ms = a.elapsed_time(b)
-        acc = accum.cpu().numpy()
-        emit("C5 path tracer 3840x2160 x 16 spp, 4 diffuse bounces (+ shadow rays) on the C4 scene", closest_rays_traced=int(traced),
-             rays_per_bounce=per_bounce.tolist(), total_ms=ms, closest_mrays_per_s=traced / ms / 1e3, paths_finished=float(acc[:, 3].sum()),
-             mean_radiance=acc[:, :3].sum(axis=0).tolist(), note="each closest-hit ray also spawns one shadow any-hit ray when lit; Mrays/s counts closest-hit rays only")
+        prm = capi.pt_params(ld, (3.0, 3.0, 2.5), (0.4, 0.5, 0.8), max_bounces=bounces)
+        seeds = np.arange(spp * (bounces + 1), dtype=np.float32) * np.float32(0.754878) + np.float32(0.5)
+        for flags, label in ((0, "no binning"), (capi.RAY_BINNING, "octahedral ray binning before bounces >= 1")):
+            accum = torch.zeros((w * h, 4), dtype=torch.float32, device=dev)
+            ctx.pathtrace_bounces(scene5, cam, w, h, prm, 1, 0, seeds[:bounces + 1], accum, flags=flags)   # warm-up pass
+            accum.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record(stream)
+            traced = ctx.pathtrace_bounces(scene5, cam, w, h, prm, spp, 0, seeds, accum, flags=flags)
+            b.record(stream)
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b)
+            acc = accum.cpu().numpy()
+            emit("C5 path tracer 3840x2160 x 16 spp, 4 bounces (+ shadow rays), device-side loop, " + label, closest_rays_traced=int(traced),
+                 total_ms=ms, closest_mrays_per_s=traced / ms / 1e3, paths_finished=float(acc[:, 3].sum()), mean_radiance=acc[:, :3].mean(axis=0).tolist(),
+                 note="each closest-hit ray also spawns one shadow any-hit ray when lit; Mrays/s counts closest-hit rays only")
