@@ -62,6 +62,16 @@ SIGNATURES = {
     "atlas_rt_pathtrace_bounce": (_i32, [_vp, _vp, _vp, _f32, _u32, _vp, _vp, _u64, _vp, _vp, _vp, _u32, _u32, C.POINTER(_u64), _u32]),
     "atlas_rt_pathtrace_bounces": (_i32, [_vp, _vp, _vp, _u32, _u32, _vp, _u32, _i32, _vp, _u64, _u64, _vp, C.POINTER(_u64), _u32]),
     "atlas_rt_bin_rays": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _u32]),
+    "atlas_rt_comm_unique_id": (_i32, [_vp]),
+    "atlas_rt_comm_init": (_i32, [_vp, _vp, _u32, _u32, C.POINTER(_vp)]),
+    "atlas_rt_comm_destroy": (None, [_vp]),
+    "atlas_rt_comm_info": (_i32, [_vp, C.POINTER(_u32), C.POINTER(_u32)]),
+    "atlas_rt_comm_synchronize": (_i32, [_vp]),
+    "atlas_rt_bvh_broadcast": (_i32, [_vp, _vp, _u32, C.POINTER(_vp)]),
+    "atlas_rt_build_scene_sharded": (_i32, [_vp, _u32, _vp, _vp, _vp, _vp, _vp, _u64, _u32, C.POINTER(_vp)]),
+    "atlas_rt_scene_replicate": (_i32, [_vp, _vp, _u32, C.POINTER(_vp)]),
+    "atlas_rt_trace_sharded": (_i32, [_vp, _vp, _vp, _u64, _u32, _f32, _f32, _vp, _u32, _u32, _i32]),
+    "atlas_rt_comm_gather": (_i32, [_vp, _vp, _u64, _vp, _vp, _vp, _u32, _u32]),
     "atlas_rt_shard_range": (_i32, [_u64, _u32, _u32, _u32, C.POINTER(_u64), C.POINTER(_u64)]),
 }
 
@@ -410,8 +420,9 @@ class Scene:
         arr = (Texture * max(1, len(tex)))(*[Texture(t.shape[1], t.shape[0], t.ctypes.data) for t in tex])
         self.ctx.check(self.ctx.L.atlas_rt_scene_set_materials(self.ctx.h, self.h, _addr(mats), mats.shape[0], arr if tex else None, len(tex)))
 
-    def download(self):
-        n, m = self.tlas.counts()
+    def download(self, instance_count=None, tlas_node_count=None):
+        """Scenes assembled by the library itself (build_scene_sharded / replicate_scene) carry no Python TLAS object: pass the counts."""
+        n, m = (tlas_node_count, instance_count) if self.tlas is None else self.tlas.counts()
         inst = np.zeros((m, 16), dtype=np.uint32)
         nodes = np.zeros((n, 16), dtype=np.float32)
         self.ctx.check(self.ctx.L.atlas_rt_scene_download(self.h, _addr(inst), _addr(nodes), 0))
@@ -451,6 +462,78 @@ def load_aemesh(path):
         return out
     finally:
         L.atlas_rt_aemesh_close(h)
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (bytes)."""
+    buf = (C.c_uint8 * 128)()
+    rc = lib().atlas_rt_comm_unique_id(buf)
+    if rc != 0:
+        raise AtlasError(f"atlas_rt_comm_unique_id -> {STATUS.get(rc, rc)} (is libnccl.so.2 loadable?)")
+    return bytes(buf)
+
+
+class Comm:
+    """atlas_rt_comm: NCCL communicator bound to a Context (one rank per GPU)."""
+
+    def __init__(self, ctx, unique_id, rank, world):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        h = _vp()
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        ctx.check(ctx.L.atlas_rt_comm_init(ctx.h, buf, rank, world, C.byref(h)))
+        self.h = h
+
+    def synchronize(self):
+        self.ctx.check(self.ctx.L.atlas_rt_comm_synchronize(self.h))
+
+    def close(self):
+        if self.h:
+            self.ctx.L.atlas_rt_comm_destroy(self.h)
+            self.h = None
+
+    def broadcast_bvh(self, bvh, root):
+        out = _vp()
+        self.ctx.check(self.ctx.L.atlas_rt_bvh_broadcast(self.h, bvh.h if bvh is not None else None, root, C.byref(out)))
+        return bvh if self.rank == root else BVH(self.ctx, out)
+
+    def build_scene_sharded(self, mesh_tris, inst_boxes, inst_records):
+        from . import workloads as W
+        m = len(mesh_tris)
+        tris = [np.ascontiguousarray(t, dtype=np.float32) for t in mesh_tris]
+        boxes = [W.tri_boxes(t) for t in tris]
+        pa = (_vp * m)(*[_addr(a) for a in boxes])
+        pt = (_vp * m)(*[_addr(t) for t in tris])
+        pc = (_u64 * m)(*[t.shape[0] for t in tris])
+        inst = np.ascontiguousarray(inst_records).view(np.uint32).reshape(-1, 16)
+        ib = np.ascontiguousarray(inst_boxes, dtype=np.float32)
+        h = _vp()
+        self.ctx.check(self.ctx.L.atlas_rt_build_scene_sharded(self.h, m, pa, pt, pc, _addr(inst), _addr(ib), ib.shape[0], 0, C.byref(h)))
+        return Scene(self.ctx, h, [], None)
+
+    def replicate_scene(self, scene, root):
+        h = _vp()
+        self.ctx.check(self.ctx.L.atlas_rt_scene_replicate(self.h, scene.h if scene is not None else None, root, C.byref(h)))
+        return scene if self.rank == root else Scene(self.ctx, h, [], None)
+
+    def trace_sharded(self, scene, rays, total_count, hits_out=None, root=0, cull_mask=MASK_ALL, t_min=0.0, t_max=INF, any_hit=False, flags=0):
+        """rays: this rank's share (host array or CUDA tensor / device pointer); hits_out (root): (total, 4) float32 host array,
+        CUDA tensor or None (a host array is made on root)."""
+        fl = flags | (DEVICE_INPUT if _is_device(rays) else 0)
+        if self.rank == root:
+            if hits_out is None:
+                hits_out = np.empty((total_count, 4), dtype=np.float32)
+            if _is_device(hits_out):
+                fl |= DEVICE_OUTPUT
+        if not _is_device(rays):
+            rays = np.ascontiguousarray(rays, dtype=np.float32)
+        self.ctx.check(self.ctx.L.atlas_rt_trace_sharded(self.h, scene.h, _addr(rays), total_count, cull_mask, t_min, t_max,
+                                                         _addr(hits_out) if self.rank == root else None, root, fl, int(any_hit)))
+        return hits_out if self.rank == root else None
+
+    def gather(self, send, nbytes, recv, sizes, offsets, root=0, flags=0):
+        sz = (_u64 * self.world)(*[int(x) for x in sizes])
+        of = (_u64 * self.world)(*[int(x) for x in offsets])
+        self.ctx.check(self.ctx.L.atlas_rt_comm_gather(self.h, _addr(send), nbytes, _addr(recv) if self.rank == root else None, sz, of, root, flags))
 
 
 def shard_range(count, rank, world, align=64):

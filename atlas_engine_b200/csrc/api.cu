@@ -554,6 +554,7 @@ int atlas_rt_scene_create(atlas_rt_context* ctx, const atlas_rt_mesh* const* mes
     scene->meshCount = mesh_count;
     scene->instanceCount = tlas->refCount;
     scene->allShading = allShading;
+    scene->partMeshes.assign(meshes, meshes + mesh_count);
     Staged st(ctx);
     cudaError_t e = cudaSuccess;
     const uint32_t* dNodeCounts = static_cast<const uint32_t*>(st.in(nodeCounts.data(), mesh_count * sizeof(uint32_t), false, &e));
@@ -641,6 +642,8 @@ void atlas_rt_scene_free(atlas_rt_scene* scene) {
     dev_free(ctx, scene->materials);
     dev_free(ctx, scene->textures);
     dev_free(ctx, scene->texelStorage);
+    for (atlas_rt_mesh* m : scene->ownedMeshes) atlas_rt_mesh_free(m);
+    for (atlas_rt_bvh* b : scene->ownedBvhs) atlas_rt_bvh_free(b);
     delete scene;
     ctx_release(ctx);
 }

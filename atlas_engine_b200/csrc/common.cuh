@@ -12,6 +12,7 @@
 
 #include <atomic>
 #include <string>
+#include <vector>
 
 #include "../../include/atlas_rt.h"
 #include "layouts.h"
@@ -158,6 +159,11 @@ struct atlas_rt_scene {
     TextureDev* textures = nullptr;
     uint32_t textureCount = 0;
     uint8_t* texelStorage = nullptr;
+    // the meshes the scene was assembled from (borrowed unless also listed as owned): atlas_rt_scene_replicate walks them
+    std::vector<const atlas_rt_mesh*> partMeshes;
+    // objects created on the scene's behalf (atlas_rt_build_scene_sharded, atlas_rt_scene_replicate): freed with the scene
+    std::vector<atlas_rt_mesh*> ownedMeshes;
+    std::vector<atlas_rt_bvh*> ownedBvhs;
 };
 
 namespace atlas {

@@ -1,12 +1,26 @@
 """Multi-GPU sharding of the traversal: one process per GPU, scene replicated, ray batch split into
-contiguous ranges, ONE all-gather of hit records per batch. Builds do not shard (a single BVH is top-down dependent);
+contiguous ranges, ONE gather of 16-byte hit records per batch. Builds do not shard (a single BVH is top-down dependent);
 independent BLASes are dealt round-robin with `blas_owner`.
 
-The reference has no multi-GPU code at all; this is the B200-native addition. torch.distributed (NCCL over
-NVLink/NVSwitch on GPU, gloo in the CPU tests) is plumbing only — no collective sits inside the traversal itself.
+The product path is in the C ABI (csrc/comm.cu: atlas_rt_comm_init / atlas_rt_build_scene_sharded / atlas_rt_scene_replicate /
+atlas_rt_trace_sharded over NCCL); `init_comm` below only hands the NCCL unique id around with torch.distributed, which is
+plumbing. The torch.distributed statements of the same exchanges further down (gather_hits*, exchange_flat_trees) are what
+the CPU tests run over gloo (tests/test_sharding_gloo.py) to check the host-side arithmetic: shares, offsets, ownership.
+The reference has no multi-GPU code at all; this is the B200-native addition.
 """
 import torch
 import torch.distributed as dist
+
+
+def init_comm(ctx):
+    """capi.Comm over all ranks of the torch.distributed job: rank 0 makes the NCCL unique id, everyone receives it."""
+    from . import capi
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    box = [capi.comm_unique_id() if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(box, src=0)
+    return capi.Comm(ctx, box[0], rank, world)
 
 
 def shard_bounds(count, rank, world, align=64):
@@ -101,6 +115,7 @@ def build_scene_sharded(ctx, mesh_tris, inst_boxes, inst_records):
             built[k] = ctx.build_blas(W.tri_boxes(tris), tris)
             local[k] = built[k].download_device()
     trees = exchange_flat_trees(local, len(mesh_tris), device)
+    torch.cuda.current_stream().synchronize()   # the broadcasts ran on torch's / NCCL's streams; the imports use the context's
     blas = [built[k] if k in built else ctx.import_bvh_device(*trees[k]) for k in range(len(mesh_tris))]
     meshes = [ctx.pack_mesh(b, t) for b, t in zip(blas, mesh_tris)]
     tl_local = {}
@@ -109,6 +124,7 @@ def build_scene_sharded(ctx, mesh_tris, inst_boxes, inst_records):
         tlas = ctx.build_tlas(inst_boxes)
         tl_local[0] = tlas.download_device()
     tl_tree = exchange_flat_trees(tl_local, 1, device)[0]
+    torch.cuda.current_stream().synchronize()
     if tlas is None:
         tlas = ctx.import_bvh_device(*tl_tree)
     scene = ctx.create_scene(meshes, inst_records, tlas)

@@ -340,10 +340,59 @@ int atlas_rt_bin_rays(atlas_rt_context* ctx, const void* rays_in, const void* pa
                       void* payload_out, uint32_t flags);
 
 /* ---------------------------------------------------------------------------------------------- multi-GPU ---- */
-/* Contiguous share of `count` rays for `rank` of `world`, aligned to `align` rays (64 keeps rayGen's 8x8 tiles whole).
- * The scene is replicated per GPU (one process and one context per GPU); ranks trace their share and the caller
- * gathers hit buffers with one NCCL all-gather (see atlas_engine_b200/sharding.py). */
+/* One process and one context per GPU of a node; NCCL (bound at run time with dlopen, so single-GPU users never need it)
+ * over NVLink / NVSwitch. The reference has no multi-GPU code: these entry points stand where its single-GPU calls stand —
+ * scene assembly (RayTracingWorld::UpdateForSoftwareRayTracing, src/engine/raytracing/RayTracingWorld.cpp:267-307) and the
+ * trace batch (RayTracingHelper::DispatchHitClosest, src/engine/renderer/helper/RayTracingHelper.cpp:346-364). No collective
+ * sits inside the traversal: the scene is replicated, rays are split, ONE gather of 16-byte hit records follows a batch. */
+
+/* Contiguous share of `count` rays for `rank` of `world`, aligned to `align` rays (64 keeps rayGen's 8x8 tiles whole). */
 int atlas_rt_shard_range(uint64_t count, uint32_t rank, uint32_t world, uint32_t align, uint64_t* begin, uint64_t* end);
+
+typedef struct atlas_rt_comm atlas_rt_comm;
+/* 128-byte NCCL unique id: create it on one rank and hand it to the others by whatever the host application uses (a file, a
+ * socket, MPI, torch.distributed). */
+int atlas_rt_comm_unique_id(void* id128);
+/* Collective over all ranks. The communicator works on the context's device, issues collectives on its own stream and
+ * orders them against the context's stream with events. */
+int atlas_rt_comm_init(atlas_rt_context* ctx, const void* id128, uint32_t rank, uint32_t world, atlas_rt_comm** out_comm);
+void atlas_rt_comm_destroy(atlas_rt_comm* comm);
+int atlas_rt_comm_info(const atlas_rt_comm* comm, uint32_t* rank, uint32_t* world);
+/* Wait for the context's stream and the communicator's stream (joins every ATLAS_RT_ASYNC sharded call issued so far). */
+int atlas_rt_comm_synchronize(atlas_rt_comm* comm);
+
+/* A flattened tree from the rank that built it (`root`, where src is given) to every other rank, where a new object is
+ * created. On root *out_bvh == src. */
+int atlas_rt_bvh_broadcast(atlas_rt_comm* comm, const atlas_rt_bvh* src, uint32_t root, atlas_rt_bvh** out_bvh);
+
+/* Scene assembly with the BLAS builds of an instanced scene split across the GPUs ("TLAS instance sets are split across
+ * GPUs"): every rank passes the SAME host arrays; rank r builds meshes r, r + world, ... as one batch
+ * (atlas_rt_build_blas_batch), every tree is broadcast from its owner, the TLAS (instance_aabbs: instance_count x 6) is built
+ * on rank 0 and broadcast, and every rank packs its copy and assembles an identical scene, which owns all its parts
+ * (atlas_rt_scene_free releases them). The result equals atlas_rt_scene_create over locally built trees bit for bit. */
+int atlas_rt_build_scene_sharded(atlas_rt_comm* comm, uint32_t mesh_count, const float* const* aabbs, const float* const* tris,
+                                 const uint64_t* counts, const void* instances64, const float* instance_aabbs,
+                                 uint64_t instance_count, uint32_t flags, atlas_rt_scene** out_scene);
+
+/* The complete scene of rank `root` (BLAS nodes, 48-byte and 96-byte triangles, TLAS, permuted instances, material and
+ * texture tables) on every rank: the "BVH replicated to every GPU" step when only one rank has built it. On root
+ * *out_scene == src; elsewhere a new scene that owns its parts. */
+int atlas_rt_scene_replicate(atlas_rt_comm* comm, const atlas_rt_scene* src, uint32_t root, atlas_rt_scene** out_scene);
+
+/* The sharded trace batch: every rank passes ITS share of the batch (atlas_rt_shard_range(total_count, rank, world, 64);
+ * host or device rays) and its replica of the scene, traces the share into compact 16-byte hit records (ATLAS_RT_HITS_ONLY)
+ * and the records are gathered on `root` in global ray order with one group of NCCL sends / receives: hits_out is only
+ * used on root (total_count x 16 B; device memory with ATLAS_RT_DEVICE_OUTPUT). any_hit selects HitAny / HitClosest;
+ * ATLAS_RT_PER_RAY_TMAX and ATLAS_RT_OPACITY are honoured. With ATLAS_RT_ASYNC the gather of one call overlaps the trace of
+ * the next (local records are double buffered); atlas_rt_comm_synchronize joins. */
+int atlas_rt_trace_sharded(atlas_rt_comm* comm, const atlas_rt_scene* scene, const void* rays_in, uint64_t total_count,
+                           uint32_t cull_mask, float t_min, float t_max, void* hits_out, uint32_t root, uint32_t flags,
+                           int any_hit);
+
+/* Variable-size gather of device memory to `root` (e.g. the image slices of a path-tracer frame rendered in
+ * ATLAS_RT_ACCUM_TILE_ORDER): every rank sends `bytes`; root receives rank r's sizes[r] bytes at recv + offsets[r]. */
+int atlas_rt_comm_gather(atlas_rt_comm* comm, const void* send, uint64_t bytes, void* recv, const uint64_t* sizes,
+                         const uint64_t* offsets, uint32_t root, uint32_t flags);
 
 #ifdef __cplusplus
 }

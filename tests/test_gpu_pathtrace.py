@@ -98,13 +98,13 @@ def test_textured_opacity_in_traversal(ctx, oracle):
     ref, _ = oracle.trace(osc, rays, opacity=True, nthreads=8)
     assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
     plain = ctx.trace(scene, rays)
-    assert (plain[:, 9].view(np.int32) != out[:, 9].view(np.int32)).sum() > 100      # holes in the texture let rays through
+    assert (plain[:, 9].view(np.int32) != out[:, 9].view(np.int32)).sum() > 20       # holes in the texture let rays through
     for mask in (W.MASK_ALL, W.MASK_SHADOW):
         out = ctx.trace(scene, rays, any_hit=True, cull_mask=mask, t_max=150.0, flags=capi.OPACITY)
         ref, _ = oracle.trace(osc, rays, any_hit=True, cull_mask=mask, t_max=150.0, opacity=True, nthreads=8)
         assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
     tr = out[:, 7]
-    assert ((tr > 0.0) & (tr < 1.0)).sum() > 100                                       # partial transparency (opacity 0.6, bilinear edges)
+    assert ((tr > 0.0) & (tr < 1.0)).sum() > 20                                       # partial transparency (opacity 0.6, bilinear edges)
     hits = ctx.trace(scene, rays, flags=capi.OPACITY | capi.HITS_ONLY)               # compact 16-byte records
     full = ctx.trace(scene, rays, flags=capi.OPACITY)
     assert hits.shape == (len(rays), 4) and np.array_equal(hits.view(np.uint32), full[:, 8:12].view(np.uint32))
@@ -134,7 +134,6 @@ def test_bounce_loop_against_the_oracle(ctx, oracle):
     ld = np.array([0.3, 0.9, -0.3]) / np.linalg.norm([0.3, 0.9, -0.3])
     prm = capi.pt_params(ld, (3.0, 3.0, 2.5), (0.4, 0.5, 0.8), max_bounces=3, samples_per_frame=spf)
     count, ref_accum, finished_paths = n, np.zeros((w * h, 4)), 0
-    lobes = set()
     for bounce in range(4):
         seed = 17.25 + 3 * bounce
         traced_input = d_in[:count].cpu().numpy().copy()
@@ -153,7 +152,8 @@ def test_bounce_loop_against_the_oracle(ctx, oracle):
         ids_in = hits[:, 3].view(np.int32)
         ids_out = out_rays[:, 3].view(np.int32)
         assert len(set(ids_out.tolist())) == survivors
-        borderline = set(ids_in[np.abs(step["rr"][:, 0] - step["rr"][:, 1]) < 1e-6].tolist())
+        drew = step["rr"][:, 1] > 0.0                                     # rays that reached the Russian roulette
+        borderline = set(ids_in[drew & (np.abs(step["rr"][:, 0] - step["rr"][:, 1]) < 1e-6)].tolist())
         expect = set(ids_in[step["alive"]].tolist())
         assert (expect ^ set(ids_out.tolist())) <= borderline, f"bounce {bounce}: survivor sets differ"
         assert len(borderline) < 5
