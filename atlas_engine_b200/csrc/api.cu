@@ -36,6 +36,7 @@ void ctx_release(atlas_rt_context* ctx) {
     if (ctx->copyOut) cudaStreamDestroy(ctx->copyOut);
     for (auto& cs : ctx->computeExtra) if (cs) cudaStreamDestroy(cs);
     cudaFree(ctx->dCounters);
+    cudaFree(ctx->dStreamState);
     cudaFreeHost(ctx->pinned);
     if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -192,6 +193,14 @@ int atlas_rt_context_create(int device, void* stream, atlas_rt_context** out_ctx
     }
     if (cudaMalloc(&ctx->dCounters, 16 * sizeof(unsigned long long)) != cudaSuccess) { delete ctx; return ATLAS_RT_ERR_OOM; }
     cudaMemset(ctx->dCounters, 0, 16 * sizeof(unsigned long long));
+    if (cudaMalloc(&ctx->dStreamState, 64 * sizeof(unsigned int)) != cudaSuccess) { cudaFree(ctx->dCounters); delete ctx; return ATLAS_RT_ERR_OOM; }
+    {   // cuStreamWaitValue32 lets the download stream wait for a chunk's completion count without the host (streaming trace)
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) ctx->waitValue32 = fn;
+        else cudaGetLastError();
+    }
+    if (const char* e = getenv("ATLAS_RT_TRACE_STREAMING")) ctx->traceStreaming = atoi(e);
     ctx->pinnedBytes = 8192;
     if (cudaMallocHost(&ctx->pinned, ctx->pinnedBytes) != cudaSuccess) { cudaFree(ctx->dCounters); delete ctx; return ATLAS_RT_ERR_OOM; }
     ctx->levelSlots = static_cast<char*>(ctx->pinned) + 4096;
@@ -681,7 +690,53 @@ static int trace_common(atlas_rt_context* ctx, const atlas_rt_scene* scene, cons
     }
     int rc = ATLAS_RT_OK;
     const uint64_t kPipeMin = 262144;
-    if (!devIn && count >= kPipeMin && ctx->copyIn && ctx->copyOut) {
+    if (!devIn && count >= kPipeMin && count < 0x7fffffffull && ctx->copyIn && ctx->copyOut && ctx->waitValue32 && ctx->traceStreaming) {
+        // Host input, streaming: ONE persistent launch traces the batch while it is still being uploaded. The upload stream
+        // copies the rays in chunks and bumps a watermark in device memory behind each chunk (a 4-byte copy from pinned
+        // memory, ordered after the chunk by the stream); the kernel only fetches rays below the watermark. Every warp
+        // reports the rays it has finished per chunk; the download stream waits on each chunk's count with
+        // cuStreamWaitValue32 and sends that chunk's results home while later chunks are still being traced. Against the
+        // chunked pipeline below (one small launch + three ordering kernels per chunk, each paying its own longest ray)
+        // this removes every per-chunk launch and leaves a single drain at the end.
+        typedef int (*WaitValue32)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+        const WaitValue32 waitValue = reinterpret_cast<WaitValue32>(ctx->waitValue32);
+        uint32_t chunks = uint32_t(std::max<uint64_t>(4, std::min<uint64_t>(48, count / 65536)));
+        if (const char* e = getenv("ATLAS_RT_STREAM_CHUNKS")) chunks = uint32_t(std::max(1, std::min(60, atoi(e))));
+        const uint32_t chunkRays = uint32_t(((count + chunks - 1) / chunks + 31) & ~uint64_t(31));
+        chunks = uint32_t((count + chunkRays - 1) / chunkRays);
+        cudaEvent_t* ev = ctx->pipeEvents;   // [0] state reset, [32] all uploaded (previous call), [33] all downloaded
+        unsigned int* marks = reinterpret_cast<unsigned int*>(static_cast<char*>(ctx->pinned) + 2048);   // watermark values, pinned
+        cudaError_t e = cudaSuccess;
+        if (ctx->streamCalls) e = cudaEventSynchronize(ev[32]);   // the previous call's upload still reads `marks`
+        for (uint32_t c = 0; c < chunks; c++) marks[c] = uint32_t(std::min<uint64_t>(count, uint64_t(c + 1) * chunkRays));
+        if (e == cudaSuccess) e = cudaMemsetAsync(ctx->dStreamState, 0, 64 * sizeof(unsigned int), ctx->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ev[0], ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copyIn, ev[0], 0);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copyOut, ev[0], 0);
+        if (e == cudaSuccess)
+            rc = launch_trace(ctx, scene, dIn, out, count, cull_mask, t_min, t_max, any, perRay, counters, true, opacity, nullptr, 0, nullptr, hitsOnly,
+                              ctx->dStreamState, ctx->dStreamState + 1, chunkRays);
+        for (uint32_t c = 0; c < chunks && e == cudaSuccess && rc == ATLAS_RT_OK; c++) {
+            const uint64_t b = uint64_t(c) * chunkRays, end = std::min<uint64_t>(count, b + chunkRays);
+            e = cudaMemcpyAsync(dIn + 3 * b, static_cast<const char*>(rays_in) + 48 * b, 48 * (end - b), cudaMemcpyHostToDevice, ctx->copyIn);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->dStreamState, marks + c, sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->copyIn);
+        }
+        if (e != cudaSuccess || rc != ATLAS_RT_OK)   // never leave the kernel waiting for rays that will not come
+            cudaMemcpyAsync(ctx->dStreamState, marks + (chunks - 1), sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->copyIn);
+        if (e == cudaSuccess) e = cudaEventRecord(ev[32], ctx->copyIn);
+        ctx->streamCalls++;
+        for (uint32_t c = 0; c < chunks && e == cudaSuccess && rc == ATLAS_RT_OK && !devOut; c++) {
+            const uint64_t b = uint64_t(c) * chunkRays, end = std::min<uint64_t>(count, b + chunkRays);
+            if (waitValue(ctx->copyOut, reinterpret_cast<unsigned long long>(ctx->dStreamState + 1 + c), unsigned(end - b), 0u /* CU_STREAM_WAIT_VALUE_GEQ */) != 0) {
+                e = cudaErrorUnknown;
+                break;
+            }
+            e = cudaMemcpyAsync(static_cast<char*>(rays_out) + 16 * outStride * b, out + outStride * b, 16 * outStride * (end - b), cudaMemcpyDeviceToHost, ctx->copyOut);
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(ev[33], ctx->copyOut);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev[33], 0);   // the context stream now orders after the downloads
+        if (e != cudaSuccess && rc == ATLAS_RT_OK) rc = fail(ctx, ATLAS_RT_ERR_CUDA, "streaming trace", e);
+    } else if (!devIn && count >= kPipeMin && ctx->copyIn && ctx->copyOut) {
         // Host input: split the batch and overlap H2D of chunk i+1, the trace of chunk i and (host output) D2H of
         // chunk i-1 on the two copy engines (pays off with pinned host memory; pageable memory still works). With
         // ATLAS_RT_DEVICE_OUTPUT the hits stay on the device, e.g. for an NCCL gather.

@@ -82,6 +82,10 @@ struct atlas_rt_context {
     uint64_t launches = 0;
     std::string error;
     unsigned long long* dCounters = nullptr;   // 16 x u64: [0..5] traversal counters / overflow flag, [8..15] ray-queue heads (one per compute stream)
+    unsigned int* dStreamState = nullptr;      // 64 x u32: [0] upload watermark of a streaming host-buffer trace, [1..] per-chunk completion counts
+    void* waitValue32 = nullptr;               // cuStreamWaitValue32 (driver entry point), or null: chunked pipeline instead of streaming
+    int traceStreaming = 1;                    // host-buffer traces as ONE persistent launch that consumes rays while they arrive
+    uint64_t streamCalls = 0;
     void* pinned = nullptr;                    // small pinned staging area for read-backs
     size_t pinnedBytes = 0;
     // copy engines used to overlap H2D / trace / D2H when a trace call is given host buffers (api.cu)
@@ -246,6 +250,8 @@ int scene_fast_flag(atlas_rt_context* ctx, atlas_rt_scene* scene, const uint32_t
 int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float4* dIn, float4* dOut, uint64_t count,
                  uint32_t cullMask, float tMin, float tMax, bool any, bool perRayTMax, bool counters, bool resetCounters = true,
                  bool opacity = false, cudaStream_t st = nullptr /* context stream */, int queueSlot = 0,
-                 const uint32_t* dCount = nullptr /* batch size on the device (<= count) */, bool hitsOnly = false /* dOut = 16-byte hit records */);
+                 const uint32_t* dCount = nullptr /* batch size on the device (<= count) */, bool hitsOnly = false /* dOut = 16-byte hit records */,
+                 const unsigned int* watermark = nullptr /* streaming input: rays uploaded so far */, unsigned int* chunkDone = nullptr,
+                 uint32_t chunkRays = 0);
 
 }   // namespace atlas

@@ -161,6 +161,21 @@ __device__ __forceinline__ bool fast_ok(const float o[3], const float d[3]) {
 
 constexpr int kBlocksPerSM = 9;
 
+// Streaming input (host rays): the batch is still being uploaded while the kernel runs. `watermark` (device memory) is
+// the number of rays that have arrived: the upload stream bumps it with a 4-byte copy behind every chunk of `chunkRays`
+// rays. `chunkDone[c]` counts finished rays of chunk c so that the download stream (cuStreamWaitValue32) can send a chunk's
+// results home as soon as its last ray is done. Null watermark = the whole batch is resident.
+struct StreamIn {
+    const unsigned int* watermark;
+    unsigned int* chunkDone;
+    uint32_t chunkRays;
+};
+__device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // Persistent-thread traversal. Each warp owns 32 ray slots and refills finished slots from a global ray counter, so
 // lanes do not idle while the longest ray of a static batch finishes (the one-thread-per-ray kernel ran at 8.5 of 32
 // active lanes). Within a warp every round is warp-uniform: either the lanes standing at an inner node take one
@@ -171,7 +186,7 @@ __global__ void __launch_bounds__(kTraceBlock, kBlocksPerSM)
 trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restrict__ permIn, const unsigned int* __restrict__ usePerm,
              uint32_t count, const uint32_t* __restrict__ countPtr, uint32_t cullMask, float tMin, float tMaxArg,
              int perRayTMax, int sceneFast, int hitsOnly, int kLeafThreshold, int kRefillThreshold, unsigned int* __restrict__ rayCounter,
-             unsigned long long* __restrict__ counters) {
+             unsigned long long* __restrict__ counters, StreamIn streamIn) {
     chain_begin();
     if (countPtr) count = min(count, *countPtr);   // batch size produced on the device (path-tracer bounces): no host round trip
     __shared__ int stack[kStack][kTraceBlock];
@@ -179,7 +194,8 @@ trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restr
     const unsigned ltMask = (1u << lane) - 1u;
     const uint32_t* __restrict__ perm = (permIn && *usePerm) ? permIn : nullptr;
     // batches kept in their own (coherent) order refill eagerly; reordered ones do better refilling half a warp at a time
-    if (!perm) kRefillThreshold = min(kRefillThreshold, 6);
+    if (!perm && !streamIn.watermark) kRefillThreshold = min(kRefillThreshold, 6);
+    bool reported = true;   // streaming: has this lane's finished ray been counted in chunkDone yet?
 
     bool alive = false, fast = false, moreRays = true, overflow = false;
     uint32_t ray = 0, sp = 0, tlasIndex = kTlasInvalid;
@@ -228,18 +244,55 @@ trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restr
         const unsigned mI = __ballot_sync(kFull, inner), mL = __ballot_sync(kFull, leafy);
         const int nI = __popc(mI), nL = __popc(mL), nDead = 32 - nI - nL;
 
-        if (moreRays && (nDead >= kRefillThreshold || nI + nL == 0)) {
+        bool refill = moreRays && (nDead >= kRefillThreshold || nI + nL == 0);
+        if (refill && streamIn.watermark && nI + nL > 0) {
+            // rays still arriving: do not claim rays that are not here yet while this warp has work — peek (non-binding) and
+            // keep traversing instead of stalling the live lanes behind the upload
+            unsigned arrived = 0, claimed = 0;
+            if (lane == 0) { arrived = ld_volatile_u32(streamIn.watermark); claimed = ld_volatile_u32(rayCounter); }
+            arrived = __shfl_sync(kFull, arrived, 0);
+            claimed = __shfl_sync(kFull, claimed, 0);
+            if (claimed + unsigned(nDead) > arrived && arrived < count) refill = false;
+        }
+        if (refill) {
             // ---- fetch new rays for the idle lanes (traceClosest.csh:18-30)
             const unsigned mDead = ~(mI | mL);
+            if (streamIn.watermark) {   // report the rays these lanes finished since the last refill, per chunk, one atomic per chunk and warp
+                __threadfence();        // their results are written before the count that releases the chunk's download
+                const bool mine = !alive && !reported;
+                const unsigned chunk = mine ? ray / streamIn.chunkRays : 0xffffffffu;
+                unsigned pending = __ballot_sync(kFull, mine);
+                while (pending) {
+                    const int leader = __ffs(pending) - 1;
+                    const unsigned c = __shfl_sync(kFull, chunk, leader);
+                    const unsigned same = __ballot_sync(kFull, mine && chunk == c);
+                    if (int(lane) == leader) atomicAdd(streamIn.chunkDone + c, unsigned(__popc(same)));
+                    pending &= ~same;
+                }
+                reported = true;
+            }
             unsigned base = 0;
             if (lane == 0) base = atomicAdd(rayCounter, unsigned(nDead));
             base = __shfl_sync(kFull, base, 0);
             if (base >= count || base + unsigned(nDead) >= count) moreRays = false;
+            if (streamIn.watermark && base < count) {   // wait until every ray this warp has just claimed has been uploaded
+                const unsigned need = min(base + unsigned(nDead), count);
+                unsigned arrived = 0;
+                unsigned spins = 0;
+                do {
+                    if (lane == 0) arrived = ld_volatile_u32(streamIn.watermark);
+                    arrived = __shfl_sync(kFull, arrived, 0);
+                    if (arrived < need) __nanosleep(256);
+                } while (arrived < need && ++spins < (1u << 24));   // bounded (seconds): a broken upload must not hang the GPU
+                if (arrived < need) overflow = true;                  // reported as a failed call
+            }
             if (!alive) {
                 const unsigned idx = base + __popc(mDead & ltMask);
                 if (idx < count && idx >= base) {
                     ray = perm ? perm[idx] : idx;   // longest-first fetch order; results still go to the ray's own slot
-                    const float4 r0 = in[3 * size_t(ray)], r1 = in[3 * size_t(ray) + 1], r2 = in[3 * size_t(ray) + 2];
+                    reported = false;
+                    // (L1-bypassing loads: in streaming mode these bytes were written by the copy engine while the kernel runs)
+                    const float4 r0 = __ldcg(in + 3 * size_t(ray)), r1 = __ldcg(in + 3 * size_t(ray) + 1), r2 = __ldcg(in + 3 * size_t(ray) + 2);
                     if (!inPlace) { out[3 * size_t(ray)] = r0; out[3 * size_t(ray) + 1] = r1; }
                     const int id = __float_as_int(r0.w);
                     hitID = -1;
@@ -396,6 +449,19 @@ trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restr
         }
     }
 
+    if (streamIn.watermark) {   // the rays finished after this warp's last refill
+        __threadfence();
+        const bool mine = !reported;
+        const unsigned chunk = mine ? ray / streamIn.chunkRays : 0xffffffffu;
+        unsigned pending = __ballot_sync(kFull, mine);
+        while (pending) {
+            const int leader = __ffs(pending) - 1;
+            const unsigned c = __shfl_sync(kFull, chunk, leader);
+            const unsigned same = __ballot_sync(kFull, mine && chunk == c);
+            if (int(lane) == leader) atomicAdd(streamIn.chunkDone + c, unsigned(__popc(same)));
+            pending &= ~same;
+        }
+    }
     if (overflow) atomicAdd(&counters[5], 1ull);
     if (COUNT) {
         const unsigned v[4] = {cTlas, cInst, cBlas, cTri};
@@ -572,7 +638,8 @@ int scene_fast_flag(atlas_rt_context* ctx, atlas_rt_scene* scene, const uint32_t
 
 int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float4* dIn, float4* dOut, uint64_t count,
                  uint32_t cullMask, float tMin, float tMax, bool any, bool perRayTMax, bool counters, bool resetCounters, bool opacity,
-                 cudaStream_t st, int queueSlot, const uint32_t* dCount, bool hitsOnly) {
+                 cudaStream_t st, int queueSlot, const uint32_t* dCount, bool hitsOnly, const unsigned int* watermark, unsigned int* chunkDone,
+                 uint32_t chunkRays) {
     if (!st) st = ctx->stream;
     if (count == 0) return ATLAS_RT_OK;
     if (count > 0x7fffffffull) return fail(ctx, ATLAS_RT_ERR_UNSUPPORTED, "more than 2^31-1 rays in one batch");
@@ -592,7 +659,8 @@ int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float
     uint32_t* perm = nullptr;
     uint8_t* bucketOf = nullptr;
     unsigned int* hist = nullptr;
-    if (ctx->traceLongestFirst && n >= uint32_t(ctx->traceLongestFirstMin) && scene->tlas->nodeCount > 0) {
+    const StreamIn streamIn{watermark, chunkDone, chunkRays ? chunkRays : 1u};
+    if (ctx->traceLongestFirst && n >= uint32_t(ctx->traceLongestFirstMin) && scene->tlas->nodeCount > 0 && !watermark) {
         ATLAS_CUDA(ctx, dev_alloc_on(st, &perm, n));
         ATLAS_CUDA(ctx, dev_alloc_on(st, &bucketOf, n));
         ATLAS_CUDA(ctx, dev_alloc_on(st, &hist, kCostBuckets + 2));
@@ -609,7 +677,7 @@ int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float
     const int pr = perRayTMax ? 1 : 0, sf = scene->fastDivision, ho = hitsOnly ? 1 : 0;
     cudaError_t launchErr = cudaSuccess;
 #define ATLAS_TRACE_LAUNCH(A, C, O) \
-    launchErr = launch_chain(ctx->chainLaunch != 0, trace_kernel<A, C, O>, grid, kTraceBlock, 0, st, sc, dIn, dOut, perm, hist ? hist + kCostBuckets + 1 : nullptr, n, dCount, cullMask, tMin, tMax, pr, sf, ho, lt, rt, rayCounter, ctx->dCounters)
+    launchErr = launch_chain(ctx->chainLaunch != 0, trace_kernel<A, C, O>, grid, kTraceBlock, 0, st, sc, dIn, dOut, perm, hist ? hist + kCostBuckets + 1 : nullptr, n, dCount, cullMask, tMin, tMax, pr, sf, ho, lt, rt, rayCounter, ctx->dCounters, streamIn)
     if (opacity) {
         if (any) { if (counters) ATLAS_TRACE_LAUNCH(true, true, true); else ATLAS_TRACE_LAUNCH(true, false, true); }
         else { if (counters) ATLAS_TRACE_LAUNCH(false, true, true); else ATLAS_TRACE_LAUNCH(false, false, true); }

@@ -320,3 +320,106 @@ def planar_uvs(tris, scale=1.0):
     """(n, 6) texture coordinates: xz of every corner times `scale`."""
     t = np.asarray(tris, dtype=np.float32).reshape(-1, 3, 3)
     return (t[:, :, [0, 2]] * np.float32(scale)).reshape(-1, 6).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------- other in-tree callers (SURVEY.md 8f-1)
+# Ray distributions of the engine's other users of HitClosest / HitAny, generated from a G-buffer (world positions P, unit
+# normals N, unit view vectors V = towards the camera) the way their shaders do. These are workload generators: the same
+# arrays go to the CUDA path and to the oracle, so their own arithmetic (float64 here) is not a parity matter.
+EPSILON = 0.1   # raytracer/common.hsh:9
+
+
+def _basis(N):
+    up = np.where((np.abs(N[:, 2]) < 0.999)[:, None], np.array([0.0, 0.0, 1.0]), np.array([1.0, 0.0, 0.0]))
+    t = np.cross(up, N)
+    t /= np.maximum(np.linalg.norm(t, axis=1, keepdims=True), 1e-30)
+    return t, np.cross(N, t)
+
+
+def _cosine_dirs(N, u):
+    """ImportanceSampleCosDir / SampleDiffuseBRDF (brdf/importanceSample.hsh:85-104, brdf/brdfSample.hsh:8-32)."""
+    N = np.asarray(N, dtype=np.float64)
+    r, phi = np.sqrt(u[:, 0]), 2.0 * np.pi * u[:, 1]
+    t, b = _basis(N)
+    d = t * (r * np.cos(phi))[:, None] + b * (r * np.sin(phi))[:, None] + N * np.sqrt(1.0 - u[:, 0])[:, None]
+    return d / np.linalg.norm(d, axis=1, keepdims=True)
+
+
+def rtao_rays(P, N, u, radius):
+    """ao/rtao.csh:81-100: one cosine-distributed ray per pixel, origin = P + dir * EPSILON + N * EPSILON, any hit within
+    `radius` (per-ray tMax in hit.x), cull mask INSTANCE_MASK_ALL."""
+    d = _cosine_dirs(N, u)
+    o = np.asarray(P, np.float64) + d * EPSILON + np.asarray(N, np.float64) * EPSILON
+    return pack_rays(o.astype(np.float32), d.astype(np.float32), t=np.full(len(o), radius, np.float32))
+
+
+def rtgi_rays(P, N, u, view_dist, bias=0.0):
+    """rtgi/rtgi.csh:110-137: cosine-distributed ray, origin offset scaled by the view distance, closest hit up to INF."""
+    uu = u.copy()
+    uu[:, 0] *= (1.0 - bias)
+    d = _cosine_dirs(N, uu)
+    off = np.maximum(1.0, np.asarray(view_dist, np.float64))[:, None]
+    o = np.asarray(P, np.float64) + d * EPSILON * off * 0.01 + np.asarray(N, np.float64) * EPSILON * 0.01 * off
+    return pack_rays(o.astype(np.float32), d.astype(np.float32))
+
+
+def reflection_rays(P, N, V, roughness, u, view_dist, bias=0.0):
+    """reflection/rtreflection.csh:104-141: GGX visible-normal importance sample (brdf/importanceSample.hsh:36-83) for
+    roughness > 0.01, the mirror direction otherwise; origin offset scaled by the view distance; closest hit up to INF."""
+    P, N, V = (np.asarray(x, np.float64) for x in (P, N, V))
+    alpha = roughness * roughness
+    uu = u.copy()
+    uu[:, 1] *= (1.0 - bias)
+    t, b = _basis(N)
+    b = b / np.maximum(np.linalg.norm(b, axis=1, keepdims=True), 1e-30)
+    Vt = np.stack([(V * t).sum(1), (V * b).sum(1), (V * N).sum(1)], axis=1)
+    Vh = np.stack([Vt[:, 0] * alpha, Vt[:, 1] * alpha, Vt[:, 2]], axis=1)
+    Vh /= np.linalg.norm(Vh, axis=1, keepdims=True)
+    phi = 2.0 * np.pi * uu[:, 0]
+    z = (1.0 - uu[:, 1]) * (1.0 + Vh[:, 2]) - Vh[:, 2]
+    s = np.sqrt(np.clip(1.0 - z * z, 0.0, 1.0))
+    H = np.stack([s * np.cos(phi), s * np.sin(phi), z], axis=1) + Vh
+    Hs = np.stack([H[:, 0] * alpha, H[:, 1] * alpha, np.maximum(H[:, 2], 0.0)], axis=1)
+    Hw = t * Hs[:, 0:1] + b * Hs[:, 1:2] + N * Hs[:, 2:3]
+    Hw /= np.maximum(np.linalg.norm(Hw, axis=1, keepdims=True), 1e-30)
+    d = 2.0 * (V * Hw).sum(1, keepdims=True) * Hw - V
+    if roughness <= 0.01:
+        d = 2.0 * (V * N).sum(1, keepdims=True) * N - V
+    d /= np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-30)
+    off = np.maximum(1.0, np.asarray(view_dist, np.float64))[:, None] * 0.1
+    o = P + d * EPSILON * 0.1 * off + N * EPSILON * off * 0.1
+    ids = np.where((d * N).sum(1) >= 0.0, np.arange(len(P)), -1)      # rays below the surface are not cast
+    return pack_rays(o.astype(np.float32), d.astype(np.float32), ids=ids)
+
+
+def ddgi_rays(lo, hi, probes=(12, 6, 12), rays_per_probe=128, inactive_every=7, seed=0):
+    """ddgi/rayGen.csh:44-83: every probe of a regular grid casts `rays_per_probe` rays along a spherical Fibonacci set
+    rotated by a random rotation; rays a probe does not use (inactive probes cast fewer) carry ID = -1; ID = probe * rays + i."""
+    rng = np.random.default_rng(seed)
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    w, x, y, z = q
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    i = np.arange(rays_per_probe) + 0.5
+    phi = 2.0 * np.pi * ((i * 0.6180339887498949) % 1.0)
+    ct = 1.0 - 2.0 * i / rays_per_probe
+    st = np.sqrt(np.clip(1.0 - ct * ct, 0.0, 1.0))
+    dirs = (np.stack([st * np.cos(phi), st * np.sin(phi), ct], axis=1) @ R.T)
+    gx, gy, gz = (np.linspace(lo[k], hi[k], probes[k] + 2)[1:-1] for k in range(3))
+    G = np.stack(np.meshgrid(gx, gy, gz, indexing="ij"), axis=-1).reshape(-1, 3)
+    o = np.repeat(G, rays_per_probe, axis=0)
+    d = np.tile(dirs, (len(G), 1))
+    ids = np.arange(len(o))
+    probe = ids // rays_per_probe
+    inactive = (probe % inactive_every == 0) & ((ids % rays_per_probe) >= rays_per_probe // 4)   # inactive probes cast a quarter of the rays
+    return pack_rays(o.astype(np.float32), d.astype(np.float32), ids=np.where(inactive, -1, ids))
+
+
+def gbuffer_from_hits(rays_out, tris_by_mesh_slot=None, normals=None):
+    """World positions of primary hits and the view vectors towards the camera: P = o + t d, V = -d; rows without a hit are
+    dropped. Returns (P, V, view_dist, keep_mask)."""
+    hit = rays_out[:, 9].view(np.int32) >= 0
+    o, d, t = rays_out[hit, 0:3].astype(np.float64), rays_out[hit, 4:7].astype(np.float64), rays_out[hit, 8].astype(np.float64)
+    return o + d * t[:, None], -d, t, hit
