@@ -716,6 +716,7 @@ static int trace_common(atlas_rt_context* ctx, const atlas_rt_scene* scene, cons
         if (e == cudaSuccess)
             rc = launch_trace(ctx, scene, dIn, out, count, cull_mask, t_min, t_max, any, perRay, counters, true, opacity, nullptr, 0, nullptr, hitsOnly,
                               ctx->dStreamState, ctx->dStreamState + 1, chunkRays);
+        if (e == cudaSuccess && rc == ATLAS_RT_OK) rc = launch_release_chunks(ctx, ctx->dStreamState + 1, chunkRays, uint32_t(count), chunks);
         for (uint32_t c = 0; c < chunks && e == cudaSuccess && rc == ATLAS_RT_OK; c++) {
             const uint64_t b = uint64_t(c) * chunkRays, end = std::min<uint64_t>(count, b + chunkRays);
             e = cudaMemcpyAsync(dIn + 3 * b, static_cast<const char*>(rays_in) + 48 * b, 48 * (end - b), cudaMemcpyHostToDevice, ctx->copyIn);

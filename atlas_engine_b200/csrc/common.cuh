@@ -156,7 +156,7 @@ struct atlas_rt_scene {
     const float4** bvhTris = nullptr;        // device array [meshCount]
     const float4** triangles = nullptr;      // device array [meshCount] of 96-byte triangle arrays (entries may be null)
     bool allShading = false;                 // every mesh has its 96-byte array: the opacity-aware variants may run
-    int fastDivision = 0;                    // all scene coordinates below 2^60: slab tests may use div_by_rcp (trace.cu)
+    int fastDivision = 0;                    // bit 0: all scene coordinates below 2^60 (slab tests may use div_by_rcp, trace.cu); bit 1: no non-zero box coordinate below 2^-60
     // material / texture tables (atlas_rt_scene_set_materials): textured opacity in traversal, shading in the path tracer
     uint32_t* materials = nullptr;           // RaytraceMaterial, 23 words each
     uint32_t materialCount = 0;
@@ -234,6 +234,8 @@ cudaError_t launch_chain(bool pdl, void (*kernel)(P...), dim3 grid, dim3 block, 
     cfg.numAttrs = pdl ? 1u : 0u;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<A>(args)...);
 }
+
+int launch_release_chunks(atlas_rt_context* ctx, unsigned int* chunkDone, uint32_t chunkRays, uint32_t count, uint32_t chunks);
 
 // Copy count*bytes from src (host or device according to `device`) into device memory on the context stream.
 cudaError_t copy_in(atlas_rt_context* ctx, void* dst, const void* src, size_t bytes, bool srcDevice);

@@ -115,10 +115,14 @@ __device__ __forceinline__ bool tri_test(const float o[3], const float d[3], con
 // RN(x * rc) is then a faithful quotient and one FMA residual + one FMA correction (Markstein's theorem) give the
 // correctly rounded x / d — three fma-pipe instructions and nothing on the XU (MUFU) pipe, which the 12 IEEE divisions
 // per node otherwise saturate (profiles/trace_r1.md: XU pipe 58 % busy in the first version).
-// Valid while nothing over/underflows: the caller only takes this path for rays whose direction components lie in
-// [2^-64, 2^64] and whose origin / scene coordinates are below 2^60 (`fast` flag); all other rays use __fdiv_rn.
-// tools/divcheck.cu compared this sequence with __fdiv_rn on 3.2e11 operand pairs (uniform and adversarial
-// mantissas, exponents over the whole admitted range) on a B200: 0 mismatches.
+// Valid while nothing over- or UNDERflows — the quotient, and the residual e, which is about 2^-24 of x, must stay normal:
+// the caller only takes this path (`fast` flag) for rays whose direction components lie in [2^-64, 2^30], whose origin
+// components are below 2^60 and either at least 2^-40 in magnitude or exactly zero in a scene whose boxes hold no
+// non-zero coordinate below 2^-60 (scene flag bit 1), in scenes with all coordinates below 2^60 (bit 0). Then every
+// numerator x = box - origin is 0 (quotient exactly 0 either way) or at least 2^-64, the quotient at least 2^-94 and the
+// residual at least 2^-118. All other rays use __fdiv_rn. tools/divcheck.cu compares this sequence with __fdiv_rn over
+// the admitted domain (uniform and adversarial mantissas, exponents over the whole range, zero numerators): 0 mismatches
+// in 3e11 operand pairs on a B200 — and shows that mismatches DO occur once the quotient or the residual goes subnormal.
 __device__ __forceinline__ float div_by_rcp(float x, float d, float rc) {
     const float q = __fmul_rn(x, rc);
     const float e = __fmaf_rn(-d, q, x);
@@ -146,15 +150,18 @@ __device__ __forceinline__ bool slab_fast(const float o[3], const float d[3], co
 }
 
 constexpr float kDirLo = 5.421010862427522e-20f;   // 2^-64
-constexpr float kDirHi = 1.8446744073709552e19f;   // 2^64
+constexpr float kDirHi = 1073741824.0f;            // 2^30
 constexpr float kPosHi = 1.152921504606847e18f;    // 2^60
+constexpr float kPosLo = 9.094947017729282e-13f;   // 2^-40
+constexpr float kCoordLo = 8.673617379884035e-19f; // 2^-60: smallest non-zero box coordinate for which origin components of exactly 0 stay fast
 
-__device__ __forceinline__ bool fast_ok(const float o[3], const float d[3]) {
-    bool ok = true;
+__device__ __forceinline__ bool fast_ok(const float o[3], const float d[3], int sceneFlags) {
+    bool ok = (sceneFlags & 1) != 0;
+    const bool zeroOk = (sceneFlags & 2) != 0;
 #pragma unroll
     for (int a = 0; a < 3; a++) {
-        const float ad = fabsf(d[a]);
-        ok = ok && (ad >= kDirLo) && (ad <= kDirHi) && (fabsf(o[a]) <= kPosHi);
+        const float ad = fabsf(d[a]), ao = fabsf(o[a]);
+        ok = ok && (ad >= kDirLo) && (ad <= kDirHi) && (ao <= kPosHi) && (ao >= kPosLo || (ao == 0.0f && zeroOk));
     }
     return ok;
 }
@@ -221,7 +228,7 @@ trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restr
     auto set_ray = [&](const float oo[3], const float dd[3]) {
 #pragma unroll
         for (int a = 0; a < 3; a++) { o[a] = oo[a]; d[a] = dd[a]; }
-        fast = sceneFast && fast_ok(o, d);
+        fast = fast_ok(o, d, sceneFast);
 #pragma unroll
         for (int a = 0; a < 3; a++) rc[a] = fast ? __frcp_rn(d[a]) : 0.0f;
     };
@@ -269,7 +276,7 @@ trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restr
                     if (int(lane) == leader) atomicAdd(streamIn.chunkDone + c, unsigned(__popc(same)));
                     pending &= ~same;
                 }
-                reported = true;
+                if (mine) reported = true;   // live lanes keep their flag: their ray is still on its way
             }
             unsigned base = 0;
             if (lane == 0) base = atomicAdd(rayCounter, unsigned(nDead));
@@ -618,6 +625,47 @@ __global__ void scene_bounds(const float4* __restrict__ tlasNodes, uint32_t tlas
     atomicMax(maxAbsBits, __float_as_uint(m));   // non-negative floats order like their bit patterns
 }
 
+// Smallest NON-ZERO coordinate magnitude in any node box of the scene (TLAS = mesh index meshCount): decides whether rays
+// with an origin component of exactly zero may take the fast division path (see div_by_rcp).
+__global__ void __launch_bounds__(256)
+scene_min_abs(const float4* __restrict__ tlasNodes, uint32_t tlasNodeCount, const float4* const* __restrict__ blasNodes,
+              const uint32_t* __restrict__ blasNodeCounts, uint32_t meshCount, unsigned int* __restrict__ minAbsBits) {
+    const uint32_t mesh = blockIdx.y;
+    const float4* N = mesh == meshCount ? tlasNodes : blasNodes[mesh];
+    const uint32_t nodes = mesh == meshCount ? tlasNodeCount : blasNodeCounts[mesh];
+    unsigned int best = 0x7f800000u;
+    for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < uint64_t(nodes) * 3; i += uint64_t(gridDim.x) * blockDim.x) {
+        const float4 v = N[(i / 3) * 4 + i % 3];   // the three float4s that hold the two boxes
+        const float c[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const unsigned int b = __float_as_uint(fabsf(c[k]));
+            if (b != 0u && b < best) best = b;
+        }
+    }
+    best = __reduce_min_sync(0xffffffffu, best);
+    if ((threadIdx.x & 31u) == 0u && best != 0x7f800000u) atomicMin(minAbsBits, best);
+}
+
+// Runs behind the streaming trace kernel on the same stream: every ray is finished by then, so every chunk's completion
+// count is set to its target. The per-warp counts inside the kernel only release chunks EARLY; this makes the release
+// unconditional, so a download stream can never be left waiting.
+__global__ void release_chunks(unsigned int* chunkDone, uint32_t chunkRays, uint32_t count) {
+    chain_begin();
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t b = uint64_t(c) * chunkRays;
+    if (b < count) atomicMax(chunkDone + c, unsigned(min(uint64_t(count), b + chunkRays) - b));
+}
+
+}   // namespace
+
+int launch_release_chunks(atlas_rt_context* ctx, unsigned int* chunkDone, uint32_t chunkRays, uint32_t count, uint32_t chunks) {
+    release_chunks<<<(chunks + 63) / 64, 64, 0, ctx->stream>>>(chunkDone, chunkRays, count);
+    ATLAS_LAUNCH_CHECK(ctx);
+    return ATLAS_RT_OK;
+}
+
+namespace {
 }   // namespace
 
 int scene_fast_flag(atlas_rt_context* ctx, atlas_rt_scene* scene, const uint32_t* dNodeCounts) {
@@ -633,6 +681,20 @@ int scene_fast_flag(atlas_rt_context* ctx, atlas_rt_scene* scene, const uint32_t
     float m;
     memcpy(&m, &bits, sizeof(m));
     scene->fastDivision = (m <= kPosHi) ? 1 : 0;
+    if (scene->fastDivision) {
+        unsigned int* dMin = dMax;
+        const unsigned int inf = 0x7f800000u;
+        memcpy(ctx->pinned, &inf, sizeof(inf));
+        ATLAS_CUDA(ctx, cudaMemcpyAsync(dMin, ctx->pinned, sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->stream));
+        scene_min_abs<<<dim3(64, scene->meshCount + 1), 256, 0, ctx->stream>>>(scene->tlas->nodes, uint32_t(scene->tlas->nodeCount), scene->blasNodes,
+                                                                               dNodeCounts, scene->meshCount, dMin);
+        ATLAS_LAUNCH_CHECK(ctx);
+        ATLAS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, dMin, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+        ATLAS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        memcpy(&bits, ctx->pinned, sizeof(bits));
+        memcpy(&m, &bits, sizeof(m));
+        if (m >= kCoordLo) scene->fastDivision |= 2;
+    }
     return ATLAS_RT_OK;
 }
 

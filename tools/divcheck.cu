@@ -17,11 +17,15 @@ __global__ void check(uint64_t seed, int iters, int mode, unsigned long long* ou
     for (int i = 0; i < iters; i++) {
         const uint64_t r = splitmix(s);
         uint32_t xb = uint32_t(r), db = uint32_t(r >> 32);
-        // exponents: d in [2^-64, 2^64], x in [2^-60, 2^60]; mode 1: adversarial mantissas (all ones / near powers of two)
-        uint32_t xe = 127 - 60 + (xb >> 23) % 121, de = 127 - 64 + (db >> 23) % 129;
+        // the admitted domain of trace.cu's fast path: d in [2^-64, 2^30], x == 0 or in [2^-64, 2^61]; mode 1: adversarial
+        // mantissas (all ones / near powers of two); mode 2: OUTSIDE the domain — x down to the subnormals, d up to 2^64 — to
+        // show that the guards are needed (mismatches expected there)
+        uint32_t xe = 127 - 64 + (xb >> 23) % 126, de = 127 - 64 + (db >> 23) % 95;
+        if (mode == 2) { xe = (xb >> 23) % 64; de = 127 - 10 + (db >> 23) % 75; }
         uint32_t xm = xb & 0x7fffff, dm = db & 0x7fffff;
         if (mode == 1) { const uint64_t q = splitmix(s); if (q & 1) dm |= 0x7ffff0; if (q & 2) xm |= 0x7fff00; if (q & 4) dm &= 0xf; if (q & 8) xm &= 0xff; }
-        const float x = __uint_as_float((xb & 0x80000000u) | (xe << 23) | xm);
+        float x = __uint_as_float((xb & 0x80000000u) | (xe << 23) | xm);
+        if (mode != 2 && (r & 0xff0000u) == 0u) x = (xb & 0x80000000u) ? -0.0f : 0.0f;   // exact zero numerators (origin on a box plane)
         const float d = __uint_as_float((db & 0x80000000u) | (de << 23) | dm);
         const float ref = __fdiv_rn(x, d);
         const float rc = __frcp_rn(d);
@@ -40,13 +44,14 @@ __global__ void check(uint64_t seed, int iters, int mode, unsigned long long* ou
 int main() {
     unsigned long long* d;
     cudaMalloc(&d, 16);
-    for (int mode = 0; mode < 2; mode++) {
+    for (int mode = 0; mode < 3; mode++) {
         cudaMemset(d, 0, 16);
         const int blocks = 148 * 16, threads = 256, iters = 1 << 14, rounds = 16;
         for (int r = 0; r < rounds; r++) check<<<blocks, threads>>>(0xABCDEFull * (r + 1) + mode, iters, mode, d);
         cudaDeviceSynchronize();
         unsigned long long h[2];
         cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+        if (mode == 2) printf("(outside the admitted domain: subnormal quotients / residuals) ");
         printf("mode %d: samples %.3e  one-step mismatches %llu  two-step mismatches %llu  (%s)\n", mode,
                double(blocks) * threads * iters * rounds, h[0], h[1], cudaGetErrorString(cudaGetLastError()));
     }
