@@ -199,8 +199,22 @@ int atlas_rt_context_create(int device, void* stream, atlas_rt_context** out_ctx
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) ctx->waitValue32 = fn;
         else cudaGetLastError();
+        fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) ctx->writeValue32 = fn;
+        else cudaGetLastError();
     }
     if (const char* e = getenv("ATLAS_RT_TRACE_STREAMING")) ctx->traceStreaming = atoi(e);
+    if (const char* e = getenv("ATLAS_RT_STREAM_SPIN_LOG2")) ctx->streamSpinLog2 = std::max(8, std::min(28, atoi(e)));
+    if (const char* e = getenv("ATLAS_RT_L2_PERSIST_MB")) ctx->l2PersistMB = std::max(0, atoi(e));
+    if (const char* e = getenv("ATLAS_RT_L2_HIT_RATIO")) ctx->l2HitRatio = float(atof(e));
+    if (ctx->l2PersistMB > 0) {   // carve persisting lines out of the L2 for the node array a trace launch declares hot
+        int maxPersist = 0, maxWindow = 0;
+        cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, device);
+        cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, device);
+        const size_t want = std::min<size_t>(size_t(ctx->l2PersistMB) << 20, size_t(maxPersist));
+        if (want == 0 || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) { cudaGetLastError(); ctx->l2PersistMB = 0; }
+        ctx->l2WindowMax = size_t(maxWindow);
+    }
     ctx->pinnedBytes = 8192;
     if (cudaMallocHost(&ctx->pinned, ctx->pinnedBytes) != cudaSuccess) { cudaFree(ctx->dCounters); delete ctx; return ATLAS_RT_ERR_OOM; }
     ctx->levelSlots = static_cast<char*>(ctx->pinned) + 4096;
@@ -564,6 +578,10 @@ int atlas_rt_scene_create(atlas_rt_context* ctx, const atlas_rt_mesh* const* mes
     scene->instanceCount = tlas->refCount;
     scene->allShading = allShading;
     scene->partMeshes.assign(meshes, meshes + mesh_count);
+    scene->hotNodes = tlas->nodes;
+    scene->hotBytes = size_t(tlas->nodeCount) * 64;
+    for (uint32_t m = 0; m < mesh_count; m++)
+        if (size_t(meshes[m]->blas->nodeCount) * 64 > scene->hotBytes) { scene->hotNodes = meshes[m]->blas->nodes; scene->hotBytes = size_t(meshes[m]->blas->nodeCount) * 64; }
     Staged st(ctx);
     cudaError_t e = cudaSuccess;
     const uint32_t* dNodeCounts = static_cast<const uint32_t*>(st.in(nodeCounts.data(), mesh_count * sizeof(uint32_t), false, &e));
@@ -690,50 +708,53 @@ static int trace_common(atlas_rt_context* ctx, const atlas_rt_scene* scene, cons
     }
     int rc = ATLAS_RT_OK;
     const uint64_t kPipeMin = 262144;
-    if (!devIn && count >= kPipeMin && count < 0x7fffffffull && ctx->copyIn && ctx->copyOut && ctx->waitValue32 && ctx->traceStreaming) {
+    if (!devIn && count >= kPipeMin && count < 0x7fffffffull && ctx->copyIn && ctx->copyOut && ctx->waitValue32 && ctx->writeValue32 && ctx->traceStreaming) {
         // Host input, streaming: ONE persistent launch traces the batch while it is still being uploaded. The upload stream
-        // copies the rays in chunks and bumps a watermark in device memory behind each chunk (a 4-byte copy from pinned
-        // memory, ordered after the chunk by the stream); the kernel only fetches rays below the watermark. Every warp
-        // reports the rays it has finished per chunk; the download stream waits on each chunk's count with
-        // cuStreamWaitValue32 and sends that chunk's results home while later chunks are still being traced. Against the
-        // chunked pipeline below (one small launch + three ordering kernels per chunk, each paying its own longest ray)
-        // this removes every per-chunk launch and leaves a single drain at the end.
-        typedef int (*WaitValue32)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
-        const WaitValue32 waitValue = reinterpret_cast<WaitValue32>(ctx->waitValue32);
+        // copies the rays in chunks and bumps a watermark in device memory behind each chunk (cuStreamWriteValue32: a
+        // stream memory operation of the channel front end — no SM and no copy engine involved, which matters because the
+        // persistent kernel owns every SM); the kernel only fetches rays below the watermark. Every warp reports the rays it
+        // has finished per chunk; the download stream waits on each chunk's count with cuStreamWaitValue32 and sends that
+        // chunk's results home while later chunks are still being traced. Against the chunked pipeline below (one small
+        // launch + three ordering kernels per chunk, each paying its own longest ray) this removes every per-chunk launch
+        // and leaves a single drain at the end.
+        // Submission order matters when streams share a hardware queue: nothing that can block (the value waits, the
+        // release kernel that depends on the trace kernel) is submitted before the work it could hold up.
+        typedef int (*StreamValue32)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+        const StreamValue32 waitValue = reinterpret_cast<StreamValue32>(ctx->waitValue32);
+        const StreamValue32 writeValue = reinterpret_cast<StreamValue32>(ctx->writeValue32);
         uint32_t chunks = uint32_t(std::max<uint64_t>(4, std::min<uint64_t>(48, count / 65536)));
         if (const char* e = getenv("ATLAS_RT_STREAM_CHUNKS")) chunks = uint32_t(std::max(1, std::min(60, atoi(e))));
         const uint32_t chunkRays = uint32_t(((count + chunks - 1) / chunks + 31) & ~uint64_t(31));
         chunks = uint32_t((count + chunkRays - 1) / chunkRays);
-        cudaEvent_t* ev = ctx->pipeEvents;   // [0] state reset, [32] all uploaded (previous call), [33] all downloaded
-        unsigned int* marks = reinterpret_cast<unsigned int*>(static_cast<char*>(ctx->pinned) + 2048);   // watermark values, pinned
-        cudaError_t e = cudaSuccess;
-        if (ctx->streamCalls) e = cudaEventSynchronize(ev[32]);   // the previous call's upload still reads `marks`
-        for (uint32_t c = 0; c < chunks; c++) marks[c] = uint32_t(std::min<uint64_t>(count, uint64_t(c + 1) * chunkRays));
-        if (e == cudaSuccess) e = cudaMemsetAsync(ctx->dStreamState, 0, 64 * sizeof(unsigned int), ctx->stream);
+        cudaEvent_t* ev = ctx->pipeEvents;   // [0] state reset, [33] all downloaded
+        const unsigned long long stateAddr = reinterpret_cast<unsigned long long>(ctx->dStreamState);
+        // 1. reset the watermark and the per-chunk counts; both copy streams start after that
+        cudaError_t e = cudaMemsetAsync(ctx->dStreamState, 0, 64 * sizeof(unsigned int), ctx->stream);
         if (e == cudaSuccess) e = cudaEventRecord(ev[0], ctx->stream);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copyIn, ev[0], 0);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copyOut, ev[0], 0);
-        if (e == cudaSuccess)
-            rc = launch_trace(ctx, scene, dIn, out, count, cull_mask, t_min, t_max, any, perRay, counters, true, opacity, nullptr, 0, nullptr, hitsOnly,
-                              ctx->dStreamState, ctx->dStreamState + 1, chunkRays);
-        if (e == cudaSuccess && rc == ATLAS_RT_OK) rc = launch_release_chunks(ctx, ctx->dStreamState + 1, chunkRays, uint32_t(count), chunks);
-        for (uint32_t c = 0; c < chunks && e == cudaSuccess && rc == ATLAS_RT_OK; c++) {
+        // 2. uploads, each followed by the watermark it justifies
+        bool started = false;
+        for (uint32_t c = 0; c < chunks && e == cudaSuccess; c++) {
             const uint64_t b = uint64_t(c) * chunkRays, end = std::min<uint64_t>(count, b + chunkRays);
             e = cudaMemcpyAsync(dIn + 3 * b, static_cast<const char*>(rays_in) + 48 * b, 48 * (end - b), cudaMemcpyHostToDevice, ctx->copyIn);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->dStreamState, marks + c, sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->copyIn);
+            if (e == cudaSuccess && writeValue(ctx->copyIn, stateAddr, unsigned(end), 0u) != 0) e = cudaErrorUnknown;
         }
-        if (e != cudaSuccess || rc != ATLAS_RT_OK)   // never leave the kernel waiting for rays that will not come
-            cudaMemcpyAsync(ctx->dStreamState, marks + (chunks - 1), sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->copyIn);
-        if (e == cudaSuccess) e = cudaEventRecord(ev[32], ctx->copyIn);
-        ctx->streamCalls++;
+        // 3. the persistent trace kernel (it may already find the first chunks in place)
+        if (e == cudaSuccess) {
+            rc = launch_trace(ctx, scene, dIn, out, count, cull_mask, t_min, t_max, any, perRay, counters, true, opacity, nullptr, 0, nullptr, hitsOnly,
+                              ctx->dStreamState, ctx->dStreamState + 1, chunkRays);
+            started = rc == ATLAS_RT_OK;
+        }
+        // 4. downloads, each behind its chunk's completion count
         for (uint32_t c = 0; c < chunks && e == cudaSuccess && rc == ATLAS_RT_OK && !devOut; c++) {
             const uint64_t b = uint64_t(c) * chunkRays, end = std::min<uint64_t>(count, b + chunkRays);
-            if (waitValue(ctx->copyOut, reinterpret_cast<unsigned long long>(ctx->dStreamState + 1 + c), unsigned(end - b), 0u /* CU_STREAM_WAIT_VALUE_GEQ */) != 0) {
-                e = cudaErrorUnknown;
-                break;
-            }
+            if (waitValue(ctx->copyOut, stateAddr + 4ull * (1 + c), unsigned(end - b), 0u /* CU_STREAM_WAIT_VALUE_GEQ */) != 0) { e = cudaErrorUnknown; break; }
             e = cudaMemcpyAsync(static_cast<char*>(rays_out) + 16 * outStride * b, out + outStride * b, 16 * outStride * (end - b), cudaMemcpyDeviceToHost, ctx->copyOut);
         }
+        // 5. behind the trace kernel: every chunk's count reaches its target no matter what (the waits above cannot be left hanging)
+        if (started) { const int rr = launch_release_chunks(ctx, ctx->dStreamState + 1, chunkRays, uint32_t(count), chunks); if (rc == ATLAS_RT_OK) rc = rr; }
+        if (started && e != cudaSuccess) writeValue(ctx->copyIn, stateAddr, unsigned(count), 0u);   // never leave the kernel waiting for rays that will not come
         if (e == cudaSuccess) e = cudaEventRecord(ev[33], ctx->copyOut);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev[33], 0);   // the context stream now orders after the downloads
         if (e != cudaSuccess && rc == ATLAS_RT_OK) rc = fail(ctx, ATLAS_RT_ERR_CUDA, "streaming trace", e);

@@ -83,9 +83,14 @@ struct atlas_rt_context {
     std::string error;
     unsigned long long* dCounters = nullptr;   // 16 x u64: [0..5] traversal counters / overflow flag, [8..15] ray-queue heads (one per compute stream)
     unsigned int* dStreamState = nullptr;      // 64 x u32: [0] upload watermark of a streaming host-buffer trace, [1..] per-chunk completion counts
-    void* waitValue32 = nullptr;               // cuStreamWaitValue32 (driver entry point), or null: chunked pipeline instead of streaming
-    int traceStreaming = 1;                    // host-buffer traces as ONE persistent launch that consumes rays while they arrive
-    uint64_t streamCalls = 0;
+    void* waitValue32 = nullptr;               // cuStreamWaitValue32 / cuStreamWriteValue32 (driver entry points), or null: chunked pipeline instead of streaming
+    void* writeValue32 = nullptr;
+    int streamSpinLog2 = 22;                   // bound of one watermark wait in the kernel: 2^22 x 256 ns, about a second
+    int traceStreaming = 0;                    // ATLAS_RT_TRACE_STREAMING=1: host-buffer traces as ONE persistent launch that consumes rays while they arrive
+                                               // (measured slower than the chunked pipeline on C2: arrival order forfeits the longest-first fetch order)
+    int l2PersistMB = 0;                       // ATLAS_RT_L2_PERSIST_MB: size of the persisting-L2 carve-out used for a scene's hottest node array (0 = off)
+    float l2HitRatio = 1.0f;
+    size_t l2WindowMax = 0;
     void* pinned = nullptr;                    // small pinned staging area for read-backs
     size_t pinnedBytes = 0;
     // copy engines used to overlap H2D / trace / D2H when a trace call is given host buffers (api.cu)
@@ -164,6 +169,8 @@ struct atlas_rt_scene {
     uint32_t textureCount = 0;
     uint8_t* texelStorage = nullptr;
     // the meshes the scene was assembled from (borrowed unless also listed as owned): atlas_rt_scene_replicate walks them
+    const void* hotNodes = nullptr;          // the largest node array of the scene (L2 access-policy window of the trace launches)
+    size_t hotBytes = 0;
     std::vector<const atlas_rt_mesh*> partMeshes;
     // objects created on the scene's behalf (atlas_rt_build_scene_sharded, atlas_rt_scene_replicate): freed with the scene
     std::vector<atlas_rt_mesh*> ownedMeshes;
@@ -220,19 +227,45 @@ __device__ __forceinline__ void chain_begin() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+// Optional L2 access-policy window of a launch (the hot node array of a scene): hits inside the window are kept as
+// persisting lines, everything else streams.
+struct L2Window {
+    const void* base = nullptr;
+    size_t bytes = 0;
+    float hitRatio = 1.0f;
+};
+
 template <typename... P, typename... A>
-cudaError_t launch_chain(bool pdl, void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+cudaError_t launch_chain_w(bool pdl, const L2Window& win, void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr{};
-    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr.val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = &attr;
-    cfg.numAttrs = pdl ? 1u : 0u;
+    cudaLaunchAttribute attrs[2]{};
+    unsigned n = 0;
+    if (pdl) {
+        attrs[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attrs[n].val.programmaticStreamSerializationAllowed = 1;
+        n++;
+    }
+    if (win.base && win.bytes) {
+        attrs[n].id = cudaLaunchAttributeAccessPolicyWindow;
+        attrs[n].val.accessPolicyWindow.base_ptr = const_cast<void*>(win.base);
+        attrs[n].val.accessPolicyWindow.num_bytes = win.bytes;
+        attrs[n].val.accessPolicyWindow.hitRatio = win.hitRatio;
+        attrs[n].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attrs[n].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        n++;
+    }
+    cfg.attrs = attrs;
+    cfg.numAttrs = n;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<A>(args)...);
+}
+
+template <typename... P, typename... A>
+cudaError_t launch_chain(bool pdl, void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+    return launch_chain_w(pdl, L2Window{}, kernel, grid, block, smem, st, std::forward<A>(args)...);
 }
 
 int launch_release_chunks(atlas_rt_context* ctx, unsigned int* chunkDone, uint32_t chunkRays, uint32_t count, uint32_t chunks);

@@ -176,6 +176,7 @@ struct StreamIn {
     const unsigned int* watermark;
     unsigned int* chunkDone;
     uint32_t chunkRays;
+    uint32_t spinBound;
 };
 __device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) {
     unsigned int v;
@@ -188,8 +189,10 @@ __device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) {
 // active lanes). Within a warp every round is warp-uniform: either the lanes standing at an inner node take one
 // traversal step, or — once enough lanes wait at a leaf / instance — those lanes process it. A ray's own visit order is
 // exactly the reference's; only the interleaving between different rays changes.
+// The opacity-aware variants carry the material offset, the triangle's uv words and the texture sampling: one CTA per SM
+// fewer (64 registers instead of 56) keeps them out of local memory.
 template <bool ANY, bool COUNT, bool OPACITY>
-__global__ void __launch_bounds__(kTraceBlock, kBlocksPerSM)
+__global__ void __launch_bounds__(kTraceBlock, OPACITY ? kBlocksPerSM - 1 : kBlocksPerSM)
 trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restrict__ permIn, const unsigned int* __restrict__ usePerm,
              uint32_t count, const uint32_t* __restrict__ countPtr, uint32_t cullMask, float tMin, float tMaxArg,
              int perRayTMax, int sceneFast, int hitsOnly, int kLeafThreshold, int kRefillThreshold, unsigned int* __restrict__ rayCounter,
@@ -290,7 +293,7 @@ trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restr
                     if (lane == 0) arrived = ld_volatile_u32(streamIn.watermark);
                     arrived = __shfl_sync(kFull, arrived, 0);
                     if (arrived < need) __nanosleep(256);
-                } while (arrived < need && ++spins < (1u << 24));   // bounded (seconds): a broken upload must not hang the GPU
+                } while (arrived < need && ++spins < streamIn.spinBound);   // bounded: a broken upload must not hang the GPU
                 if (arrived < need) overflow = true;                  // reported as a failed call
             }
             if (!alive) {
@@ -710,7 +713,8 @@ int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float
     const uint32_t n = uint32_t(count);
     // small batches get fewer persistent warps so that each still refills its lanes many times (>= traceRaysPerWarp rays per warp)
     const uint32_t wantBlocks = std::max<uint32_t>(uint32_t(ctx->smCount) * 2u, n / (uint32_t(ctx->traceRaysPerWarp) * (kTraceBlock / 32)));
-    const uint32_t grid = std::min<uint32_t>(std::min<uint32_t>((n + kTraceBlock - 1) / kTraceBlock, wantBlocks), uint32_t(ctx->smCount) * uint32_t(ctx->traceBlocksPerSM));
+    const uint32_t blocksPerSM = opacity ? std::min(ctx->traceBlocksPerSM, kBlocksPerSM - 1) : ctx->traceBlocksPerSM;
+    const uint32_t grid = std::min<uint32_t>(std::min<uint32_t>((n + kTraceBlock - 1) / kTraceBlock, wantBlocks), uint32_t(ctx->smCount) * blocksPerSM);
     const int lt = ctx->traceLeafThreshold, rt = ctx->traceRefillThreshold;
     // words 0-5: visit counters + overflow flag (kept across the chunks of one pipelined call), word 6: the ray queue head
     // (words 8-15: ray-queue heads, one per compute stream, for launches that run side by side)
@@ -721,7 +725,7 @@ int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float
     uint32_t* perm = nullptr;
     uint8_t* bucketOf = nullptr;
     unsigned int* hist = nullptr;
-    const StreamIn streamIn{watermark, chunkDone, chunkRays ? chunkRays : 1u};
+    const StreamIn streamIn{watermark, chunkDone, chunkRays ? chunkRays : 1u, 1u << ctx->streamSpinLog2};
     if (ctx->traceLongestFirst && n >= uint32_t(ctx->traceLongestFirstMin) && scene->tlas->nodeCount > 0 && !watermark) {
         ATLAS_CUDA(ctx, dev_alloc_on(st, &perm, n));
         ATLAS_CUDA(ctx, dev_alloc_on(st, &bucketOf, n));
@@ -737,9 +741,16 @@ int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float
         ctx->launches++;
     }
     const int pr = perRayTMax ? 1 : 0, sf = scene->fastDivision, ho = hitsOnly ? 1 : 0;
+    L2Window win;
+    if (ctx->l2PersistMB > 0 && scene->hotNodes && scene->hotBytes) {
+        win.base = scene->hotNodes;
+        win.bytes = std::min(scene->hotBytes, ctx->l2WindowMax);
+        // the carve-out holds hitRatio * window bytes: scale the ratio down when the window is larger than the carve-out
+        win.hitRatio = std::min(ctx->l2HitRatio, float(double(size_t(ctx->l2PersistMB) << 20) / double(win.bytes)));
+    }
     cudaError_t launchErr = cudaSuccess;
 #define ATLAS_TRACE_LAUNCH(A, C, O) \
-    launchErr = launch_chain(ctx->chainLaunch != 0, trace_kernel<A, C, O>, grid, kTraceBlock, 0, st, sc, dIn, dOut, perm, hist ? hist + kCostBuckets + 1 : nullptr, n, dCount, cullMask, tMin, tMax, pr, sf, ho, lt, rt, rayCounter, ctx->dCounters, streamIn)
+    launchErr = launch_chain_w(ctx->chainLaunch != 0, win, trace_kernel<A, C, O>, grid, kTraceBlock, 0, st, sc, dIn, dOut, perm, hist ? hist + kCostBuckets + 1 : nullptr, n, dCount, cullMask, tMin, tMax, pr, sf, ho, lt, rt, rayCounter, ctx->dCounters, streamIn)
     if (opacity) {
         if (any) { if (counters) ATLAS_TRACE_LAUNCH(true, true, true); else ATLAS_TRACE_LAUNCH(true, false, true); }
         else { if (counters) ATLAS_TRACE_LAUNCH(false, true, true); else ATLAS_TRACE_LAUNCH(false, false, true); }
