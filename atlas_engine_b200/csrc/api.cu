@@ -605,6 +605,11 @@ int atlas_rt_scene_create(atlas_rt_context* ctx, const atlas_rt_mesh* const* mes
             if (e != cudaSuccess) rc = fail(ctx, ATLAS_RT_ERR_CUDA, "reorder_instances", e);
         }
     }
+    if (rc == ATLAS_RT_OK) {   // (synchronises) which of the opacity-aware traces of the path tracer can run as plain ones
+        std::vector<uint64_t> triCounts(mesh_count);
+        for (uint32_t m = 0; m < mesh_count; m++) triCounts[m] = meshes[m]->triCount;
+        rc = scene_opacity_flags(ctx, scene, triCounts.data());
+    }
     if (rc == ATLAS_RT_OK) rc = sync_unless_async(ctx, flags);
     if (rc != ATLAS_RT_OK) { atlas_rt_scene_free(scene); return rc; }
     *out_scene = scene;
@@ -708,7 +713,7 @@ static int trace_common(atlas_rt_context* ctx, const atlas_rt_scene* scene, cons
     }
     int rc = ATLAS_RT_OK;
     const uint64_t kPipeMin = 262144;
-    if (!devIn && count >= kPipeMin && count < 0x7fffffffull && ctx->copyIn && ctx->copyOut && ctx->waitValue32 && ctx->writeValue32 && ctx->traceStreaming) {
+    if (!devIn && count >= kPipeMin && count < 0x7fffffffull && ctx->copyIn && ctx->copyOut && ctx->waitValue32 && ctx->writeValue32 && ctx->traceStreaming && !(flags & ATLAS_RT_COUNTERS)) {
         // Host input, streaming: ONE persistent launch traces the batch while it is still being uploaded. The upload stream
         // copies the rays in chunks and bumps a watermark in device memory behind each chunk (cuStreamWriteValue32: a
         // stream memory operation of the channel front end — no SM and no copy engine involved, which matters because the

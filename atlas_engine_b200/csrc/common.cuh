@@ -169,6 +169,10 @@ struct atlas_rt_scene {
     uint32_t textureCount = 0;
     uint8_t* texelStorage = nullptr;
     // the meshes the scene was assembled from (borrowed unless also listed as owned): atlas_rt_scene_replicate walks them
+    // every triangle of every 96-byte array has opacity exactly 1 (no textured opacity either): HitClosestTransparency then
+    // accepts exactly what HitClosest accepts, so the path tracer may run the plain 48-byte variant with identical results;
+    // if in addition every instance carries the shadow bit, HitAnyTransparency's result is 1 - hit of plain HitAny
+    bool allOpaque = false, allShadowBit = false;
     const void* hotNodes = nullptr;          // the largest node array of the scene (L2 access-policy window of the trace launches)
     size_t hotBytes = 0;
     std::vector<const atlas_rt_mesh*> partMeshes;
@@ -282,6 +286,7 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
 
 // traversal entry points (trace.cu)
 int scene_fast_flag(atlas_rt_context* ctx, atlas_rt_scene* scene, const uint32_t* dNodeCounts);
+int scene_opacity_flags(atlas_rt_context* ctx, atlas_rt_scene* scene, const uint64_t* triCounts);
 int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float4* dIn, float4* dOut, uint64_t count,
                  uint32_t cullMask, float tMin, float tMax, bool any, bool perRayTMax, bool counters, bool resetCounters = true,
                  bool opacity = false, cudaStream_t st = nullptr /* context stream */, int queueSlot = 0,

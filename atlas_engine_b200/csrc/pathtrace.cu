@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(128)
 shade_finish(const float4* __restrict__ rays, const float4* __restrict__ payloadIn, const float4* __restrict__ shadowRays, const uint32_t* __restrict__ slotOf,
              uint32_t n, const uint32_t* __restrict__ countPtr, atlas_rt_pt_params prm, float seed, uint32_t bounce, SceneTables sc,
              float4* __restrict__ raysOut, float4* __restrict__ payloadOut, float* __restrict__ accum, uint32_t accumTileOrder, uint32_t width, uint32_t height,
-             uint32_t* __restrict__ outCount) {
+             uint32_t* __restrict__ outCount, int shadowIsPlainAnyHit) {
     chain_begin();
     const uint32_t count = batch_count(n, countPtr);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -330,7 +330,10 @@ shade_finish(const float4* __restrict__ rays, const float4* __restrict__ payload
                 light_surface(sf, prm);
                 if (prm.light_count > 0) {
                     const uint32_t slot = slotOf[i];
-                    const float visibility = (sf.NdotL > 0.0f && slot != kNoSlot) ? shadowRays[3 * size_t(slot) + 1].w : 0.0f;   // HitAnyTransparency's result
+                    // HitAnyTransparency's result; in an all-opaque scene the shadow batch ran as plain HitAny: 1 - hit
+                    float visibility = 0.0f;
+                    if (sf.NdotL > 0.0f && slot != kNoSlot)
+                        visibility = shadowIsPlainAnyHit ? (__float_as_int(shadowRays[3 * size_t(slot) + 2].y) >= 0 ? 0.0f : 1.0f) : shadowRays[3 * size_t(slot) + 1].w;
                     const V3 reflectance = (eval_diffuse(sf) + eval_specular(sf)) * sf.opacity;
                     V3 rad = V3{prm.light_radiance[0], prm.light_radiance[1], prm.light_radiance[2]} * 1.0f;
                     rad = rad * visibility;
@@ -585,7 +588,12 @@ int enqueue_bounce(atlas_rt_context* ctx, const atlas_rt_scene* scene, const atl
                    const float4* payloadIn, uint32_t n, uint32_t* dCounts, float4* raysOut, float4* payloadOut, float4* shadow, uint32_t* slotOf,
                    float* accum, uint32_t accumTileOrder, uint32_t width, uint32_t height, unsigned long long* dTraced) {
     const bool pdl = ctx->chainLaunch != 0;
-    int rc = launch_trace(ctx, scene, rays, rays, n, ATLAS_RT_MASK_ALL, 0.0f, ATLAS_RT_INF, false, false, false, true, true, nullptr, 0, dCounts);
+    // OPACITY_CHECK traces (PathTracingRenderer.cpp:186, rayHit.csh:331). Where every triangle is fully opaque the
+    // *Transparency variants accept exactly what the plain ones accept (and both closest-hit loops restore the ray the same
+    // way), so the cheaper 48-byte kernels run instead, bit for bit the same; the shadow batch additionally needs every
+    // instance to carry the shadow bit, because plain HitAny treats culled instances differently (bvh.hsh:387-390).
+    const bool closestOpacity = !scene->allOpaque, shadowOpacity = !(scene->allOpaque && scene->allShadowBit);
+    int rc = launch_trace(ctx, scene, rays, rays, n, ATLAS_RT_MASK_ALL, 0.0f, ATLAS_RT_INF, false, false, false, true, closestOpacity, nullptr, 0, dCounts);
     if (rc != ATLAS_RT_OK) return rc;
     const SceneTables sc = tables_of(scene);
     const uint32_t grid = (n + 127) / 128;
@@ -593,12 +601,12 @@ int enqueue_bounce(atlas_rt_context* ctx, const atlas_rt_scene* scene, const atl
                                  shadow, slotOf, dCounts + 2, dTraced));
     ctx->launches++;
     // HitAnyTransparency(ray, INSTANCE_MASK_SHADOW, 0.0, lightDistance - 2.0 * EPSILON), lightDistance = INF
-    rc = launch_trace(ctx, scene, shadow, shadow, n, ATLAS_RT_MASK_SHADOW, 0.0f, ATLAS_RT_INF - 2.0f * kEpsilon, true, false, false, true, true, nullptr, 0,
+    rc = launch_trace(ctx, scene, shadow, shadow, n, ATLAS_RT_MASK_SHADOW, 0.0f, ATLAS_RT_INF - 2.0f * kEpsilon, true, false, false, true, shadowOpacity, nullptr, 0,
                       dCounts + 2);
     if (rc != ATLAS_RT_OK) return rc;
     ATLAS_CUDA(ctx, launch_chain(pdl, shade_finish, grid, 128, 0, ctx->stream, static_cast<const float4*>(rays), payloadIn, static_cast<const float4*>(shadow),
                                  static_cast<const uint32_t*>(slotOf), n, static_cast<const uint32_t*>(dCounts), prm, seed, bounce, sc, raysOut, payloadOut, accum,
-                                 accumTileOrder, width, height, dCounts + 1));
+                                 accumTileOrder, width, height, dCounts + 1, shadowOpacity ? 0 : 1));
     ctx->launches++;
     return ATLAS_RT_OK;
 }

@@ -191,7 +191,9 @@ __device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) {
 // exactly the reference's; only the interleaving between different rays changes.
 // The opacity-aware variants carry the material offset, the triangle's uv words and the texture sampling: one CTA per SM
 // fewer (64 registers instead of 56) keeps them out of local memory.
-template <bool ANY, bool COUNT, bool OPACITY>
+// STREAM (host rays still arriving, see StreamIn) is a template parameter so that the resident-batch instantiations carry
+// none of its state: at the 56-register cap even a dead flag costs moves in the hot loop (measured: 4 % on C2).
+template <bool ANY, bool COUNT, bool OPACITY, bool STREAM>
 __global__ void __launch_bounds__(kTraceBlock, OPACITY ? kBlocksPerSM - 1 : kBlocksPerSM)
 trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restrict__ permIn, const unsigned int* __restrict__ usePerm,
              uint32_t count, const uint32_t* __restrict__ countPtr, uint32_t cullMask, float tMin, float tMaxArg,
@@ -204,7 +206,7 @@ trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restr
     const unsigned ltMask = (1u << lane) - 1u;
     const uint32_t* __restrict__ perm = (permIn && *usePerm) ? permIn : nullptr;
     // batches kept in their own (coherent) order refill eagerly; reordered ones do better refilling half a warp at a time
-    if (!perm && !streamIn.watermark) kRefillThreshold = min(kRefillThreshold, 6);
+    if (!perm && !STREAM) kRefillThreshold = min(kRefillThreshold, 6);
     bool reported = true;   // streaming: has this lane's finished ray been counted in chunkDone yet?
 
     bool alive = false, fast = false, moreRays = true, overflow = false;
@@ -255,7 +257,7 @@ trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restr
         const int nI = __popc(mI), nL = __popc(mL), nDead = 32 - nI - nL;
 
         bool refill = moreRays && (nDead >= kRefillThreshold || nI + nL == 0);
-        if (refill && streamIn.watermark && nI + nL > 0) {
+        if (STREAM && refill && nI + nL > 0) {
             // rays still arriving: do not claim rays that are not here yet while this warp has work — peek (non-binding) and
             // keep traversing instead of stalling the live lanes behind the upload
             unsigned arrived = 0, claimed = 0;
@@ -267,7 +269,7 @@ trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restr
         if (refill) {
             // ---- fetch new rays for the idle lanes (traceClosest.csh:18-30)
             const unsigned mDead = ~(mI | mL);
-            if (streamIn.watermark) {   // report the rays these lanes finished since the last refill, per chunk, one atomic per chunk and warp
+            if (STREAM) {   // report the rays these lanes finished since the last refill, per chunk, one atomic per chunk and warp
                 __threadfence();        // their results are written before the count that releases the chunk's download
                 const bool mine = !alive && !reported;
                 const unsigned chunk = mine ? ray / streamIn.chunkRays : 0xffffffffu;
@@ -285,7 +287,7 @@ trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restr
             if (lane == 0) base = atomicAdd(rayCounter, unsigned(nDead));
             base = __shfl_sync(kFull, base, 0);
             if (base >= count || base + unsigned(nDead) >= count) moreRays = false;
-            if (streamIn.watermark && base < count) {   // wait until every ray this warp has just claimed has been uploaded
+            if (STREAM && base < count) {   // wait until every ray this warp has just claimed has been uploaded
                 const unsigned need = min(base + unsigned(nDead), count);
                 unsigned arrived = 0;
                 unsigned spins = 0;
@@ -300,9 +302,13 @@ trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restr
                 const unsigned idx = base + __popc(mDead & ltMask);
                 if (idx < count && idx >= base) {
                     ray = perm ? perm[idx] : idx;   // longest-first fetch order; results still go to the ray's own slot
-                    reported = false;
-                    // (L1-bypassing loads: in streaming mode these bytes were written by the copy engine while the kernel runs)
-                    const float4 r0 = __ldcg(in + 3 * size_t(ray)), r1 = __ldcg(in + 3 * size_t(ray) + 1), r2 = __ldcg(in + 3 * size_t(ray) + 2);
+                    if (STREAM) reported = false;
+                    float4 r0, r1, r2;
+                    if (STREAM) {   // L1-bypassing loads: these bytes were written by the copy engine while the kernel runs
+                        r0 = __ldcg(in + 3 * size_t(ray)); r1 = __ldcg(in + 3 * size_t(ray) + 1); r2 = __ldcg(in + 3 * size_t(ray) + 2);
+                    } else {                    // the three quarters of a ray share cache lines: let L1 serve the second and third
+                        r0 = in[3 * size_t(ray)]; r1 = in[3 * size_t(ray) + 1]; r2 = in[3 * size_t(ray) + 2];
+                    }
                     if (!inPlace) { out[3 * size_t(ray)] = r0; out[3 * size_t(ray) + 1] = r1; }
                     const int id = __float_as_int(r0.w);
                     hitID = -1;
@@ -459,7 +465,7 @@ trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restr
         }
     }
 
-    if (streamIn.watermark) {   // the rays finished after this warp's last refill
+    if (STREAM) {   // the rays finished after this warp's last refill
         __threadfence();
         const bool mine = !reported;
         const unsigned chunk = mine ? ray / streamIn.chunkRays : 0xffffffffu;
@@ -662,6 +668,54 @@ __global__ void release_chunks(unsigned int* chunkDone, uint32_t chunkRays, uint
 
 }   // namespace
 
+namespace {
+// flags[0] |= 1 when some triangle's opacity (d2.w of the 96-byte record) is not exactly 1; flags[0] |= 2 when some instance
+// lacks the shadow bit. blockIdx.y = mesh, or meshCount for the instance array.
+__global__ void __launch_bounds__(256)
+scene_opacity_scan(const float4* const* __restrict__ triangles, const unsigned long long* __restrict__ triCounts, uint32_t meshCount,
+                   const float4* __restrict__ instances, unsigned long long instanceCount, unsigned int* __restrict__ flags) {
+    const uint32_t mesh = blockIdx.y;
+    unsigned int bad = 0;
+    if (mesh == meshCount) {
+        for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < instanceCount; i += (unsigned long long)gridDim.x * blockDim.x)
+            if ((uint32_t(__float_as_int(instances[4 * i + 3].w)) & ATLAS_RT_MASK_SHADOW) == 0u) bad |= 2u;
+    } else if (triangles[mesh]) {
+        const float4* T = triangles[mesh];
+        for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < triCounts[mesh]; i += (unsigned long long)gridDim.x * blockDim.x)
+            if (T[6 * i + 5].w != 1.0f) bad |= 1u;
+    } else {
+        bad |= 1u;
+    }
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31u) == 0u && bad) atomicOr(flags, bad);
+}
+}   // namespace
+
+int scene_opacity_flags(atlas_rt_context* ctx, atlas_rt_scene* scene, const uint64_t* triCounts) {
+    scene->allOpaque = scene->allShadowBit = false;
+    if (!scene->allShading) return ATLAS_RT_OK;
+    unsigned long long* dCounts = nullptr;
+    ATLAS_CUDA(ctx, dev_alloc(ctx, &dCounts, scene->meshCount));
+    unsigned int* dFlags = reinterpret_cast<unsigned int*>(ctx->dCounters + 7);
+    cudaError_t e = cudaMemcpyAsync(dCounts, triCounts, scene->meshCount * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(dFlags, 0, sizeof(unsigned int), ctx->stream);
+    if (e == cudaSuccess) {
+        scene_opacity_scan<<<dim3(32, scene->meshCount + 1), 256, 0, ctx->stream>>>(scene->triangles, dCounts, scene->meshCount, scene->instances,
+                                                                                    scene->instanceCount, dFlags);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->pinned, dFlags, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    dev_free(ctx, dCounts);
+    if (e != cudaSuccess) return fail(ctx, ATLAS_RT_ERR_CUDA, "scene opacity scan", e);
+    unsigned int bits = 0;
+    memcpy(&bits, ctx->pinned, sizeof(bits));
+    scene->allOpaque = (bits & 1u) == 0u;
+    scene->allShadowBit = (bits & 2u) == 0u;
+    return ATLAS_RT_OK;
+}
+
 int launch_release_chunks(atlas_rt_context* ctx, unsigned int* chunkDone, uint32_t chunkRays, uint32_t count, uint32_t chunks) {
     release_chunks<<<(chunks + 63) / 64, 64, 0, ctx->stream>>>(chunkDone, chunkRays, count);
     ATLAS_LAUNCH_CHECK(ctx);
@@ -750,7 +804,8 @@ int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float
     }
     cudaError_t launchErr = cudaSuccess;
 #define ATLAS_TRACE_LAUNCH(A, C, O) \
-    launchErr = launch_chain_w(ctx->chainLaunch != 0, win, trace_kernel<A, C, O>, grid, kTraceBlock, 0, st, sc, dIn, dOut, perm, hist ? hist + kCostBuckets + 1 : nullptr, n, dCount, cullMask, tMin, tMax, pr, sf, ho, lt, rt, rayCounter, ctx->dCounters, streamIn)
+    launchErr = (watermark && !C) ? launch_chain_w(ctx->chainLaunch != 0, win, trace_kernel<A, false, O, true>, grid, kTraceBlock, 0, st, sc, dIn, dOut, perm, hist ? hist + kCostBuckets + 1 : nullptr, n, dCount, cullMask, tMin, tMax, pr, sf, ho, lt, rt, rayCounter, ctx->dCounters, streamIn) : \
+                launch_chain_w(ctx->chainLaunch != 0, win, trace_kernel<A, C, O, false>, grid, kTraceBlock, 0, st, sc, dIn, dOut, perm, hist ? hist + kCostBuckets + 1 : nullptr, n, dCount, cullMask, tMin, tMax, pr, sf, ho, lt, rt, rayCounter, ctx->dCounters, streamIn)
     if (opacity) {
         if (any) { if (counters) ATLAS_TRACE_LAUNCH(true, true, true); else ATLAS_TRACE_LAUNCH(true, false, true); }
         else { if (counters) ATLAS_TRACE_LAUNCH(false, true, true); else ATLAS_TRACE_LAUNCH(false, false, true); }

@@ -117,9 +117,13 @@ def unpack_payload(p):
     return np.stack([lo(h[:, 0]), hi(h[:, 0]), lo(h[:, 2])], 1), np.stack([lo(h[:, 1]), hi(h[:, 1]), hi(h[:, 2])], 1)
 
 
-def test_bounce_loop_against_the_oracle(ctx, oracle):
+@pytest.mark.parametrize("with_texture", [True, False])
+def test_bounce_loop_against_the_oracle(ctx, oracle, with_texture):
+    """with_texture=False: every triangle is fully opaque and every instance carries the shadow bit, so the library runs the
+    OPACITY_CHECK traces as plain 48-byte ones — the oracle still runs HitClosestTransparency / HitAnyTransparency, and the
+    results must stay bit-identical."""
     import torch
-    scene, osc, ib, keep = pt_scene(ctx, oracle)
+    scene, osc, ib, keep = pt_scene(ctx, oracle, with_texture=with_texture)
     w, h, spf = 96, 64, 2
     cam = W.camera_frame((30.0, 40.0, -20.0), (30.0, 0.0, 30.0), aspect=w / h)
     n = w * h * spf
