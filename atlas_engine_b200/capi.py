@@ -61,6 +61,9 @@ SIGNATURES = {
     "atlas_rt_scene_set_materials": (_i32, [_vp, _vp, _vp, _u32, _vp, _u32]),
     "atlas_rt_pathtrace_bounce": (_i32, [_vp, _vp, _vp, _f32, _u32, _vp, _vp, _u64, _vp, _vp, _vp, _u32, _u32, C.POINTER(_u64), _u32]),
     "atlas_rt_pathtrace_bounces": (_i32, [_vp, _vp, _vp, _u32, _u32, _vp, _u32, _i32, _vp, _u64, _u64, _vp, C.POINTER(_u64), _u32]),
+    "atlas_rt_pathtrace_bounces_interleaved": (_i32, [_vp, _vp, _vp, _u32, _u32, _vp, _u32, _i32, _vp, _u32, _u32, _u32, _vp, C.POINTER(_u64),
+                                                      C.POINTER(_u64), _u32]),
+    "atlas_rt_image_from_shards": (_i32, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _u32]),
     "atlas_rt_bin_rays": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _u32]),
     "atlas_rt_comm_unique_id": (_i32, [_vp]),
     "atlas_rt_comm_init": (_i32, [_vp, _vp, _u32, _u32, C.POINTER(_vp)]),
@@ -318,6 +321,22 @@ class Context:
         self.check(self.L.atlas_rt_pathtrace_bounces(self.h, scene.h, C.byref(cam), width, height, C.byref(params), frames, first_sample_count,
                                                      _addr(seeds), slot_begin, slot_end, _addr(accum), C.byref(n) if count_rays else None, flags))
         return int(n.value) if count_rays else None
+
+    def pathtrace_bounces_interleaved(self, scene, camera, width, height, params, frames, first_sample_count, seeds, part, parts, block_pixels,
+                                      accum_local=None, flags=0, count_rays=True):
+        """One of `parts` interleaved shards of the frame into a COMPACT accumulation buffer; accum_local=None only returns the
+        shard's pixel count. Returns (local_pixels, closest-hit rays traced or None)."""
+        eye, origin, right, bottom = camera
+        cam = Camera((_f32 * 3)(*eye), (_f32 * 3)(*origin), (_f32 * 3)(*right), (_f32 * 3)(*bottom))
+        seeds = np.ascontiguousarray(seeds, dtype=np.float32)
+        lp, n = _u64(), _u64()
+        self.check(self.L.atlas_rt_pathtrace_bounces_interleaved(self.h, scene.h, C.byref(cam), width, height, C.byref(params), frames, first_sample_count,
+                                                                 _addr(seeds), part, parts, block_pixels, _addr(accum_local), C.byref(lp),
+                                                                 C.byref(n) if (count_rays and accum_local is not None) else None, flags))
+        return int(lp.value), (int(n.value) if (count_rays and accum_local is not None) else None)
+
+    def image_from_shards(self, gathered, width, height, parts, block_pixels, image, flags=0):
+        self.check(self.L.atlas_rt_image_from_shards(self.h, _addr(gathered), width, height, parts, block_pixels, _addr(image), flags | DEVICE_INPUT | DEVICE_OUTPUT))
 
     def bin_rays(self, rays_in, payload_in, count, rays_out, payload_out, flags=0):
         self.check(self.L.atlas_rt_bin_rays(self.h, _addr(rays_in), _addr(payload_in), count, _addr(rays_out), _addr(payload_out),

@@ -53,14 +53,37 @@ __device__ __forceinline__ float random_seeded(float x, float& seed) {   // floa
     return r;
 }
 
+// Which storage slots of a frame a call renders. Contiguous: [begin, end). Interleaved (parts > 0): the blocks of `block`
+// slots whose number is congruent to `part` modulo `parts` — neighbouring blocks go to different GPUs, so sky and
+// geometry, cheap and expensive parts of the image, are dealt evenly. local index <-> slot:
+//   slot = ((local / block) * parts + part) * block + local % block.
+struct SlotShard {
+    unsigned long long begin, end;   // contiguous range (parts == 0); with parts > 0: end = total slots of the frame
+    uint32_t part, parts, block;
+};
+__host__ __device__ inline unsigned long long shard_slot(const SlotShard& sh, unsigned long long local) {
+    if (sh.parts == 0u) return sh.begin + local;
+    return ((local / sh.block) * sh.parts + sh.part) * sh.block + local % sh.block;
+}
+__host__ __device__ inline unsigned long long shard_count(const SlotShard& sh) {
+    if (sh.parts == 0u) return sh.end - sh.begin;
+    const unsigned long long blocks = (sh.end + sh.block - 1) / sh.block;            // blocks of the frame, the last one may be short
+    if (sh.part >= blocks) return 0;
+    const unsigned long long mine = (blocks - sh.part + sh.parts - 1) / sh.parts;    // blocks part, part + parts, ...
+    const unsigned long long lastBlock = sh.part + (mine - 1) * sh.parts;
+    const unsigned long long lastLen = (lastBlock == blocks - 1) ? sh.end - lastBlock * sh.block : sh.block;
+    return (mine - 1) * sh.block + lastLen;
+}
+
 // ------------------------------------------------------------------------------------------------ ray generation
 // rayGen.csh:25-91, one thread per STORAGE slot (the shader's slot <-> pixel mapping is a bijection, so walking the slots
 // gives the same buffer and lets a caller generate any contiguous range of it — the unit of multi-GPU sharding).
 __global__ void raygen_kernel(atlas_rt_camera cam, uint32_t width, uint32_t height, uint32_t samples, const float* __restrict__ jitter,
-                              float jx0, float jy0, uint64_t slotBegin, uint64_t slotEnd, float4* __restrict__ out) {
+                              float jx0, float jy0, SlotShard shard, unsigned long long count, float4* __restrict__ out) {
     chain_begin();
-    const uint64_t slot = slotBegin + blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
-    if (slot >= slotEnd) return;
+    const uint64_t o = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;   // local index = position in the output buffer
+    if (o >= count) return;
+    const uint64_t slot = shard_slot(shard, o);
     const uint32_t index = uint32_t(slot / samples), s = uint32_t(slot % samples);
     const uint32_t perfX = width / 8u, perfY = height / 8u, overX = width % 8u, overY = height % 8u;
     const uint32_t full = perfX * perfY * 64u, rightStrip = overX * perfY * 8u;
@@ -86,7 +109,6 @@ __global__ void raygen_kernel(atlas_rt_camera cam, uint32_t width, uint32_t heig
     d.z = ((cam.origin[2] + cam.right[2] * cu) + cam.bottom[2] * cv) - cam.eye[2];
     d = normalize(d);
     const int id = int((y * width + x) * samples + s);   // Flatten2D(pixel, resolution) * samples + sample
-    const uint64_t o = slot - slotBegin;
     out[3 * o + 0] = make_float4(cam.eye[0], cam.eye[1], cam.eye[2], __int_as_float(id));
     out[3 * o + 1] = make_float4(d.x, d.y, d.z, 0.0f);
     out[3 * o + 2] = make_float4(0.0f, __int_as_float(0), 0.0f, 0.0f);
@@ -301,7 +323,7 @@ __global__ void __launch_bounds__(128)
 shade_finish(const float4* __restrict__ rays, const float4* __restrict__ payloadIn, const float4* __restrict__ shadowRays, const uint32_t* __restrict__ slotOf,
              uint32_t n, const uint32_t* __restrict__ countPtr, atlas_rt_pt_params prm, float seed, uint32_t bounce, SceneTables sc,
              float4* __restrict__ raysOut, float4* __restrict__ payloadOut, float* __restrict__ accum, uint32_t accumTileOrder, uint32_t width, uint32_t height,
-             uint32_t* __restrict__ outCount, int shadowIsPlainAnyHit) {
+             uint32_t* __restrict__ outCount, int shadowIsPlainAnyHit, SlotShard shard) {
     chain_begin();
     const uint32_t count = batch_count(n, countPtr);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -435,6 +457,11 @@ shade_finish(const float4* __restrict__ rays, const float4* __restrict__ payload
                     if (gx < perfX && gy < perfY) at = ((y & 7u) * 8u + (x & 7u)) + (gy * perfX + gx) * 64u;
                     else if (gx >= perfX && gy < perfY) at = y * overX + (x - perfX * 8u) + perfX * perfY * 64u;
                     else at = x * overY + (y - perfY * 8u) + perfX * perfY * 64u + overX * perfY * 8u;
+                    if (accumTileOrder == 2u) {   // compact index inside this call's interleaved shard (the buffer holds only its pixels)
+                        const unsigned long long slot0 = (unsigned long long)at * prm.samples_per_frame;
+                        const unsigned long long blk = slot0 / shard.block;
+                        at = uint32_t(((blk / shard.parts) * shard.block + slot0 % shard.block) / prm.samples_per_frame);
+                    }
                 }
                 float* px = accum + 4 * size_t(at);
                 atomicAdd(px + 0, radiance.x); atomicAdd(px + 1, radiance.y); atomicAdd(px + 2, radiance.z); atomicAdd(px + 3, 1.0f);
@@ -586,7 +613,7 @@ int enqueue_binning(atlas_rt_context* ctx, const float4* rays, const float4* pay
 // dCounts: [0] = rays in this batch (read), [1] = survivors (accumulated), [2] = shadow rays (accumulated; both start at 0).
 int enqueue_bounce(atlas_rt_context* ctx, const atlas_rt_scene* scene, const atlas_rt_pt_params& prm, float seed, uint32_t bounce, float4* rays,
                    const float4* payloadIn, uint32_t n, uint32_t* dCounts, float4* raysOut, float4* payloadOut, float4* shadow, uint32_t* slotOf,
-                   float* accum, uint32_t accumTileOrder, uint32_t width, uint32_t height, unsigned long long* dTraced) {
+                   float* accum, uint32_t accumTileOrder, uint32_t width, uint32_t height, unsigned long long* dTraced, const SlotShard& shard) {
     const bool pdl = ctx->chainLaunch != 0;
     // OPACITY_CHECK traces (PathTracingRenderer.cpp:186, rayHit.csh:331). Where every triangle is fully opaque the
     // *Transparency variants accept exactly what the plain ones accept (and both closest-hit loops restore the ray the same
@@ -606,7 +633,7 @@ int enqueue_bounce(atlas_rt_context* ctx, const atlas_rt_scene* scene, const atl
     if (rc != ATLAS_RT_OK) return rc;
     ATLAS_CUDA(ctx, launch_chain(pdl, shade_finish, grid, 128, 0, ctx->stream, static_cast<const float4*>(rays), payloadIn, static_cast<const float4*>(shadow),
                                  static_cast<const uint32_t*>(slotOf), n, static_cast<const uint32_t*>(dCounts), prm, seed, bounce, sc, raysOut, payloadOut, accum,
-                                 accumTileOrder, width, height, dCounts + 1, shadowOpacity ? 0 : 1));
+                                 accumTileOrder, width, height, dCounts + 1, shadowOpacity ? 0 : 1, shard));
     ctx->launches++;
     return ATLAS_RT_OK;
 }
@@ -636,7 +663,8 @@ int atlas_rt_generate_primary_rays(atlas_rt_context* ctx, const atlas_rt_camera*
         if (e == cudaSuccess) e = cudaMemcpyAsync(dJit, jitter, size_t(samples) * 8, cudaMemcpyHostToDevice, ctx->stream);
     }
     if (e != cudaSuccess) return done(fail(ctx, ATLAS_RT_ERR_CUDA, "primary rays: staging", e));
-    raygen_kernel<<<uint32_t((count + 127) / 128), 128, 0, ctx->stream>>>(*camera, width, height, samples, dJit, 0.5f, 0.5f, 0, count, dOut);
+    raygen_kernel<<<uint32_t((count + 127) / 128), 128, 0, ctx->stream>>>(*camera, width, height, samples, dJit, 0.5f, 0.5f, SlotShard{0ull, count, 0u, 0u, 1u},
+                                                                          count, dOut);
     ctx->launches++;
     e = cudaGetLastError();
     if (e == cudaSuccess && !devOut) e = copy_out(ctx, rays_out, dOut, count * 48, false);
@@ -703,7 +731,7 @@ int atlas_rt_pathtrace_bounce(atlas_rt_context* ctx, const atlas_rt_scene* scene
     ctx->launches++;
     int rc = enqueue_bounce(ctx, scene, *params, seed, bounce, const_cast<float4*>(static_cast<const float4*>(rays_in)), static_cast<const float4*>(payload_in), n,
                             dCounts, static_cast<float4*>(rays_out), static_cast<float4*>(payload_out), shadow, slotOf, accum,
-                            (flags & ATLAS_RT_ACCUM_TILE_ORDER) ? 1u : 0u, width, height, nullptr);
+                            (flags & ATLAS_RT_ACCUM_TILE_ORDER) ? 1u : 0u, width, height, nullptr, SlotShard{0ull, 0ull, 0u, 0u, 1u});
     if (rc != ATLAS_RT_OK) return done(rc);
     e = cudaMemcpyAsync(ctx->pinned, dCounts + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -714,16 +742,10 @@ int atlas_rt_pathtrace_bounce(atlas_rt_context* ctx, const atlas_rt_scene* scene
     return done(ATLAS_RT_OK);
 }
 
-int atlas_rt_pathtrace_bounces(atlas_rt_context* ctx, const atlas_rt_scene* scene, const atlas_rt_camera* camera, uint32_t width, uint32_t height,
-                               const atlas_rt_pt_params* params, uint32_t frames, int32_t first_sample_count, const float* seeds, uint64_t slot_begin,
-                               uint64_t slot_end, float* accum, uint64_t* rays_traced, uint32_t flags) {
-    if (!ctx || !scene || scene->ctx->device != ctx->device || !camera || !params || !seeds || !accum || !width || !height || !params->samples_per_frame)
-        return fail(ctx, ATLAS_RT_ERR_INVALID, "bad argument");
-    if (!scene->allShading) return fail(ctx, ATLAS_RT_ERR_INVALID, "the path tracer shades from the 96-byte triangles: call atlas_rt_mesh_pack_shading on every mesh");
-    const uint64_t total = uint64_t(width) * height * params->samples_per_frame;
-    if (slot_end == 0) slot_end = total;
-    if (slot_begin > slot_end || slot_end > total) return fail(ctx, ATLAS_RT_ERR_INVALID, "slot range outside the frame");
-    const uint64_t count = slot_end - slot_begin;
+static int pathtrace_frames(atlas_rt_context* ctx, const atlas_rt_scene* scene, const atlas_rt_camera* camera, uint32_t width, uint32_t height,
+                            const atlas_rt_pt_params* params, uint32_t frames, int32_t first_sample_count, const float* seeds, const SlotShard& shard,
+                            uint32_t accumMode, float* accum, uint64_t* rays_traced, uint32_t flags) {
+    const uint64_t count = shard_count(shard);
     if (count > 0x7fffffffull) return fail(ctx, ATLAS_RT_ERR_UNSUPPORTED, "more than 2^31-1 rays per frame");
     ATLAS_CUDA(ctx, cudaSetDevice(ctx->device));
     if (rays_traced) *rays_traced = 0;
@@ -749,13 +771,12 @@ int atlas_rt_pathtrace_bounces(atlas_rt_context* ctx, const atlas_rt_scene* scen
     if (e != cudaSuccess) return done(fail(ctx, ATLAS_RT_ERR_CUDA, "path tracer buffers", e));
     const bool pdl = ctx->chainLaunch != 0;
     const uint32_t bounces = params->max_bounces;
-    const uint32_t tileOrder = (flags & ATLAS_RT_ACCUM_TILE_ORDER) ? 1u : 0u;
     for (uint32_t f = 0; f < frames; f++) {
         float jit[2];
         atlas_rt_sample_jitter(first_sample_count + int32_t(f), jit);
         int cur = 0;
         e = launch_chain(pdl, raygen_kernel, (n + 127) / 128, 128, 0, ctx->stream, *camera, width, height, params->samples_per_frame,
-                         static_cast<const float*>(nullptr), jit[0], jit[1], slot_begin, slot_end, rays[cur]);
+                         static_cast<const float*>(nullptr), jit[0], jit[1], shard, (unsigned long long)count, rays[cur]);
         ctx->launches++;
         if (e == cudaSuccess) e = launch_chain(pdl, set_words, 1, 1, 0, ctx->stream, dCounts, n, 0u, 0u);
         ctx->launches++;
@@ -768,7 +789,7 @@ int atlas_rt_pathtrace_bounces(atlas_rt_context* ctx, const atlas_rt_scene* scen
                 std::swap(pay[cur], pay[2]);
             }
             const int rc = enqueue_bounce(ctx, scene, *params, seeds[size_t(f) * (bounces + 1) + b], b, rays[cur], pay[cur], n, dCounts, rays[cur ^ 1], pay[cur ^ 1],
-                                          shadow, slotOf, accum, tileOrder, width, height, dTraced);
+                                          shadow, slotOf, accum, accumMode, width, height, dTraced, shard);
             if (rc != ATLAS_RT_OK) return done(rc);
             e = launch_chain(pdl, next_bounce_counts, 1, 1, 0, ctx->stream, dCounts);
             ctx->launches++;
@@ -783,6 +804,67 @@ int atlas_rt_pathtrace_bounces(atlas_rt_context* ctx, const atlas_rt_scene* scen
         if (rays_traced) memcpy(rays_traced, ctx->pinned, sizeof(uint64_t));
     }
     return done(ATLAS_RT_OK);
+}
+
+int atlas_rt_pathtrace_bounces(atlas_rt_context* ctx, const atlas_rt_scene* scene, const atlas_rt_camera* camera, uint32_t width, uint32_t height,
+                               const atlas_rt_pt_params* params, uint32_t frames, int32_t first_sample_count, const float* seeds, uint64_t slot_begin,
+                               uint64_t slot_end, float* accum, uint64_t* rays_traced, uint32_t flags) {
+    if (!ctx || !scene || scene->ctx->device != ctx->device || !camera || !params || !seeds || !accum || !width || !height || !params->samples_per_frame)
+        return fail(ctx, ATLAS_RT_ERR_INVALID, "bad argument");
+    if (!scene->allShading) return fail(ctx, ATLAS_RT_ERR_INVALID, "the path tracer shades from the 96-byte triangles: call atlas_rt_mesh_pack_shading on every mesh");
+    const uint64_t total = uint64_t(width) * height * params->samples_per_frame;
+    if (slot_end == 0) slot_end = total;
+    if (slot_begin > slot_end || slot_end > total) return fail(ctx, ATLAS_RT_ERR_INVALID, "slot range outside the frame");
+    return pathtrace_frames(ctx, scene, camera, width, height, params, frames, first_sample_count, seeds, SlotShard{slot_begin, slot_end, 0u, 0u, 1u},
+                            (flags & ATLAS_RT_ACCUM_TILE_ORDER) ? 1u : 0u, accum, rays_traced, flags);
+}
+
+int atlas_rt_pathtrace_bounces_interleaved(atlas_rt_context* ctx, const atlas_rt_scene* scene, const atlas_rt_camera* camera, uint32_t width, uint32_t height,
+                                           const atlas_rt_pt_params* params, uint32_t frames, int32_t first_sample_count, const float* seeds, uint32_t part,
+                                           uint32_t parts, uint32_t block_pixels, float* accum_local, uint64_t* local_pixels, uint64_t* rays_traced,
+                                           uint32_t flags) {
+    if (!ctx || !scene || scene->ctx->device != ctx->device || !camera || !params || !seeds || !width || !height || !params->samples_per_frame || !parts ||
+        part >= parts || !block_pixels || (block_pixels % 64u) != 0u)
+        return fail(ctx, ATLAS_RT_ERR_INVALID, "bad argument (block_pixels must be a multiple of 64: whole rayGen tiles)");
+    if (!scene->allShading) return fail(ctx, ATLAS_RT_ERR_INVALID, "the path tracer shades from the 96-byte triangles: call atlas_rt_mesh_pack_shading on every mesh");
+    const uint64_t total = uint64_t(width) * height * params->samples_per_frame;
+    const SlotShard shard{0ull, total, part, parts, block_pixels * params->samples_per_frame};
+    if (local_pixels) *local_pixels = shard_count(shard) / params->samples_per_frame;
+    if (!accum_local) return ATLAS_RT_OK;   // size query
+    return pathtrace_frames(ctx, scene, camera, width, height, params, frames, first_sample_count, seeds, shard, 2u, accum_local, rays_traced, flags);
+}
+
+// gathered: the shards' compact accumulation buffers one after the other (shard p first); image: y * width + x.
+static __global__ void assemble_image(const float4* __restrict__ gathered, uint32_t width, uint32_t height, uint32_t parts, uint32_t blockPixels,
+                               float4* __restrict__ image) {
+    const uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pixel >= width * height) return;
+    const uint32_t x = pixel % width, y = pixel / width;
+    const uint32_t perfX = width / 8u, perfY = height / 8u, overX = width % 8u, overY = height % 8u;
+    const uint32_t gx = x / 8u, gy = y / 8u;
+    uint32_t at;
+    if (gx < perfX && gy < perfY) at = ((y & 7u) * 8u + (x & 7u)) + (gy * perfX + gx) * 64u;
+    else if (gx >= perfX && gy < perfY) at = y * overX + (x - perfX * 8u) + perfX * perfY * 64u;
+    else at = x * overY + (y - perfY * 8u) + perfX * perfY * 64u + overX * perfY * 8u;
+    const uint32_t blk = at / blockPixels, part = blk % parts;
+    // pixels of the shards before `part`
+    unsigned long long base = 0;
+    const SlotShard all{0ull, (unsigned long long)width * height, 0u, parts, blockPixels};
+    for (uint32_t p = 0; p < part; p++) { SlotShard sh = all; sh.part = p; base += shard_count(sh); }
+    image[pixel] = gathered[base + (unsigned long long)(blk / parts) * blockPixels + at % blockPixels];
+}
+
+int atlas_rt_image_from_shards(atlas_rt_context* ctx, const float* gathered, uint32_t width, uint32_t height, uint32_t parts, uint32_t block_pixels,
+                               float* image, uint32_t flags) {
+    if (!ctx || !gathered || !image || !width || !height || !parts || !block_pixels) return fail(ctx, ATLAS_RT_ERR_INVALID, "bad argument");
+    if ((flags & (ATLAS_RT_DEVICE_INPUT | ATLAS_RT_DEVICE_OUTPUT)) != (ATLAS_RT_DEVICE_INPUT | ATLAS_RT_DEVICE_OUTPUT))
+        return fail(ctx, ATLAS_RT_ERR_UNSUPPORTED, "atlas_rt_image_from_shards works on device-resident buffers");
+    ATLAS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t n = width * height;
+    assemble_image<<<(n + 255) / 256, 256, 0, ctx->stream>>>(reinterpret_cast<const float4*>(gathered), width, height, parts, block_pixels, reinterpret_cast<float4*>(image));
+    ATLAS_LAUNCH_CHECK(ctx);
+    if (!(flags & ATLAS_RT_ASYNC)) ATLAS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ATLAS_RT_OK;
 }
 
 }

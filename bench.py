@@ -37,7 +37,7 @@ N_RAYS = 1_000_000
 SETTLE_S = 0.4        # seconds of untimed load before a timed region: the first ~100 ms after an idle spell run at ramping clocks
 WORKLOAD = "C2: synthetic 1M-triangle random soup (seed 1234): BLAS build + 1M random-direction closest-hit rays per GPU (seed 5678 + rank)"
 WORKLOAD_C5 = ("C5: path tracer, 3840x2160, 4 bounces (+ shadow rays), one sample pass per step, on the C4 scene (64 BLASes, 10k instances, "
-               "1.02M triangles); image tiles split across GPUs in rayGen order, rays generated on the device, one gather of the image")
+               "1.02M triangles); blocks of 64 rayGen tiles dealt round-robin to the GPUs, rays generated on the device, one gather of the image")
 
 
 def config_c2(world):
@@ -608,9 +608,11 @@ def batch_build_figure(ctx, dev, stream):
 
 
 def run_c5(args, ctx, comm, dev, stream, rank, world, local_rank, timed_loop, barrier, max_over_ranks, real_stdout):
-    """BASELINE configs[4], STRONG scaling: the image's rayGen slots are split into `world` contiguous ranges, every rank runs
-    the whole bounce loop for its range on the device (atlas_rt_pathtrace_bounces, no host rays), and one NCCL gather brings
-    the tile-ordered image slices to rank 0. A step = one sample pass (1 spp) of the full image + that gather."""
+    """BASELINE configs[4], STRONG scaling: the frame's rayGen slots are cut into blocks of 64 tiles that are dealt round-robin
+    to the ranks (a contiguous split gives one GPU the sky and another all the bounces: measured 1.34x on 2 GPUs), every rank
+    runs the whole bounce loop for its blocks on the device (atlas_rt_pathtrace_bounces_interleaved, no host rays) into a
+    compact buffer, and one NCCL gather brings the buffers to rank 0 (atlas_rt_image_from_shards puts the pixels in place).
+    A step = one sample pass (1 spp) of the full image + that gather."""
     import torch
     import torch.distributed as dist
     from atlas_engine_b200 import capi, sharding, workloads as W
@@ -630,18 +632,21 @@ def run_c5(args, ctx, comm, dev, stream, rank, world, local_rank, timed_loop, ba
     cam = W.camera_frame((1000.0, 260.0, -300.0), (1000.0, 60.0, 1000.0), aspect=w / h)
     ld = np.array([0.3, 0.9, -0.3]) / np.linalg.norm([0.3, 0.9, -0.3])
     prm = capi.pt_params(ld, (3.0, 3.0, 2.5), (0.4, 0.5, 0.8), max_bounces=bounces)
-    bounds = [sharding.shard_bounds(w * h, r, world) for r in range(world)]
-    sb, se = bounds[rank]
-    part = torch.zeros((w * h, 4), dtype=torch.float32, device=dev)
+    # interleaved shards: blocks of 64 tiles (4096 pixels) dealt round-robin, so every GPU gets the same mix of sky and geometry
+    block = 4096
+    sizes_px = [ctx.pathtrace_bounces_interleaved(scene, cam, w, h, prm, 1, 0, np.zeros(bounces + 1, np.float32), r, world, block)[0] for r in range(world)]
+    part = torch.zeros((sizes_px[rank], 4), dtype=torch.float32, device=dev)
+    gathered = torch.zeros((w * h, 4), dtype=torch.float32, device=dev) if rank == 0 else None
     image = torch.zeros((w * h, 4), dtype=torch.float32, device=dev) if rank == 0 else None
-    sizes, offsets = [(e - b) * 16 for b, e in bounds], [b * 16 for b, _ in bounds]
-    flags = capi.ACCUM_TILE_ORDER | capi.ASYNC | (capi.RAY_BINNING if os.environ.get("ATLAS_BENCH_BINNING") else 0)
+    sizes = [n * 16 for n in sizes_px]
+    offsets = [sum(sizes[:r]) for r in range(world)]
+    flags = capi.ASYNC | (capi.RAY_BINNING if os.environ.get("ATLAS_BENCH_BINNING") else 0)
 
     def step(k):
         seeds = (np.arange(bounces + 1, dtype=np.float32) + np.float32(k * (bounces + 1))) * np.float32(0.754878) + np.float32(0.5)
-        ctx.pathtrace_bounces(scene, cam, w, h, prm, 1, k, seeds, part, slot_begin=sb, slot_end=se, flags=flags, count_rays=False)
+        ctx.pathtrace_bounces_interleaved(scene, cam, w, h, prm, 1, k, seeds, rank, world, block, accum_local=part, flags=flags, count_rays=False)
         if world > 1:
-            comm.gather(part[sb:se], (se - sb) * 16, image, sizes, offsets, flags=capi.ASYNC)
+            comm.gather(part, sizes[rank], gathered, sizes, offsets, flags=capi.ASYNC)
 
     def join():
         if world > 1:
@@ -658,18 +663,22 @@ def run_c5(args, ctx, comm, dev, stream, rank, world, local_rank, timed_loop, ba
     # rays per step: count them once (same seeds as step 0) outside the timed region
     part.zero_()
     seeds0 = np.arange(bounces + 1, dtype=np.float32) * np.float32(0.754878) + np.float32(0.5)
-    traced = ctx.pathtrace_bounces(scene, cam, w, h, prm, 1, 0, seeds0, part, slot_begin=sb, slot_end=se, flags=capi.ACCUM_TILE_ORDER)
+    _, traced = ctx.pathtrace_bounces_interleaved(scene, cam, w, h, prm, 1, 0, seeds0, rank, world, block, accum_local=part)
     total = torch.tensor([traced], dtype=torch.float64, device=dev)
     parity = None
     if world > 1:
         dist.all_reduce(total)
-        comm.gather(part[sb:se], (se - sb) * 16, image, sizes, offsets)
-        if rank == 0:   # the gathered image of the sharded frame == the frame rendered whole on one GPU
-            whole = torch.zeros((w * h, 4), dtype=torch.float32, device=dev)
-            ctx.pathtrace_bounces(scene, cam, w, h, prm, 1, 0, seeds0, whole, flags=capi.ACCUM_TILE_ORDER)
-            a, b = image.cpu().numpy(), whole.cpu().numpy()
-            ok = bool(np.array_equal(a[:, 3], b[:, 3]) and np.allclose(a[:, :3], b[:, :3], rtol=1e-5, atol=1e-6))
-            parity = {"gathered_image_equals_single_gpu_frame": ok, "ok": ok}
+    if world > 1:
+        comm.gather(part, sizes[rank], gathered, sizes, offsets)
+    else:
+        gathered = part
+    if rank == 0:   # the gathered, re-assembled image of the sharded frame == the frame rendered whole on one GPU
+        ctx.image_from_shards(gathered, w, h, world, block, image)
+        whole = torch.zeros((w * h, 4), dtype=torch.float32, device=dev)
+        ctx.pathtrace_bounces(scene, cam, w, h, prm, 1, 0, seeds0, whole)
+        a, b = image.cpu().numpy(), whole.cpu().numpy()
+        ok = bool(np.array_equal(a[:, 3], b[:, 3]) and np.allclose(a[:, :3], b[:, :3], rtol=1e-5, atol=1e-6))
+        parity = {"assembled_image_equals_single_gpu_frame": ok, "ok": ok}
     rays_per_step = float(total.item())
     line = {"metric": "pathtrace_closest_hit", "value": rays_per_step / ms / 1e3, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

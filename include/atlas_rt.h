@@ -332,6 +332,20 @@ int atlas_rt_pathtrace_bounces(atlas_rt_context* ctx, const atlas_rt_scene* scen
                                int32_t first_sample_count, const float* seeds, uint64_t slot_begin, uint64_t slot_end,
                                float* accum, uint64_t* rays_traced, uint32_t flags);
 
+/* The same, for one of `parts` INTERLEAVED shards of the frame: the frame's rayGen slots are cut into blocks of
+ * block_pixels pixels (a multiple of 64 = whole 8x8 tiles) and shard `part` renders blocks part, part + parts, ... —
+ * neighbouring blocks of the image go to different GPUs, so sky and geometry are dealt evenly (a contiguous split of a
+ * landscape frame gives one GPU the sky and the other all the bounces). accum_local is COMPACT: local_pixels x 4 floats
+ * holding only this shard's pixels, blocks in order; pass accum_local == NULL to query local_pixels. After one gather of
+ * the shards' buffers (shard 0 first) atlas_rt_image_from_shards puts every pixel at y * width + x. */
+int atlas_rt_pathtrace_bounces_interleaved(atlas_rt_context* ctx, const atlas_rt_scene* scene, const atlas_rt_camera* camera,
+                                           uint32_t width, uint32_t height, const atlas_rt_pt_params* params, uint32_t frames,
+                                           int32_t first_sample_count, const float* seeds, uint32_t part, uint32_t parts,
+                                           uint32_t block_pixels, float* accum_local, uint64_t* local_pixels,
+                                           uint64_t* rays_traced, uint32_t flags);
+int atlas_rt_image_from_shards(atlas_rt_context* ctx, const float* gathered, uint32_t width, uint32_t height, uint32_t parts,
+                               uint32_t block_pixels, float* image, uint32_t flags);
+
 /* Ray binning between bounces — raytracer/tracing.hsh:18-29 (DetermineRayBin: 8x8 octahedral direction bins),
  * binningOffset.csh, binning.csh; call site RayTracingHelper.cpp:304-344 (commented out in the reference). Rays (and their
  * 16-byte payloads, if given) are moved to their bin's segment; inside a bin they keep their order (the shader's order

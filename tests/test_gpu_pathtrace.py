@@ -246,6 +246,36 @@ def test_device_side_bounce_loop_and_slot_sharding(ctx, oracle):
     assert np.allclose(untiled[:, :3], ref[:, :3], rtol=1e-5, atol=1e-6)
 
 
+def test_interleaved_shards_assemble_the_whole_frame(ctx, oracle):
+    """Three interleaved shards (what three GPUs would render) gathered one after the other and put back by
+    atlas_rt_image_from_shards == the frame rendered whole; resolution with ragged tile borders, 2 samples per frame."""
+    import torch
+    scene, osc, ib, keep = pt_scene(ctx, oracle, n_inst=40, seed=8)
+    w, h, spf, bounces, frames, parts, block = 108, 61, 2, 3, 2, 3, 128
+    cam = W.camera_frame((30.0, 40.0, -20.0), (30.0, 0.0, 30.0), aspect=w / h)
+    ld = np.array([0.2, 0.8, 0.4]) / np.linalg.norm([0.2, 0.8, 0.4])
+    prm = capi.pt_params(ld, (3.0, 3.0, 2.5), (0.4, 0.5, 0.8), max_bounces=bounces, samples_per_frame=spf)
+    seeds = np.arange(frames * (bounces + 1), dtype=np.float32) * np.float32(1.25) + np.float32(0.75)
+    dev = torch.device("cuda", 0)
+    whole = torch.zeros((w * h, 4), dtype=torch.float32, device=dev)
+    traced_whole = ctx.pathtrace_bounces(scene, cam, w, h, prm, frames, 4, seeds, whole)
+    sizes = [ctx.pathtrace_bounces_interleaved(scene, cam, w, h, prm, frames, 4, seeds, p, parts, block)[0] for p in range(parts)]
+    assert sum(sizes) == w * h and max(sizes) - min(sizes) <= block
+    gathered = torch.zeros((w * h, 4), dtype=torch.float32, device=dev)
+    traced, off = 0, 0
+    for p in range(parts):
+        n, t = ctx.pathtrace_bounces_interleaved(scene, cam, w, h, prm, frames, 4, seeds, p, parts, block, accum_local=gathered[off:off + sizes[p]])
+        assert n == sizes[p]
+        traced += t
+        off += n
+    assert traced == traced_whole
+    image = torch.empty_like(whole)
+    ctx.image_from_shards(gathered, w, h, parts, block, image)
+    a, b = image.cpu().numpy(), whole.cpu().numpy()
+    assert np.array_equal(a[:, 3], b[:, 3]) and np.all(b[:, 3] == frames * spf)
+    assert np.allclose(a[:, :3], b[:, :3], rtol=1e-5, atol=1e-6)
+
+
 def test_c5_sample_pass_at_full_resolution(ctx, oracle):
     """BASELINE configs[4]: one 3840x2160 sample pass of the 4-bounce path tracer on the instanced scene; the first bounce's
     8.3M closest hits are compared with the oracle on a 100k-ray sample, the image invariants over all pixels."""
