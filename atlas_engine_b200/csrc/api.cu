@@ -35,6 +35,7 @@ void ctx_release(atlas_rt_context* ctx) {
     if (ctx->copyIn) cudaStreamDestroy(ctx->copyIn);
     if (ctx->copyOut) cudaStreamDestroy(ctx->copyOut);
     for (auto& cs : ctx->computeExtra) if (cs) cudaStreamDestroy(cs);
+    if (ctx->sortStream) cudaStreamDestroy(ctx->sortStream);
     cudaFree(ctx->dCounters);
     cudaFree(ctx->dStreamState);
     cudaFreeHost(ctx->pinned);
@@ -222,9 +223,17 @@ int atlas_rt_context_create(int device, void* stream, atlas_rt_context** out_ctx
     if (cudaStreamCreateWithFlags(&ctx->copyOut, cudaStreamNonBlocking) != cudaSuccess) ctx->copyOut = nullptr;
     for (auto& cs : ctx->computeExtra)
         if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) cs = nullptr;
+    {
+        int prLow = 0, prHigh = 0;
+        cudaDeviceGetStreamPriorityRange(&prLow, &prHigh);
+        if (cudaStreamCreateWithPriority(&ctx->sortStream, cudaStreamNonBlocking, prHigh) != cudaSuccess) ctx->sortStream = nullptr;
+    }
+    if (const char* e = getenv("ATLAS_RT_STREAM_BLOCKS_PER_SM")) ctx->streamBlocksPerSM = std::max(1, std::min(8, atoi(e)));
+    if (const char* e = getenv("ATLAS_RT_TRACE_MIN_BLOCKS_PER_SM")) ctx->traceMinBlocksPerSM = std::max(1, std::min(9, atoi(e)));
+    ctx->pipeTimeline = getenv("ATLAS_RT_PIPE_TIMELINE") != nullptr;
     if (const char* e = getenv("ATLAS_RT_PIPE_STREAMS")) ctx->pipeStreams = std::max(1, std::min(8, atoi(e)));
     for (auto& ev : ctx->pipeEvents)
-        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { ev = nullptr; ctx->copyIn = nullptr; }
+        if (cudaEventCreateWithFlags(&ev, ctx->pipeTimeline ? cudaEventDefault : cudaEventDisableTiming) != cudaSuccess) { ev = nullptr; ctx->copyIn = nullptr; }
     if (build_init_device(ctx) != ATLAS_RT_OK) { ctx_release(ctx); return ATLAS_RT_ERR_CUDA; }
     *out_ctx = ctx;
     return ATLAS_RT_OK;
@@ -713,42 +722,54 @@ static int trace_common(atlas_rt_context* ctx, const atlas_rt_scene* scene, cons
     }
     int rc = ATLAS_RT_OK;
     const uint64_t kPipeMin = 262144;
-    if (!devIn && count >= kPipeMin && count < 0x7fffffffull && ctx->copyIn && ctx->copyOut && ctx->waitValue32 && ctx->writeValue32 && ctx->traceStreaming && !(flags & ATLAS_RT_COUNTERS)) {
+    if (!devIn && count >= kPipeMin && count < 0x7fffffffull && ctx->copyIn && ctx->copyOut && ctx->sortStream && ctx->waitValue32 && ctx->traceStreaming &&
+        !(flags & ATLAS_RT_COUNTERS) && scene->tlas->nodeCount > 0) {
         // Host input, streaming: ONE persistent launch traces the batch while it is still being uploaded. The upload stream
-        // copies the rays in chunks and bumps a watermark in device memory behind each chunk (cuStreamWriteValue32: a
-        // stream memory operation of the channel front end — no SM and no copy engine involved, which matters because the
-        // persistent kernel owns every SM); the kernel only fetches rays below the watermark. Every warp reports the rays it
-        // has finished per chunk; the download stream waits on each chunk's count with cuStreamWaitValue32 and sends that
-        // chunk's results home while later chunks are still being traced. Against the chunked pipeline below (one small
-        // launch + three ordering kernels per chunk, each paying its own longest ray) this removes every per-chunk launch
-        // and leaves a single drain at the end.
+        // copies the rays in chunks; behind each chunk a high-priority stream puts the chunk's rays in longest-first order (the
+        // three small ordering kernels of a resident batch) and then moves a watermark in device memory to the end of the
+        // chunk; the persistent kernel (one CTA per SM fewer than a resident launch, so those small kernels find room) only
+        // fetches rays below the watermark, through the permutation. Every warp reports the rays it has finished per chunk;
+        // the download stream waits on each chunk's count with cuStreamWaitValue32 and sends that chunk's results home while
+        // later chunks are still being traced. Against the chunked pipeline below (one launch per chunk, each with its own
+        // ramp-up and drain) the lanes of one launch refill across chunk boundaries, and only the last chunk drains.
         // Submission order matters when streams share a hardware queue: nothing that can block (the value waits, the
         // release kernel that depends on the trace kernel) is submitted before the work it could hold up.
         typedef int (*StreamValue32)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
         const StreamValue32 waitValue = reinterpret_cast<StreamValue32>(ctx->waitValue32);
-        const StreamValue32 writeValue = reinterpret_cast<StreamValue32>(ctx->writeValue32);
-        uint32_t chunks = uint32_t(std::max<uint64_t>(4, std::min<uint64_t>(48, count / 65536)));
-        if (const char* e = getenv("ATLAS_RT_STREAM_CHUNKS")) chunks = uint32_t(std::max(1, std::min(60, atoi(e))));
+        uint32_t chunks = uint32_t(std::max<uint64_t>(4, std::min<uint64_t>(16, (count + 62500) / 125000)));
+        if (const char* e = getenv("ATLAS_RT_STREAM_CHUNKS")) chunks = uint32_t(std::max(1, std::min(32, atoi(e))));
         const uint32_t chunkRays = uint32_t(((count + chunks - 1) / chunks + 31) & ~uint64_t(31));
         chunks = uint32_t((count + chunkRays - 1) / chunkRays);
-        cudaEvent_t* ev = ctx->pipeEvents;   // [0] state reset, [33] all downloaded
+        cudaEvent_t* ev = ctx->pipeEvents;   // [0] state reset, [1+c] chunk c uploaded, [33] all downloaded
         const unsigned long long stateAddr = reinterpret_cast<unsigned long long>(ctx->dStreamState);
-        // 1. reset the watermark and the per-chunk counts; both copy streams start after that
+        uint32_t* dPerm = nullptr;
+        uint8_t* dBucket = nullptr;
+        unsigned int* dHist = nullptr;
+        // 1. reset the watermark and the per-chunk counts; the other streams start after that
         cudaError_t e = cudaMemsetAsync(ctx->dStreamState, 0, 64 * sizeof(unsigned int), ctx->stream);
+        if (e == cudaSuccess) e = dev_alloc(ctx, &dPerm, count);
+        if (e == cudaSuccess) e = dev_alloc(ctx, &dBucket, count);
+        if (e == cudaSuccess) e = dev_alloc(ctx, &dHist, size_t(chunks) * 128);
         if (e == cudaSuccess) e = cudaEventRecord(ev[0], ctx->stream);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copyIn, ev[0], 0);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copyOut, ev[0], 0);
-        // 2. uploads, each followed by the watermark it justifies
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->sortStream, ev[0], 0);
+        // 2. uploads, each followed (on the ordering stream) by the chunk's sort and the watermark it justifies
         bool started = false;
-        for (uint32_t c = 0; c < chunks && e == cudaSuccess; c++) {
+        for (uint32_t c = 0; c < chunks && e == cudaSuccess && rc == ATLAS_RT_OK; c++) {
             const uint64_t b = uint64_t(c) * chunkRays, end = std::min<uint64_t>(count, b + chunkRays);
-            e = cudaMemcpyAsync(dIn + 3 * b, static_cast<const char*>(rays_in) + 48 * b, 48 * (end - b), cudaMemcpyHostToDevice, ctx->copyIn);
-            if (e == cudaSuccess && writeValue(ctx->copyIn, stateAddr, unsigned(end), 0u) != 0) e = cudaErrorUnknown;
+            cudaStream_t up = ctx->copyIn;   // (two upload streams were tried: the copy engine serves one stream's copies first, which only delays every second chunk)
+            e = cudaMemcpyAsync(dIn + 3 * b, static_cast<const char*>(rays_in) + 48 * b, 48 * (end - b), cudaMemcpyHostToDevice, up);
+            if (e == cudaSuccess) e = cudaEventRecord(ev[1 + c], up);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->sortStream, ev[1 + c], 0);
+            if (e == cudaSuccess) rc = launch_chunk_sort(ctx, scene, ctx->sortStream, dIn + 3 * b, uint32_t(end - b), uint32_t(b), dBucket + b, dHist + size_t(c) * 128,
+                                                         dPerm + b, ctx->dStreamState);
+            if (ctx->pipeTimeline && chunks <= 16 && e == cudaSuccess) e = cudaEventRecord(ev[17 + c], ctx->sortStream);
         }
         // 3. the persistent trace kernel (it may already find the first chunks in place)
-        if (e == cudaSuccess) {
+        if (e == cudaSuccess && rc == ATLAS_RT_OK) {
             rc = launch_trace(ctx, scene, dIn, out, count, cull_mask, t_min, t_max, any, perRay, counters, true, opacity, nullptr, 0, nullptr, hitsOnly,
-                              ctx->dStreamState, ctx->dStreamState + 1, chunkRays);
+                              ctx->dStreamState, ctx->dStreamState + 1, chunkRays, dPerm);
             started = rc == ATLAS_RT_OK;
         }
         // 4. downloads, each behind its chunk's completion count
@@ -759,10 +780,31 @@ static int trace_common(atlas_rt_context* ctx, const atlas_rt_scene* scene, cons
         }
         // 5. behind the trace kernel: every chunk's count reaches its target no matter what (the waits above cannot be left hanging)
         if (started) { const int rr = launch_release_chunks(ctx, ctx->dStreamState + 1, chunkRays, uint32_t(count), chunks); if (rc == ATLAS_RT_OK) rc = rr; }
-        if (started && e != cudaSuccess) writeValue(ctx->copyIn, stateAddr, unsigned(count), 0u);   // never leave the kernel waiting for rays that will not come
+        if (started && (e != cudaSuccess || rc != ATLAS_RT_OK)) {   // never leave the kernel waiting for rays that will not come
+            const unsigned int all = unsigned(count);
+            cudaMemcpyAsync(ctx->dStreamState, &all, sizeof(all), cudaMemcpyHostToDevice, ctx->copyIn);
+        }
         if (e == cudaSuccess) e = cudaEventRecord(ev[33], ctx->copyOut);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev[33], 0);   // the context stream now orders after the downloads
+        // the ordering stream's scratch is released behind the trace kernel (the context stream has just been ordered after it)
+        if (started) { cudaEventRecord(ev[34], ctx->sortStream); cudaStreamWaitEvent(ctx->stream, ev[34], 0); }
+        else cudaStreamSynchronize(ctx->sortStream);
+        dev_free(ctx, dPerm);
+        dev_free(ctx, dBucket);
+        dev_free(ctx, dHist);
         if (e != cudaSuccess && rc == ATLAS_RT_OK) rc = fail(ctx, ATLAS_RT_ERR_CUDA, "streaming trace", e);
+        if (ctx->pipeTimeline && chunks <= 16 && rc == ATLAS_RT_OK && cudaStreamSynchronize(ctx->stream) == cudaSuccess) {
+            fprintf(stderr, "[atlas_rt streaming timeline] %u chunks:", chunks);
+            for (uint32_t c = 0; c < chunks; c++) {
+                float up = 0.0f, pub = 0.0f;
+                cudaEventElapsedTime(&up, ev[0], ev[1 + c]);
+                cudaEventElapsedTime(&pub, ev[0], ev[17 + c]);
+                fprintf(stderr, " [%u up %.3f sorted %.3f]", c, up, pub);
+            }
+            float all = 0.0f;
+            cudaEventElapsedTime(&all, ev[0], ev[33]);
+            fprintf(stderr, " all %.3f ms\n", all);
+        }
     } else if (!devIn && count >= kPipeMin && ctx->copyIn && ctx->copyOut) {
         // Host input: split the batch and overlap H2D of chunk i+1, the trace of chunk i and (host output) D2H of
         // chunk i-1 on the two copy engines (pays off with pinned host memory; pageable memory still works). With
@@ -802,8 +844,9 @@ static int trace_common(atlas_rt_context* ctx, const atlas_rt_scene* scene, cons
             char* hOut = static_cast<char*>(rays_out) + 16 * outStride * b;
             const int slot = int(c % nStreams);
             cudaStream_t cs = slot ? ctx->computeExtra[slot - 1] : ctx->stream;
-            e = cudaMemcpyAsync(dIn + 3 * b, hIn, 48 * (end - b), cudaMemcpyHostToDevice, ctx->copyIn);
-            if (e == cudaSuccess) e = cudaEventRecord(ev[1 + c], ctx->copyIn);
+            cudaStream_t up = ctx->copyIn;   // (two upload streams were tried: the copy engine serves one stream's copies first, which only delays every second chunk)
+            e = cudaMemcpyAsync(dIn + 3 * b, hIn, 48 * (end - b), cudaMemcpyHostToDevice, up);
+            if (e == cudaSuccess) e = cudaEventRecord(ev[1 + c], up);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, ev[1 + c], 0);
             if (e != cudaSuccess) break;
             float4* dst = out + outStride * b;   // host output of whole rays: in place on the staging buffer (out == dIn)
@@ -816,6 +859,18 @@ static int trace_common(atlas_rt_context* ctx, const atlas_rt_scene* scene, cons
         if (e == cudaSuccess) e = cudaEventRecord(ev[33], ctx->copyOut);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev[33], 0);   // the context stream now orders after the downloads
         if (e != cudaSuccess && rc == ATLAS_RT_OK) rc = fail(ctx, ATLAS_RT_ERR_CUDA, "pipelined trace", e);
+        if (ctx->pipeTimeline && rc == ATLAS_RT_OK && cudaEventSynchronize(ev[33]) == cudaSuccess) {
+            fprintf(stderr, "[atlas_rt timeline] %u chunks:", chunks);
+            for (uint32_t c = 0; c < chunks; c++) {
+                float up = 0.0f, tr = 0.0f;
+                cudaEventElapsedTime(&up, ev[0], ev[1 + c]);
+                cudaEventElapsedTime(&tr, ev[0], ev[17 + c]);
+                fprintf(stderr, " [%u up %.3f traced %.3f]", c, up, tr);
+            }
+            float all = 0.0f;
+            cudaEventElapsedTime(&all, ev[0], ev[33]);
+            fprintf(stderr, " all %.3f ms\n", all);
+        }
     } else {
         if (!devIn) {
             cudaError_t e = copy_in(ctx, dIn, rays_in, count * 48, false);
@@ -831,6 +886,7 @@ static int trace_common(atlas_rt_context* ctx, const atlas_rt_scene* scene, cons
         if (ctx->copyIn) cudaStreamSynchronize(ctx->copyIn);
         if (ctx->copyOut) cudaStreamSynchronize(ctx->copyOut);
         for (auto& cs : ctx->computeExtra) if (cs) cudaStreamSynchronize(cs);
+        if (ctx->sortStream) cudaStreamSynchronize(ctx->sortStream);
     }
     dev_free(ctx, dIn);
     dev_free(ctx, dOut);

@@ -97,7 +97,8 @@ struct atlas_rt_context {
     cudaStream_t copyIn = nullptr, copyOut = nullptr;
     cudaStream_t computeExtra[7] = {};   // extra compute streams: the chunks of a pipelined host-buffer trace run side by side
     int pipeStreams = 8;                 // compute streams such a call uses (the context stream + computeExtra)
-    cudaEvent_t pipeEvents[34] = {};   // pipelined host-buffer trace: [0] staging ready, [1+c] chunk c uploaded, [17+c] chunk c traced, [33] all done
+    cudaEvent_t pipeEvents[36] = {};   // pipelined host-buffer trace: [0] staging ready, [1+c] chunk c uploaded, [17+c] chunk c traced, [33] all done;
+                                       // streaming trace: [1+c] chunk c uploaded (c < 32), [33] all downloaded, [34] ordering stream done
     void* levelSlots = nullptr;                // pinned: per-level flags the builder's kernels write for the host (build.cu)
     // scheduling knobs of the persistent traversal kernel (trace.cu); ATLAS_RT_TRACE_* environment variables override
     int traceLeafThreshold = 8;     // lanes waiting at a leaf before the warp runs a leaf round
@@ -108,6 +109,10 @@ struct atlas_rt_context {
     int traceLongestFirst = 1;      // fetch rays longest-estimated-path first (hides the drain of the longest rays)
     int traceLongestFirstMin = 65536;
     int traceRaysPerWarp = 96;      // small batches use fewer persistent warps so each warp still sees this many rays
+    int traceMinBlocksPerSM = 2;    // ... but never fewer CTAs than this per SM
+    int streamBlocksPerSM = 7;      // CTAs per SM of a streaming launch (the per-chunk ordering kernels need the rest of the SM)
+    bool pipeTimeline = false;      // ATLAS_RT_PIPE_TIMELINE: per-chunk upload / trace completion times of the chunked pipeline on stderr
+    cudaStream_t sortStream = nullptr;   // high-priority stream of a streaming launch's per-chunk ordering kernels
     // worker contexts (own stream + own pinned level flags each) that atlas_rt_build_blas_batch builds on side by side
     atlas_rt_context* workers[16] = {};
     int batchWorkers = 8;
@@ -292,6 +297,8 @@ int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float
                  bool opacity = false, cudaStream_t st = nullptr /* context stream */, int queueSlot = 0,
                  const uint32_t* dCount = nullptr /* batch size on the device (<= count) */, bool hitsOnly = false /* dOut = 16-byte hit records */,
                  const unsigned int* watermark = nullptr /* streaming input: rays uploaded so far */, unsigned int* chunkDone = nullptr,
-                 uint32_t chunkRays = 0);
+                 uint32_t chunkRays = 0, const uint32_t* streamPerm = nullptr /* streaming: fetch order, written chunk by chunk behind the watermark */);
+int launch_chunk_sort(atlas_rt_context* ctx, const atlas_rt_scene* scene, cudaStream_t st, const float4* rays, uint32_t n, uint32_t indexBase,
+                      uint8_t* bucketOf, unsigned int* hist, uint32_t* perm, unsigned int* watermark);
 
 }   // namespace atlas

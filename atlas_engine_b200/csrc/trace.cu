@@ -194,7 +194,7 @@ __device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) {
 // STREAM (host rays still arriving, see StreamIn) is a template parameter so that the resident-batch instantiations carry
 // none of its state: at the 56-register cap even a dead flag costs moves in the hot loop (measured: 4 % on C2).
 template <bool ANY, bool COUNT, bool OPACITY, bool STREAM>
-__global__ void __launch_bounds__(kTraceBlock, OPACITY ? kBlocksPerSM - 1 : kBlocksPerSM)
+__global__ void __launch_bounds__(kTraceBlock, (OPACITY || STREAM) ? kBlocksPerSM - 1 : kBlocksPerSM)
 trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restrict__ permIn, const unsigned int* __restrict__ usePerm,
              uint32_t count, const uint32_t* __restrict__ countPtr, uint32_t cullMask, float tMin, float tMaxArg,
              int perRayTMax, int sceneFast, int hitsOnly, int kLeafThreshold, int kRefillThreshold, unsigned int* __restrict__ rayCounter,
@@ -204,7 +204,8 @@ trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restr
     __shared__ int stack[kStack][kTraceBlock];
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     const unsigned ltMask = (1u << lane) - 1u;
-    const uint32_t* __restrict__ perm = (permIn && *usePerm) ? permIn : nullptr;
+    // (streaming: the permutation is written chunk by chunk while the kernel runs and is always used; usePerm is null)
+    const uint32_t* __restrict__ perm = (permIn && (STREAM || *usePerm)) ? permIn : nullptr;
     // batches kept in their own (coherent) order refill eagerly; reordered ones do better refilling half a warp at a time
     if (!perm && !STREAM) kRefillThreshold = min(kRefillThreshold, 6);
     bool reported = true;   // streaming: has this lane's finished ray been counted in chunkDone yet?
@@ -301,7 +302,7 @@ trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restr
             if (!alive) {
                 const unsigned idx = base + __popc(mDead & ltMask);
                 if (idx < count && idx >= base) {
-                    ray = perm ? perm[idx] : idx;   // longest-first fetch order; results still go to the ray's own slot
+                    ray = perm ? (STREAM ? __ldcg(perm + idx) : perm[idx]) : idx;   // longest-first fetch order; results still go to the ray's own slot
                     if (STREAM) reported = false;
                     float4 r0, r1, r2;
                     if (STREAM) {   // L1-bypassing loads: these bytes were written by the copy engine while the kernel runs
@@ -590,11 +591,19 @@ __global__ void ray_cost_offsets(unsigned int* __restrict__ hist, uint32_t count
 
 __global__ void __launch_bounds__(kSortBlock)
 ray_cost_scatter(const uint8_t* __restrict__ bucketOf, uint32_t count, const uint32_t* __restrict__ countPtr, unsigned int* __restrict__ offsets,
-                 uint32_t* __restrict__ perm) {
+                 uint32_t* __restrict__ perm, uint32_t indexBase, int always) {
     chain_begin();
     if (countPtr) count = min(count, *countPtr);
     __shared__ unsigned int cnt[kCostBuckets], base[kCostBuckets];
-    if (offsets[kCostBuckets + 1] == 0u) return;   // coherent batch: the trace kernel ignores the permutation
+    if (offsets[kCostBuckets + 1] == 0u) {   // coherent batch: the trace kernel ignores the permutation ...
+        if (always) {                        // ... except in a streaming launch, which always reads it: buffer order
+            for (uint32_t k = 0; k < uint32_t(kSortPerThread); k++) {
+                const uint32_t i = blockIdx.x * (kSortBlock * kSortPerThread) + k * kSortBlock + threadIdx.x;
+                if (i < count) perm[i] = i + indexBase;
+            }
+        }
+        return;
+    }
     if (threadIdx.x < kCostBuckets) cnt[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t first = blockIdx.x * (kSortBlock * kSortPerThread);
@@ -611,7 +620,7 @@ ray_cost_scatter(const uint8_t* __restrict__ bucketOf, uint32_t count, const uin
 #pragma unroll
     for (int k = 0; k < kSortPerThread; k++) {
         const uint32_t i = first + k * kSortBlock + threadIdx.x;
-        if (bk[k] != 0xffu) perm[base[bk[k]] + rank[k]] = i;
+        if (bk[k] != 0xffu) perm[base[bk[k]] + rank[k]] = i + indexBase;
     }
 }
 
@@ -716,6 +725,32 @@ int scene_opacity_flags(atlas_rt_context* ctx, atlas_rt_scene* scene, const uint
     return ATLAS_RT_OK;
 }
 
+// Streaming launch: one chunk of the batch has arrived in `rays` (device memory). Its rays are put in longest-first order
+// (the three ordering kernels of a resident batch, over the chunk only; indices written are batch-global) and the watermark
+// the persistent trace kernel polls is then moved to the end of the chunk — by a one-thread kernel behind the scatter, so
+// that the permutation is complete (and visible) before any warp can claim a ray of the chunk.
+namespace {
+__global__ void publish_watermark(unsigned int* watermark, unsigned int value) {
+    chain_begin();
+    __threadfence();
+    atomicMax(watermark, value);
+    __threadfence_system();
+}
+}   // namespace
+
+int launch_chunk_sort(atlas_rt_context* ctx, const atlas_rt_scene* scene, cudaStream_t st, const float4* rays, uint32_t n, uint32_t indexBase,
+                      uint8_t* bucketOf, unsigned int* hist, uint32_t* perm, unsigned int* watermark) {
+    ATLAS_CUDA(ctx, cudaMemsetAsync(hist, 0, (kCostBuckets + 2) * sizeof(unsigned int), st));
+    const uint32_t sortGrid = (n + kSortBlock * kSortPerThread - 1) / (kSortBlock * kSortPerThread);
+    const bool pdl = ctx->chainLaunch != 0;
+    ATLAS_CUDA(ctx, launch_chain(false, ray_cost_histogram, sortGrid, kSortBlock, 0, st, rays, n, (const uint32_t*)nullptr, scene->tlas->nodes, bucketOf, hist));
+    ATLAS_CUDA(ctx, launch_chain(pdl, ray_cost_offsets, 1, 32, 0, st, hist, n, (const uint32_t*)nullptr));
+    ATLAS_CUDA(ctx, launch_chain(pdl, ray_cost_scatter, sortGrid, kSortBlock, 0, st, bucketOf, n, (const uint32_t*)nullptr, hist, perm, indexBase, 1));
+    ATLAS_CUDA(ctx, launch_chain(pdl, publish_watermark, 1, 1, 0, st, watermark, indexBase + n));
+    ctx->launches += 4;
+    return ATLAS_RT_OK;
+}
+
 int launch_release_chunks(atlas_rt_context* ctx, unsigned int* chunkDone, uint32_t chunkRays, uint32_t count, uint32_t chunks) {
     release_chunks<<<(chunks + 63) / 64, 64, 0, ctx->stream>>>(chunkDone, chunkRays, count);
     ATLAS_LAUNCH_CHECK(ctx);
@@ -758,7 +793,7 @@ int scene_fast_flag(atlas_rt_context* ctx, atlas_rt_scene* scene, const uint32_t
 int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float4* dIn, float4* dOut, uint64_t count,
                  uint32_t cullMask, float tMin, float tMax, bool any, bool perRayTMax, bool counters, bool resetCounters, bool opacity,
                  cudaStream_t st, int queueSlot, const uint32_t* dCount, bool hitsOnly, const unsigned int* watermark, unsigned int* chunkDone,
-                 uint32_t chunkRays) {
+                 uint32_t chunkRays, const uint32_t* streamPerm) {
     if (!st) st = ctx->stream;
     if (count == 0) return ATLAS_RT_OK;
     if (count > 0x7fffffffull) return fail(ctx, ATLAS_RT_ERR_UNSUPPORTED, "more than 2^31-1 rays in one batch");
@@ -766,8 +801,10 @@ int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float
                 scene->materials, scene->textures, scene->materialCount, scene->textureCount};
     const uint32_t n = uint32_t(count);
     // small batches get fewer persistent warps so that each still refills its lanes many times (>= traceRaysPerWarp rays per warp)
-    const uint32_t wantBlocks = std::max<uint32_t>(uint32_t(ctx->smCount) * 2u, n / (uint32_t(ctx->traceRaysPerWarp) * (kTraceBlock / 32)));
-    const uint32_t blocksPerSM = opacity ? std::min(ctx->traceBlocksPerSM, kBlocksPerSM - 1) : ctx->traceBlocksPerSM;
+    const uint32_t wantBlocks = std::max<uint32_t>(uint32_t(ctx->smCount) * uint32_t(ctx->traceMinBlocksPerSM), n / (uint32_t(ctx->traceRaysPerWarp) * (kTraceBlock / 32)));
+    // a streaming launch leaves room on every SM for the small ordering kernels that run beside it on another stream
+    const uint32_t blocksPerSM = watermark ? uint32_t(std::min(ctx->traceBlocksPerSM, ctx->streamBlocksPerSM))
+                                           : (opacity ? std::min(ctx->traceBlocksPerSM, kBlocksPerSM - 1) : ctx->traceBlocksPerSM);
     const uint32_t grid = std::min<uint32_t>(std::min<uint32_t>((n + kTraceBlock - 1) / kTraceBlock, wantBlocks), uint32_t(ctx->smCount) * blocksPerSM);
     const int lt = ctx->traceLeafThreshold, rt = ctx->traceRefillThreshold;
     // words 0-5: visit counters + overflow flag (kept across the chunks of one pipelined call), word 6: the ray queue head
@@ -791,7 +828,7 @@ int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float
         ctx->launches++;
         ATLAS_CUDA(ctx, launch_chain(pdl, ray_cost_offsets, 1, 32, 0, st, hist, n, dCount));
         ctx->launches++;
-        ATLAS_CUDA(ctx, launch_chain(pdl, ray_cost_scatter, sortGrid, kSortBlock, 0, st, bucketOf, n, dCount, hist, perm));
+        ATLAS_CUDA(ctx, launch_chain(pdl, ray_cost_scatter, sortGrid, kSortBlock, 0, st, bucketOf, n, dCount, hist, perm, 0u, 0));
         ctx->launches++;
     }
     const int pr = perRayTMax ? 1 : 0, sf = scene->fastDivision, ho = hitsOnly ? 1 : 0;
@@ -804,7 +841,7 @@ int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float
     }
     cudaError_t launchErr = cudaSuccess;
 #define ATLAS_TRACE_LAUNCH(A, C, O) \
-    launchErr = (watermark && !C) ? launch_chain_w(ctx->chainLaunch != 0, win, trace_kernel<A, false, O, true>, grid, kTraceBlock, 0, st, sc, dIn, dOut, perm, hist ? hist + kCostBuckets + 1 : nullptr, n, dCount, cullMask, tMin, tMax, pr, sf, ho, lt, rt, rayCounter, ctx->dCounters, streamIn) : \
+    launchErr = (watermark && !C) ? launch_chain_w(ctx->chainLaunch != 0, win, trace_kernel<A, false, O, true>, grid, kTraceBlock, 0, st, sc, dIn, dOut, streamPerm, (const unsigned int*)nullptr, n, dCount, cullMask, tMin, tMax, pr, sf, ho, lt, rt, rayCounter, ctx->dCounters, streamIn) : \
                 launch_chain_w(ctx->chainLaunch != 0, win, trace_kernel<A, C, O, false>, grid, kTraceBlock, 0, st, sc, dIn, dOut, perm, hist ? hist + kCostBuckets + 1 : nullptr, n, dCount, cullMask, tMin, tMax, pr, sf, ho, lt, rt, rayCounter, ctx->dCounters, streamIn)
     if (opacity) {
         if (any) { if (counters) ATLAS_TRACE_LAUNCH(true, true, true); else ATLAS_TRACE_LAUNCH(true, false, true); }

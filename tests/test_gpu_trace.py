@@ -207,3 +207,56 @@ def test_leaf_root_blas_is_traversable(ctx, oracle):
     bt, btri, _ = oracle.brute_force(osc, rays)
     assert np.array_equal(out[:, 8], bt) and np.array_equal(out[:, 9].view(np.int32), btri)
     assert (btri >= 0).mean() > 0.05
+
+
+def test_streaming_host_buffer_trace(ctx, oracle):
+    """ATLAS_RT_TRACE_STREAMING=1: a host-buffer trace runs as ONE persistent launch fed chunk by chunk (upload stream ->
+    per-chunk ordering kernels -> watermark), results going home per finished chunk. Every variant must give the bits of
+    the device-pointer call (which test_full_size_c2_properties pins to the oracle); a sample is checked against the oracle
+    here as well."""
+    import os
+    import torch
+    tris = W.soup(200_000, seed=77)
+    boxes = W.tri_boxes(tris)
+    root = np.concatenate([boxes[:, :3].min(0), boxes[:, 3:].max(0)])[None].astype(np.float32)
+    n = 400_000
+    rays = W.random_rays(n, root[0, :3], root[0, 3:], seed=99)
+    rays[::1000, 3] = np.int32(-1).view(np.float32)       # dead IDs ...
+    rays[5::1000, 4] = np.float32(np.nan)                 # ... and NaN directions finish at fetch time
+    rays[:, 8] = np.float32(0.4)                          # per-ray tMax of the any-hit variant
+    old = os.environ.get("ATLAS_RT_TRACE_STREAMING")
+    os.environ["ATLAS_RT_TRACE_STREAMING"] = "1"
+    try:
+        sctx = capi.Context(0)
+    finally:
+        if old is None:
+            del os.environ["ATLAS_RT_TRACE_STREAMING"]
+        else:
+            os.environ["ATLAS_RT_TRACE_STREAMING"] = old
+    try:
+        scene, osc, keep = gpu_and_oracle_scene(sctx, oracle, [tris], root, W.identity_instance())
+        d_rays = torch.from_numpy(rays).cuda()
+        d_out = torch.empty_like(d_rays)
+        sctx.trace(scene, d_rays, n, out=d_out)                                   # resident batch: the reference bits
+        want = d_out.cpu().numpy()
+        ref, _ = oracle.trace(osc, rays[:20000], nthreads=8)
+        assert np.array_equal(want[:20000].view(np.uint32), ref.view(np.uint32))
+        launches = sctx.launches()
+        got = sctx.trace(scene, rays)                                             # pageable host memory, whole rays
+        # one persistent launch + 4 ordering launches per chunk + the release kernel (the chunked pipeline would need 4 per chunk)
+        assert sctx.launches() - launches <= 4 * 4 + 2
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        h_r = torch.from_numpy(rays).pin_memory()
+        h_h = torch.empty((n, 4), dtype=torch.float32).pin_memory()
+        for _ in range(3):                                                        # pinned memory, 16-byte hit records, repeated calls
+            h_h.zero_()
+            sctx.check(sctx.L.atlas_rt_trace_closest(sctx.h, scene.h, h_r.data_ptr(), n, capi.MASK_ALL, 0.0, capi.INF, h_h.data_ptr(), capi.HITS_ONLY))
+            assert np.array_equal(h_h.numpy().view(np.uint32), want[:, 8:12].view(np.uint32))
+        sctx.trace(scene, d_rays, n, out=d_out, any_hit=True, flags=capi.PER_RAY_TMAX)
+        want_any = d_out.cpu().numpy()
+        got_any = sctx.trace(scene, rays, any_hit=True, flags=capi.PER_RAY_TMAX)
+        assert np.array_equal(got_any.view(np.uint32), want_any.view(np.uint32))
+        sctx.check(sctx.L.atlas_rt_trace_closest(sctx.h, scene.h, rays.ctypes.data, n, capi.MASK_ALL, 0.0, capi.INF, d_out.data_ptr(), capi.DEVICE_OUTPUT))
+        assert np.array_equal(d_out.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    finally:
+        sctx.close()

@@ -18,4 +18,4 @@ for w in ("c2", "c5"):
     except Exception as e:
         print(w, "N=$N FAILED", e)
 PY
-tail -3 $O/r2_scale_c2_$N.err $O/r2_scale_c5_$N.err
+for f in $O/r2_scale_c2_$N.err $O/r2_scale_c5_$N.err; do tail -n 2 $f; done; true
