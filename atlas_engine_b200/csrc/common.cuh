@@ -110,6 +110,7 @@ struct atlas_rt_context {
     int traceLongestFirstMin = 65536;
     int traceRaysPerWarp = 96;      // small batches use fewer persistent warps so each warp still sees this many rays
     int traceMinBlocksPerSM = 2;    // ... but never fewer CTAs than this per SM
+    int ptLanes = 4;                // ATLAS_RT_PT_LANES: sample passes of one atlas_rt_pathtrace_bounces call that run side by side (1..4)
     int streamBlocksPerSM = 7;      // CTAs per SM of a streaming launch (the per-chunk ordering kernels need the rest of the SM)
     bool pipeTimeline = false;      // ATLAS_RT_PIPE_TIMELINE: per-chunk upload / trace completion times of the chunked pipeline on stderr
     cudaStream_t sortStream = nullptr;   // high-priority stream of a streaming launch's per-chunk ordering kernels

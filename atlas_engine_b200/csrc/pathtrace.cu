@@ -593,17 +593,26 @@ __global__ void next_bounce_counts(uint32_t* p) {   // survivors become the next
     p[0] = p[1]; p[1] = 0u; p[2] = 0u;
 }
 
+// dst += src (float4 records): the accumulation buffer of a second lane of sample passes joins the caller's
+__global__ void __launch_bounds__(256) add_accum(float4* __restrict__ dst, const float4* __restrict__ src, unsigned long long n) {
+    for (unsigned long long i = blockIdx.x * 256ull + threadIdx.x; i < n; i += gridDim.x * 256ull) {
+        const float4 a = dst[i], b = src[i];
+        dst[i] = make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
+    }
+}
+
 SceneTables tables_of(const atlas_rt_scene* scene) {
     return SceneTables{scene->instances, scene->triangles, scene->materials, scene->textures, scene->materialCount, scene->textureCount};
 }
 
 int enqueue_binning(atlas_rt_context* ctx, const float4* rays, const float4* payload, uint32_t n, const uint32_t* dCount, float4* raysOut,
-                    float4* payloadOut, uint32_t* chunkHist) {
+                    float4* payloadOut, uint32_t* chunkHist, cudaStream_t st = nullptr) {
+    if (!st) st = ctx->stream;
     const uint32_t chunks = (n + kBinChunk - 1) / kBinChunk;
     const bool pdl = ctx->chainLaunch != 0;
-    ATLAS_CUDA(ctx, launch_chain(pdl, bin_count, chunks, 256, 0, ctx->stream, rays, n, dCount, chunkHist));
-    ATLAS_CUDA(ctx, launch_chain(pdl, bin_offsets, 1, 96, 0, ctx->stream, chunkHist, chunks));
-    ATLAS_CUDA(ctx, launch_chain(pdl, bin_scatter, chunks, 256, 0, ctx->stream, rays, payload, n, dCount, static_cast<const uint32_t*>(chunkHist), raysOut, payloadOut));
+    ATLAS_CUDA(ctx, launch_chain(pdl, bin_count, chunks, 256, 0, st, rays, n, dCount, chunkHist));
+    ATLAS_CUDA(ctx, launch_chain(pdl, bin_offsets, 1, 96, 0, st, chunkHist, chunks));
+    ATLAS_CUDA(ctx, launch_chain(pdl, bin_scatter, chunks, 256, 0, st, rays, payload, n, dCount, static_cast<const uint32_t*>(chunkHist), raysOut, payloadOut));
     ctx->launches += 3;
     return ATLAS_RT_OK;
 }
@@ -613,25 +622,28 @@ int enqueue_binning(atlas_rt_context* ctx, const float4* rays, const float4* pay
 // dCounts: [0] = rays in this batch (read), [1] = survivors (accumulated), [2] = shadow rays (accumulated; both start at 0).
 int enqueue_bounce(atlas_rt_context* ctx, const atlas_rt_scene* scene, const atlas_rt_pt_params& prm, float seed, uint32_t bounce, float4* rays,
                    const float4* payloadIn, uint32_t n, uint32_t* dCounts, float4* raysOut, float4* payloadOut, float4* shadow, uint32_t* slotOf,
-                   float* accum, uint32_t accumTileOrder, uint32_t width, uint32_t height, unsigned long long* dTraced, const SlotShard& shard) {
+                   float* accum, uint32_t accumTileOrder, uint32_t width, uint32_t height, unsigned long long* dTraced, const SlotShard& shard,
+                   cudaStream_t st = nullptr, int lane = 0) {
+    if (!st) st = ctx->stream;
     const bool pdl = ctx->chainLaunch != 0;
     // OPACITY_CHECK traces (PathTracingRenderer.cpp:186, rayHit.csh:331). Where every triangle is fully opaque the
     // *Transparency variants accept exactly what the plain ones accept (and both closest-hit loops restore the ray the same
     // way), so the cheaper 48-byte kernels run instead, bit for bit the same; the shadow batch additionally needs every
     // instance to carry the shadow bit, because plain HitAny treats culled instances differently (bvh.hsh:387-390).
     const bool closestOpacity = !scene->allOpaque, shadowOpacity = !(scene->allOpaque && scene->allShadowBit);
-    int rc = launch_trace(ctx, scene, rays, rays, n, ATLAS_RT_MASK_ALL, 0.0f, ATLAS_RT_INF, false, false, false, true, closestOpacity, nullptr, 0, dCounts);
+    // (lanes: sample passes running side by side, each on its own stream with its own ray-queue head)
+    int rc = launch_trace(ctx, scene, rays, rays, n, ATLAS_RT_MASK_ALL, 0.0f, ATLAS_RT_INF, false, false, false, lane == 0, closestOpacity, st, lane, dCounts);
     if (rc != ATLAS_RT_OK) return rc;
     const SceneTables sc = tables_of(scene);
     const uint32_t grid = (n + 127) / 128;
-    ATLAS_CUDA(ctx, launch_chain(pdl, shade_prepare, grid, 128, 0, ctx->stream, static_cast<const float4*>(rays), n, static_cast<const uint32_t*>(dCounts), prm, sc,
+    ATLAS_CUDA(ctx, launch_chain(pdl, shade_prepare, grid, 128, 0, st, static_cast<const float4*>(rays), n, static_cast<const uint32_t*>(dCounts), prm, sc,
                                  shadow, slotOf, dCounts + 2, dTraced));
     ctx->launches++;
     // HitAnyTransparency(ray, INSTANCE_MASK_SHADOW, 0.0, lightDistance - 2.0 * EPSILON), lightDistance = INF
-    rc = launch_trace(ctx, scene, shadow, shadow, n, ATLAS_RT_MASK_SHADOW, 0.0f, ATLAS_RT_INF - 2.0f * kEpsilon, true, false, false, true, shadowOpacity, nullptr, 0,
+    rc = launch_trace(ctx, scene, shadow, shadow, n, ATLAS_RT_MASK_SHADOW, 0.0f, ATLAS_RT_INF - 2.0f * kEpsilon, true, false, false, lane == 0, shadowOpacity, st, lane,
                       dCounts + 2);
     if (rc != ATLAS_RT_OK) return rc;
-    ATLAS_CUDA(ctx, launch_chain(pdl, shade_finish, grid, 128, 0, ctx->stream, static_cast<const float4*>(rays), payloadIn, static_cast<const float4*>(shadow),
+    ATLAS_CUDA(ctx, launch_chain(pdl, shade_finish, grid, 128, 0, st, static_cast<const float4*>(rays), payloadIn, static_cast<const float4*>(shadow),
                                  static_cast<const uint32_t*>(slotOf), n, static_cast<const uint32_t*>(dCounts), prm, seed, bounce, sc, raysOut, payloadOut, accum,
                                  accumTileOrder, width, height, dCounts + 1, shadowOpacity ? 0 : 1, shard));
     ctx->launches++;
@@ -752,51 +764,107 @@ static int pathtrace_frames(atlas_rt_context* ctx, const atlas_rt_scene* scene, 
     if (count == 0 || frames == 0) return ATLAS_RT_OK;
     const uint32_t n = uint32_t(count);
     const bool binning = (flags & ATLAS_RT_RAY_BINNING) != 0;
-    float4 *rays[3] = {nullptr, nullptr, nullptr}, *pay[3] = {nullptr, nullptr, nullptr}, *shadow = nullptr;
-    uint32_t *slotOf = nullptr, *dCounts = nullptr, *hist = nullptr;
+    // Sample passes are independent until they add into the image, and a pass ends in small, latency-bound launches (the
+    // later bounces: a few hundred thousand rays, each launch as long as its longest ray). With more than one pass to do
+    // they therefore run on up to ctx->ptLanes LANES — pass f on lane f % lanes, each lane its own stream, ray / payload /
+    // shadow buffers, counters and ray-queue head — so that one pass's tail overlaps another's big first bounces. Lane 0
+    // accumulates into the caller's buffer, the others into zeroed buffers of their own that are added to it in lane order
+    // at the end: the result is deterministic (it differs from the one-lane result only in the order of the float adds).
+    constexpr int kMaxLanes = 4;
+    const int lanes = int(std::max<uint32_t>(1u, std::min<uint32_t>(std::min<uint32_t>(frames, uint32_t(ctx->ptLanes)), kMaxLanes)));
+    const unsigned long long accumRecords = accumMode == 2u ? count / params->samples_per_frame : (unsigned long long)width * height;
+    struct Lane {
+        cudaStream_t st = nullptr;
+        float4 *rays[3] = {nullptr, nullptr, nullptr}, *pay[3] = {nullptr, nullptr, nullptr}, *shadow = nullptr;
+        uint32_t *slotOf = nullptr, *dCounts = nullptr, *hist = nullptr;
+        float* accum = nullptr;
+    } L[kMaxLanes];
     unsigned long long* dTraced = nullptr;
     auto done = [&](int rc) {
-        for (int k = 0; k < 3; k++) { dev_free(ctx, rays[k]); dev_free(ctx, pay[k]); }
-        dev_free(ctx, shadow); dev_free(ctx, slotOf); dev_free(ctx, dCounts); dev_free(ctx, hist); dev_free(ctx, dTraced);
+        if (rc != ATLAS_RT_OK) for (int l = 1; l < lanes; l++) if (L[l].st) cudaStreamSynchronize(L[l].st);   // nothing may still use what is freed below
+        for (int l = 0; l < lanes; l++) {
+            for (int k = 0; k < 3; k++) { dev_free(ctx, L[l].rays[k]); dev_free(ctx, L[l].pay[k]); }
+            dev_free(ctx, L[l].shadow); dev_free(ctx, L[l].slotOf); dev_free(ctx, L[l].dCounts); dev_free(ctx, L[l].hist);
+            if (l > 0) dev_free(ctx, L[l].accum);
+        }
+        dev_free(ctx, dTraced);
         return rc;
     };
     cudaError_t e = cudaSuccess;
-    for (int k = 0; k < (binning ? 3 : 2) && e == cudaSuccess; k++) { e = dev_alloc(ctx, &rays[k], size_t(n) * 3); if (e == cudaSuccess) e = dev_alloc(ctx, &pay[k], n); }
-    if (e == cudaSuccess) e = dev_alloc(ctx, &shadow, size_t(n) * 3);
-    if (e == cudaSuccess) e = dev_alloc(ctx, &slotOf, n);
-    if (e == cudaSuccess) e = dev_alloc(ctx, &dCounts, 4);
-    if (e == cudaSuccess && binning) e = dev_alloc(ctx, &hist, size_t((n + kBinChunk - 1) / kBinChunk) * kBins);
+    int usable = 1;
+    for (int l = 1; l < lanes; l++) if (ctx->computeExtra[l - 1]) usable = l + 1; else break;
+    const int nl = std::min(lanes, usable);
+    for (int l = 0; l < nl && e == cudaSuccess; l++) {
+        L[l].st = l == 0 ? ctx->stream : ctx->computeExtra[l - 1];
+        for (int k = 0; k < (binning ? 3 : 2) && e == cudaSuccess; k++) { e = dev_alloc(ctx, &L[l].rays[k], size_t(n) * 3); if (e == cudaSuccess) e = dev_alloc(ctx, &L[l].pay[k], n); }
+        if (e == cudaSuccess) e = dev_alloc(ctx, &L[l].shadow, size_t(n) * 3);
+        if (e == cudaSuccess) e = dev_alloc(ctx, &L[l].slotOf, n);
+        if (e == cudaSuccess) e = dev_alloc(ctx, &L[l].dCounts, 4);
+        if (e == cudaSuccess && binning) e = dev_alloc(ctx, &L[l].hist, size_t((n + kBinChunk - 1) / kBinChunk) * kBins);
+        if (l == 0) L[l].accum = accum;
+        else {
+            if (e == cudaSuccess) e = dev_alloc(ctx, &L[l].accum, size_t(accumRecords) * 4);
+            if (e == cudaSuccess) e = cudaMemsetAsync(L[l].accum, 0, size_t(accumRecords) * 16, ctx->stream);
+        }
+    }
     if (e == cudaSuccess) e = dev_alloc(ctx, &dTraced, 1);
     if (e == cudaSuccess) e = cudaMemsetAsync(dTraced, 0, sizeof(unsigned long long), ctx->stream);
+    // the other lanes start behind everything the context stream has done so far (the caller's inputs, the buffers above)
+    cudaEvent_t* ev = ctx->pipeEvents;
+    if (e == cudaSuccess && nl > 1) e = cudaEventRecord(ev[0], ctx->stream);
+    for (int l = 1; l < nl && e == cudaSuccess; l++) e = cudaStreamWaitEvent(L[l].st, ev[0], 0);
     if (e != cudaSuccess) return done(fail(ctx, ATLAS_RT_ERR_CUDA, "path tracer buffers", e));
+    // With several lanes the launches are NOT chained as programmatic dependent launches: a chained kernel's CTAs become
+    // resident as soon as slots free up and wait there for their predecessor, i.e. the tail of one lane's trace kernel would fill
+    // with the waiting CTAs of the same lane's next kernel instead of the runnable CTAs of another lane (measured on a 1/8 shard
+    // of C5: 4 lanes 3.55 ms per pass chained, 2.10 ms unchained; one lane 3.94 / 4.10 ms).
+    struct ChainOff {
+        atlas_rt_context* c; int saved;
+        ChainOff(atlas_rt_context* ctx, bool off) : c(ctx), saved(ctx->chainLaunch) { if (off) c->chainLaunch = 0; }
+        ~ChainOff() { c->chainLaunch = saved; }
+    } chainOff(ctx, nl > 1);
     const bool pdl = ctx->chainLaunch != 0;
     const uint32_t bounces = params->max_bounces;
     for (uint32_t f = 0; f < frames; f++) {
+        const int l = int(f % uint32_t(nl));
+        Lane& ln = L[l];
         float jit[2];
         atlas_rt_sample_jitter(first_sample_count + int32_t(f), jit);
         int cur = 0;
-        e = launch_chain(pdl, raygen_kernel, (n + 127) / 128, 128, 0, ctx->stream, *camera, width, height, params->samples_per_frame,
-                         static_cast<const float*>(nullptr), jit[0], jit[1], shard, (unsigned long long)count, rays[cur]);
+        e = launch_chain(pdl, raygen_kernel, (n + 127) / 128, 128, 0, ln.st, *camera, width, height, params->samples_per_frame,
+                         static_cast<const float*>(nullptr), jit[0], jit[1], shard, (unsigned long long)count, ln.rays[cur]);
         ctx->launches++;
-        if (e == cudaSuccess) e = launch_chain(pdl, set_words, 1, 1, 0, ctx->stream, dCounts, n, 0u, 0u);
+        if (e == cudaSuccess) e = launch_chain(pdl, set_words, 1, 1, 0, ln.st, ln.dCounts, n, 0u, 0u);
         ctx->launches++;
         if (e != cudaSuccess) return done(fail(ctx, ATLAS_RT_ERR_CUDA, "raygen", e));
         for (uint32_t b = 0; b <= bounces; b++) {
             if (binning && b > 0) {   // RayTracingHelper.cpp:304-344 (dormant in the reference): order the rays by direction bin
-                const int rc = enqueue_binning(ctx, rays[cur], pay[cur], n, dCounts, rays[2], pay[2], hist);
+                const int rc = enqueue_binning(ctx, ln.rays[cur], ln.pay[cur], n, ln.dCounts, ln.rays[2], ln.pay[2], ln.hist, ln.st);
                 if (rc != ATLAS_RT_OK) return done(rc);
-                std::swap(rays[cur], rays[2]);
-                std::swap(pay[cur], pay[2]);
+                std::swap(ln.rays[cur], ln.rays[2]);
+                std::swap(ln.pay[cur], ln.pay[2]);
             }
-            const int rc = enqueue_bounce(ctx, scene, *params, seeds[size_t(f) * (bounces + 1) + b], b, rays[cur], pay[cur], n, dCounts, rays[cur ^ 1], pay[cur ^ 1],
-                                          shadow, slotOf, accum, accumMode, width, height, dTraced, shard);
+            const int rc = enqueue_bounce(ctx, scene, *params, seeds[size_t(f) * (bounces + 1) + b], b, ln.rays[cur], ln.pay[cur], n, ln.dCounts, ln.rays[cur ^ 1],
+                                          ln.pay[cur ^ 1], ln.shadow, ln.slotOf, ln.accum, accumMode, width, height, dTraced, shard, ln.st, l);
             if (rc != ATLAS_RT_OK) return done(rc);
-            e = launch_chain(pdl, next_bounce_counts, 1, 1, 0, ctx->stream, dCounts);
+            e = launch_chain(pdl, next_bounce_counts, 1, 1, 0, ln.st, ln.dCounts);
             ctx->launches++;
             if (e != cudaSuccess) return done(fail(ctx, ATLAS_RT_ERR_CUDA, "counters", e));
             cur ^= 1;
         }
     }
+    // join: the context stream continues behind every lane, then the lanes' images are added in lane order
+    for (int l = 1; l < nl && e == cudaSuccess; l++) {
+        e = cudaEventRecord(ev[l], L[l].st);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev[l], 0);
+    }
+    for (int l = 1; l < nl && e == cudaSuccess; l++) {
+        add_accum<<<uint32_t(std::min<unsigned long long>((accumRecords + 255) / 256, 148ull * 8)), 256, 0, ctx->stream>>>(reinterpret_cast<float4*>(accum),
+                                                                                                     reinterpret_cast<const float4*>(L[l].accum), accumRecords);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) return done(fail(ctx, ATLAS_RT_ERR_CUDA, "path tracer lanes", e));
     if (rays_traced || !(flags & ATLAS_RT_ASYNC)) {
         if (rays_traced) e = cudaMemcpyAsync(ctx->pinned, dTraced, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

@@ -177,6 +177,9 @@ struct StreamIn {
     unsigned int* chunkDone;
     uint32_t chunkRays;
     uint32_t spinBound;
+    // (every variant) batch size known only on the device: CTAs beyond what that many rays need leave at once, so a small
+    // late bounce of the path tracer does not fill the machine with idle persistent warps while another lane has work
+    uint32_t raysPerBlock, minBlocks;
 };
 __device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) {
     unsigned int v;
@@ -200,7 +203,10 @@ trace_kernel(SceneDev sc, const float4* in, float4* out, const uint32_t* __restr
              int perRayTMax, int sceneFast, int hitsOnly, int kLeafThreshold, int kRefillThreshold, unsigned int* __restrict__ rayCounter,
              unsigned long long* __restrict__ counters, StreamIn streamIn) {
     chain_begin();
-    if (countPtr) count = min(count, *countPtr);   // batch size produced on the device (path-tracer bounces): no host round trip
+    if (countPtr) {   // batch size produced on the device (path-tracer bounces): no host round trip
+        count = min(count, *countPtr);
+        if (streamIn.raysPerBlock && blockIdx.x >= max(streamIn.minBlocks, count / streamIn.raysPerBlock + 1u)) return;
+    }
     __shared__ int stack[kStack][kTraceBlock];
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     const unsigned ltMask = (1u << lane) - 1u;
@@ -816,7 +822,9 @@ int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float
     uint32_t* perm = nullptr;
     uint8_t* bucketOf = nullptr;
     unsigned int* hist = nullptr;
-    const StreamIn streamIn{watermark, chunkDone, chunkRays ? chunkRays : 1u, 1u << ctx->streamSpinLog2};
+    const bool shrink = dCount != nullptr && ctx->ptLanes > 1;
+    const StreamIn streamIn{watermark, chunkDone, chunkRays ? chunkRays : 1u, 1u << ctx->streamSpinLog2,
+                            shrink ? uint32_t(ctx->traceRaysPerWarp) * (kTraceBlock / 32) : 0u, uint32_t(ctx->smCount) * uint32_t(ctx->traceMinBlocksPerSM)};
     if (ctx->traceLongestFirst && n >= uint32_t(ctx->traceLongestFirstMin) && scene->tlas->nodeCount > 0 && !watermark) {
         ATLAS_CUDA(ctx, dev_alloc_on(st, &perm, n));
         ATLAS_CUDA(ctx, dev_alloc_on(st, &bucketOf, n));

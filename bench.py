@@ -36,7 +36,7 @@ N_TRIS = 1_000_000
 N_RAYS = 1_000_000
 SETTLE_S = 0.4        # seconds of untimed load before a timed region: the first ~100 ms after an idle spell run at ramping clocks
 WORKLOAD = "C2: synthetic 1M-triangle random soup (seed 1234): BLAS build + 1M random-direction closest-hit rays per GPU (seed 5678 + rank)"
-WORKLOAD_C5 = ("C5: path tracer, 3840x2160, 4 bounces (+ shadow rays), one sample pass per step, on the C4 scene (64 BLASes, 10k instances, "
+WORKLOAD_C5 = ("C5: path tracer, 3840x2160 x 16 spp, 4 bounces (+ shadow rays), one 16-spp frame per step, on the C4 scene (64 BLASes, 10k instances, "
                "1.02M triangles); blocks of 64 rayGen tiles dealt round-robin to the GPUs, rays generated on the device, one gather of the image")
 
 
@@ -612,7 +612,8 @@ def run_c5(args, ctx, comm, dev, stream, rank, world, local_rank, timed_loop, ba
     to the ranks (a contiguous split gives one GPU the sky and another all the bounces: measured 1.34x on 2 GPUs), every rank
     runs the whole bounce loop for its blocks on the device (atlas_rt_pathtrace_bounces_interleaved, no host rays) into a
     compact buffer, and one NCCL gather brings the buffers to rank 0 (atlas_rt_image_from_shards puts the pixels in place).
-    A step = one sample pass (1 spp) of the full image + that gather."""
+    A step = one frame of the configuration: 16 sample passes (16 spp) of the full image, issued as ONE call (the passes run on
+    two lanes side by side inside the library, see pathtrace.cu) + that gather."""
     import torch
     import torch.distributed as dist
     from atlas_engine_b200 import capi, sharding, workloads as W
@@ -629,6 +630,7 @@ def run_c5(args, ctx, comm, dev, stream, rank, world, local_rank, timed_loop, ba
     scene = ctx.create_scene(gm, ir, tlas)
     scene.set_materials(capi.make_materials(1))
     w, h, bounces = 3840, 2160, 4
+    spp = int(os.environ.get("ATLAS_BENCH_C5_SPP", "16"))
     cam = W.camera_frame((1000.0, 260.0, -300.0), (1000.0, 60.0, 1000.0), aspect=w / h)
     ld = np.array([0.3, 0.9, -0.3]) / np.linalg.norm([0.3, 0.9, -0.3])
     prm = capi.pt_params(ld, (3.0, 3.0, 2.5), (0.4, 0.5, 0.8), max_bounces=bounces)
@@ -642,9 +644,11 @@ def run_c5(args, ctx, comm, dev, stream, rank, world, local_rank, timed_loop, ba
     offsets = [sum(sizes[:r]) for r in range(world)]
     flags = capi.ASYNC | (capi.RAY_BINNING if os.environ.get("ATLAS_BENCH_BINNING") else 0)
 
+    def seeds_of(k):
+        return (np.arange(spp * (bounces + 1), dtype=np.float32) + np.float32(k * spp * (bounces + 1))) * np.float32(0.754878) + np.float32(0.5)
+
     def step(k):
-        seeds = (np.arange(bounces + 1, dtype=np.float32) + np.float32(k * (bounces + 1))) * np.float32(0.754878) + np.float32(0.5)
-        ctx.pathtrace_bounces_interleaved(scene, cam, w, h, prm, 1, k, seeds, rank, world, block, accum_local=part, flags=flags, count_rays=False)
+        ctx.pathtrace_bounces_interleaved(scene, cam, w, h, prm, spp, k * spp, seeds_of(k), rank, world, block, accum_local=part, flags=flags, count_rays=False)
         if world > 1:
             comm.gather(part, sizes[rank], gathered, sizes, offsets, flags=capi.ASYNC)
 
@@ -662,8 +666,8 @@ def run_c5(args, ctx, comm, dev, stream, rank, world, local_rank, timed_loop, ba
     clocks = clk.summary()
     # rays per step: count them once (same seeds as step 0) outside the timed region
     part.zero_()
-    seeds0 = np.arange(bounces + 1, dtype=np.float32) * np.float32(0.754878) + np.float32(0.5)
-    _, traced = ctx.pathtrace_bounces_interleaved(scene, cam, w, h, prm, 1, 0, seeds0, rank, world, block, accum_local=part)
+    seeds0 = seeds_of(0)
+    _, traced = ctx.pathtrace_bounces_interleaved(scene, cam, w, h, prm, spp, 0, seeds0, rank, world, block, accum_local=part)
     total = torch.tensor([traced], dtype=torch.float64, device=dev)
     parity = None
     if world > 1:
@@ -675,14 +679,15 @@ def run_c5(args, ctx, comm, dev, stream, rank, world, local_rank, timed_loop, ba
     if rank == 0:   # the gathered, re-assembled image of the sharded frame == the frame rendered whole on one GPU
         ctx.image_from_shards(gathered, w, h, world, block, image)
         whole = torch.zeros((w * h, 4), dtype=torch.float32, device=dev)
-        ctx.pathtrace_bounces(scene, cam, w, h, prm, 1, 0, seeds0, whole)
+        ctx.pathtrace_bounces(scene, cam, w, h, prm, spp, 0, seeds0, whole)
         a, b = image.cpu().numpy(), whole.cpu().numpy()
         ok = bool(np.array_equal(a[:, 3], b[:, 3]) and np.allclose(a[:, :3], b[:, :3], rtol=1e-5, atol=1e-6))
         parity = {"assembled_image_equals_single_gpu_frame": ok, "ok": ok}
     rays_per_step = float(total.item())
     line = {"metric": "pathtrace_closest_hit", "value": rays_per_step / ms / 1e3, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD_C5, "width": w, "height": h, "bounces": bounces, "closest_hit_rays_per_step": rays_per_step,
+            "config": {"workload": WORKLOAD_C5, "width": w, "height": h, "bounces": bounces, "spp_per_step": spp, "closest_hit_rays_per_step": rays_per_step,
+                       "lanes": int(os.environ.get("ATLAS_RT_PT_LANES", "4")),
                        "note": "Mrays/s counts closest-hit rays only; every lit hit also casts one shadow (any-hit, opacity-aware) ray",
                        "l2": "per-step working set (rays 8.3M x 48 B x 2 + scene 112 MB) exceeds the 126 MB L2; no flush",
                        "binning": bool(flags & capi.RAY_BINNING)},

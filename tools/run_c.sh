@@ -1,4 +1,6 @@
 #!/bin/bash
-for bps in 7 6 4; do
-ATLAS_RT_TRACE_STREAMING=1 ATLAS_RT_STREAM_BLOCKS_PER_SM=$bps ATLAS_RT_STREAM_CHUNKS=8 ATLAS_RT_PIPE_TIMELINE=1 timeout 200 python tools/prof_targets.py e2e 2>&1 | grep timeline | tail -2
+timeout 300 python -m pytest tests/test_gpu_pathtrace.py tests/test_gpu_callers.py -m gpu -q --tb=short -x 2>&1 | tail -3
+for parts in 1 2 4 8; do
+for lanes in 1 4; do ATLAS_RT_PT_LANES=$lanes timeout 200 python tools/c5_shard_time.py $parts 2>&1 | tail -1; done
 done
+ATLAS_RT_PT_LANES=3 timeout 200 python tools/c5_shard_time.py 1 2>&1 | tail -1
