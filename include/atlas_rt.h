@@ -326,7 +326,11 @@ int atlas_rt_pathtrace_bounce(atlas_rt_context* ctx, const atlas_rt_scene* scene
  * image across GPUs, 64 * samples_per_frame slots per 8x8 tile. accum: device, width*height x 4 floats, indexed by pixel or,
  * with ATLAS_RT_ACCUM_TILE_ORDER, by tile-order index (then a slot range owns a contiguous slice). rays_traced (may be
  * NULL) receives the number of closest-hit rays traced. ATLAS_RT_RAY_BINNING adds the reference's direction binning pass
- * before every bounce after the first. */
+ * before every bounce after the first.
+ * With frames > 1 the passes run on up to four lanes side by side (ATLAS_RT_PT_LANES): pass f on lane f mod lanes, every lane
+ * with buffers and a stream of its own; lane 0 adds into accum, the other lanes into private images that are added to accum in
+ * lane order before the call's work ends on the context stream. The image is deterministic and equals the one-lane image up
+ * to the order of the float additions per pixel. */
 int atlas_rt_pathtrace_bounces(atlas_rt_context* ctx, const atlas_rt_scene* scene, const atlas_rt_camera* camera,
                                uint32_t width, uint32_t height, const atlas_rt_pt_params* params, uint32_t frames,
                                int32_t first_sample_count, const float* seeds, uint64_t slot_begin, uint64_t slot_end,
