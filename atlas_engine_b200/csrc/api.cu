@@ -228,7 +228,7 @@ int atlas_rt_context_create(int device, void* stream, atlas_rt_context** out_ctx
         cudaDeviceGetStreamPriorityRange(&prLow, &prHigh);
         if (cudaStreamCreateWithPriority(&ctx->sortStream, cudaStreamNonBlocking, prHigh) != cudaSuccess) ctx->sortStream = nullptr;
     }
-    if (const char* e = getenv("ATLAS_RT_PT_LANES")) ctx->ptLanes = std::max(1, std::min(4, atoi(e)));
+    if (const char* e = getenv("ATLAS_RT_PT_LANES")) ctx->ptLanes = std::max(1, std::min(8, atoi(e)));
     if (const char* e = getenv("ATLAS_RT_STREAM_BLOCKS_PER_SM")) ctx->streamBlocksPerSM = std::max(1, std::min(8, atoi(e)));
     if (const char* e = getenv("ATLAS_RT_TRACE_MIN_BLOCKS_PER_SM")) ctx->traceMinBlocksPerSM = std::max(1, std::min(9, atoi(e)));
     ctx->pipeTimeline = getenv("ATLAS_RT_PIPE_TIMELINE") != nullptr;

@@ -770,7 +770,7 @@ static int pathtrace_frames(atlas_rt_context* ctx, const atlas_rt_scene* scene, 
     // shadow buffers, counters and ray-queue head — so that one pass's tail overlaps another's big first bounces. Lane 0
     // accumulates into the caller's buffer, the others into zeroed buffers of their own that are added to it in lane order
     // at the end: the result is deterministic (it differs from the one-lane result only in the order of the float adds).
-    constexpr int kMaxLanes = 4;
+    constexpr int kMaxLanes = 8;
     const int lanes = int(std::max<uint32_t>(1u, std::min<uint32_t>(std::min<uint32_t>(frames, uint32_t(ctx->ptLanes)), kMaxLanes)));
     const unsigned long long accumRecords = accumMode == 2u ? count / params->samples_per_frame : (unsigned long long)width * height;
     struct Lane {

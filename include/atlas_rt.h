@@ -327,7 +327,7 @@ int atlas_rt_pathtrace_bounce(atlas_rt_context* ctx, const atlas_rt_scene* scene
  * with ATLAS_RT_ACCUM_TILE_ORDER, by tile-order index (then a slot range owns a contiguous slice). rays_traced (may be
  * NULL) receives the number of closest-hit rays traced. ATLAS_RT_RAY_BINNING adds the reference's direction binning pass
  * before every bounce after the first.
- * With frames > 1 the passes run on up to four lanes side by side (ATLAS_RT_PT_LANES): pass f on lane f mod lanes, every lane
+ * With frames > 1 the passes run on four (ATLAS_RT_PT_LANES: up to eight) lanes side by side: pass f on lane f mod lanes, every lane
  * with buffers and a stream of its own; lane 0 adds into accum, the other lanes into private images that are added to accum in
  * lane order before the call's work ends on the context stream. The image is deterministic and equals the one-lane image up
  * to the order of the float additions per pixel. */

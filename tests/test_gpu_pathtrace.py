@@ -320,3 +320,43 @@ def test_c5_sample_pass_at_full_resolution(ctx, oracle):
     sky = np.minimum(np.array([0.4, 0.5, 0.8]), 10.0)
     pix = rays[idx][miss][:, 3].view(np.int32)
     assert np.allclose(acc[pix, :3], sky, rtol=1e-6)    # primary rays that miss see the sky
+
+
+def test_sample_pass_lanes_give_the_same_image(ctx, oracle):
+    """The sample passes of one atlas_rt_pathtrace_bounces call run on up to ATLAS_RT_PT_LANES lanes side by side (own stream and
+    buffers each, images added in lane order). One lane (strictly sequential passes), the default four and eight must trace
+    the same rays and give the same image up to the order of the per-pixel float additions; a repeated call is bit-identical."""
+    import os
+    import torch
+    dev = torch.device("cuda", 0)
+    w, h, spf, bounces, frames = 120, 72, 1, 4, 7
+    cam = W.camera_frame((30.0, 40.0, -20.0), (30.0, 0.0, 30.0), aspect=w / h)
+    ld = np.array([0.2, 0.8, 0.4]) / np.linalg.norm([0.2, 0.8, 0.4])
+    prm = capi.pt_params(ld, (3.0, 3.0, 2.5), (0.4, 0.5, 0.8), max_bounces=bounces, samples_per_frame=spf)
+    seeds = np.arange(frames * (bounces + 1), dtype=np.float32) * np.float32(1.37) + np.float32(0.25)
+    images, traced = {}, {}
+    old = os.environ.get("ATLAS_RT_PT_LANES")
+    try:
+        for lanes in (1, 4, 8):
+            os.environ["ATLAS_RT_PT_LANES"] = str(lanes)
+            c = capi.Context(0)
+            try:
+                scene, osc, ib, keep = pt_scene(c, oracle, n_inst=40, seed=8)
+                accum = torch.zeros((w * h, 4), dtype=torch.float32, device=dev)
+                traced[lanes] = c.pathtrace_bounces(scene, cam, w, h, prm, frames, 3, seeds, accum)
+                images[lanes] = accum.cpu().numpy().copy()
+                if lanes == 4:
+                    accum.zero_()
+                    c.pathtrace_bounces(scene, cam, w, h, prm, frames, 3, seeds, accum)
+                    assert np.array_equal(accum.cpu().numpy().view(np.uint32), images[4].view(np.uint32))   # deterministic
+            finally:
+                c.close()
+    finally:
+        if old is None:
+            os.environ.pop("ATLAS_RT_PT_LANES", None)
+        else:
+            os.environ["ATLAS_RT_PT_LANES"] = old
+    assert traced[1] == traced[4] == traced[8] > frames * w * h
+    for lanes in (4, 8):
+        assert np.array_equal(images[lanes][:, 3], images[1][:, 3]) and np.all(images[1][:, 3] == frames * spf)
+        assert np.allclose(images[lanes][:, :3], images[1][:, :3], rtol=1e-5, atol=1e-6)
