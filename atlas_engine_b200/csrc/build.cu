@@ -36,12 +36,18 @@
 namespace atlas {
 namespace {
 
-constexpr uint32_t kSubtreeMax = 1024;   // refs a shared-memory subtree CTA can hold
+#ifndef ATLAS_SUBTREE_MAX
+#define ATLAS_SUBTREE_MAX 1024
+#define ATLAS_SUBTREE_BLOCK 256
+#define ATLAS_SUBTREE_CTAS 2
+#endif
+constexpr uint32_t kSubtreeMax = ATLAS_SUBTREE_MAX;   // refs a shared-memory subtree CTA can hold
+constexpr int kSubCtasPerSM = ATLAS_SUBTREE_CTAS;
 constexpr uint32_t kSubtreeBins = 32;    // ... and the bin count it supports (one bin per lane)
 constexpr int kSmemBin = 9;              // stride of a bin record in SHARED memory: odd, so lanes on different bins hit different banks
 constexpr uint32_t kChunk = 1024;        // refs per CTA pass in the big-node kernels
 constexpr int kBigBlock = 256;
-constexpr int kSubBlock = 256;
+constexpr int kSubBlock = ATLAS_SUBTREE_BLOCK;
 constexpr int kSubWarps = kSubBlock / 32;
 
 enum TaskKind : int32_t { kObject = 0, kMedian = 1, kDone = 2, kSpatial = 3, kPending = 4 };
@@ -1715,11 +1721,11 @@ __device__ inline void build_cta_node(const SubNode nd, const SmallTask& task, u
 constexpr uint32_t kSubNodes = kSubtreeMax / 2;   // most nodes one level of a subtree can hold (each has >= 2 refs)
 constexpr size_t kSubtreeSmem = size_t(4) * kSubtreeMax * sizeof(float4) + size_t(2) * kSubNodes * sizeof(SubNode) +
                                 size_t(kSubWarps) * 2 * kSubtreeBins * kSubBinWords * sizeof(int) + size_t(2) * kSubNodes * sizeof(uint16_t);
-static_assert(2 * (kSubtreeSmem + 1024 + 128) <= 228 * 1024, "two subtree CTAs must fit one SM");
+static_assert(kSubCtasPerSM * (kSubtreeSmem + 1024 + 128) <= 228 * 1024, "the subtree CTAs must fit one SM");
 
 // Persistent: the grid is sized for the machine (two CTAs per SM) and every CTA draws subtrees from a ticket counter until
 // none are left, so the launch does not need the subtree count on the host (no round trip after the level loop).
-__global__ void __launch_bounds__(kSubBlock, 2)
+__global__ void __launch_bounds__(kSubBlock, kSubCtasPerSM)
 build_subtrees(const SmallTask* __restrict__ small, float4* const lo0, float4* const hi0, float4* const lo1,
                float4* const hi1, float4* nodes, uint32_t* __restrict__ order, uint8_t* __restrict__ eon,
                LevelInfo* __restrict__ info, uint32_t budget, uint32_t maxSmall) {
@@ -2068,7 +2074,7 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
     // the subtrees are enqueued straight behind the last level (the kernel reads their number on the device); the one
     // read-back that follows waits for the whole build
     if (!rootLeaf) {
-        ATLAS_CUDA_C(ctx, launch_chain(pdl, build_subtrees, uint32_t(ctx->smCount) * 2u, kSubBlock, kSubtreeSmem, st, B.small, B.lo[0], B.hi[0], B.lo[1],
+        ATLAS_CUDA_C(ctx, launch_chain(pdl, build_subtrees, uint32_t(ctx->smCount) * uint32_t(kSubCtasPerSM), kSubBlock, kSubtreeSmem, st, B.small, B.lo[0], B.hi[0], B.lo[1],
                                        B.hi[1], B.nodes, B.order, B.eon, B.info, B.budget, maxSmall));
         ctx->launches++;
     }
