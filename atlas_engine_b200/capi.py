@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libatlas_rt.so")
 
 DEVICE_INPUT, DEVICE_OUTPUT, ASYNC, PER_RAY_TMAX, COUNTERS, OPACITY = 1, 2, 4, 8, 16, 32
-RAY_BINNING, ACCUM_TILE_ORDER, HITS_ONLY = 64, 128, 256
+RAY_BINNING, ACCUM_TILE_ORDER, HITS_ONLY, PEER_OUTPUT = 64, 128, 256, 512
 MASK_ALL, MASK_SHADOW = 1 << 7, 1 << 6
 INF = 1e12
 STATUS = {0: "OK", -1: "ERR_INVALID", -2: "ERR_CUDA", -3: "ERR_OOM", -4: "ERR_UNSUPPORTED", -5: "ERR_STACK"}
@@ -75,6 +75,7 @@ SIGNATURES = {
     "atlas_rt_scene_replicate": (_i32, [_vp, _vp, _u32, C.POINTER(_vp)]),
     "atlas_rt_trace_sharded": (_i32, [_vp, _vp, _vp, _u64, _u32, _f32, _f32, _vp, _u32, _u32, _i32]),
     "atlas_rt_comm_gather": (_i32, [_vp, _vp, _u64, _vp, _vp, _vp, _u32, _u32]),
+    "atlas_rt_comm_peer_hits": (_i32, [_vp, C.POINTER(_vp)]),
     "atlas_rt_shard_range": (_i32, [_u64, _u32, _u32, _u32, C.POINTER(_u64), C.POINTER(_u64)]),
 }
 
@@ -539,15 +540,21 @@ class Comm:
         CUDA tensor or None (a host array is made on root)."""
         fl = flags | (DEVICE_INPUT if _is_device(rays) else 0)
         if self.rank == root:
-            if hits_out is None:
+            if hits_out is None and not (flags & PEER_OUTPUT):   # (peer output: the records may stay in the root's window)
                 hits_out = np.empty((total_count, 4), dtype=np.float32)
             if _is_device(hits_out):
                 fl |= DEVICE_OUTPUT
         if not _is_device(rays):
             rays = np.ascontiguousarray(rays, dtype=np.float32)
         self.ctx.check(self.ctx.L.atlas_rt_trace_sharded(self.h, scene.h, _addr(rays), total_count, cull_mask, t_min, t_max,
-                                                         _addr(hits_out) if self.rank == root else None, root, fl, int(any_hit)))
+                                                         _addr(hits_out) if (self.rank == root and hits_out is not None) else None, root, fl, int(any_hit)))
         return hits_out if self.rank == root else None
+
+    def peer_hits(self):
+        """Device address of the most recent PEER_OUTPUT call's records in the root's window (0 elsewhere / before the first call)."""
+        p = _vp()
+        self.ctx.check(self.ctx.L.atlas_rt_comm_peer_hits(self.h, C.byref(p)))
+        return int(p.value or 0)
 
     def gather(self, send, nbytes, recv, sizes, offsets, root=0, flags=0):
         sz = (_u64 * self.world)(*[int(x) for x in sizes])

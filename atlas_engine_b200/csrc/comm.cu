@@ -59,6 +59,26 @@ NcclApi& nccl() {
     return api;
 }
 
+// ---- peer-memory window (atlas_rt_trace_sharded with ATLAS_RT_PEER_OUTPUT) -------------------------------------------
+constexpr size_t kWindowFlagBytes = 4096;   // done[slot][rank] counters (u32), at the start of the root's window allocation
+
+// Runs behind a rank's trace launch on the same stream (the launch, and with it every hit record it stored into the root's
+// memory, is complete): publish "rank r has finished call k" in the root's memory.
+__global__ void peer_signal(unsigned int* flag, unsigned int value) {
+    chain_begin();
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned int*>(flag) = value;
+    __threadfence_system();
+}
+struct PeerFlagPtrs { unsigned int* f[64]; };
+// Root: tell every rank (in ITS memory, where it polls) that the slot of call k has been consumed and may be written again.
+__global__ void peer_release(PeerFlagPtrs p, uint32_t world, unsigned int value) {
+    if (threadIdx.x < world) {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned int*>(p.f[threadIdx.x]) = value;
+    }
+}
+
 }   // namespace
 }   // namespace atlas
 
@@ -72,6 +92,15 @@ struct atlas_rt_comm {
     uint64_t hitsCapacity = 0;
     uint64_t calls = 0;
     void* pinned = nullptr;                 // header exchange
+    // peer-memory window of atlas_rt_trace_sharded(ATLAS_RT_PEER_OUTPUT): the traversal kernels of all ranks store their
+    // hit records straight into the root's buffer over NVLink; flags written the same way tell the root when a rank is done
+    bool peerReady = false;
+    uint32_t peerRoot = 0;
+    uint64_t peerCapacity = 0;              // records per slot
+    uint64_t peerCalls = 0;
+    char* window = nullptr;                 // root: own allocation; elsewhere the root's, opened through CUDA IPC: [4096 B flags][2 slots][capacity] records
+    unsigned int* localFlag = nullptr;      // this rank's "root has consumed call k" counter (written by the root over NVLink)
+    unsigned int* peerFlags[64] = {};       // root: every rank's localFlag
 };
 
 using namespace atlas;
@@ -126,6 +155,128 @@ int ctx_after_comm(atlas_rt_comm* c) {
     return ATLAS_RT_OK;
 }
 
+// ---- peer-memory window ---------------------------------------------------------------------------------------------
+struct PeerHandles { cudaIpcMemHandle_t flag, window; };
+static_assert(sizeof(PeerHandles) == 128, "two 64-byte IPC handles");
+
+void peer_teardown(atlas_rt_comm* c) {
+    if (c->window) { if (c->rank == c->peerRoot) cudaFree(c->window); else cudaIpcCloseMemHandle(c->window); }
+    for (uint32_t r = 0; r < 64; r++) if (c->peerFlags[r] && c->peerFlags[r] != c->localFlag) cudaIpcCloseMemHandle(c->peerFlags[r]);
+    if (c->localFlag) cudaFree(c->localFlag);
+    c->window = nullptr;
+    c->localFlag = nullptr;
+    memset(c->peerFlags, 0, sizeof(c->peerFlags));
+    c->peerReady = false;
+    c->peerCapacity = 0;
+    c->peerCalls = 0;
+}
+
+// Collective: (re)create the window for `capacity` records per slot on `root` and open it everywhere else.
+int peer_setup(atlas_rt_comm* c, uint64_t capacity, uint32_t root) {
+    atlas_rt_context* ctx = c->ctx;
+    if (c->world > 64) return fail(ctx, ATLAS_RT_ERR_UNSUPPORTED, "peer window: more than 64 ranks");
+    ATLAS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ATLAS_CUDA(ctx, cudaStreamSynchronize(c->stream));
+    peer_teardown(c);
+    c->peerRoot = root;
+    ATLAS_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&c->localFlag), 256));
+    ATLAS_CUDA(ctx, cudaMemset(c->localFlag, 0, 256));
+    PeerHandles mine;
+    memset(&mine, 0, sizeof(mine));
+    ATLAS_CUDA(ctx, cudaIpcGetMemHandle(&mine.flag, c->localFlag));
+    if (c->rank == root) {
+        ATLAS_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&c->window), kWindowFlagBytes + 2 * capacity * 16));
+        ATLAS_CUDA(ctx, cudaMemset(c->window, 0, kWindowFlagBytes));
+        ATLAS_CUDA(ctx, cudaIpcGetMemHandle(&mine.window, c->window));
+    }
+    // exchange: one 128-byte broadcast per rank
+    std::vector<PeerHandles> all(c->world);
+    PeerHandles* dev = nullptr;
+    ATLAS_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&dev), sizeof(PeerHandles) * c->world));
+    cudaError_t e = cudaMemcpy(dev + c->rank, &mine, sizeof(mine), cudaMemcpyHostToDevice);
+    int rc = e == cudaSuccess ? ATLAS_RT_OK : fail(ctx, ATLAS_RT_ERR_CUDA, "peer window: handle upload", e);
+    for (uint32_t r = 0; r < c->world && rc == ATLAS_RT_OK; r++) rc = bcast(c, dev + r, sizeof(PeerHandles), r);
+    if (rc == ATLAS_RT_OK) {
+        e = cudaStreamSynchronize(c->stream);
+        if (e == cudaSuccess) e = cudaMemcpy(all.data(), dev, sizeof(PeerHandles) * c->world, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(ctx, ATLAS_RT_ERR_CUDA, "peer window: handle exchange", e);
+    }
+    cudaFree(dev);
+    if (rc != ATLAS_RT_OK) return rc;
+    if (c->rank == root) {
+        for (uint32_t r = 0; r < c->world; r++) {
+            if (r == root) { c->peerFlags[r] = c->localFlag; continue; }
+            void* p = nullptr;
+            e = cudaIpcOpenMemHandle(&p, all[r].flag, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) return fail(ctx, ATLAS_RT_ERR_CUDA, "peer window: cudaIpcOpenMemHandle (a rank's flag)", e);
+            c->peerFlags[r] = static_cast<unsigned int*>(p);
+        }
+    } else {
+        void* p = nullptr;
+        e = cudaIpcOpenMemHandle(&p, all[root].window, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail(ctx, ATLAS_RT_ERR_CUDA, "peer window: cudaIpcOpenMemHandle (the root's window; needs NVLink / PCIe peer access between the GPUs)", e);
+        c->window = static_cast<char*>(p);
+    }
+    c->peerCapacity = capacity;
+    c->peerReady = true;
+    return ATLAS_RT_OK;
+}
+
+// The sharded trace batch with the gather fused into the traversal: every rank's kernel stores each hit record, as the ray
+// finishes, at its global position in the ROOT's window (P2P stores over NVLink / NVSwitch; the root's own kernel writes
+// locally), so the transfer rides along with the traversal and no collective, copy kernel or copy engine touches the data.
+// Flow control is two counters per rank, both written over NVLink and polled locally with cuStreamWaitValue32: done[slot][r]
+// in the root's memory (rank r has finished call k), consumed in rank r's memory (the root has used call k's slot, which
+// call k + 2 writes again).
+int trace_sharded_peer(atlas_rt_comm* c, const atlas_rt_scene* scene, const void* rays_in, uint64_t total_count, uint32_t cull_mask, float t_min,
+                       float t_max, void* hits_out, uint32_t root, uint32_t flags, int any_hit) {
+    atlas_rt_context* ctx = c->ctx;
+    if (!ctx->waitValue32) return fail(ctx, ATLAS_RT_ERR_UNSUPPORTED, "ATLAS_RT_PEER_OUTPUT needs cuStreamWaitValue32");
+    typedef int (*StreamValue32)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+    const StreamValue32 waitValue = reinterpret_cast<StreamValue32>(ctx->waitValue32);
+    if (!c->peerReady || c->peerRoot != root || c->peerCapacity < total_count) {
+        const int rc = peer_setup(c, std::max<uint64_t>(total_count, 64), root);
+        if (rc != ATLAS_RT_OK) return rc;
+    }
+    uint64_t b = 0, e = 0;
+    atlas_rt_shard_range(total_count, c->rank, c->world, 64, &b, &e);
+    const uint64_t local = e - b;
+    const uint64_t k = c->peerCalls;
+    const uint32_t slot = uint32_t(k & 1);
+    float4* slotBase = reinterpret_cast<float4*>(c->window + kWindowFlagBytes) + size_t(slot) * c->peerCapacity;
+    unsigned int* done = reinterpret_cast<unsigned int*>(c->window) + slot * 64u;
+    // the slot was last written by call k - 2: wait (locally) until the root has consumed that
+    if (k >= 2 && waitValue(ctx->stream, reinterpret_cast<unsigned long long>(c->localFlag), unsigned(k - 1), 0u /* GEQ */) != 0)
+        return fail(ctx, ATLAS_RT_ERR_CUDA, "peer window: cuStreamWaitValue32");
+    if (local) {
+        const uint32_t tf = (flags & (ATLAS_RT_DEVICE_INPUT | ATLAS_RT_PER_RAY_TMAX | ATLAS_RT_OPACITY)) | ATLAS_RT_DEVICE_OUTPUT | ATLAS_RT_HITS_ONLY | ATLAS_RT_ASYNC;
+        const int rc = any_hit ? atlas_rt_trace_any(ctx, scene, rays_in, local, cull_mask, t_min, t_max, slotBase + b, tf)
+                               : atlas_rt_trace_closest(ctx, scene, rays_in, local, cull_mask, t_min, t_max, slotBase + b, tf);
+        if (rc != ATLAS_RT_OK) return rc;
+    }
+    ATLAS_CUDA(ctx, launch_chain(ctx->chainLaunch != 0, peer_signal, 1, 1, 0, ctx->stream, done + c->rank, unsigned(k + 1)));
+    ctx->launches++;
+    if (c->rank == root) {
+        // the root's communicator stream: wait for every rank, hand the records on, release the slot
+        for (uint32_t r = 0; r < c->world; r++)
+            if (waitValue(c->stream, reinterpret_cast<unsigned long long>(done + r), unsigned(k + 1), 0u) != 0) return fail(ctx, ATLAS_RT_ERR_CUDA, "peer window: cuStreamWaitValue32");
+        if (hits_out && total_count)
+            ATLAS_CUDA(ctx, cudaMemcpyAsync(hits_out, slotBase, total_count * 16, (flags & ATLAS_RT_DEVICE_OUTPUT) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+        PeerFlagPtrs ptrs;
+        memcpy(ptrs.f, c->peerFlags, sizeof(ptrs.f));
+        peer_release<<<1, 64, 0, c->stream>>>(ptrs, c->world, unsigned(k + 1));
+        ctx->launches++;
+        ATLAS_CUDA(ctx, cudaGetLastError());
+        ATLAS_CUDA(ctx, cudaEventRecord(c->gathered[slot], c->stream));
+    }
+    c->peerCalls++;
+    if (!(flags & ATLAS_RT_ASYNC)) {
+        ATLAS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ATLAS_CUDA(ctx, cudaStreamSynchronize(c->stream));
+    }
+    return ATLAS_RT_OK;
+}
+
 }   // namespace
 
 extern "C" {
@@ -170,6 +321,8 @@ void atlas_rt_comm_destroy(atlas_rt_comm* c) {
     atlas_rt_context* ctx = c->ctx;
     cudaSetDevice(ctx->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(ctx->stream);
+    peer_teardown(c);
     if (c->comm) nccl().CommDestroy(c->comm);
     for (int k = 0; k < 2; k++) {
         if (c->hits[k]) cudaFree(c->hits[k]);
@@ -480,6 +633,7 @@ int atlas_rt_trace_sharded(atlas_rt_comm* c, const atlas_rt_scene* scene, const 
     atlas_rt_shard_range(total_count, c->rank, c->world, 64, &b, &e);
     const uint64_t local = e - b;
     if (local && !rays_in) return fail(ctx, ATLAS_RT_ERR_INVALID, "rays_in is null");
+    if (flags & ATLAS_RT_PEER_OUTPUT) return trace_sharded_peer(c, scene, rays_in, total_count, cull_mask, t_min, t_max, hits_out, root, flags, any_hit);
     if (c->rank == root && total_count && !hits_out) return fail(ctx, ATLAS_RT_ERR_INVALID, "hits_out is null on the root");
     const int slot = int(c->calls & 1);
     if (local > c->hitsCapacity) {   // (re)allocate both local buffers; rare
@@ -534,6 +688,14 @@ int atlas_rt_trace_sharded(atlas_rt_comm* c, const atlas_rt_scene* scene, const 
         ATLAS_CUDA(ctx, cudaStreamSynchronize(c->stream));
         ATLAS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    return ATLAS_RT_OK;
+}
+
+int atlas_rt_comm_peer_hits(atlas_rt_comm* c, const void** hits) {
+    if (!c || !hits) return ATLAS_RT_ERR_INVALID;
+    *hits = nullptr;
+    if (!c->peerReady || c->rank != c->peerRoot || c->peerCalls == 0) return ATLAS_RT_OK;
+    *hits = reinterpret_cast<const float4*>(c->window + kWindowFlagBytes) + size_t((c->peerCalls - 1) & 1) * c->peerCapacity;
     return ATLAS_RT_OK;
 }
 

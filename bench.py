@@ -40,12 +40,18 @@ WORKLOAD_C5 = ("C5: path tracer, 3840x2160 x 16 spp, 4 bounces (+ shadow rays), 
                "1.02M triangles); blocks of 64 rayGen tiles dealt round-robin to the GPUs, rays generated on the device, one gather of the image")
 
 
+PEER = os.environ.get("ATLAS_BENCH_GATHER", "nccl") == "peer"
+
+
 def config_c2(world):
     return {"workload": WORKLOAD, "rays_per_gpu": N_RAYS, "triangles": N_TRIS, "bvh": "replicated per GPU",
             "l2": "no flush kernel: steps alternate between two scene replicas and two ray buffers (352 MB between reuses > 126 MB L2), same at every N",
             "output": "16-byte hit records (t, hitID, hitInstanceID, v) per ray",
-            "gather": "one NCCL gather of the hit records to rank 0 per step through atlas_rt_trace_sharded (C ABI), overlapped with the next step's trace, "
-                      "joined inside the timed region; N = 1: none"}
+            "gather": ("fused into the traversal: every rank's kernel stores its hit records straight into rank 0's memory over NVLink (CUDA IPC window, "
+                       "atlas_rt_trace_sharded with ATLAS_RT_PEER_OUTPUT), completion counters polled with cuStreamWaitValue32, joined inside the timed region; N = 1: none")
+            if PEER else
+                      ("one NCCL gather of the hit records to rank 0 per step through atlas_rt_trace_sharded (C ABI), overlapped with the next step's trace, "
+                       "joined inside the timed region; N = 1: none")}
 
 
 def peaks():
@@ -370,7 +376,10 @@ def main():
         if world == 1:
             ctx.trace(scenes[s], d_rays[s], N_RAYS, out=d_hits[s], flags=capi.ASYNC | capi.HITS_ONLY)
         else:
-            comm.trace_sharded(scenes[s], d_rays[s], world * N_RAYS, hits_out=gathered[s], flags=capi.ASYNC)
+            if PEER:   # every rank's traversal kernel stores its records straight into rank 0's window over NVLink: no gather step
+                comm.trace_sharded(scenes[s], d_rays[s], world * N_RAYS, hits_out=None, flags=capi.ASYNC | capi.PEER_OUTPUT | capi.DEVICE_OUTPUT)
+            else:
+                comm.trace_sharded(scenes[s], d_rays[s], world * N_RAYS, hits_out=gathered[s], flags=capi.ASYNC)
 
     def trace_join():
         if world > 1:
@@ -396,7 +405,13 @@ def main():
     parity = None
     if world > 1:
         ok_hits = ok_scene = True
-        comm.trace_sharded(scenes[0], d_rays[0], world * N_RAYS, hits_out=gathered[0])
+        if PEER:   # the records the kernels of all ranks put into rank 0's window, handed on to `gathered` by the library
+            if rank == 0:
+                gathered[0].zero_()
+            comm.trace_sharded(scenes[0], d_rays[0], world * N_RAYS, hits_out=gathered[0], flags=capi.PEER_OUTPUT)
+            comm.synchronize()
+        else:
+            comm.trace_sharded(scenes[0], d_rays[0], world * N_RAYS, hits_out=gathered[0])
         if rank == 0:
             got = gathered[0].cpu().numpy().view(np.uint32)
             lo, hi = root[0, :3], root[0, 3:]

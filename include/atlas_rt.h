@@ -62,6 +62,7 @@ typedef enum atlas_rt_status {
 #define ATLAS_RT_COUNTERS      (1u << 4)   /* trace_*: also count visited nodes / triangles (slower; for parity + roofline) */
 #define ATLAS_RT_RAY_BINNING   (1u << 6)   /* pathtrace_bounces: order the rays of bounce >= 1 by the reference's 8x8 octahedral direction bins */
 #define ATLAS_RT_ACCUM_TILE_ORDER (1u << 7) /* pathtrace_*: index the accumulation buffer in rayGen's tile order instead of y * width + x */
+#define ATLAS_RT_PEER_OUTPUT   (1u << 9)   /* trace_sharded: every rank's traversal kernel stores its hit records straight into the root's memory (NVLink P2P), no gather */
 #define ATLAS_RT_HITS_ONLY     (1u << 8)   /* trace_*: rays_out receives count x 16-byte hit records (the ray's `hit` vec4: t, bits(hitID),
                                               bits(hitInstanceID), v) instead of 48-byte rays — the compact stream the multi-GPU gather moves */
 
@@ -406,6 +407,17 @@ int atlas_rt_scene_replicate(atlas_rt_comm* comm, const atlas_rt_scene* src, uin
 int atlas_rt_trace_sharded(atlas_rt_comm* comm, const atlas_rt_scene* scene, const void* rays_in, uint64_t total_count,
                            uint32_t cull_mask, float t_min, float t_max, void* hits_out, uint32_t root, uint32_t flags,
                            int any_hit);
+
+/* ATLAS_RT_PEER_OUTPUT on atlas_rt_trace_sharded fuses the gather into the traversal: the root owns a window of device memory
+ * (made by the library, opened by every other rank through CUDA IPC - the GPUs must have peer access), and every rank's
+ * traversal kernel stores each 16-byte hit record at its global position in that window as the ray finishes (P2P stores over
+ * NVLink / NVSwitch). No collective, copy kernel or copy engine touches the records; two counters per rank, also written
+ * over NVLink and polled locally (cuStreamWaitValue32), tell the root when a rank has finished a call and the ranks when
+ * the root has consumed a slot (two slots: call k + 1 traces while call k is handed on). hits_out on the root may be NULL:
+ * the records then stay in the window, where atlas_rt_comm_peer_hits finds the most recent call's (valid after
+ * atlas_rt_comm_synchronize and until the second-next call). The first call (and any call with a larger total_count or
+ * another root) is collective and synchronises: it creates the window. Results are bit-identical to the NCCL path. */
+int atlas_rt_comm_peer_hits(atlas_rt_comm* comm, const void** hits);
 
 /* Variable-size gather of device memory to `root` (e.g. the image slices of a path-tracer frame rendered in
  * ATLAS_RT_ACCUM_TILE_ORDER): every rank sends `bytes`; root receives rank r's sizes[r] bytes at recv + offsets[r]. */

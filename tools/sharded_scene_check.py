@@ -1,7 +1,8 @@
 """Multi-GPU check (torchrun, N ranks) of the C-ABI multi-GPU entry points (csrc/comm.cu, NCCL):
   1. atlas_rt_build_scene_sharded (BLAS builds dealt round-robin, trees broadcast, TLAS from rank 0) gives, on every rank, a
      scene that is byte-identical to one built entirely on that rank;
-  2. atlas_rt_trace_sharded: every rank traces its share, the root's gathered 16-byte hit records equal a single-GPU trace;
+  2. atlas_rt_trace_sharded: every rank traces its share, the root's gathered 16-byte hit records equal a single-GPU trace
+     (NCCL gather, and the peer-memory window where the traversal kernels store straight into the root's memory);
   3. atlas_rt_scene_replicate: rank 0's complete scene (96-byte triangles, materials, textures) on every rank traces
      identically (closest + opacity-aware any-hit);
   4. the path tracer sharded by rayGen slot ranges + atlas_rt_comm_gather of the tile-ordered image == the single-GPU image.
@@ -51,6 +52,24 @@ for any_hit in (False, True):
         ok &= np.array_equal(hits.view(np.uint32), ref[:, 8:12].view(np.uint32))
         ok &= np.array_equal(d_hits.cpu().numpy().view(np.uint32), ref[:, 8:12].view(np.uint32))
 results["gathered_hits_equal_single_gpu"] = bool(ok)
+
+# ---- 2b. the same with the gather fused into the traversal (ATLAS_RT_PEER_OUTPUT): every rank's kernel stores its records in
+# rank 0's window over NVLink; several calls in a row exercise both window slots and the flow-control counters
+ok = True
+for rep in range(5):
+    any_hit = bool(rep & 1)
+    ref = ctx.trace(local_scene, rays, any_hit=any_hit, t_max=90.0)
+    d_hits = torch.zeros((count, 4), dtype=torch.float32, device=dev) if rank == 0 else None
+    if rep < 3:
+        comm.trace_sharded(scene, torch.from_numpy(rays[b:e]).to(dev), count, hits_out=d_hits, any_hit=any_hit, t_max=90.0, flags=capi.PEER_OUTPUT)
+        got = d_hits.cpu().numpy() if rank == 0 else None
+    else:   # host rays in, host records out on the root
+        got = comm.trace_sharded(scene, rays[b:e], count, hits_out=np.zeros((count, 4), np.float32) if rank == 0 else None, any_hit=any_hit, t_max=90.0,
+                                 flags=capi.PEER_OUTPUT)
+    comm.synchronize()
+    if rank == 0:
+        ok &= np.array_equal(got.view(np.uint32), ref[:, 8:12].view(np.uint32))
+results["peer_window_hits_equal_single_gpu"] = bool(ok)
 
 # ---- 3. replicate rank 0's complete scene (shading triangles, materials, an opacity texture)
 mats = capi.make_materials(3)
