@@ -1,16 +1,12 @@
 #!/bin/bash
-# usage: bash tools/run_c.sh N   -- C2 weak scaling with the NCCL gather and with the peer-memory window
-O=gpurun_out
-N=$1
-for mode in nccl peer; do
-ATLAS_BENCH_GATHER=$mode timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2955$N bench.py --gpus $N --steps 20 --warmup 5 --no-extras --no-cpu-baseline > $O/r2_peer_${mode}_$N.json 2> $O/r2_peer_${mode}_$N.err
-python - <<PY
-import json
+B="timeout 300 python bench.py --steps 20 --warmup 5 --no-extras --no-cpu-baseline"
+show() { python -c "
+import json,sys
 try:
-    d = json.loads(open("$O/r2_peer_${mode}_$N.json").read().strip().splitlines()[-1])
-    print("$mode N=$N value", round(d["value"], 1), "ms/step", round(d["ms_per_step"], 4), "e2e", round(d["e2e"]["value"], 1), "parity", d.get("parity"), "launches", d.get("gpu_launches"))
-except Exception as e:
-    print("$mode N=$N FAILED", e)
-PY
-tail -n 3 $O/r2_peer_${mode}_$N.err | cut -c1-300
+    d=json.loads(sys.stdin.read()); print('$1', 'e2e_ms', round(d['e2e']['ms_per_step'],4), 'equal', d['e2e'].get('host_records_equal_device_path'))
+except Exception as e: print('$1', 'FAILED', e)"; }
+$B 2>/dev/null | show default
+for l in "32,64,128,192,192,192,96,32" "48,96,192,192,192,192,96,48" "32,48,96,128,128,128,64,32" "96,96,128,128,128,128,96,48" "96,96,96,96,96,96,64,32" "96,96,96,96,96,96,48,32"; do
+ATLAS_RT_TRACE_MIN_BLOCKS_PER_SM=1 ATLAS_RT_PIPE_RPW=$l $B 2>/dev/null | show "minblocks1_rpw_$l"
 done
+ATLAS_RT_PIPE_RPW="96,96,96,96,96,96,64,32" $B 2>/dev/null | show "minblocks2_rpw_96,96,96,96,96,96,64,32"
