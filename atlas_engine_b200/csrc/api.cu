@@ -186,6 +186,7 @@ int atlas_rt_context_create(int device, void* stream, atlas_rt_context** out_ctx
     if (const char* e = getenv("ATLAS_RT_TRACE_BLOCKS_PER_SM")) ctx->traceBlocksPerSM = std::max(1, std::min(9, atoi(e)));
     if (const char* e = getenv("ATLAS_RT_BIN_CTAS_PER_SM")) ctx->binCtasPerSM = std::max(1, std::min(8, atoi(e)));
     if (const char* e = getenv("ATLAS_RT_CHAIN_LAUNCH")) ctx->chainLaunch = atoi(e);
+    if (const char* e = getenv("ATLAS_RT_BUILD_WIDE")) ctx->buildWide = atoi(e);
     if (const char* e = getenv("ATLAS_RT_BATCH_WORKERS")) ctx->batchWorkers = std::max(1, std::min(16, atoi(e)));
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {

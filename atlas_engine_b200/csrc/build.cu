@@ -359,7 +359,94 @@ bin_big(const Task* __restrict__ tasks, const LevelInfo* __restrict__ info, cons
 }
 
 // ------------------------------------------------------------------------------------------------ child creation
+// ---- wide levels: the part of the tree below the big levels, level by level over the WHOLE tree (ATLAS_RT_BUILD_WIDE=1) ----
+// Instead of one CTA per <= 1024-ref subtree with the refs in shared memory (build_subtrees), every node of a level — whatever
+// subtree it belongs to — is one entry of a per-size-class list in global memory, the refs stay in the (L2-resident)
+// ping-pong arrays, and one kernel per level hands the entries of each class to CTAs / warps / half warps / lanes. No barrier
+// ever waits for another node; the only synchronisation is the launch boundary between two levels.
+constexpr int kWideClasses = 5;   // 0: 2..4 refs (one lane), 1: 5..8 (one lane), 2: 9..16 with <= 16 bins (half warp), 3: up to 256 (warp), 4: more (CTA)
+struct WideLists {
+    SmallTask* list[kWideClasses];
+    uint32_t* count;              // [kWideClasses], device
+    uint32_t cap[kWideClasses];
+};
+__device__ __forceinline__ int wide_class(uint32_t count, uint32_t bins) {
+    if (count <= 4u) return 0;
+    if (count <= 8u) return 1;
+    if (count <= 16u && bins <= 16u) return 2;
+    return count <= 256u ? 3 : 4;
+}
+struct WideNode {   // what the node builders read: absolute first slot, ref count, absolute flattened index, box
+    uint32_t start, count, rel;
+    float lo[3], hi[3];
+};
+struct WideEmit {
+    WideLists next;
+    LevelInfo* info;
+    uint32_t budget, depth, buf;   // of the children: binning budget, depth, which ref buffer holds them
+    __device__ __forceinline__ void push(uint32_t start, uint32_t count, uint32_t rel, const Box3& b) const {
+        const int c = wide_class(count, bins_at_depth(budget, depth));
+        const uint32_t i = atomicAdd(&next.count[c], 1u);
+        if (i >= next.cap[c]) { info->overflow = 1u; return; }
+        SmallTask st;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { st.lo[k] = b.lo[k]; st.hi[k] = b.hi[k]; }
+        st.start = start; st.count = count; st.flatIdx = rel; st.depth = depth; st.buf = buf; st.pad = 0;
+        next.list[c][i] = st;
+    }
+};
+
+// The same, for the level kernels, where every node of the tree pushes: one same-address atomic per child serialises in the L2
+// (measured: 0.8 ns each, 230 us for the 300 k pushes of one level). Lane-per-node code aggregates the lanes of a warp that push to
+// the same class (one atomic per warp and class); group code (one pushing lane per warp / half warp / CTA) reserves kWideChunk
+// slots at a time and marks what it did not use as holes (count 0) at the end of the kernel.
+struct WideEmitAgg {
+    WideEmit e;
+    __device__ __forceinline__ void push(uint32_t start, uint32_t count, uint32_t rel, const Box3& b) const {
+        const int c = wide_class(count, bins_at_depth(e.budget, e.depth));
+        const unsigned lane = threadIdx.x & 31u;
+        const unsigned peers = __match_any_sync(__activemask(), c);
+        const int leader = __ffs(int(peers)) - 1;
+        uint32_t base = 0;
+        if (int(lane) == leader) base = atomicAdd(&e.next.count[c], uint32_t(__popc(peers)));
+        base = __shfl_sync(peers, base, leader);
+        const uint32_t i = base + uint32_t(__popc(peers & ((1u << lane) - 1u)));
+        if (i >= e.next.cap[c]) { e.info->overflow = 1u; return; }
+        SmallTask st;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { st.lo[k] = b.lo[k]; st.hi[k] = b.hi[k]; }
+        st.start = start; st.count = count; st.flatIdx = rel; st.depth = e.depth; st.buf = e.buf; st.pad = 0;
+        e.next.list[c][i] = st;
+    }
+};
+constexpr uint32_t kWideChunk = 8;
+struct ChunkState { uint32_t base[kWideClasses], used[kWideClasses]; };   // shared memory, one per pushing lane
+struct WideEmitChunk {
+    WideEmit e;
+    ChunkState* cs;
+    __device__ __forceinline__ void push(uint32_t start, uint32_t count, uint32_t rel, const Box3& b) const {
+        const int c = wide_class(count, bins_at_depth(e.budget, e.depth));
+        if (cs->used[c] >= kWideChunk) { cs->base[c] = atomicAdd(&e.next.count[c], kWideChunk); cs->used[c] = 0u; }
+        const uint32_t i = cs->base[c] + cs->used[c]++;
+        if (i >= e.next.cap[c]) { e.info->overflow = 1u; return; }
+        SmallTask st;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { st.lo[k] = b.lo[k]; st.hi[k] = b.hi[k]; }
+        st.start = start; st.count = count; st.flatIdx = rel; st.depth = e.depth; st.buf = e.buf; st.pad = 0;
+        e.next.list[c][i] = st;
+    }
+};
+__device__ __forceinline__ void chunk_flush(const WideLists& next, ChunkState* cs) {   // by the lane that pushed through cs
+    for (int c = 0; c < kWideClasses; c++)
+        for (uint32_t k = cs->used[c]; k < kWideChunk; k++) {
+            const uint32_t i = cs->base[c] + k;
+            if (i < next.cap[c]) next.list[c][i].count = 0u;
+        }
+}
+
 struct Lists {
+    WideLists wide;
+    uint32_t wideOn;
     Task* next;
     SmallTask* small;
     LevelInfo* info;
@@ -373,6 +460,10 @@ __device__ __forceinline__ void enqueue_child(const Lists& L, const Box3& box, u
                                               uint32_t flatIdx, uint32_t depth) {
     if (count <= 1u) return;
     if (count <= kSubtreeMax && bins_at_depth(L.budget, depth) <= kSubtreeBins) {
+        if (L.wideOn) {
+            WideEmit{L.wide, L.info, L.budget, depth, L.nextBuf}.push(start, count, flatIdx, box);
+            return;
+        }
         const uint32_t s = atomicAdd(&L.info->nSmall, 1u);
         if (s >= L.maxSmall) { L.info->overflow = 1u; return; }
         SmallTask st;
@@ -1212,6 +1303,17 @@ __device__ __forceinline__ SubNode make_subnode(uint32_t start, uint32_t count, 
     return n;
 }
 
+// Where a builder puts the children (with more than one ref) of the node it has just split. The shared-memory subtree kernel
+// appends them to the CTA's list of the next level; the wide (whole-tree, global-memory) level kernel sorts them into the
+// next level's per-size-class lists (WideEmit, below).
+struct SmemEmit {
+    SubNode* list;
+    uint32_t* counter;
+    __device__ __forceinline__ void push(uint32_t start, uint32_t count, uint32_t rel, const Box3& b) const {
+        list[atomicAdd(counter, 1u)] = make_subnode(start, count, rel, b);
+    }
+};
+
 constexpr uint32_t kTinyMax = 4;    // nodes with at most this many refs are handled by ONE lane (32 nodes per warp)
 constexpr uint32_t kSmallMax = 8;   // ... and so are nodes with up to this many, in packs of their own (longer unrolled code)
 
@@ -1227,11 +1329,11 @@ struct LaneRef {
 // smaller costs selects the same (axis, j). Boxes are grown with float min/max here: no atomics are involved, and on
 // inputs without -0.0 (the documented exception, flagged by the builder) fminf/fmaxf and the ordered-int reductions of
 // the other paths give the same bits.
-template <uint32_t MAXN>
-__device__ inline void build_tiny_node(const SubNode nd, const SmallTask& task, uint32_t depth, uint32_t budget,
+template <uint32_t MAXN, typename NodeT, typename Emit>
+__device__ inline void build_tiny_node(const NodeT nd, const SmallTask& task, uint32_t depth, uint32_t budget,
                                        const float4* __restrict__ cLo, const float4* __restrict__ cHi, float4* __restrict__ nLo,
                                        float4* __restrict__ nHi, float4* nodes, uint32_t* __restrict__ order, uint8_t* __restrict__ eon,
-                                       SubNode* nextList, uint32_t* sNext, unsigned long long* sStats) {
+                                       const Emit em, unsigned long long* sStats) {
     const uint32_t n = nd.count, s = nd.start;
     const uint32_t nb = bins_at_depth(budget, depth);
     const uint32_t flatIdx = task.flatIdx + nd.rel;
@@ -1354,8 +1456,8 @@ __device__ inline void build_tiny_node(const SubNode nd, const SmallTask& task, 
     N[1] = make_float4(f.hi[1], f.hi[2], g.lo[0], g.lo[1]);
     N[2] = make_float4(g.lo[2], g.hi[0], g.hi[1], g.hi[2]);
     N[3] = make_float4(__int_as_float(ptr1), __int_as_float(ptr2), 0.0f, 0.0f);
-    if (nFirst > 1u) nextList[atomicAdd(sNext, 1u)] = make_subnode(s, nFirst, nd.rel + 1u, f);
-    if (nSecond > 1u) nextList[atomicAdd(sNext, 1u)] = make_subnode(s + nFirst, nSecond, nd.rel + nFirst, g);
+    if (nFirst > 1u) em.push(s, nFirst, nd.rel + 1u, f);
+    if (nSecond > 1u) em.push(s + nFirst, nSecond, nd.rel + nFirst, g);
     uint32_t doneFirst = 0, doneSecond = 0;
 #pragma unroll
     for (uint32_t i = 0; i < MAXN; i++) {
@@ -1384,10 +1486,10 @@ __device__ __forceinline__ OBox obox_of_ref(const float4& l, const float4& h) {
 // one node of a subtree: Build #2 (BVH.cpp:343-406) = FindObjectSplit else PerformMedianSplit, then the flattened node
 // record and the stable partition. The three axes are binned one after the other in the group's single-axis bin array
 // (shared-memory atomics on the ordered-int image) and swept with one bin per lane (group_sweep_single).
-template <int G>
-__device__ inline void build_group_node(const SubNode nd, const SmallTask& task, uint32_t depth, uint32_t budget, float4* cLo, float4* cHi,
+template <int G, typename NodeT, typename Emit>
+__device__ inline void build_group_node(const NodeT nd, const SmallTask& task, uint32_t depth, uint32_t budget, float4* cLo, float4* cHi,
                                         float4* __restrict__ nLo, float4* __restrict__ nHi, float4* nodes, uint32_t* __restrict__ order,
-                                        uint8_t* __restrict__ eon, SubNode* nextList, uint32_t* sNext, unsigned long long* sStats,
+                                        uint8_t* __restrict__ eon, const Emit em, unsigned long long* sStats,
                                         int* bins /*[32][kSubBinWords]*/) {
     const LaneGroup<G> g;
     const uint32_t lane = g.lane;
@@ -1533,8 +1635,8 @@ __device__ inline void build_group_node(const SubNode nd, const SmallTask& task,
         N[1] = make_float4(f.hi[1], f.hi[2], h2.lo[0], h2.lo[1]);
         N[2] = make_float4(h2.lo[2], h2.hi[0], h2.hi[1], h2.hi[2]);
         N[3] = make_float4(__int_as_float(ptr1), __int_as_float(ptr2), 0.0f, 0.0f);
-        if (nFirst > 1u) nextList[atomicAdd(sNext, 1u)] = make_subnode(s, nFirst, nd.rel + 1u, f);
-        if (nSecond > 1u) nextList[atomicAdd(sNext, 1u)] = make_subnode(s + nFirst, nSecond, nd.rel + nFirst, h2);
+        if (nFirst > 1u) em.push(s, nFirst, nd.rel + 1u, f);
+        if (nSecond > 1u) em.push(s + nFirst, nSecond, nd.rel + nFirst, h2);
     }
     // ---- stable partition into the other buffer (or straight to the final slot for one-ref children)
     uint32_t doneFirst = 0, doneSecond = 0;
@@ -1582,9 +1684,10 @@ struct CtaSplit {   // one axis' sweep result, handed from the sweeping warp to 
 // The whole CTA builds one node: the refs are binned on all three axes in one pass by all threads, warps 0..2 sweep one
 // axis each, and the partition gives every warp a contiguous slice. Same decisions as build_group_node; the median
 // fallback (rare) is handed to warp 0's group path. Contains barriers: every thread of the CTA must call it.
-__device__ inline void build_cta_node(const SubNode nd, const SmallTask& task, uint32_t depth, uint32_t budget, float4* cLo, float4* cHi,
+template <typename NodeT, typename Emit>
+__device__ inline void build_cta_node(const NodeT nd, const SmallTask& task, uint32_t depth, uint32_t budget, float4* cLo, float4* cHi,
                                       float4* __restrict__ nLo, float4* __restrict__ nHi, float4* nodes, uint32_t* __restrict__ order,
-                                      uint8_t* __restrict__ eon, SubNode* nextList, uint32_t* sNext, unsigned long long* sStats,
+                                      uint8_t* __restrict__ eon, const Emit em, unsigned long long* sStats,
                                       int* bins3 /*[3][32][kSubBinWords]*/, CtaSplit* sSplit /*[3]*/, uint32_t* sWarpFirst /*[kSubWarps]*/) {
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t n = nd.count, s = nd.start;
@@ -1645,7 +1748,7 @@ __device__ inline void build_cta_node(const SubNode nd, const SmallTask& task, u
     const float nodeCost = __fmul_rn(__uint2float_rn(n), surface_area(blo, bhi));
     if (axis < 0 || cost >= nodeCost) {
         // PerformMedianSplit: rare up here; warp 0 runs the group path on the node (it bins again on its own)
-        if (warp == 0u) build_group_node<32>(nd, task, depth, budget, cLo, cHi, nLo, nHi, nodes, order, eon, nextList, sNext, sStats, bins3);
+        if (warp == 0u) build_group_node<32>(nd, task, depth, budget, cLo, cHi, nLo, nHi, nodes, order, eon, em, sStats, bins3);
         __syncthreads();
         return;
     }
@@ -1667,8 +1770,8 @@ __device__ inline void build_cta_node(const SubNode nd, const SmallTask& task, u
         N[1] = make_float4(f.hi[1], f.hi[2], h2.lo[0], h2.lo[1]);
         N[2] = make_float4(h2.lo[2], h2.hi[0], h2.hi[1], h2.hi[2]);
         N[3] = make_float4(__int_as_float(ptr1), __int_as_float(ptr2), 0.0f, 0.0f);
-        if (nFirst > 1u) nextList[atomicAdd(sNext, 1u)] = make_subnode(s, nFirst, nd.rel + 1u, f);
-        if (nSecond > 1u) nextList[atomicAdd(sNext, 1u)] = make_subnode(s + nFirst, nSecond, nd.rel + nFirst, h2);
+        if (nFirst > 1u) em.push(s, nFirst, nd.rel + 1u, f);
+        if (nSecond > 1u) em.push(s + nFirst, nSecond, nd.rel + nFirst, h2);
     }
     // ---- stable partition: warp w owns refs [w * per, (w + 1) * per)
     const uint32_t per = ((n + kSubBlock - 1u) / kSubBlock) * 32u;
@@ -1779,7 +1882,7 @@ build_subtrees(const SmallTask* __restrict__ small, float4* const lo0, float4* c
         if (tid < 5) sCls[tid] = 0;
         __syncthreads();
         const SubNode* curList = lists + (level & 1u) * kSubNodes;
-        SubNode* nextList = lists + ((level + 1u) & 1u) * kSubNodes;
+        const SmemEmit em{lists + ((level + 1u) & 1u) * kSubNodes, &sNext};
         float4* cLo = sLo + cur * kSubtreeMax;
         float4* cHi = sHi + cur * kSubtreeMax;
         float4* nLo = sLo + (cur ^ 1u) * kSubtreeMax;
@@ -1798,24 +1901,22 @@ build_subtrees(const SmallTask* __restrict__ small, float4* const lo0, float4* c
         const uint32_t nTiny = sCls[0], nHalf = sCls[1], nWarp = sCls[2], nSmallN = sCls[3], nCta = sCls[4];
         // the biggest nodes (top of the subtree) by the whole CTA, one after the other
         for (uint32_t k = 0; k < nCta; k++)
-            build_cta_node(curList[sCtaIdx[k]], task, depth, budget, cLo, cHi, nLo, nHi, nodes, order, eon, nextList, &sNext, sStats, wBins,
+            build_cta_node(curList[sCtaIdx[k]], task, depth, budget, cLo, cHi, nLo, nHi, nodes, order, eon, em, sStats, wBins,
                            sSplit, sWarpFirst);
         // larger nodes first (they are the long poles of the level): one warp each
         for (uint32_t k = warp; k < nWarp; k += kSubWarps)
-            build_group_node<32>(curList[clsA[kSubNodes - 1u - k]], task, depth, budget, cLo, cHi, nLo, nHi, nodes, order, eon, nextList, &sNext,
-                                 sStats, binsW);
+            build_group_node<32>(curList[clsA[kSubNodes - 1u - k]], task, depth, budget, cLo, cHi, nLo, nHi, nodes, order, eon, em, sStats, binsW);
         // 9..16 refs: one half warp each
         for (uint32_t k = warp * 2u + half; k < nHalf; k += kSubWarps * 2u)
-            build_group_node<16>(curList[clsB[k]], task, depth, budget, cLo, cHi, nLo, nHi, nodes, order, eon, nextList, &sNext, sStats, binsH);
+            build_group_node<16>(curList[clsB[k]], task, depth, budget, cLo, cHi, nLo, nHi, nodes, order, eon, em, sStats, binsH);
         __syncwarp();
         // 5..8 refs and 2..4 refs: one lane each, in packs of 32 handed out from the last warp backwards so that they
         // land on the warps the classes above loaded least
         for (uint32_t k = (kSubBlock - 1u - tid); k < nSmallN; k += kSubBlock)
-            build_tiny_node<kSmallMax>(curList[clsB[kSubNodes - 1u - k]], task, depth, budget, cLo, cHi, nLo, nHi, nodes, order, eon, nextList,
-                                       &sNext, sStats);
+            build_tiny_node<kSmallMax>(curList[clsB[kSubNodes - 1u - k]], task, depth, budget, cLo, cHi, nLo, nHi, nodes, order, eon, em, sStats);
         __syncwarp();
         for (uint32_t k = (kSubBlock - 1u - tid); k < nTiny; k += kSubBlock)
-            build_tiny_node<kTinyMax>(curList[clsA[k]], task, depth, budget, cLo, cHi, nLo, nHi, nodes, order, eon, nextList, &sNext, sStats);
+            build_tiny_node<kTinyMax>(curList[clsA[k]], task, depth, budget, cLo, cHi, nLo, nHi, nodes, order, eon, em, sStats);
         __syncthreads();
         nCur = sNext;
         cur ^= 1u;
@@ -1828,6 +1929,134 @@ build_subtrees(const SmallTask* __restrict__ small, float4* const lo0, float4* c
         if (sStats[2]) atomicMax(&info->stats[5], sStats[2]);
     }
   }
+}
+
+// Between two wide levels: the level's node count goes to the host (pinned flag: count + 1; 1 = the tree is finished), and
+// the counters the level will fill for its successor are cleared.
+__global__ void wide_prepare(const uint32_t* __restrict__ curCount, uint32_t* __restrict__ nextCount, volatile uint32_t* hostFlag) {
+    chain_begin();
+    uint32_t total = 0;
+    for (int c = 0; c < kWideClasses; c++) total += curCount[c];
+    for (int c = 0; c < 8; c++) nextCount[c] = 0u;   // five counts + the three work tickets of the group classes
+    *hostFlag = total + 1u;
+    __threadfence_system();
+}
+
+#ifndef ATLAS_WIDE_GROUP_CTAS
+#define ATLAS_WIDE_GROUP_CTAS 3
+#define ATLAS_WIDE_TINY_CTAS 2
+#endif
+constexpr int kWideGroupCtas = ATLAS_WIDE_GROUP_CTAS, kWideTinyCtas = ATLAS_WIDE_TINY_CTAS;
+constexpr size_t kWideSmem = size_t(kSubWarps) * 2 * kSubtreeBins * kSubBinWords * sizeof(int);
+
+// One level of the whole tree below the big levels. Every entry of the level's lists is built by the unit its size class
+// names — the same node builders as the shared-memory kernel, reading and writing the global ping-pong ref arrays — and its
+// children go to the next level's lists.
+template <int CLASSES, int CTAS>   // CLASSES: bit c set = this instantiation builds the entries of size class c
+__global__ void __launch_bounds__(kSubBlock, CTAS)
+wide_level(WideLists cur, WideLists next, float4* const lo0, float4* const hi0, float4* const lo1, float4* const hi1, float4* nodes,
+           uint32_t* __restrict__ order, uint8_t* __restrict__ eon, LevelInfo* __restrict__ info, uint32_t budget) {
+    chain_begin();
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    int* wBins = reinterpret_cast<int*>(smemRaw);   // [warps][2 half-warp groups][32][kSubBinWords]
+    __shared__ CtaSplit sSplit[3];
+    __shared__ uint32_t sWarpFirst[kSubWarps];
+    __shared__ unsigned long long sStats[3];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, half = lane >> 4;
+    __shared__ ChunkState sChunk[kSubWarps * 2];   // [warp][half]: the CTA builder pushes through [0], a warp through [warp][0], a half warp through its own
+    if (tid < 3) sStats[tid] = 0;
+    if (tid < kSubWarps * 2)
+        for (int c = 0; c < kWideClasses; c++) { sChunk[tid].base[c] = 0xffffffffu; sChunk[tid].used[c] = kWideChunk; }
+    __syncthreads();
+    SmallTask zero;   // the builders add the node's position to its task's: absolute positions, so a task at the origin
+    zero.start = 0; zero.flatIdx = 0; zero.count = 0; zero.depth = 0; zero.buf = 0; zero.pad = 0;
+    int* binsW = wBins + (warp * 2) * kSubtreeBins * kSubBinWords;
+    int* binsH = binsW + half * kSubtreeBins * kSubBinWords;
+    auto node_of = [](const SmallTask& t) {
+        WideNode nd;
+        nd.start = t.start; nd.count = t.count; nd.rel = t.flatIdx;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { nd.lo[k] = t.lo[k]; nd.hi[k] = t.hi[k]; }
+        return nd;
+    };
+#define ATLAS_WIDE_ARGS(t, EM) node_of(t), zero, (t).depth, budget, (t).buf ? lo1 : lo0, (t).buf ? hi1 : hi0, (t).buf ? lo0 : lo1, (t).buf ? hi0 : hi1, nodes, order, eon, \
+                               EM, sStats
+#define ATLAS_WIDE_EMIT(t) WideEmit{next, info, budget, (t).depth + 1u, (t).buf ^ 1u}
+    // the biggest nodes: the whole CTA (uniform trip count: the builder contains barriers)
+    const uint32_t nCta = (CLASSES & 16) ? min(cur.count[4], cur.cap[4]) : 0u;
+    // (entries are drawn from tickets, words 5..7 of the level's counters: the lists of the group classes have holes in a
+    // pattern that a fixed stride would hand to the same units every time, and the nodes of a class differ in size)
+    __shared__ uint32_t sTicket;
+    while (nCta) {
+        __syncthreads();
+        if (tid == 0) sTicket = atomicAdd(&cur.count[7], 1u);
+        __syncthreads();
+        const uint32_t k = sTicket;
+        if (k >= nCta) break;
+        const SmallTask t = cur.list[4][k];
+        if (t.count < 2u) continue;   // a hole (uniform for the CTA)
+        build_cta_node(ATLAS_WIDE_ARGS(t, (WideEmitChunk{ATLAS_WIDE_EMIT(t), &sChunk[0]})), wBins, sSplit, sWarpFirst);
+    }
+    // one warp each, handed out from the far end of the grid so that they land on CTAs the class above did not load
+    const uint32_t nWarp = (CLASSES & 8) ? min(cur.count[3], cur.cap[3]) : 0u;
+    // (several entries per ticket only when every unit gets plenty of them: the first levels have a few big nodes)
+    const uint32_t stepW = nWarp >= gridDim.x * kSubWarps * 8u ? kWideChunk : 1u;
+    while (nWarp) {
+        uint32_t first = 0;
+        if (lane == 0) first = atomicAdd(&cur.count[6], stepW);
+        first = __shfl_sync(kFullMask, first, 0);
+        if (first >= nWarp) break;
+        for (uint32_t k = first; k < min(first + stepW, nWarp); k++) {
+            const SmallTask t = cur.list[3][k];
+            if (t.count < 2u) continue;
+            build_group_node<32>(ATLAS_WIDE_ARGS(t, (WideEmitChunk{ATLAS_WIDE_EMIT(t), &sChunk[warp * 2]})), binsW);
+        }
+    }
+    const uint32_t nHalf = (CLASSES & 4) ? min(cur.count[2], cur.cap[2]) : 0u;
+    {
+        // the two half warps of a warp draw ONE ticket and take alternate entries of it, so that they run the builder in the same
+        // instruction stream (it is written for that); an entry that is a hole idles its half for one iteration only
+        const uint32_t stepH = nHalf >= gridDim.x * kSubWarps * 16u ? kWideChunk : 1u;
+        while (nHalf) {
+            uint32_t first = 0;
+            if (lane == 0) first = atomicAdd(&cur.count[5], 2u * stepH);
+            first = __shfl_sync(kFullMask, first, 0);
+            if (first >= nHalf) break;
+            for (uint32_t j = 0; j < stepH; j++) {
+                const uint32_t k = first + 2u * j + half;
+                if (k < nHalf) {
+                    const SmallTask t = cur.list[2][k];
+                    if (t.count >= 2u)
+                        build_group_node<16>(ATLAS_WIDE_ARGS(t, (WideEmitChunk{ATLAS_WIDE_EMIT(t), &sChunk[warp * 2 + half]})), binsH);
+                }
+                __syncwarp();
+            }
+        }
+    }
+    __syncwarp();
+    const uint32_t nSmallN = (CLASSES & 2) ? min(cur.count[1], cur.cap[1]) : 0u;
+    for (uint32_t k = blockIdx.x * kSubBlock + tid; k < nSmallN; k += gridDim.x * kSubBlock) {
+        const SmallTask t = cur.list[1][k];
+        if (t.count < 2u) continue;
+        build_tiny_node<kSmallMax>(ATLAS_WIDE_ARGS(t, (WideEmitAgg{ATLAS_WIDE_EMIT(t)})));
+    }
+    __syncwarp();
+    const uint32_t nTiny = (CLASSES & 1) ? min(cur.count[0], cur.cap[0]) : 0u;
+    for (uint32_t k = blockIdx.x * kSubBlock + tid; k < nTiny; k += gridDim.x * kSubBlock) {
+        const SmallTask t = cur.list[0][k];
+        if (t.count < 2u) continue;
+        build_tiny_node<kTinyMax>(ATLAS_WIDE_ARGS(t, (WideEmitAgg{ATLAS_WIDE_EMIT(t)})));
+    }
+#undef ATLAS_WIDE_ARGS
+#undef ATLAS_WIDE_EMIT
+    __syncthreads();
+    // slots reserved but not used become holes
+    if ((CLASSES & 28) && (tid & 15u) == 0u) chunk_flush(next, &sChunk[tid >> 4]);
+    if (tid == 0) {
+        if (sStats[0]) atomicAdd(&info->stats[3], sStats[0]);
+        if (sStats[1]) atomicAdd(&info->stats[4], sStats[1]);
+        if (sStats[2]) atomicMax(&info->stats[5], sStats[2]);
+    }
 }
 
 template <typename T>
@@ -1901,7 +2130,14 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
     }
     float4 *tmpLlo = nullptr, *tmpLhi = nullptr, *tmpRlo = nullptr, *tmpRhi = nullptr, *strad = nullptr;
     uint32_t* spaCounts = nullptr;
+    // wide levels (ATLAS_RT_BUILD_WIDE): two sets of per-class node lists + their counters
+    const bool wide = ctx->buildWide != 0;
+    WideLists W[2];
+    memset(W, 0, sizeof(W));
+    uint32_t* wideCounts = nullptr;
     auto cleanup = [&]() {
+        for (int k = 0; k < 2; k++) for (int c = 0; c < kWideClasses; c++) dev_free(ctx, W[k].list[c]);
+        dev_free(ctx, wideCounts);
         for (int k = 0; k < 2; k++) { dev_free(ctx, B.lo[k]); dev_free(ctx, B.hi[k]); dev_free(ctx, B.tasks[k]); }
         dev_free(ctx, B.small); dev_free(ctx, B.info); dev_free(ctx, B.root); dev_free(ctx, B.bins);
         dev_free(ctx, B.spaBins); dev_free(ctx, B.medAcc); dev_free(ctx, B.chunkBase); dev_free(ctx, B.chunkFirst); dev_free(ctx, B.chunkInfo);
@@ -1927,6 +2163,18 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
     ATLAS_CUDA_C(ctx, dev_alloc(ctx, &B.chunkFirst, maxChunks));
     ATLAS_CUDA_C(ctx, dev_alloc(ctx, &B.chunkInfo, maxChunks));
     ATLAS_CUDA_C(ctx, dev_alloc(ctx, &B.rootBox, 8));
+    if (wide) {
+        const uint32_t div[kWideClasses] = {2u, 5u, 9u, 9u, 257u};   // fewest refs a node of the class holds
+        ATLAS_CUDA_C(ctx, dev_alloc(ctx, &wideCounts, 16));
+        ATLAS_CUDA_C(ctx, cudaMemsetAsync(wideCounts, 0, 16 * sizeof(uint32_t), st));
+        for (int k = 0; k < 2; k++) {
+            W[k].count = wideCounts + 8 * k;
+            for (int c = 0; c < kWideClasses; c++) {
+                W[k].cap[c] = cap / div[c] + 2u + uint32_t(ctx->smCount) * 4u * uint32_t(kSubWarps) * 2u * kWideChunk;   // + the holes a level can leave
+                ATLAS_CUDA_C(ctx, dev_alloc(ctx, &W[k].list[c], W[k].cap[c]));
+            }
+        }
+    }
     ATLAS_CUDA_C(ctx, cudaMemsetAsync(B.info, 0, sizeof(LevelInfo), st));
     ATLAS_CUDA_C(ctx, cudaMemsetAsync(B.root, 0, sizeof(RootSplit), st));
     ATLAS_CUDA_C(ctx, cudaMemsetAsync(out->endOfNode, 0, cap, st));
@@ -1989,7 +2237,7 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
         const uint32_t warpGrid = (tasksBound * 32u + 127u) / 128u;
         const size_t binSmem = size_t(3) * nb * kSmemBin * sizeof(int);
         Task* tasks = B.tasks[cur];
-        Lists L{B.tasks[cur ^ 1u], B.small, B.info, B.nodes, B.budget, cur ^ 1u, maxTasks, maxSmall};
+        Lists L{W[0], wide ? 1u : 0u, B.tasks[cur ^ 1u], B.small, B.info, B.nodes, B.budget, cur ^ 1u, maxTasks, maxSmall};
         const float4 *rlo = B.lo[cur], *rhi = B.hi[cur];
         float4 *wlo = B.lo[cur ^ 1u], *whi = B.hi[cur ^ 1u];
 
@@ -2073,7 +2321,39 @@ int build_bvh(atlas_rt_context* ctx, const float* dAabbs, const float* dTris, ui
     }
     // the subtrees are enqueued straight behind the last level (the kernel reads their number on the device); the one
     // read-back that follows waits for the whole build
-    if (!rootLeaf) {
+    if (!rootLeaf && wide) {
+        // the rest of the tree level by level: list set 0 holds what the big levels handed down; the host stays kLookahead
+        // levels ahead of the device and stops at the first level it learns was empty
+        constexpr uint32_t kWideRing = 128;
+        volatile uint32_t* wflags = flags + kFlagRing;
+        for (uint32_t k = 0; k < kWideRing; k++) wflags[k] = 0u;
+        const uint32_t wgrid = uint32_t(ctx->smCount) * uint32_t(kSubCtasPerSM);
+        int cw = 0;
+        for (uint32_t lvl = 0; lvl < 100000u; lvl++) {
+            if (lvl >= kLookahead) {
+                const uint32_t seen = lvl - kLookahead;
+                for (uint64_t spins = 0; wflags[seen % kWideRing] == 0u; spins++) {
+                    if ((spins & 0xfffu) == 0xfffu) {
+                        const cudaError_t q = cudaStreamQuery(st);
+                        if (q != cudaSuccess && q != cudaErrorNotReady) { cleanup(); return fail(ctx, ATLAS_RT_ERR_CUDA, "wide level loop", q); }
+                        if (q == cudaSuccess && wflags[seen % kWideRing] == 0u) { cleanup(); return fail(ctx, ATLAS_RT_ERR_CUDA, "wide level flag never written"); }
+                    }
+                }
+                if (wflags[seen % kWideRing] == 1u) break;   // that level had no node: the tree was complete before it
+                if (lvl >= kWideRing) wflags[lvl % kWideRing] = 0u;   // (consumed kWideRing - kLookahead levels ago)
+            }
+            ATLAS_CUDA_C(ctx, launch_chain(pdl, wide_prepare, 1, 1, 0, st, static_cast<const uint32_t*>(W[cw].count), W[cw ^ 1].count, wflags + lvl % kWideRing));
+            ctx->launches++;
+            ATLAS_CUDA_C(ctx, launch_chain(pdl, wide_level<16, 2>, wgrid, kSubBlock, kWideSmem, st, W[cw], W[cw ^ 1], B.lo[0], B.hi[0], B.lo[1], B.hi[1], B.nodes,
+                                           B.order, B.eon, B.info, B.budget));
+            ATLAS_CUDA_C(ctx, launch_chain(pdl, wide_level<12, kWideGroupCtas>, uint32_t(ctx->smCount) * kWideGroupCtas, kSubBlock, kWideSmem, st, W[cw], W[cw ^ 1], B.lo[0],
+                                           B.hi[0], B.lo[1], B.hi[1], B.nodes, B.order, B.eon, B.info, B.budget));
+            ATLAS_CUDA_C(ctx, launch_chain(pdl, wide_level<3, kWideTinyCtas>, uint32_t(ctx->smCount) * kWideTinyCtas, kSubBlock, kWideSmem, st, W[cw], W[cw ^ 1], B.lo[0],
+                                           B.hi[0], B.lo[1], B.hi[1], B.nodes, B.order, B.eon, B.info, B.budget));
+            ctx->launches += 3;
+            cw ^= 1;
+        }
+    } else if (!rootLeaf) {
         ATLAS_CUDA_C(ctx, launch_chain(pdl, build_subtrees, uint32_t(ctx->smCount) * uint32_t(kSubCtasPerSM), kSubBlock, kSubtreeSmem, st, B.small, B.lo[0], B.hi[0], B.lo[1],
                                        B.hi[1], B.nodes, B.order, B.eon, B.info, B.budget, maxSmall));
         ctx->launches++;

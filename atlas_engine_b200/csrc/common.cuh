@@ -105,6 +105,7 @@ struct atlas_rt_context {
     int traceRefillThreshold = 10;  // idle lanes before the warp fetches new rays (swept again with the final kernel: 8-12 is best, 16 costs 1.5-3 %)
     int traceBlocksPerSM = 9;
     int chainLaunch = 1;         // builder level loop as a chain of programmatic dependent launches
+    int buildWide = 0;           // ATLAS_RT_BUILD_WIDE=1: the tree below the big levels level by level over global memory instead of per-subtree in shared memory
     int binCtasPerSM = 2;        // CTAs per SM of the builder's binning kernel (each merges its shared bins into global ones)
     int traceLongestFirst = 1;      // fetch rays longest-estimated-path first (hides the drain of the longest rays)
     int traceLongestFirstMin = 65536;

@@ -124,3 +124,43 @@ def test_bad_arguments(ctx):
     empty = ctx.build_blas(np.zeros((0, 6), np.float32), np.zeros((0, 9), np.float32))
     assert empty.counts() == (0, 0)
     empty.free()
+
+
+def test_wide_level_builder_gives_the_same_trees(oracle):
+    """ATLAS_RT_BUILD_WIDE=1 replaces the shared-memory subtree kernel by level kernels over the whole tree (global-memory refs,
+    per-size-class node lists; measured slower, kept as an option): every tree of the battery must still carry the reference's
+    digest, and the statistics must agree with the oracle."""
+    from atlas_engine_b200 import capi
+    with open(os.path.join(GOLD, "build_hashes.json")) as f:
+        gold = json.load(f)
+    old = os.environ.get("ATLAS_RT_BUILD_WIDE")
+    os.environ["ATLAS_RT_BUILD_WIDE"] = "1"
+    try:
+        wctx = capi.Context(0)
+    finally:
+        if old is None:
+            del os.environ["ATLAS_RT_BUILD_WIDE"]
+        else:
+            os.environ["ATLAS_RT_BUILD_WIDE"] = old
+    try:
+        for name, tris in CS.build_cases().items():
+            boxes = W.tri_boxes(tris)
+            b = wctx.build_blas(boxes, tris)
+            nodes, order, eon = b.download()
+            st = b.stats()
+            b.free()
+            assert digest(nodes, order, eon) == gold["blas"][name], name
+            o = oracle.build_blas(boxes, tris)
+            assert st["median_splits"] == o.stats["median_splits"] and st["sort_fallbacks"] == o.stats["sort_fallbacks"], name
+        for name, boxes in CS.tlas_cases().items():
+            b = wctx.build_tlas(boxes)
+            nodes, order, eon = b.download()
+            b.free()
+            assert digest(nodes, order, eon) == gold["tlas"][name], name
+        tris = W.soup(300_000, seed=21)
+        a = wctx.build_blas(W.tri_boxes(tris), tris)
+        o = oracle.build_blas(W.tri_boxes(tris), tris)
+        assert CS.same_tree(*a.download(), o)
+        a.free()
+    finally:
+        wctx.close()

@@ -1,12 +1,18 @@
 #!/bin/bash
-B="timeout 300 python bench.py --steps 20 --warmup 5 --no-extras --no-cpu-baseline"
-show() { python -c "
-import json,sys
-try:
-    d=json.loads(sys.stdin.read()); print('$1', 'e2e_ms', round(d['e2e']['ms_per_step'],4), 'equal', d['e2e'].get('host_records_equal_device_path'))
-except Exception as e: print('$1', 'FAILED', e)"; }
-$B 2>/dev/null | show default
-for l in "32,64,128,192,192,192,96,32" "48,96,192,192,192,192,96,48" "32,48,96,128,128,128,64,32" "96,96,128,128,128,128,96,48" "96,96,96,96,96,96,64,32" "96,96,96,96,96,96,48,32"; do
-ATLAS_RT_TRACE_MIN_BLOCKS_PER_SM=1 ATLAS_RT_PIPE_RPW=$l $B 2>/dev/null | show "minblocks1_rpw_$l"
-done
-ATLAS_RT_PIPE_RPW="96,96,96,96,96,96,64,32" $B 2>/dev/null | show "minblocks2_rpw_96,96,96,96,96,96,64,32"
+ATLAS_RT_BUILD_WIDE=1 timeout 500 python -m pytest tests/test_gpu_build.py -m gpu -q --tb=short -x 2>&1 | tail -3
+for w in 1; do ATLAS_RT_BUILD_WIDE=$w timeout 300 python bench.py --steps 5 --warmup 3 --no-extras --no-cpu-baseline 2>&1 | grep "build samples"; done
+ATLAS_RT_BUILD_WIDE=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:wide_level -c 200 --csv --log-file gpurun_out/wide_launches.csv python tools/prof_targets.py c2 > /dev/null 2>&1
+python tools/ncu_summary.py launches gpurun_out/wide_launches.csv | head -6
+python - <<PY
+import csv
+rows=list(csv.reader(open("gpurun_out/wide_launches.csv")))
+h=[i for i,r in enumerate(rows) if r and r[0]=="ID"][0]
+H=rows[h]; ki,vi=H.index("Kernel Name"),H.index("Metric Value")
+out=[]
+for r in rows[h+1:]:
+    if len(r)>vi:
+        n=r[ki]
+        cls="c" if "<16" in n else ("g" if "<12" in n else "t")
+        out.append((cls,float(r[vi].replace(",",""))/1000))
+print(" ".join(f"{c}{t:.0f}" for c,t in out[:75]))
+PY
