@@ -1,18 +1,9 @@
 #!/bin/bash
-ATLAS_RT_BUILD_WIDE=1 timeout 500 python -m pytest tests/test_gpu_build.py -m gpu -q --tb=short -x 2>&1 | tail -3
-for w in 1; do ATLAS_RT_BUILD_WIDE=$w timeout 300 python bench.py --steps 5 --warmup 3 --no-extras --no-cpu-baseline 2>&1 | grep "build samples"; done
-ATLAS_RT_BUILD_WIDE=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:wide_level -c 200 --csv --log-file gpurun_out/wide_launches.csv python tools/prof_targets.py c2 > /dev/null 2>&1
-python tools/ncu_summary.py launches gpurun_out/wide_launches.csv | head -6
-python - <<PY
-import csv
-rows=list(csv.reader(open("gpurun_out/wide_launches.csv")))
-h=[i for i,r in enumerate(rows) if r and r[0]=="ID"][0]
-H=rows[h]; ki,vi=H.index("Kernel Name"),H.index("Metric Value")
-out=[]
-for r in rows[h+1:]:
-    if len(r)>vi:
-        n=r[ki]
-        cls="c" if "<16" in n else ("g" if "<12" in n else "t")
-        out.append((cls,float(r[vi].replace(",",""))/1000))
-print(" ".join(f"{c}{t:.0f}" for c,t in out[:75]))
-PY
+O=gpurun_out
+timeout 700 python -m pytest tests -m gpu -q --tb=short -x > $O/pytest9.log 2>&1; tail -4 $O/pytest9.log
+NCU="ncu --clock-control none"
+PT='regex:trace_kernel|shade_|raygen|ray_cost|bin_count|bin_offsets|bin_scatter|set_words|next_bounce|add_accum'
+timeout 400 $NCU --metrics gpu__time_duration.sum -c 1500 --csv --log-file $O/r2_launches_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras --profile > $O/r2_launches_bench.out 2>&1
+timeout 300 $NCU --metrics gpu__time_duration.sum -k "$PT" -c 600 --csv --log-file $O/r2_launches_c5.csv python tools/prof_targets.py c5 > $O/r2_launches_c5.out 2>&1
+python tools/ncu_summary.py launches $O/r2_launches_bench.csv | head -30
+python tools/ncu_summary.py launches $O/r2_launches_c5.csv | head -20
