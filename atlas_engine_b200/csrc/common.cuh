@@ -299,7 +299,8 @@ int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float
                  bool opacity = false, cudaStream_t st = nullptr /* context stream */, int queueSlot = 0,
                  const uint32_t* dCount = nullptr /* batch size on the device (<= count) */, bool hitsOnly = false /* dOut = 16-byte hit records */,
                  const unsigned int* watermark = nullptr /* streaming input: rays uploaded so far */, unsigned int* chunkDone = nullptr,
-                 uint32_t chunkRays = 0, const uint32_t* streamPerm = nullptr /* streaming: fetch order, written chunk by chunk behind the watermark */);
+                 uint32_t chunkRays = 0, const uint32_t* streamPerm = nullptr /* streaming: fetch order, written chunk by chunk behind the watermark */,
+                 int chain = -1 /* kernels of this call as programmatic dependent launches: 1 / 0, -1 = the context's setting */);
 int launch_chunk_sort(atlas_rt_context* ctx, const atlas_rt_scene* scene, cudaStream_t st, const float4* rays, uint32_t n, uint32_t indexBase,
                       uint8_t* bucketOf, unsigned int* hist, uint32_t* perm, unsigned int* watermark);
 

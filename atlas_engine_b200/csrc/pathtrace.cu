@@ -606,10 +606,10 @@ SceneTables tables_of(const atlas_rt_scene* scene) {
 }
 
 int enqueue_binning(atlas_rt_context* ctx, const float4* rays, const float4* payload, uint32_t n, const uint32_t* dCount, float4* raysOut,
-                    float4* payloadOut, uint32_t* chunkHist, cudaStream_t st = nullptr) {
+                    float4* payloadOut, uint32_t* chunkHist, cudaStream_t st = nullptr, int chain = -1) {
     if (!st) st = ctx->stream;
     const uint32_t chunks = (n + kBinChunk - 1) / kBinChunk;
-    const bool pdl = ctx->chainLaunch != 0;
+    const bool pdl = chain < 0 ? ctx->chainLaunch != 0 : chain != 0;
     ATLAS_CUDA(ctx, launch_chain(pdl, bin_count, chunks, 256, 0, st, rays, n, dCount, chunkHist));
     ATLAS_CUDA(ctx, launch_chain(pdl, bin_offsets, 1, 96, 0, st, chunkHist, chunks));
     ATLAS_CUDA(ctx, launch_chain(pdl, bin_scatter, chunks, 256, 0, st, rays, payload, n, dCount, static_cast<const uint32_t*>(chunkHist), raysOut, payloadOut));
@@ -623,16 +623,16 @@ int enqueue_binning(atlas_rt_context* ctx, const float4* rays, const float4* pay
 int enqueue_bounce(atlas_rt_context* ctx, const atlas_rt_scene* scene, const atlas_rt_pt_params& prm, float seed, uint32_t bounce, float4* rays,
                    const float4* payloadIn, uint32_t n, uint32_t* dCounts, float4* raysOut, float4* payloadOut, float4* shadow, uint32_t* slotOf,
                    float* accum, uint32_t accumTileOrder, uint32_t width, uint32_t height, unsigned long long* dTraced, const SlotShard& shard,
-                   cudaStream_t st = nullptr, int lane = 0) {
+                   cudaStream_t st = nullptr, int lane = 0, int chain = -1) {
     if (!st) st = ctx->stream;
-    const bool pdl = ctx->chainLaunch != 0;
+    const bool pdl = chain < 0 ? ctx->chainLaunch != 0 : chain != 0;
     // OPACITY_CHECK traces (PathTracingRenderer.cpp:186, rayHit.csh:331). Where every triangle is fully opaque the
     // *Transparency variants accept exactly what the plain ones accept (and both closest-hit loops restore the ray the same
     // way), so the cheaper 48-byte kernels run instead, bit for bit the same; the shadow batch additionally needs every
     // instance to carry the shadow bit, because plain HitAny treats culled instances differently (bvh.hsh:387-390).
     const bool closestOpacity = !scene->allOpaque, shadowOpacity = !(scene->allOpaque && scene->allShadowBit);
     // (lanes: sample passes running side by side, each on its own stream with its own ray-queue head)
-    int rc = launch_trace(ctx, scene, rays, rays, n, ATLAS_RT_MASK_ALL, 0.0f, ATLAS_RT_INF, false, false, false, lane == 0, closestOpacity, st, lane, dCounts);
+    int rc = launch_trace(ctx, scene, rays, rays, n, ATLAS_RT_MASK_ALL, 0.0f, ATLAS_RT_INF, false, false, false, lane == 0, closestOpacity, st, lane, dCounts, false, nullptr, nullptr, 0, nullptr, chain);
     if (rc != ATLAS_RT_OK) return rc;
     const SceneTables sc = tables_of(scene);
     const uint32_t grid = (n + 127) / 128;
@@ -641,7 +641,7 @@ int enqueue_bounce(atlas_rt_context* ctx, const atlas_rt_scene* scene, const atl
     ctx->launches++;
     // HitAnyTransparency(ray, INSTANCE_MASK_SHADOW, 0.0, lightDistance - 2.0 * EPSILON), lightDistance = INF
     rc = launch_trace(ctx, scene, shadow, shadow, n, ATLAS_RT_MASK_SHADOW, 0.0f, ATLAS_RT_INF - 2.0f * kEpsilon, true, false, false, lane == 0, shadowOpacity, st, lane,
-                      dCounts + 2);
+                      dCounts + 2, false, nullptr, nullptr, 0, nullptr, chain);
     if (rc != ATLAS_RT_OK) return rc;
     ATLAS_CUDA(ctx, launch_chain(pdl, shade_finish, grid, 128, 0, st, static_cast<const float4*>(rays), payloadIn, static_cast<const float4*>(shadow),
                                  static_cast<const uint32_t*>(slotOf), n, static_cast<const uint32_t*>(dCounts), prm, seed, bounce, sc, raysOut, payloadOut, accum,
@@ -818,12 +818,8 @@ static int pathtrace_frames(atlas_rt_context* ctx, const atlas_rt_scene* scene, 
     // resident as soon as slots free up and wait there for their predecessor, i.e. the tail of one lane's trace kernel would fill
     // with the waiting CTAs of the same lane's next kernel instead of the runnable CTAs of another lane (measured on a 1/8 shard
     // of C5: 4 lanes 3.55 ms per pass chained, 2.10 ms unchained; one lane 3.94 / 4.10 ms).
-    struct ChainOff {
-        atlas_rt_context* c; int saved;
-        ChainOff(atlas_rt_context* ctx, bool off) : c(ctx), saved(ctx->chainLaunch) { if (off) c->chainLaunch = 0; }
-        ~ChainOff() { c->chainLaunch = saved; }
-    } chainOff(ctx, nl > 1);
-    const bool pdl = ctx->chainLaunch != 0;
+    const int chain = nl > 1 ? 0 : -1;
+    const bool pdl = nl > 1 ? false : ctx->chainLaunch != 0;
     const uint32_t bounces = params->max_bounces;
     for (uint32_t f = 0; f < frames; f++) {
         const int l = int(f % uint32_t(nl));
@@ -839,13 +835,13 @@ static int pathtrace_frames(atlas_rt_context* ctx, const atlas_rt_scene* scene, 
         if (e != cudaSuccess) return done(fail(ctx, ATLAS_RT_ERR_CUDA, "raygen", e));
         for (uint32_t b = 0; b <= bounces; b++) {
             if (binning && b > 0) {   // RayTracingHelper.cpp:304-344 (dormant in the reference): order the rays by direction bin
-                const int rc = enqueue_binning(ctx, ln.rays[cur], ln.pay[cur], n, ln.dCounts, ln.rays[2], ln.pay[2], ln.hist, ln.st);
+                const int rc = enqueue_binning(ctx, ln.rays[cur], ln.pay[cur], n, ln.dCounts, ln.rays[2], ln.pay[2], ln.hist, ln.st, chain);
                 if (rc != ATLAS_RT_OK) return done(rc);
                 std::swap(ln.rays[cur], ln.rays[2]);
                 std::swap(ln.pay[cur], ln.pay[2]);
             }
             const int rc = enqueue_bounce(ctx, scene, *params, seeds[size_t(f) * (bounces + 1) + b], b, ln.rays[cur], ln.pay[cur], n, ln.dCounts, ln.rays[cur ^ 1],
-                                          ln.pay[cur ^ 1], ln.shadow, ln.slotOf, ln.accum, accumMode, width, height, dTraced, shard, ln.st, l);
+                                          ln.pay[cur ^ 1], ln.shadow, ln.slotOf, ln.accum, accumMode, width, height, dTraced, shard, ln.st, l, chain);
             if (rc != ATLAS_RT_OK) return done(rc);
             e = launch_chain(pdl, next_bounce_counts, 1, 1, 0, ln.st, ln.dCounts);
             ctx->launches++;

@@ -799,8 +799,9 @@ int scene_fast_flag(atlas_rt_context* ctx, atlas_rt_scene* scene, const uint32_t
 int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float4* dIn, float4* dOut, uint64_t count,
                  uint32_t cullMask, float tMin, float tMax, bool any, bool perRayTMax, bool counters, bool resetCounters, bool opacity,
                  cudaStream_t st, int queueSlot, const uint32_t* dCount, bool hitsOnly, const unsigned int* watermark, unsigned int* chunkDone,
-                 uint32_t chunkRays, const uint32_t* streamPerm) {
+                 uint32_t chunkRays, const uint32_t* streamPerm, int chain) {
     if (!st) st = ctx->stream;
+    const bool chained = chain < 0 ? ctx->chainLaunch != 0 : chain != 0;   // programmatic dependent launches between this call's kernels
     if (count == 0) return ATLAS_RT_OK;
     if (count > 0x7fffffffull) return fail(ctx, ATLAS_RT_ERR_UNSUPPORTED, "more than 2^31-1 rays in one batch");
     SceneDev sc{scene->tlas->nodes, scene->instances, scene->blasNodes, scene->bvhTris, scene->triangles,
@@ -831,7 +832,7 @@ int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float
         ATLAS_CUDA(ctx, dev_alloc_on(st, &hist, kCostBuckets + 2));
         ATLAS_CUDA(ctx, cudaMemsetAsync(hist, 0, (kCostBuckets + 2) * sizeof(unsigned int), st));
         const uint32_t sortGrid = (n + kSortBlock * kSortPerThread - 1) / (kSortBlock * kSortPerThread);
-        const bool pdl = ctx->chainLaunch != 0;
+        const bool pdl = chained;
         ATLAS_CUDA(ctx, launch_chain(pdl, ray_cost_histogram, sortGrid, kSortBlock, 0, st, dIn, n, dCount, scene->tlas->nodes, bucketOf, hist));
         ctx->launches++;
         ATLAS_CUDA(ctx, launch_chain(pdl, ray_cost_offsets, 1, 32, 0, st, hist, n, dCount));
@@ -849,8 +850,8 @@ int launch_trace(atlas_rt_context* ctx, const atlas_rt_scene* scene, const float
     }
     cudaError_t launchErr = cudaSuccess;
 #define ATLAS_TRACE_LAUNCH(A, C, O) \
-    launchErr = (watermark && !C) ? launch_chain_w(ctx->chainLaunch != 0, win, trace_kernel<A, false, O, true>, grid, kTraceBlock, 0, st, sc, dIn, dOut, streamPerm, (const unsigned int*)nullptr, n, dCount, cullMask, tMin, tMax, pr, sf, ho, lt, rt, rayCounter, ctx->dCounters, streamIn) : \
-                launch_chain_w(ctx->chainLaunch != 0, win, trace_kernel<A, C, O, false>, grid, kTraceBlock, 0, st, sc, dIn, dOut, perm, hist ? hist + kCostBuckets + 1 : nullptr, n, dCount, cullMask, tMin, tMax, pr, sf, ho, lt, rt, rayCounter, ctx->dCounters, streamIn)
+    launchErr = (watermark && !C) ? launch_chain_w(chained, win, trace_kernel<A, false, O, true>, grid, kTraceBlock, 0, st, sc, dIn, dOut, streamPerm, (const unsigned int*)nullptr, n, dCount, cullMask, tMin, tMax, pr, sf, ho, lt, rt, rayCounter, ctx->dCounters, streamIn) : \
+                launch_chain_w(chained, win, trace_kernel<A, C, O, false>, grid, kTraceBlock, 0, st, sc, dIn, dOut, perm, hist ? hist + kCostBuckets + 1 : nullptr, n, dCount, cullMask, tMin, tMax, pr, sf, ho, lt, rt, rayCounter, ctx->dCounters, streamIn)
     if (opacity) {
         if (any) { if (counters) ATLAS_TRACE_LAUNCH(true, true, true); else ATLAS_TRACE_LAUNCH(true, false, true); }
         else { if (counters) ATLAS_TRACE_LAUNCH(false, true, true); else ATLAS_TRACE_LAUNCH(false, false, true); }
