@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libatlas_rt.so")
 
 DEVICE_INPUT, DEVICE_OUTPUT, ASYNC, PER_RAY_TMAX, COUNTERS, OPACITY = 1, 2, 4, 8, 16, 32
-RAY_BINNING, ACCUM_TILE_ORDER, HITS_ONLY, PEER_OUTPUT = 64, 128, 256, 512
+RAY_BINNING, ACCUM_TILE_ORDER, HITS_ONLY, PEER_OUTPUT, PIPELINED = 64, 128, 256, 512, 1024
 MASK_ALL, MASK_SHADOW = 1 << 7, 1 << 6
 INF = 1e12
 STATUS = {0: "OK", -1: "ERR_INVALID", -2: "ERR_CUDA", -3: "ERR_OOM", -4: "ERR_UNSUPPORTED", -5: "ERR_STACK"}
@@ -73,6 +73,7 @@ SIGNATURES = {
     "atlas_rt_bvh_broadcast": (_i32, [_vp, _vp, _u32, C.POINTER(_vp)]),
     "atlas_rt_build_scene_sharded": (_i32, [_vp, _u32, _vp, _vp, _vp, _vp, _vp, _u64, _u32, C.POINTER(_vp)]),
     "atlas_rt_scene_replicate": (_i32, [_vp, _vp, _u32, C.POINTER(_vp)]),
+    "atlas_rt_trace_join": (_i32, [_vp]),
     "atlas_rt_trace_sharded": (_i32, [_vp, _vp, _vp, _u64, _u32, _f32, _f32, _vp, _u32, _u32, _i32]),
     "atlas_rt_comm_gather": (_i32, [_vp, _vp, _u64, _vp, _vp, _vp, _u32, _u32]),
     "atlas_rt_comm_peer_hits": (_i32, [_vp, C.POINTER(_vp)]),
@@ -342,6 +343,10 @@ class Context:
     def bin_rays(self, rays_in, payload_in, count, rays_out, payload_out, flags=0):
         self.check(self.L.atlas_rt_bin_rays(self.h, _addr(rays_in), _addr(payload_in), count, _addr(rays_out), _addr(payload_out),
                                             flags | DEVICE_INPUT | DEVICE_OUTPUT))
+
+    def trace_join(self):
+        """Order the context stream after every ASYNC | PIPELINED host-buffer trace call made so far."""
+        self.check(self.L.atlas_rt_trace_join(self.h))
 
     def trace_counters(self):
         out = np.zeros(6, dtype=np.uint64)

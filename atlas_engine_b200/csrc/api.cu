@@ -36,6 +36,7 @@ void ctx_release(atlas_rt_context* ctx) {
     if (ctx->copyOut) cudaStreamDestroy(ctx->copyOut);
     for (auto& cs : ctx->computeExtra) if (cs) cudaStreamDestroy(cs);
     if (ctx->sortStream) cudaStreamDestroy(ctx->sortStream);
+    for (int k = 0; k < 2; k++) { cudaFree(ctx->stageIn[k]); cudaFree(ctx->stageOut[k]); }
     cudaFree(ctx->dCounters);
     cudaFree(ctx->dStreamState);
     cudaFreeHost(ctx->pinned);
@@ -250,6 +251,7 @@ void atlas_rt_context_destroy(atlas_rt_context* ctx) {
 
 int atlas_rt_context_synchronize(atlas_rt_context* ctx) {
     if (!ctx) return ATLAS_RT_ERR_INVALID;
+    if (ctx->pendingJoin) { const int rc = atlas_rt_trace_join(ctx); if (rc != ATLAS_RT_OK) return rc; }   // pipelined host-buffer traces in flight
     ATLAS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ATLAS_RT_OK;
 }
@@ -698,16 +700,46 @@ static int trace_common(atlas_rt_context* ctx, const atlas_rt_scene* scene, cons
     ATLAS_CUDA(ctx, cudaSetDevice(ctx->device));
     const bool devIn = flags & ATLAS_RT_DEVICE_INPUT, devOut = flags & ATLAS_RT_DEVICE_OUTPUT;
     float4 *dIn = nullptr, *dOut = nullptr;
+    bool pipelinedCall = false;
     const float4* in = static_cast<const float4*>(rays_in);
     float4* out = static_cast<float4*>(rays_out);
-    if (!devIn) {
-        ATLAS_CUDA(ctx, dev_alloc(ctx, &dIn, count * 3));
-        in = dIn;
-    }
     // ATLAS_RT_HITS_ONLY: the output is one 16-byte hit record per ray (never in place on the 48-byte rays)
     const bool hitsOnly = (flags & ATLAS_RT_HITS_ONLY) != 0;
     const size_t outStride = hitsOnly ? 1 : 3;   // float4s per ray in the output
-    if (!devOut) {
+    // ATLAS_RT_PIPELINED calls use two persistent staging sets in turn (a stream-ordered allocation would tie this call's first
+    // operation to the previous call's last download, through the pool, and undo the overlap)
+    const bool wantPipelined = (flags & ATLAS_RT_PIPELINED) && (flags & ATLAS_RT_ASYNC) && !devIn && !devOut && count >= 262144 && ctx->copyIn && ctx->copyOut &&
+                               !ctx->traceStreaming && !(flags & ATLAS_RT_COUNTERS);
+    int stageSet = -1;
+    if (wantPipelined) {
+        stageSet = ctx->stageNext;
+        ctx->stageNext ^= 1;
+        const size_t needIn = size_t(count) * 48, needOut = hitsOnly ? size_t(count) * 16 : 0;
+        if (ctx->stageInBytes[stageSet] < needIn || ctx->stageOutBytes[stageSet] < needOut) {   // (re)size: rare, synchronises
+            ATLAS_CUDA(ctx, cudaDeviceSynchronize());
+            if (ctx->stageInBytes[stageSet] < needIn) {
+                cudaFree(ctx->stageIn[stageSet]); ctx->stageIn[stageSet] = nullptr; ctx->stageInBytes[stageSet] = 0;
+                ATLAS_CUDA(ctx, cudaMalloc(&ctx->stageIn[stageSet], needIn));
+                ctx->stageInBytes[stageSet] = needIn;
+            }
+            if (ctx->stageOutBytes[stageSet] < needOut) {
+                cudaFree(ctx->stageOut[stageSet]); ctx->stageOut[stageSet] = nullptr; ctx->stageOutBytes[stageSet] = 0;
+                ATLAS_CUDA(ctx, cudaMalloc(&ctx->stageOut[stageSet], needOut));
+                ctx->stageOutBytes[stageSet] = needOut;
+            }
+        }
+        // the call that used this set two calls ago must be through with it before the uploads overwrite it
+        if (ctx->stageUsed[stageSet]) ATLAS_CUDA(ctx, cudaStreamWaitEvent(ctx->copyIn, ctx->pipeEvents[36 + stageSet], 0));
+        in = static_cast<const float4*>(ctx->stageIn[stageSet]);
+        out = hitsOnly ? static_cast<float4*>(ctx->stageOut[stageSet]) : static_cast<float4*>(ctx->stageIn[stageSet]);
+    }
+    float4* const stagedIn = stageSet >= 0 ? static_cast<float4*>(ctx->stageIn[stageSet]) : nullptr;
+    if (!devIn && stageSet < 0) {
+        ATLAS_CUDA(ctx, dev_alloc(ctx, &dIn, count * 3));
+        in = dIn;
+    }
+    if (stagedIn) dIn = stagedIn;   // (not owned by this call: see the release below)
+    if (!devOut && stageSet < 0) {
         if (dIn && !hitsOnly) out = dIn;   // in-place on the staging buffer
         else {
             const cudaError_t ea = dev_alloc(ctx, &dOut, count * outStride);
@@ -718,8 +750,7 @@ static int trace_common(atlas_rt_context* ctx, const atlas_rt_scene* scene, cons
     const bool perRay = (flags & ATLAS_RT_PER_RAY_TMAX) != 0, counters = (flags & ATLAS_RT_COUNTERS) != 0;
     const bool opacity = (flags & ATLAS_RT_OPACITY) != 0;
     if (opacity && !scene->allShading) {
-        dev_free(ctx, dIn);
-        dev_free(ctx, dOut);
+        if (stageSet < 0) { dev_free(ctx, dIn); dev_free(ctx, dOut); }
         return fail(ctx, ATLAS_RT_ERR_INVALID, "ATLAS_RT_OPACITY needs atlas_rt_mesh_pack_shading on every mesh of the scene (before atlas_rt_scene_create)");
     }
     int rc = ATLAS_RT_OK;
@@ -859,7 +890,15 @@ static int trace_common(atlas_rt_context* ctx, const atlas_rt_scene* scene, cons
             if (e == cudaSuccess && !devOut) e = cudaMemcpyAsync(hOut, dst, 16 * outStride * (end - b), cudaMemcpyDeviceToHost, ctx->copyOut);
         }
         if (e == cudaSuccess) e = cudaEventRecord(ev[33], ctx->copyOut);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev[33], 0);   // the context stream now orders after the downloads
+        // ATLAS_RT_PIPELINED (with ATLAS_RT_ASYNC, host output): the call's completion is NOT ordered into the context stream, so the
+        // next such call starts uploading while this one's last chunks are still being traced and sent home (the calls share the
+        // copy / compute streams, which keep each of them in order). atlas_rt_trace_join orders the context stream after the last one.
+        pipelinedCall = stageSet >= 0 && rc == ATLAS_RT_OK && e == cudaSuccess;
+        if (pipelinedCall) {
+            ctx->pendingJoin = true;
+            e = cudaEventRecord(ctx->pipeEvents[36 + stageSet], ctx->copyOut);
+            ctx->stageUsed[stageSet] = true;
+        } else if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev[33], 0);   // the context stream now orders after the downloads
         if (e != cudaSuccess && rc == ATLAS_RT_OK) rc = fail(ctx, ATLAS_RT_ERR_CUDA, "pipelined trace", e);
         if (ctx->pipeTimeline && rc == ATLAS_RT_OK && cudaEventSynchronize(ev[33]) == cudaSuccess) {
             fprintf(stderr, "[atlas_rt timeline] %u chunks:", chunks);
@@ -890,8 +929,13 @@ static int trace_common(atlas_rt_context* ctx, const atlas_rt_scene* scene, cons
         for (auto& cs : ctx->computeExtra) if (cs) cudaStreamSynchronize(cs);
         if (ctx->sortStream) cudaStreamSynchronize(ctx->sortStream);
     }
-    dev_free(ctx, dIn);
-    dev_free(ctx, dOut);
+    if (stageSet >= 0) {
+        // persistent staging: nothing to release; a failed or fallen-back call must not leave the set in flight unaccounted
+        if (!pipelinedCall) { cudaStreamSynchronize(ctx->copyIn); cudaStreamSynchronize(ctx->copyOut); for (auto& cs : ctx->computeExtra) if (cs) cudaStreamSynchronize(cs); cudaStreamSynchronize(ctx->stream); }
+    } else {
+        dev_free(ctx, dIn);
+        dev_free(ctx, dOut);
+    }
     if (rc != ATLAS_RT_OK) return rc;
     if (flags & ATLAS_RT_ASYNC) return ATLAS_RT_OK;
     // synchronous call: also report rays that ran out of the reference's 32-entry stack
@@ -911,6 +955,21 @@ int atlas_rt_trace_closest(atlas_rt_context* ctx, const atlas_rt_scene* scene, c
 int atlas_rt_trace_any(atlas_rt_context* ctx, const atlas_rt_scene* scene, const void* rays_in, uint64_t count,
                        uint32_t cull_mask, float t_min, float t_max, void* rays_out, uint32_t flags) {
     return trace_common(ctx, scene, rays_in, count, cull_mask, t_min, t_max, rays_out, flags, true);
+}
+
+int atlas_rt_trace_join(atlas_rt_context* ctx) {
+    if (!ctx) return ATLAS_RT_ERR_INVALID;
+    ATLAS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->pendingJoin) {
+        ATLAS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pipeEvents[33], 0));
+        for (auto& cs : ctx->computeExtra) {   // (the chunk traces of those calls; implied by the downloads, made explicit for device-side consumers)
+            if (!cs) continue;
+            ATLAS_CUDA(ctx, cudaEventRecord(ctx->pipeEvents[35], cs));
+            ATLAS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pipeEvents[35], 0));
+        }
+        ctx->pendingJoin = false;
+    }
+    return ATLAS_RT_OK;
 }
 
 int atlas_rt_trace_counters(atlas_rt_context* ctx, uint64_t out[6]) {

@@ -97,8 +97,8 @@ struct atlas_rt_context {
     cudaStream_t copyIn = nullptr, copyOut = nullptr;
     cudaStream_t computeExtra[7] = {};   // extra compute streams: the chunks of a pipelined host-buffer trace run side by side
     int pipeStreams = 8;                 // compute streams such a call uses (the context stream + computeExtra)
-    cudaEvent_t pipeEvents[36] = {};   // pipelined host-buffer trace: [0] staging ready, [1+c] chunk c uploaded, [17+c] chunk c traced, [33] all done;
-                                       // streaming trace: [1+c] chunk c uploaded (c < 32), [33] all downloaded, [34] ordering stream done
+    cudaEvent_t pipeEvents[38] = {};   // pipelined host-buffer trace: [0] staging ready, [1+c] chunk c uploaded, [17+c] chunk c traced, [33] all done;
+                                       // streaming trace: [1+c] chunk c uploaded (c < 32), [33] all downloaded, [34] ordering stream done; [35] join scratch, [36], [37] pipelined call on staging set 0 / 1 done
     void* levelSlots = nullptr;                // pinned: per-level flags the builder's kernels write for the host (build.cu)
     // scheduling knobs of the persistent traversal kernel (trace.cu); ATLAS_RT_TRACE_* environment variables override
     int traceLeafThreshold = 8;     // lanes waiting at a leaf before the warp runs a leaf round
@@ -113,6 +113,12 @@ struct atlas_rt_context {
     int traceMinBlocksPerSM = 2;    // ... but never fewer CTAs than this per SM
     int ptLanes = 4;                // ATLAS_RT_PT_LANES: sample passes of one atlas_rt_pathtrace_bounces call that run side by side (1..4)
     int streamBlocksPerSM = 7;      // CTAs per SM of a streaming launch (the per-chunk ordering kernels need the rest of the SM)
+    void* stageIn[2] = {nullptr, nullptr};   // persistent staging of ATLAS_RT_PIPELINED host-buffer traces, two sets used in turn
+    void* stageOut[2] = {nullptr, nullptr};
+    size_t stageInBytes[2] = {0, 0}, stageOutBytes[2] = {0, 0};
+    bool stageUsed[2] = {false, false};
+    int stageNext = 0;
+    bool pendingJoin = false;       // ATLAS_RT_PIPELINED host-buffer traces are in flight that the context stream has not been ordered after
     bool pipeTimeline = false;      // ATLAS_RT_PIPE_TIMELINE: per-chunk upload / trace completion times of the chunked pipeline on stderr
     cudaStream_t sortStream = nullptr;   // high-priority stream of a streaming launch's per-chunk ordering kernels
     // worker contexts (own stream + own pinned level flags each) that atlas_rt_build_blas_batch builds on side by side

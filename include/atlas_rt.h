@@ -62,6 +62,7 @@ typedef enum atlas_rt_status {
 #define ATLAS_RT_COUNTERS      (1u << 4)   /* trace_*: also count visited nodes / triangles (slower; for parity + roofline) */
 #define ATLAS_RT_RAY_BINNING   (1u << 6)   /* pathtrace_bounces: order the rays of bounce >= 1 by the reference's 8x8 octahedral direction bins */
 #define ATLAS_RT_ACCUM_TILE_ORDER (1u << 7) /* pathtrace_*: index the accumulation buffer in rayGen's tile order instead of y * width + x */
+#define ATLAS_RT_PIPELINED     (1u << 10)  /* trace_* with host buffers and ATLAS_RT_ASYNC: successive calls overlap; atlas_rt_trace_join before the results are used */
 #define ATLAS_RT_PEER_OUTPUT   (1u << 9)   /* trace_sharded: every rank's traversal kernel stores its hit records straight into the root's memory (NVLink P2P), no gather */
 #define ATLAS_RT_HITS_ONLY     (1u << 8)   /* trace_*: rays_out receives count x 16-byte hit records (the ray's `hit` vec4: t, bits(hitID),
                                               bits(hitInstanceID), v) instead of 48-byte rays — the compact stream the multi-GPU gather moves */
@@ -240,6 +241,15 @@ int atlas_rt_trace_any(atlas_rt_context* ctx, const atlas_rt_scene* scene, const
  * out = tlasNodes, instances entered, blasNodes, triangles tested, max stack depth, rays that overflowed the stack.
  * These are the visit counts SURVEY.md 8(d) turns into algorithmic bytes. */
 int atlas_rt_trace_counters(atlas_rt_context* ctx, uint64_t out[6]);
+
+/* Host-buffer trace calls made with ATLAS_RT_ASYNC | ATLAS_RT_PIPELINED (host rays in, host results out) do not order their
+ * completion into the context stream: the next such call starts uploading while the previous one's last chunks are still being
+ * traced and downloaded - a renderer's double-buffered batches (different host output buffers; the same input buffer may be
+ * reused) keep PCIe and the GPU busy across call boundaries. atlas_rt_trace_join orders the context stream after every such
+ * call made so far; the results are in the host buffers once the context stream has been synchronised after it
+ * (atlas_rt_context_synchronize joins by itself). Stack-overflow reports (ATLAS_RT_ERR_STACK) are not available for such
+ * calls. The calls use two persistent device staging sets in turn, so at most two of them are in flight; a third waits. */
+int atlas_rt_trace_join(atlas_rt_context* ctx);
 
 /* ------------------------------------------------------------------------------------------- path tracer ---- */
 typedef struct atlas_rt_camera {

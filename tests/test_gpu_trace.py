@@ -260,3 +260,41 @@ def test_streaming_host_buffer_trace(ctx, oracle):
         assert np.array_equal(d_out.cpu().numpy().view(np.uint32), want.view(np.uint32))
     finally:
         sctx.close()
+
+
+def test_pipelined_host_buffer_calls(ctx, oracle):
+    """ATLAS_RT_ASYNC | ATLAS_RT_PIPELINED: successive host-buffer trace calls overlap (two persistent staging sets used in turn,
+    completion not ordered into the context stream until atlas_rt_trace_join / atlas_rt_context_synchronize). Five calls in a
+    row with different rays and alternating result buffers, closest and any-hit, 16-byte records and whole rays: every buffer
+    must hold what the device-pointer call gives; a synchronous call issued while pipelined ones are in flight is correct too."""
+    import torch
+    tris = W.soup(150_000, seed=31)
+    boxes = W.tri_boxes(tris)
+    root = np.concatenate([boxes[:, :3].min(0), boxes[:, 3:].max(0)])[None].astype(np.float32)
+    scene, osc, keep = gpu_and_oracle_scene(ctx, oracle, [tris], root, W.identity_instance())
+    n = 300_000
+    batches = [W.random_rays(n, root[0, :3], root[0, 3:], seed=500 + k) for k in range(5)]
+    for b in batches:
+        b[:, 8] = np.float32(0.5)
+    d_out = torch.empty((n, 12), dtype=torch.float32, device="cuda")
+    want = []
+    for k, b in enumerate(batches):
+        ctx.trace(scene, torch.from_numpy(b).cuda(), n, out=d_out, any_hit=bool(k & 1), flags=capi.PER_RAY_TMAX if (k & 1) else 0)
+        want.append(d_out.cpu().numpy().copy())
+    ref, _ = oracle.trace(osc, batches[0][:20000], nthreads=8)
+    assert np.array_equal(want[0][:20000].view(np.uint32), ref.view(np.uint32))
+    h_in = [torch.from_numpy(b).pin_memory() for b in batches]
+    for hits_only in (True, False):
+        width = 4 if hits_only else 12
+        h_out = [torch.zeros((n, width), dtype=torch.float32).pin_memory() for _ in batches]
+        fl = capi.ASYNC | capi.PIPELINED | (capi.HITS_ONLY if hits_only else 0)
+        for k in range(5):
+            fn = ctx.L.atlas_rt_trace_any if (k & 1) else ctx.L.atlas_rt_trace_closest
+            ctx.check(fn(ctx.h, scene.h, h_in[k].data_ptr(), n, capi.MASK_ALL, 0.0, capi.INF, h_out[k].data_ptr(), fl | (capi.PER_RAY_TMAX if (k & 1) else 0)))
+        mid = ctx.trace(scene, batches[2])                       # an ordinary synchronous call in between
+        assert np.array_equal(mid.view(np.uint32), want[2].view(np.uint32))
+        ctx.synchronize()                                        # joins the pipelined calls
+        for k in range(5):
+            got = h_out[k].numpy()
+            exp = want[k][:, 8:12] if hits_only else want[k]
+            assert np.array_equal(got.view(np.uint32), exp.view(np.uint32)), (hits_only, k)
