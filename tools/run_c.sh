@@ -1,9 +1,10 @@
 #!/bin/bash
-O=gpurun_out
-timeout 700 python -m pytest tests -m gpu -q --tb=short -x > $O/pytest9.log 2>&1; tail -4 $O/pytest9.log
-NCU="ncu --clock-control none"
-PT='regex:trace_kernel|shade_|raygen|ray_cost|bin_count|bin_offsets|bin_scatter|set_words|next_bounce|add_accum'
-timeout 400 $NCU --metrics gpu__time_duration.sum -c 1500 --csv --log-file $O/r2_launches_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras --profile > $O/r2_launches_bench.out 2>&1
-timeout 300 $NCU --metrics gpu__time_duration.sum -k "$PT" -c 600 --csv --log-file $O/r2_launches_c5.csv python tools/prof_targets.py c5 > $O/r2_launches_c5.out 2>&1
-python tools/ncu_summary.py launches $O/r2_launches_bench.csv | head -30
-python tools/ncu_summary.py launches $O/r2_launches_c5.csv | head -20
+B="timeout 300 python bench.py --steps 30 --warmup 5 --no-extras --no-cpu-baseline"
+show() { python -c "
+import json,sys
+try:
+    d=json.loads(sys.stdin.read()); print('$1', 'e2e_ms', round(d['e2e']['ms_per_step'],4), 'latency', round(d['e2e']['latency_ms_one_synchronous_call'],4), 'equal', d['e2e'].get('host_records_equal_device_path'))
+except Exception as e: print('$1', 'FAILED', e)"; }
+for ch in 4 6 8 12; do ATLAS_RT_PIPE_CHUNKS=$ch $B 2>/dev/null | show chunks$ch; done
+ATLAS_RT_PIPE_CHUNKS=6 ATLAS_RT_TRACE_RAYS_PER_WARP=192 ATLAS_RT_TRACE_MIN_BLOCKS_PER_SM=1 $B 2>/dev/null | show chunks6_rpw192
+ATLAS_RT_PIPE_CHUNKS=8 ATLAS_RT_TRACE_RAYS_PER_WARP=192 ATLAS_RT_TRACE_MIN_BLOCKS_PER_SM=1 $B 2>/dev/null | show chunks8_rpw192
