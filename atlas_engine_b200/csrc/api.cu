@@ -31,6 +31,11 @@ void ctx_release(atlas_rt_context* ctx) {
     for (auto& w : ctx->workers) if (w) { atlas_rt_context_destroy(w); w = nullptr; }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    // calls that were not ordered into the context stream (pipelined host-buffer traces) may still be using the other streams
+    if (ctx->copyIn) cudaStreamSynchronize(ctx->copyIn);
+    if (ctx->copyOut) cudaStreamSynchronize(ctx->copyOut);
+    for (auto& cs : ctx->computeExtra) if (cs) cudaStreamSynchronize(cs);
+    if (ctx->sortStream) cudaStreamSynchronize(ctx->sortStream);
     for (auto& ev : ctx->pipeEvents) if (ev) cudaEventDestroy(ev);
     if (ctx->copyIn) cudaStreamDestroy(ctx->copyIn);
     if (ctx->copyOut) cudaStreamDestroy(ctx->copyOut);
