@@ -450,6 +450,7 @@ void atlas_rt_bvh_free(atlas_rt_bvh* bvh) {
     if (!bvh) return;
     atlas_rt_context* ctx = bvh->ctx;
     cudaSetDevice(ctx->device);
+    if (ctx->pendingJoin) atlas_rt_trace_join(ctx);   // pipelined traces in flight may still read it: the frees below are ordered on the context stream
     dev_free(ctx, bvh->nodes);
     dev_free(ctx, bvh->order);
     dev_free(ctx, bvh->endOfNode);
@@ -562,6 +563,7 @@ void atlas_rt_mesh_free(atlas_rt_mesh* mesh) {
     if (!mesh) return;
     cudaSetDevice(mesh->ctx->device);
     atlas_rt_context* ctx = mesh->ctx;
+    if (ctx->pendingJoin) atlas_rt_trace_join(ctx);
     dev_free(ctx, mesh->tris);
     dev_free(ctx, mesh->tris96);
     delete mesh;
@@ -685,6 +687,7 @@ void atlas_rt_scene_free(atlas_rt_scene* scene) {
     if (!scene) return;
     cudaSetDevice(scene->ctx->device);
     atlas_rt_context* ctx = scene->ctx;
+    if (ctx->pendingJoin) atlas_rt_trace_join(ctx);
     dev_free(ctx, scene->instances);
     dev_free(ctx, scene->blasNodes);
     dev_free(ctx, scene->bvhTris);
