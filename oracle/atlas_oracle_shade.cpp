@@ -6,9 +6,10 @@
 // Every function cites the reference lines it follows (paths relative to /root/reference). Third-party arithmetic:
 // glm 0.9.8.0 (vcpkg.json:45-48; header-only, NOT under /root/reference) — normalize / dot / cross / packHalf2x16 /
 // packUnorm4x8 are restated from glm's published source; the GLSL built-ins (unpackHalf2x16, unpackUnorm4x8, normalize,
-// ...) from the GLSL 4.60 specification. Nothing here is pinned by a golden vector of the reference (it has none for these
-// functions, and neither its shaders nor MeshData::BuildBVH can run in this container: no Vulkan device): PARITY UNPINNED
-// for this file; the CUDA kernels are compared against it.
+// ...) from the GLSL 4.60 specification. Pinned against the reference's own compiled code: pack_signed_3x10_1x2
+// (Common::Packing::PackSignedVector3x10_1x2 in oracle/_ref, tests/test_oracle_vs_ref.py). Nothing else here is pinned by a
+// golden vector of the reference (it has none for these functions, and neither its shaders nor MeshData::BuildBVH can run in
+// this container: no Vulkan device): PARITY UNPINNED for the rest of this file; the CUDA kernels are compared against it.
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -112,6 +113,12 @@ void oracle_pack_shading_words(const float* tris, const float* normals, const fl
         o[9] = pack_unorm4x8(col + 4);
         o[10] = pack_unorm4x8(col + 8);
     }
+}
+
+// The restatement of Common::Packing::PackSignedVector3x10_1x2 by itself, so that tests/test_oracle_vs_ref.py can pin it
+// against the reference's compiled function (oracle/_ref: common/Packing.cpp).
+void oracle_pack_signed_3x10_1x2(const float* vec4s, uint64_t n, int32_t* out) {
+    for (uint64_t i = 0; i < n; i++) out[i] = int32_t(pack_signed_3x10_1x2(vec4s[4 * i], vec4s[4 * i + 1], vec4s[4 * i + 2], vec4s[4 * i + 3]));
 }
 
 }   // extern "C"

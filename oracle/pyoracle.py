@@ -122,6 +122,13 @@ class Ref:
         self.lib.ref_bvh_intersect_closest(bvh.handle, _ptr(rays8), n, _ptr(tuv), _ptr(idx), nthreads)
         return tuv, idx
 
+    def pack_signed(self, vec4s):
+        """Atlas::Common::Packing::PackSignedVector3x10_1x2 (the reference's compiled code) over (n, 4) float32 vectors."""
+        v = np.ascontiguousarray(vec4s, dtype=np.float32).reshape(-1, 4)
+        out = np.zeros(v.shape[0], dtype=np.int32)
+        self.lib.ref_pack_signed_3x10_1x2(_ptr(v), C.c_uint64(v.shape[0]), _ptr(out))
+        return out
+
     def intersect_any(self, bvh, rays8, nthreads=1):
         rays8 = _f32c(rays8)
         n = rays8.shape[0]
@@ -260,6 +267,12 @@ class Oracle:
         self.lib.oracle_pt_shade(_ptr(scene.instances), scene._tri96_ptrs, *scene.material_args(), _ptr(rays), _ptr(pay), _ptr(vis), n,
                                  C.byref(params), seed, bounce, _ptr(alive), _ptr(ro), _ptr(po), _ptr(fin), _ptr(rr))
         return dict(alive=alive.astype(bool), rays=ro, payload=po, finished=fin, rr=rr)
+
+    def pack_signed(self, vec4s):
+        v = np.ascontiguousarray(vec4s, dtype=np.float32).reshape(-1, 4)
+        out = np.zeros(v.shape[0], dtype=np.int32)
+        self.lib.oracle_pack_signed_3x10_1x2(_ptr(v), C.c_uint64(v.shape[0]), _ptr(out))
+        return out
 
     def ray_bins(self, rays):
         rays = _f32c(rays).reshape(-1, 12)

@@ -4,6 +4,7 @@
 // lie under /root/reference; never linked into or called by the product library.
 #include "volume/BVH.h"
 #include "jobsystem/JobSystem.h"
+#include "common/Packing.h"
 
 #include <cstring>
 #include <thread>
@@ -158,6 +159,13 @@ void ref_bvh_intersect_any(void* h, const float* rays, uint64_t n, uint8_t* out_
         if (b < e) pool.emplace_back(work, b, e);
     }
     for (auto& t : pool) t.join();
+}
+
+// Common::Packing::PackSignedVector3x10_1x2 (common/Packing.cpp:24-35), the reference's own code: n vec4s in, n words out.
+// (The packed normals / tangents / bitangents of GPUTriangle, mesh/MeshData.cpp:205-210, are made by exactly this function.)
+void ref_pack_signed_3x10_1x2(const float* vec4s, uint64_t n, int32_t* out) {
+    for (uint64_t i = 0; i < n; i++)
+        out[i] = Common::Packing::PackSignedVector3x10_1x2(glm::vec4(vec4s[4 * i], vec4s[4 * i + 1], vec4s[4 * i + 2], vec4s[4 * i + 3]));
 }
 
 }

@@ -74,3 +74,23 @@ def test_oracle_matches_golden_arrays(oracle):
         t = oracle.build_blas(W.tri_boxes(tris), tris)
         assert np.array_equal(t.nodes, g[name + "_nodes"]) and np.array_equal(t.order, g[name + "_order"])
         assert np.array_equal(t.end_of_node, g[name + "_flags"])
+
+
+def test_packed_normal_word_matches_the_reference_function(ref, oracle):
+    """Common::Packing::PackSignedVector3x10_1x2 (common/Packing.cpp:24-35) makes the packed normals / tangent / bitangent of
+    GPUTriangle (mesh/MeshData.cpp:205-210). The reference's own compiled function (oracle/_ref) against the restatement inside
+    oracle/atlas_oracle_shade.cpp: unit vectors, the whole [-1, 1] cube, out-of-range values, zeros, infinities and NaNs (the
+    float -> int conversion of the x86 build: 0x80000000)."""
+    rng = np.random.default_rng(17)
+    v = rng.uniform(-1.0, 1.0, (400_000, 4)).astype(np.float32)
+    n = rng.normal(size=(200_000, 3)).astype(np.float32)
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    v[:200_000, :3] = n
+    v[:200_000, 3] = 0.0
+    v[200_000:200_500] = rng.uniform(-3.0, 3.0, (500, 4)).astype(np.float32)
+    special = np.array([[1, 1, 1, 1], [-1, -1, -1, -1], [0, 0, 0, 0], [-0.0, 0.0, -0.0, 0.0], [np.nan, 0.5, -0.5, 0.0], [0.25, np.nan, np.nan, np.nan],
+                        [np.inf, -np.inf, 1e30, -1e30], [1.0 - 2 ** -24, -1.0 + 2 ** -24, 2 ** -126, -(2 ** -126)]], dtype=np.float32)
+    v[-len(special):] = special
+    a, b = ref.pack_signed(v), oracle.pack_signed(v)
+    assert np.array_equal(a, b)
+    assert int(a[-len(special) + 4]) & 0x3ff == 0 and (int(a[-len(special) + 6]) & 0xffffffff) == 0x80000000   # the x86 conversion of NaN / inf
